@@ -1,0 +1,129 @@
+/* socioreasoner_b200.h -- C ABI of the B200-native SocioReasoner hot path (libsocioreasoner_b200.so).
+ *
+ * The reference (AMAP-ML/SocioReasoner) has NO native/FFI interface: its seam is the Python strategy
+ * class hierarchy (roll/distributed/strategy/strategy.py:16-138) and every op below is reached there
+ * through a pip library (torch/cuBLAS, flash-attn, HF transformers eager code).  Each entry point cites
+ * the reference call site whose arithmetic it replaces; `HF:` = transformers/models/qwen2_5_vl/
+ * modeling_qwen2_5_vl.py (the third-party module the reference imports at
+ * mcore_adapter/src/mcore_adapter/models/qwen2_5_vl/modeling_qwen2_5_vl.py:190-200 and
+ * roll/models/model_providers.py:123-127).
+ *
+ * Conventions: plain pointers + sizes, no torch types.  All pointers are DEVICE pointers unless a name ends
+ * in `_host`.  `stream` is a cudaStream_t passed as void*.  Return 0 on success, negative on error
+ * (sr_last_error() returns a thread-local message).  No hidden allocations, no global state besides
+ * per-process caches of driver entry points / function attributes.  bf16 = __nv_bfloat16 storage,
+ * fp32 accumulation.  Every kernel is sm_100a-only; there is no CPU or non-Blackwell fallback.
+ */
+#ifndef SOCIOREASONER_B200_H
+#define SOCIOREASONER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR_ABI_VERSION 1
+
+/* error codes */
+#define SR_OK 0
+#define SR_ERR_INVALID (-1)
+#define SR_ERR_CUDA (-2)
+#define SR_ERR_DRIVER (-3)
+#define SR_ERR_UNSUPPORTED (-4)
+
+/* GEMM epilogues */
+#define SR_EPI_NONE 0     /* C = A.W^T (+bias)                                            */
+#define SR_EPI_RESIDUAL 1 /* C = A.W^T (+bias) + residual                                 */
+#define SR_EPI_SWIGLU 2   /* C[:, j] = silu(gate_j) * up_j ; W rows packed [16 gate|16 up] */
+#define SR_EPI_GELU 3     /* C = gelu_erf(A.W^T + bias)                                   */
+
+#define SR_DTYPE_BF16 0
+#define SR_DTYPE_F32 1
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* sr_last_error(void);
+int sr_abi_version(void);
+/* 0 if the current CUDA device is compute capability 10.x (B200), else SR_ERR_UNSUPPORTED. */
+int sr_device_check(void);
+
+/* ---- dense contraction (tcgen05 + TMA) ------------------------------------------------------
+ * C[M, n_out] = epilogue(A[M,K] . W[N,K]^T), bf16 inputs, fp32 accumulate in TMEM.
+ * Replaces torch.nn.functional.linear / Conv3d-as-GEMM at HF:91-114 (patch embed), HF:214,285 (ViT qkv,
+ * proj), HF:77-88 (ViT MLP), HF:133-146 (merger), HF:704-707 (decoder q/k/v/o), HF:611-624 (decoder MLP),
+ * HF:1385 (lm_head).  lda/ldw/ldc/ldr are row strides in ELEMENTS (multiples of 8).  bias: fp32[N] or NULL.
+ * SR_EPI_SWIGLU: W/bias rows are packed in groups of 32 = [16 gate rows | 16 up rows]; n_out = N/2.
+ * block_n: 0 = auto (256 for M > 64, else 32), or 32 / 128 / 256. */
+int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, const float* bias,
+                 const void* residual, int64_t ldr, int M, int N, int K, int epilogue, int out_dtype, int block_n,
+                 void* stream);
+
+/* ---- attention (tcgen05 + TMA) --------------------------------------------------------------
+ * Variable-length softmax(Q K^T * scale) V; query row r attends key rows k with row_lo[r] <= k < row_hi[r].
+ * Replaces flash_attn_varlen_func / eager per-window attention at HF:244-283 (ViT windowed + full attention,
+ * cu_window_seqlens / cu_seqlens) and the causal GQA prefill attention at HF:740-756.
+ * Q [n_q_rows, n_q_heads, 128], K [n_k_rows, n_kv_heads, 128] (head_dim 80 zero-padded to 128), strides in elements;
+ * Vt [n_kv_heads*head_dim_v, n_vt_cols] = V transposed (row stride vt_row_stride); O [n_q_rows, n_q_heads, head_dim_v].
+ * tiles: int32[n_tiles][4] = {q_row0, q_nrows(<=128), kv_lo, kv_hi}; row_lo/row_hi: int32[n_q_rows].
+ * head_dim_v: 80 (ViT) or 128 (decoder). */
+int sr_attention_fwd(const void* Q, int64_t q_row_stride, int64_t q_head_stride, int n_q_rows, int n_q_heads,
+                     const void* K, int64_t k_row_stride, int64_t k_head_stride, int n_k_rows, int n_kv_heads,
+                     const void* Vt, int64_t vt_row_stride, int n_vt_cols, void* O, int64_t o_row_stride,
+                     int64_t o_head_stride, const int32_t* tiles, int n_tiles, const int32_t* row_lo,
+                     const int32_t* row_hi, float scale, int head_dim_v, void* stream);
+
+/* Decode-step attention: one query token per sample against its KV cache (the reference's vLLM decode step,
+ * roll/distributed/strategy/vllm_strategy.py:114-141; HF:740-756 with use_cache).  q [batch, n_q_heads*128] (ldq),
+ * Kc [rows, n_kv_heads, 128], Vt [n_kv_heads*128, ldvt]; sample b attends cache rows [kv_start[b], +kv_len[b]). */
+int sr_decode_attention(const void* q, int64_t ldq, const void* Kc, const void* Vt, int64_t ldvt, const int32_t* kv_start,
+                        const int32_t* kv_len, int max_len, void* out, int64_t ldo, int batch, int n_q_heads,
+                        int n_kv_heads, float scale, void* stream);
+
+/* ---- HBM-bound element-wise / gather kernels ------------------------------------------------ */
+/* RMSNorm, fp32 math (HF:57-71; mcore_adapter/src/mcore_adapter/models/model_utils.py:91-106). dim in {256,1280,2048}. */
+int sr_rmsnorm_bf16(const void* x, int64_t ldx, const float* weight, void* y, int64_t ldy, int rows, int dim, float eps,
+                    void* stream);
+/* dst[i,:] = src[idx[i],:] (idx NULL = identity); src bf16 or fp32 (cast to bf16).  Window re-order and its inverse
+ * (HF:478-485,511-513), last-token rows for the LM head. */
+int sr_gather_rows(const void* src, int64_t lds, int src_dtype, const int32_t* idx, void* dst, int64_t ldd, int rows,
+                   int cols, void* stream);
+/* out[i,:] = vis_idx[i] >= 0 ? vis[vis_idx[i],:] : table[ids[i],:]  (embed_tokens + masked_scatter, HF:1299-1307;
+ * mcore_adapter/.../qwen2_5_vl/modeling_qwen2_5_vl.py:294-315). */
+int sr_embed_scatter(const void* table, int64_t ldt, const int64_t* ids, const void* vis, int64_t ldv,
+                     const int32_t* vis_idx, void* out, int64_t ldo, int rows, int cols, void* stream);
+/* ViT 2-D rotary table cos/sin [n,40] fp32 from per-patch (h,w) indices (HF:117-130,382-409). inv_freq fp32[20]. */
+int sr_vit_rope_table(const int32_t* hpos, const int32_t* wpos, const float* inv_freq, float* cos_out, float* sin_out,
+                      int n, void* stream);
+/* Decoder M-RoPE table cos/sin [S,64] fp32 from pos3 int64[3,S] with section select (t,h,w) = (sec_t,sec_h,sec_w)
+ * (mcore_adapter/.../qwen2_5_vl/modeling_qwen2_5_vl.py:21-75; HF:595-608,627-669). inv_freq fp32[64]. */
+int sr_mrope_table(const int64_t* pos3, const float* inv_freq, float* cos_out, float* sin_out, int S, int sec_t,
+                   int sec_h, int sec_w, void* stream);
+/* ViT: split qkv [n, 3*16*80], apply 2-D RoPE (HF:156-167), write Qp/Kp [n,16,128] (zero-padded) and Vt [16*80, ldvt]. */
+int sr_vit_rope_split(const void* qkv, int64_t ldqkv, const float* cosb, const float* sinb, void* Qp, void* Kp, void* Vt,
+                      int64_t ldvt, int n, void* stream);
+/* Decoder: M-RoPE on q (in place) and k; append k -> Kc[cache_row[s]], v -> Vt[:, cache_row[s]] (KV cache). */
+int sr_mrope_kv(void* qkv, int64_t ldqkv, const float* cosb, const float* sinb, const int32_t* cache_row, void* Kc,
+                void* Vt, int64_t ldvt, int S, int n_q_heads, int n_kv_heads, void* stream);
+
+/* ---- LM-head tail --------------------------------------------------------------------------- */
+/* Greedy token: argmax over V per row (first index on ties). logits bf16 or fp32. */
+int sr_argmax_rows(const void* logits, int64_t ld, int dtype, int rows, int V, int64_t* out, void* stream);
+/* log_probs_from_logits / entropy_from_logits (roll/utils/functionals.py:193-205). Either output may be NULL. */
+int sr_logprob_entropy(const void* logits, int64_t ld, int dtype, int rows, int V, const int64_t* labels, float* logprob,
+                       float* entropy, void* stream);
+
+/* ---- mask epilogue + IoU -------------------------------------------------------------------- */
+/* seg_strategy.py:47-65: per object pick argmax(scores) of 3 candidates, bilinear up-sample h x w -> image_size^2
+ * (align_corners=False), > 0, OR over objects, cv2.INTER_NEAREST resize to out_size^2, uint8 {0,1}. */
+int sr_mask_epilogue(const float* low_res_logits, const float* scores, int n_obj, int h, int w, int image_size,
+                     int out_size, uint8_t* out_mask, void* stream);
+/* compute_giou (rlvr_socioseg_vlm_pipeline_infer.py:45-58): iou[i] = |p&g| / |p|g| on >0 masks, empty union ->
+ * empty_value (1.0 infer pipeline, 0.0 reward worker socioseg_rule_reward_worker.py:181-199). counts (optional)
+ * int32[n_masks][2] = {inter, union}. */
+int sr_mask_iou(const uint8_t* pred, const uint8_t* gt, int n_masks, int64_t n_pix, float empty_value, float* iou,
+                int32_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOCIOREASONER_B200_H */

@@ -1,0 +1,170 @@
+"""Oracle restatements of the small in-tree algorithms on the hot path (TEST INFRASTRUCTURE).
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).
+Pure numpy / torch on CPU; no CUDA, no imports from the product package.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------------------------
+# M-RoPE position ids -- reference semantics (NOT transformers 5.x semantics).
+# Follows mcore_adapter/src/mcore_adapter/models/qwen2_5_vl/modeling_qwen2_5_vl.py:319-441 and its
+# call site roll/pipeline/rlvr/rlvr_socioseg_vlm_pipeline_infer.py:330-368.
+# Image temporal index is 0 (second_per_grid_t = 0 for images, :368-376), i.e. t = text_len + st_idx.
+# ----------------------------------------------------------------------------------------------
+def get_rope_index(
+    input_ids: torch.Tensor,
+    image_grid_thw: Optional[torch.Tensor],
+    attention_mask: Optional[torch.Tensor] = None,
+    *,
+    spatial_merge_size: int = 2,
+    image_token_id: int = 151655,
+    vision_start_token_id: int = 151652,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Returns (position_ids [3,B,S] int64, rope_deltas [B,1])."""
+    if image_grid_thw is None:
+        # text-only branch, reference :421-441
+        if attention_mask is not None:
+            position_ids = attention_mask.long().cumsum(-1) - 1
+            position_ids.masked_fill_(attention_mask == 0, 1)
+            position_ids = position_ids.unsqueeze(0).expand(3, -1, -1)
+            mx = position_ids.max(0)[0].max(-1, keepdim=True)[0]
+            return position_ids.clone(), mx + 1 - attention_mask.shape[-1]
+        B, S = input_ids.shape
+        return (
+            torch.arange(S).view(1, 1, -1).expand(3, B, -1).clone(),
+            torch.zeros(B, 1, dtype=input_ids.dtype),
+        )
+    if attention_mask is None:
+        attention_mask = torch.ones_like(input_ids)
+    B, S = input_ids.shape
+    position_ids = torch.ones(3, B, S, dtype=input_ids.dtype)  # padded slots keep 1, reference :338-345
+    deltas = []
+    image_index = 0
+    for i in range(B):
+        ids = input_ids[i][attention_mask[i] == 1]
+        toks = ids.tolist()
+        starts = torch.argwhere(ids == vision_start_token_id).squeeze(1)
+        image_nums = int((ids[starts + 1] == image_token_id).sum()) if len(starts) else 0
+        pos_list: List[torch.Tensor] = []
+        st = 0
+        for _ in range(image_nums):
+            ed = toks.index(image_token_id, st)
+            t, h, w = (int(x) for x in image_grid_thw[image_index])
+            image_index += 1
+            gh, gw = h // spatial_merge_size, w // spatial_merge_size
+            text_len = ed - st
+            st_idx = int(pos_list[-1].max()) + 1 if pos_list else 0
+            pos_list.append(torch.arange(text_len).view(1, -1).expand(3, -1) + st_idx)
+            t_index = torch.zeros(t * gh * gw, dtype=torch.long)  # images: second_per_grid_t == 0
+            h_index = torch.arange(gh).view(1, -1, 1).expand(t, -1, gw).flatten()
+            w_index = torch.arange(gw).view(1, 1, -1).expand(t, gh, -1).flatten()
+            pos_list.append(torch.stack([t_index, h_index, w_index]) + text_len + st_idx)
+            st = ed + t * gh * gw
+        if st < len(toks):
+            st_idx = int(pos_list[-1].max()) + 1 if pos_list else 0
+            pos_list.append(torch.arange(len(toks) - st).view(1, -1).expand(3, -1) + st_idx)
+        llm_positions = torch.cat(pos_list, dim=1).reshape(3, -1)
+        position_ids[:, i, attention_mask[i] == 1] = llm_positions
+        deltas.append(int(llm_positions.max()) + 1 - S)
+    return position_ids, torch.tensor(deltas).unsqueeze(1)
+
+
+# ----------------------------------------------------------------------------------------------
+# log-prob / entropy from logits -- roll/utils/functionals.py:193-205 and the masking wrappers
+# roll/distributed/strategy/strategy.py:123-138.
+# ----------------------------------------------------------------------------------------------
+def log_probs_from_logits(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    lp = F.log_softmax(logits.float(), dim=-1)
+    return lp.gather(dim=-1, index=labels.unsqueeze(-1)).squeeze(-1)
+
+
+def entropy_from_logits(logits: torch.Tensor) -> torch.Tensor:
+    logits = logits.float()
+    pd = F.softmax(logits, dim=-1)
+    return torch.logsumexp(logits, dim=-1) - torch.sum(pd * logits, dim=-1)
+
+
+def op_compute_log_probs(logits, input_ids, attention_mask):
+    labels = input_ids[:, 1:].clone()
+    labels[attention_mask[:, 1:] == 0] = 0
+    return log_probs_from_logits(logits[:, :-1], labels) * attention_mask[:, 1:]
+
+
+def op_compute_entropy(logits, attention_mask):
+    return entropy_from_logits(logits)[:, :-1] * attention_mask[:, 1:]
+
+
+# ----------------------------------------------------------------------------------------------
+# Mask epilogue -- roll/distributed/strategy/seg_strategy.py:37-69.  SAM2's predictor (external
+# `sam2`, un-vendored, not installed) ends with bilinear up-sampling of the low-res mask logits to the
+# image size and a `> mask_threshold (0.0)` test; that tail is restated here with the same torch call
+# (F.interpolate bilinear, align_corners=False) on SYNTHETIC low-res logits.
+# ----------------------------------------------------------------------------------------------
+def mask_epilogue(
+    low_res_logits: torch.Tensor,  # [n_obj, 3, h, w] float32
+    scores: torch.Tensor,  # [n_obj, 3] float32
+    image_size: int = 756,
+    out_size: int = 768,
+) -> np.ndarray:
+    import cv2
+
+    if low_res_logits.shape[0] == 0:  # seg_strategy.py:40-45 -- empty prompt list
+        return np.zeros((out_size, out_size), dtype=np.uint8)
+    mask = np.zeros((image_size, image_size), dtype=np.uint8)
+    for o in range(low_res_logits.shape[0]):
+        up = F.interpolate(
+            low_res_logits[o : o + 1].float(), (image_size, image_size), mode="bilinear", align_corners=False
+        )[0]
+        pred_masks = (up > 0.0).numpy()
+        best = pred_masks[int(np.argmax(scores[o].numpy()))]  # seg_strategy.py:59
+        mask = np.logical_or(mask, best).astype(np.uint8)  # seg_strategy.py:60
+    return cv2.resize(mask, (out_size, out_size), interpolation=cv2.INTER_NEAREST)  # :65
+
+
+def compute_giou(pred_mask: np.ndarray, gt_mask: np.ndarray) -> float:
+    """roll/pipeline/rlvr/rlvr_socioseg_vlm_pipeline_infer.py:45-58 (both-empty -> 1.0)."""
+    p = pred_mask > 0
+    g = gt_mask > 0
+    inter = np.logical_and(p, g).sum()
+    union = np.logical_or(p, g).sum()
+    if union == 0:
+        return 1.0
+    return float(inter / union)
+
+
+def compute_iou_reward(pred_mask: np.ndarray, gt_mask: np.ndarray) -> float:
+    """roll/pipeline/rlvr/rewards/socioseg_rule_reward_worker.py:181-199 (empty union / shape mismatch -> 0.0)."""
+    if pred_mask.shape != gt_mask.shape:
+        return 0.0
+    p = pred_mask > 0
+    g = gt_mask > 0
+    union = np.logical_or(p, g).sum()
+    if union == 0:
+        return 0.0
+    return float(np.logical_and(p, g).sum() / union)
+
+
+# ----------------------------------------------------------------------------------------------
+# DP sharding of whole samples -- roll/distributed/scheduler/protocol.py:550-617 (chunk sizes follow
+# np.array_split) and decorator.py:106-180 (dispatch by dp rank, concat in rank order on collect).
+# ----------------------------------------------------------------------------------------------
+def dp_chunk_indices(batch: int, dp_size: int) -> List[np.ndarray]:
+    return [np.asarray(c) for c in np.array_split(np.arange(batch), dp_size)]
+
+
+# ----------------------------------------------------------------------------------------------
+# postprocess_generate -- roll/utils/functionals.py:768-872 (the part the strategy contract needs:
+# pad to sequence_length, split prompt/response, masks).  M-RoPE response positions follow the last
+# prompt position + 1.. (:838-852).
+# ----------------------------------------------------------------------------------------------
+def pad_generate_output(output: torch.Tensor, sequence_length: int, pad_token_id: int) -> torch.Tensor:
+    if output.shape[1] >= sequence_length:
+        return output[:, :sequence_length]
+    return F.pad(output, (0, sequence_length - output.shape[1]), value=pad_token_id)

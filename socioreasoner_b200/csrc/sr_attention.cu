@@ -1,0 +1,337 @@
+// sr_attention.cu -- variable-length softmax(Q K^T * scale) V on tcgen05 tensor cores (sm_100a).
+//
+// One kernel serves the three attention shapes of the hot path:
+//   * ViT windowed attention  (HF modeling_qwen2_5_vl.py:244-283 with cu_window_seqlens; 28 of 32 blocks)
+//   * ViT full attention      (same code with per-image cu_seqlens; blocks 7/15/23/31)
+//   * decoder causal GQA prefill (HF:740-756; 16 q heads / 2 kv heads, head_dim 128)
+// which the reference reaches through flash-attn 2 (mma.sync) or an eager per-window python loop.
+//
+// Generic formulation: query row r attends keys k with row_lo[r] <= k < row_hi[r] (absolute key-row indices).
+// A work tile = up to 128 consecutive query rows + the key range [kv_lo, kv_hi) that covers all their ranges
+// (host-built list, see socioreasoner_b200/attention_plan.py).  Windows, images, samples and causality are all
+// expressed through (tiles, row_lo, row_hi); rows of one tile never straddle samples.
+//
+// Layouts (bf16):  Q [rows, heads, 128]  K [rows, kv_heads, 128]  (head_dim 80 of the ViT zero-padded to 128)
+//                  Vt [kv_heads * HDV, key columns]  (V transposed, so both MMAs are K-major)   O [rows, heads, HDV]
+//
+// CTA = (tile, q head).  warp 0: TMA producer (Q once, K/V 2-stage ring).  warp 1: one thread issues
+// S = Q K^T (M128 N128 K128) into a double-buffered TMEM S and PV = P V (M128 N=HDV K128) into TMEM.
+// warps 2-5: one query row per thread: tcgen05.ld S, mask, online softmax in fp32 (exp2), P -> bf16 into
+// 128B-swizzled smem (A operand of the PV MMA), O accumulated in registers with the usual rescale.
+#include "sr_host.h"
+
+namespace sr {
+
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_BM = 128;   // query rows per tile
+constexpr int ATT_BN = 128;   // keys per block
+constexpr int ATT_D = 128;    // (padded) qk head dim
+
+struct AttnParams {
+  __nv_bfloat16* O;
+  int64_t o_row_stride, o_head_stride;
+  const int4* tiles;  // {q_row0, q_nrows, kv_lo, kv_hi}
+  const int* row_lo;
+  const int* row_hi;
+  float scale_log2;
+  int group;  // q heads per kv head
+};
+
+template <int HDV>
+struct AttnCfg {
+  static constexpr int kQBytes = ATT_BM * ATT_D * 2;      // 32 KB (2 boxes)
+  static constexpr int kKBytes = ATT_BN * ATT_D * 2;      // 32 KB (2 boxes)
+  static constexpr int kVBoxBytes = HDV * 128;            // [HDV rows x 64 keys]
+  static constexpr int kVBytes = 2 * kVBoxBytes;
+  static constexpr int kKVStage = kKBytes + ((kVBytes + 1023) / 1024) * 1024;
+  static constexpr int kPBytes = ATT_BM * ATT_BN * 2;     // 32 KB
+  static constexpr int kSmemBytes = kQBytes + 2 * kKVStage + kPBytes + 1024 + 256;
+};
+
+template <int HDV>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using Cfg = AttnCfg<HDV>;
+  static_assert(HDV % 16 == 0 && HDV <= 128, "HDV");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Cfg::kQBytes;
+  uint8_t* sP = sKV + 2 * Cfg::kKVStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;    // [2]
+  uint64_t* p_ready = bars + 7;
+  uint64_t* pv_full = bars + 8;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int4 tile = p.tiles[blockIdx.x];
+  const int q_row0 = tile.x, q_nrows = tile.y, kv_lo = tile.z, kv_hi = tile.w;
+  const int head = blockIdx.y;
+  const int kv_head = head / p.group;
+  const int nblk = (kv_hi - kv_lo + ATT_BN - 1) / ATT_BN;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_ready, 128);
+    mbar_init(pv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t kTmemPV = 256;
+
+  if (nblk > 0) {
+    if (warp_idx == 0) {
+      // ---------------- TMA producer ----------------
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+        tma_load_3d(sQ, &tmQ, q_full, 0, head, q_row0);
+        tma_load_3d(sQ + 16384, &tmQ, q_full, 64, head, q_row0);
+        for (int j = 0; j < nblk; ++j) {
+          const int s = j & 1;
+          const uint32_t ph = (j >> 1) & 1;
+          mbar_wait(&kv_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], Cfg::kKBytes + Cfg::kVBytes);
+          uint8_t* sK = sKV + s * Cfg::kKVStage;
+          uint8_t* sV = sK + Cfg::kKBytes;
+          const int kbase = kv_lo + j * ATT_BN;
+          tma_load_3d(sK, &tmK, &kv_full[s], 0, kv_head, kbase);
+          tma_load_3d(sK + 16384, &tmK, &kv_full[s], 64, kv_head, kbase);
+          tma_load_2d(sV, &tmV, &kv_full[s], kbase, kv_head * HDV);
+          tma_load_2d(sV + Cfg::kVBoxBytes, &tmV, &kv_full[s], kbase + 64, kv_head * HDV);
+        }
+      }
+    } else if (warp_idx == 1) {
+      // ---------------- MMA issuer ----------------
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, ATT_BN);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, HDV);
+        const uint32_t aQ = smem_u32(sQ);
+        const uint32_t aP = smem_u32(sP);
+        auto issue_s = [&](int j) {
+          const int s = j & 1;
+          mbar_wait(&kv_full[s], (j >> 1) & 1);
+          tc_fence_after();
+          const uint32_t aK = smem_u32(sKV + s * Cfg::kKVStage);
+          const uint32_t tS = tmem_base + static_cast<uint32_t>(s * ATT_BN);
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(aQ + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
+            const uint64_t db = umma_desc_k_sw128(aK + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
+            umma_bf16_ss(tS, da, db, idesc_s, k != 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[s]);
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        for (int j = 0; j < nblk; ++j) {
+          if (j + 1 < nblk) issue_s(j + 1);
+          mbar_wait(p_ready, j & 1);
+          tc_fence_after();
+          const int s = j & 1;
+          const uint32_t aV = smem_u32(sKV + s * Cfg::kKVStage + Cfg::kKBytes);
+#pragma unroll
+          for (int k = 0; k < ATT_BN / 16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(aP + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
+            const uint64_t db = umma_desc_k_sw128(aV + (k >> 2) * Cfg::kVBoxBytes) + static_cast<uint64_t>((k & 3) * 2);
+            umma_bf16_ss(tmem_base + kTmemPV, da, db, idesc_pv, k != 0 ? 1u : 0u);
+          }
+          umma_commit(pv_full);
+          umma_commit(&kv_empty[s]);
+        }
+      }
+    } else {
+      // ---------------- softmax / output warps: one query row per thread ----------------
+      const int quarter = warp_idx & 3;
+      const int r = quarter * 32 + lane;
+      const bool row_ok = r < q_nrows;
+      int lo = 0, hi = 0;
+      if (row_ok) {
+        lo = __ldg(p.row_lo + q_row0 + r);
+        hi = __ldg(p.row_hi + q_row0 + r);
+      }
+      const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+      float m = -INFINITY, l = 0.f;
+      float o[HDV];
+#pragma unroll
+      for (int i = 0; i < HDV; ++i) o[i] = 0.f;
+      uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
+      const int sw = r & 7;
+
+      for (int j = 0; j < nblk; ++j) {
+        const int s = j & 1;
+        const int kbase = kv_lo + j * ATT_BN;
+        mbar_wait(&s_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + lane_off + static_cast<uint32_t>(s * ATT_BN);
+        // pass 1: row max
+        float mx = m;
+#pragma unroll 1
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = kbase + c * 32 + i;
+            const float sv = (key >= lo && key < hi) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
+            mx = fmaxf(mx, sv);
+          }
+        }
+        const float m_use = (mx == -INFINITY) ? 0.f : mx;
+        const float alpha = exp2f(m - m_use);
+        float rowsum = 0.f;
+        // pass 2: probabilities -> bf16 P tile (K-major, 128B swizzle: 16B chunk index XOR (row & 7))
+#pragma unroll 1
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + c * 32, v);
+          tmem_ld_wait();
+          float pr[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = kbase + c * 32 + i;
+            const float sv = (key >= lo && key < hi) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
+            pr[i] = exp2f(sv - m_use);
+            rowsum += pr[i];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int unit = c * 4 + u;  // 16-byte unit (8 keys) within the 128-key row
+            uint4 pk;
+            pk.x = pack_bf16x2(pr[u * 8 + 0], pr[u * 8 + 1]);
+            pk.y = pack_bf16x2(pr[u * 8 + 2], pr[u * 8 + 3]);
+            pk.z = pack_bf16x2(pr[u * 8 + 4], pr[u * 8 + 5]);
+            pk.w = pack_bf16x2(pr[u * 8 + 6], pr[u * 8 + 7]);
+            uint8_t* dst = prow + (unit >> 3) * 16384 + (((unit & 7) ^ sw) << 4);
+            *reinterpret_cast<uint4*>(dst) = pk;
+          }
+        }
+        l = l * alpha + rowsum;
+        m = mx;
+        tc_fence_before();         // our TMEM reads of S / PV are ordered before the MMAs released below
+        fence_proxy_async_smem();  // P (generic-proxy stores) visible to the tensor-core (async) proxy
+        mbar_arrive(p_ready);
+        // O = O * alpha + P V
+        mbar_wait(pv_full, j & 1);
+        tc_fence_after();
+        const uint32_t tPV = tmem_base + lane_off + kTmemPV;
+#pragma unroll
+        for (int c = 0; c < HDV / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tPV + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[c * 16 + i] = o[c * 16 + i] * alpha + __uint_as_float(v[i]);
+        }
+      }
+      if (row_ok) {
+        const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+        __nv_bfloat16* dst = p.O + static_cast<int64_t>(q_row0 + r) * p.o_row_stride + static_cast<int64_t>(head) * p.o_head_stride;
+#pragma unroll
+        for (int g = 0; g < HDV / 8; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv);
+          pk.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
+          pk.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
+          pk.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int HDV>
+static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p, int n_tiles,
+                       int n_heads, cudaStream_t stream) {
+  using Cfg = AttnCfg<HDV>;
+  auto kern = attn_fwd_kernel<HDV>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  dim3 grid(n_tiles, n_heads);
+  kern<<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(q, k, v, p);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+}  // namespace sr
+
+extern "C" int sr_attention_fwd(const void* Q, int64_t q_row_stride, int64_t q_head_stride, int n_q_rows, int n_q_heads,
+                                const void* K, int64_t k_row_stride, int64_t k_head_stride, int n_k_rows, int n_kv_heads,
+                                const void* Vt, int64_t vt_row_stride, int n_vt_cols, void* O, int64_t o_row_stride,
+                                int64_t o_head_stride, const int32_t* tiles, int n_tiles, const int32_t* row_lo,
+                                const int32_t* row_hi, float scale, int head_dim_v, void* stream) {
+  using namespace sr;
+  SR_REQUIRE(Q && K && Vt && O && tiles && row_lo && row_hi, "sr_attention_fwd: null pointer");
+  SR_REQUIRE(n_tiles > 0 && n_q_heads > 0 && n_kv_heads > 0 && n_q_heads % n_kv_heads == 0, "sr_attention_fwd: bad head/tile counts");
+  SR_REQUIRE(head_dim_v == 80 || head_dim_v == 128, "sr_attention_fwd: head_dim_v must be 80 or 128");
+  SR_REQUIRE(q_row_stride % 8 == 0 && q_head_stride % 8 == 0 && k_row_stride % 8 == 0 && k_head_stride % 8 == 0 &&
+                 vt_row_stride % 8 == 0 && o_row_stride % 8 == 0 && o_head_stride % 8 == 0,
+             "sr_attention_fwd: strides must be multiples of 8 elements");
+  SR_REQUIRE((reinterpret_cast<uintptr_t>(O) & 15) == 0 && (reinterpret_cast<uintptr_t>(tiles) & 15) == 0,
+             "sr_attention_fwd: O / tiles must be 16B aligned");
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[3] = {(uint64_t)ATT_D, (uint64_t)n_q_heads, (uint64_t)n_q_rows};
+    uint64_t strides[2] = {(uint64_t)q_head_stride * 2, (uint64_t)q_row_stride * 2};
+    uint32_t box[3] = {64, 1, (uint32_t)ATT_BM};
+    int rc = encode_tmap_bf16(&tmQ, Q, 3, dims, strides, box, 128);
+    if (rc != SR_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)ATT_D, (uint64_t)n_kv_heads, (uint64_t)n_k_rows};
+    uint64_t strides[2] = {(uint64_t)k_head_stride * 2, (uint64_t)k_row_stride * 2};
+    uint32_t box[3] = {64, 1, (uint32_t)ATT_BN};
+    int rc = encode_tmap_bf16(&tmK, K, 3, dims, strides, box, 128);
+    if (rc != SR_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)n_vt_cols, (uint64_t)n_kv_heads * (uint64_t)head_dim_v};
+    uint64_t strides[1] = {(uint64_t)vt_row_stride * 2};
+    uint32_t box[2] = {64, (uint32_t)head_dim_v};
+    int rc = encode_tmap_bf16(&tmV, Vt, 2, dims, strides, box, 128);
+    if (rc != SR_OK) return rc;
+  }
+  AttnParams p;
+  p.O = reinterpret_cast<__nv_bfloat16*>(O);
+  p.o_row_stride = o_row_stride;
+  p.o_head_stride = o_head_stride;
+  p.tiles = reinterpret_cast<const int4*>(tiles);
+  p.row_lo = row_lo;
+  p.row_hi = row_hi;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.group = n_q_heads / n_kv_heads;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (head_dim_v == 80) return launch_attn<80>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
+  return launch_attn<128>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
+}

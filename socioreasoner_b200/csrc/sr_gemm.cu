@@ -1,0 +1,330 @@
+// sr_gemm.cu -- C[M,N] = epilogue(A[M,K] . W[N,K]^T) on tcgen05 tensor cores (sm_100a).
+//
+// Replaces every nn.Linear the reference reaches through cuBLAS on the hot path (SURVEY.md 2.2 rows
+// K1,K4,K8,K9,K10,K13,K15,K16): HF modeling_qwen2_5_vl.py:91-114 (patch embed as GEMM), :214/:285
+// (ViT qkv/proj), :77-88 (ViT SwiGLU MLP), :133-146 (merger), :704-707 (decoder q/k/v/o), :611-624
+// (decoder MLP), :1385 (lm_head).
+//
+// Design (one CTA per SM, persistent over output tiles, warp-specialised):
+//   warp 0   : TMA producer  -- cp.async.bulk.tensor 2D boxes [64 x 128] (A) and [64 x BLOCK_N] (W), 128B swizzle,
+//              kStages-deep mbarrier ring.
+//   warp 1   : MMA issuer    -- one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per k-block into a
+//              double-buffered TMEM accumulator (2 x BLOCK_N fp32 columns); tcgen05.commit frees smem stages
+//              and publishes finished accumulators.
+//   warps 2-5: epilogue      -- tcgen05.ld 32 lanes x 32 columns, fused bias / residual / SwiGLU / GELU,
+//              bf16 (or fp32) vector stores.  Overlaps with the next tile's MMAs through the 2nd TMEM buffer.
+// Both operands are K-major (activations [M,K] row-major; weights in nn.Linear layout [N,K]).
+#include "sr_host.h"
+#include "../../include/socioreasoner_b200.h"
+
+namespace sr {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  void* C;
+  const float* bias;      // [N] fp32 or null
+  const void* residual;   // bf16 [M, ldr] or null
+  int64_t ldc, ldr;
+  int M, N, K;
+  int num_m_blocks, num_n_blocks;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : ((BLOCK_N >= 128) ? 6 : 8);
+  static constexpr int kABytes = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+SR_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+SR_DEVINL float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BLOCK_N, int EPI, bool OUT_F32>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 4);
+    mbar_init(&tmem_empty_bar[1], 4);
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_k_blocks = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+
+  if (warp_idx == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.num_m_blocks;
+        const int n_blk = tile / p.num_m_blocks;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * GEMM_BLOCK_K, m_blk * GEMM_BLOCK_M);
+          tma_load_2d(sa + Cfg::kABytes, &tmB, &full_bar[stage], kb * GEMM_BLOCK_K, n_blk * BLOCK_N);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16_ss(tmem_d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ---------------- epilogue warps (2..5) ----------------
+    const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.num_m_blocks;
+      const int n_blk = tile / p.num_m_blocks;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * GEMM_BLOCK_M + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(chunk * 32), v);
+        tmem_ld_wait();
+        const int col0 = n_blk * BLOCK_N + chunk * 32;
+        if (EPI == SR_EPI_SWIGLU) {
+          // packed weight rows: [16 gate | 16 up] per 32 columns -> 16 outputs at col0/2
+          const int oc0 = col0 >> 1;
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float g = __uint_as_float(v[j]);
+            float u = __uint_as_float(v[16 + j]);
+            if (p.bias != nullptr && col0 + 31 < p.N) {
+              g += __ldg(p.bias + col0 + j);
+              u += __ldg(p.bias + col0 + 16 + j);
+            }
+            o[j] = silu(g) * u;
+          }
+          if (row_ok && oc0 < (p.N >> 1)) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + oc0;
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+              uint4 pk;
+              pk.x = pack_bf16x2(o[g8 * 8 + 0], o[g8 * 8 + 1]);
+              pk.y = pack_bf16x2(o[g8 * 8 + 2], o[g8 * 8 + 3]);
+              pk.z = pack_bf16x2(o[g8 * 8 + 4], o[g8 * 8 + 5]);
+              pk.w = pack_bf16x2(o[g8 * 8 + 6], o[g8 * 8 + 7]);
+              *reinterpret_cast<uint4*>(dst + g8 * 8) = pk;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int col = col0 + g8 * 8;
+            if (col >= p.N) break;  // N % 8 == 0 (checked on the host)
+            float x[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g8 * 8 + j]);
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+            }
+            if (EPI == SR_EPI_GELU) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+            }
+            if (row_ok) {
+              if (EPI == SR_EPI_RESIDUAL) {
+                const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
+                                                                static_cast<int64_t>(row) * p.ldr + col);
+                x[0] += bf16_lo(r.x); x[1] += bf16_hi(r.x); x[2] += bf16_lo(r.y); x[3] += bf16_hi(r.y);
+                x[4] += bf16_lo(r.z); x[5] += bf16_hi(r.z); x[6] += bf16_lo(r.w); x[7] += bf16_hi(r.w);
+              }
+              if (OUT_F32) {
+                float* dst = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
+                *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+              } else {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
+                uint4 pk;
+                pk.x = pack_bf16x2(x[0], x[1]);
+                pk.y = pack_bf16x2(x[2], x[3]);
+                pk.z = pack_bf16x2(x[4], x[5]);
+                pk.w = pack_bf16x2(x[6], x[7]);
+                *reinterpret_cast<uint4*>(dst) = pk;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  // ---------------- teardown ----------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int EPI, bool OUT_F32>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI, OUT_F32>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+template <int BLOCK_N>
+static int dispatch_epi(int epi, int out_f32, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t s) {
+  if (out_f32) {
+    if (epi != SR_EPI_NONE) {
+      set_last_error("fp32 output supports SR_EPI_NONE only");
+      return SR_ERR_UNSUPPORTED;
+    }
+    return launch_gemm<BLOCK_N, SR_EPI_NONE, true>(a, b, p, s);
+  }
+  switch (epi) {
+    case SR_EPI_NONE: return launch_gemm<BLOCK_N, SR_EPI_NONE, false>(a, b, p, s);
+    case SR_EPI_RESIDUAL: return launch_gemm<BLOCK_N, SR_EPI_RESIDUAL, false>(a, b, p, s);
+    case SR_EPI_SWIGLU: return launch_gemm<BLOCK_N, SR_EPI_SWIGLU, false>(a, b, p, s);
+    case SR_EPI_GELU: return launch_gemm<BLOCK_N, SR_EPI_GELU, false>(a, b, p, s);
+  }
+  set_last_error("unknown epilogue %d", epi);
+  return SR_ERR_INVALID;
+}
+
+}  // namespace sr
+
+extern "C" int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                            const float* bias, const void* residual, int64_t ldr, int M, int N, int K, int epilogue,
+                            int out_dtype, int block_n, void* stream) {
+  using namespace sr;
+  SR_REQUIRE(A && W && C, "sr_gemm_bf16: null operand");
+  SR_REQUIRE(M > 0 && N > 0 && K > 0, "sr_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+  SR_REQUIRE(N % 8 == 0, "sr_gemm_bf16: N=%d must be a multiple of 8", N);
+  SR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "sr_gemm_bf16: lda/ldw must be >=K and multiples of 8");
+  SR_REQUIRE(epilogue != SR_EPI_RESIDUAL || (residual && ldr % 8 == 0), "sr_gemm_bf16: residual epilogue needs residual, ldr%%8==0");
+  const int n_out = (epilogue == SR_EPI_SWIGLU) ? N / 2 : N;
+  SR_REQUIRE(epilogue != SR_EPI_SWIGLU || N % 32 == 0, "sr_gemm_bf16: SwiGLU needs N %% 32 == 0 (16-gate/16-up packing)");
+  SR_REQUIRE(ldc >= n_out && ldc % (out_dtype == SR_DTYPE_F32 ? 4 : 8) == 0, "sr_gemm_bf16: bad ldc=%lld", (long long)ldc);
+  SR_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, "sr_gemm_bf16: C not 16B aligned");
+  SR_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "sr_gemm_bf16: bias not 16B aligned");
+
+  int bn = block_n;
+  if (bn == 0) bn = (M <= 64) ? 32 : 256;
+  SR_REQUIRE(bn == 32 || bn == 128 || bn == 256, "sr_gemm_bf16: block_n must be 0/32/128/256");
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {(uint32_t)GEMM_BLOCK_K, (uint32_t)GEMM_BLOCK_M};
+    int rc = encode_tmap_bf16(&tmA, A, 2, dims, strides, box, 128);
+    if (rc != SR_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {(uint32_t)GEMM_BLOCK_K, (uint32_t)bn};
+    int rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box, 128);
+    if (rc != SR_OK) return rc;
+  }
+  GemmParams p;
+  p.C = C;
+  p.bias = bias;
+  p.residual = residual;
+  p.ldc = ldc;
+  p.ldr = ldr;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m_blocks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  p.num_n_blocks = (N + bn - 1) / bn;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int f32 = out_dtype == SR_DTYPE_F32;
+  if (bn == 256) return dispatch_epi<256>(epilogue, f32, tmA, tmB, p, s);
+  if (bn == 128) return dispatch_epi<128>(epilogue, f32, tmA, tmB, p, s);
+  return dispatch_epi<32>(epilogue, f32, tmA, tmB, p, s);
+}

@@ -1,0 +1,118 @@
+// sr_host.cu -- host helpers (see sr_host.h) + library-level C-ABI entry points.
+#include "sr_host.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/socioreasoner_b200.h"
+
+namespace sr {
+
+static thread_local char g_err[1024] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_last_error() { return g_err; }
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int max_smem_optin() {
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) n = 0;
+  return n;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_last_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return SR_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_last_error("tensor map base %p not 16-byte aligned", base);
+    return SR_ERR_INVALID;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0) {
+        set_last_error("tensor map stride[%d]=%llu bytes not a multiple of 16", i, (unsigned long long)gstr[i - 1]);
+        return SR_ERR_INVALID;
+      }
+    }
+  }
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: CUresult=%d (rank=%d dims=%llu,%llu box=%u,%u)", (int)r, rank,
+                   (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0), bx[0], rank > 1 ? bx[1] : 0);
+    return SR_ERR_DRIVER;
+  }
+  return SR_OK;
+}
+
+}  // namespace sr
+
+extern "C" {
+
+const char* sr_last_error(void) { return sr::get_last_error(); }
+
+int sr_abi_version(void) { return SR_ABI_VERSION; }
+
+int sr_device_check(void) {
+  int dev = 0;
+  SR_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  SR_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  SR_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) {
+    sr::set_last_error("device %d is sm_%d%d; this library contains sm_100a code only", dev, major, minor);
+    return SR_ERR_UNSUPPORTED;
+  }
+  return SR_OK;
+}
+
+}  // extern "C"

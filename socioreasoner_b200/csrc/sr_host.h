@@ -1,0 +1,42 @@
+// sr_host.h -- host-side helpers shared by the C-ABI translation units: error reporting, the
+// cuTensorMapEncodeTiled driver entry point (resolved at run time, no link-time libcuda dependency),
+// SM count cache.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "sr_common.cuh"
+
+namespace sr {
+
+void set_last_error(const char* fmt, ...);
+const char* get_last_error();
+
+int sm_count();            // SMs of the current device (cached per device)
+int max_smem_optin();      // max dynamic shared memory per block (opt-in)
+
+// Encode a bf16 tiled tensor map.  rank 2 or 3; dims/strides innermost first; strides in BYTES for
+// dims 1.. (dim 0 is contiguous).  box = box extents (elements).  swizzle_bytes in {0, 32, 64, 128}.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box, int swizzle_bytes);
+
+#define SR_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::sr::set_last_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return SR_ERR_CUDA;                                                              \
+    }                                                                                        \
+  } while (0)
+
+#define SR_REQUIRE(cond, ...)                \
+  do {                                       \
+    if (!(cond)) {                           \
+      ::sr::set_last_error(__VA_ARGS__);     \
+      return SR_ERR_INVALID;           \
+    }                                        \
+  } while (0)
+
+}  // namespace sr

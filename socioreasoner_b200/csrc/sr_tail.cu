@@ -1,0 +1,316 @@
+// sr_tail.cu -- decode-step attention, LM-head tail (argmax, log-prob / entropy), mask epilogue and IoU.
+// All HBM/latency-bound; reported against the HBM roofline.
+#include "sr_host.h"
+
+namespace sr {
+
+// ------------------------------------------------------------------------------------------------
+// Block reductions (blockDim multiple of 32, <= 1024)
+// ------------------------------------------------------------------------------------------------
+SR_DEVINL float block_max(float v, float* sbuf) {
+  v = warp_max(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sbuf[warp] = v;
+  __syncthreads();
+  float r = (lane < nw) ? sbuf[lane] : -INFINITY;
+  r = warp_max(r);
+  return r;
+}
+SR_DEVINL float block_sum(float v, float* sbuf) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) sbuf[warp] = v;
+  __syncthreads();
+  float r = (lane < nw) ? sbuf[lane] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode-step attention: one new query token per sample against its KV cache (the vLLM decode kernel's job
+// in the reference, roll/distributed/strategy/vllm_strategy.py:114-141; HF eager equivalent HF:740-756 with
+// use_cache).  q [B, nq, 128] (row stride ldq), Kc [rows, nkv, 128], Vt [nkv*128, ldvt]; sample b attends cache
+// rows [kv_start[b], kv_start[b] + kv_len[b]).  One CTA per (sample, q head).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
+                                                         const __nv_bfloat16* __restrict__ Kc,
+                                                         const __nv_bfloat16* __restrict__ Vt, int64_t ldvt,
+                                                         const int* __restrict__ kv_start, const int* __restrict__ kv_len,
+                                                         __nv_bfloat16* __restrict__ out, int64_t ldo, int nq, int nkv,
+                                                         float scale_log2) {
+  extern __shared__ float sc[];  // [max_len] scores / probabilities
+  __shared__ float sq[128];
+  __shared__ float red[32];
+  const int b = blockIdx.x, h = blockIdx.y, kvh = h / (nq / nkv);
+  const int start = __ldg(kv_start + b), len = __ldg(kv_len + b);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 128) sq[tid] = __bfloat162float(q[static_cast<int64_t>(b) * ldq + h * 128 + tid]) * scale_log2;
+  __syncthreads();
+  // scores: each warp owns keys warp, warp+8, ...; lanes split the 128-dim dot product (8 B per lane, coalesced 256 B row)
+  float lmax = -INFINITY;
+  for (int k = warp; k < len; k += 8) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(Kc + (static_cast<int64_t>(start + k) * nkv + kvh) * 128) + lane);
+    float d = bf16_lo(u.x) * sq[lane * 4] + bf16_hi(u.x) * sq[lane * 4 + 1] + bf16_lo(u.y) * sq[lane * 4 + 2] +
+              bf16_hi(u.y) * sq[lane * 4 + 3];
+    d = warp_sum(d);
+    if (lane == 0) sc[k] = d;
+    lmax = fmaxf(lmax, d);
+  }
+  const float mx = block_max(lmax, red);
+  float lsum = 0.f;
+  for (int k = tid; k < len; k += 256) {
+    const float pv = exp2f(sc[k] - mx);
+    sc[k] = pv;
+    lsum += pv;
+  }
+  const float tot = block_sum(lsum, red);  // also orders the sc[] writes before the reads below
+  const float inv = tot > 0.f ? 1.f / tot : 0.f;
+  // o[d] = sum_k p[k] * Vt[kvh*128 + d, start + k]: warp per d, lanes stride the (contiguous) key axis
+  for (int d = warp; d < 128; d += 8) {
+    const __nv_bfloat16* vrow = Vt + static_cast<int64_t>(kvh * 128 + d) * ldvt + start;
+    float acc = 0.f;
+    for (int k = lane; k < len; k += 32) acc += sc[k] * __bfloat162float(__ldg(vrow + k));
+    acc = warp_sum(acc);
+    if (lane == 0) out[static_cast<int64_t>(b) * ldo + h * 128 + d] = __float2bfloat16(acc * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// argmax over the vocabulary (greedy decode; first index wins ties, as torch.argmax).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+SR_DEVINL float to_f32(T v);
+template <>
+SR_DEVINL float to_f32<float>(float v) { return v; }
+template <>
+SR_DEVINL float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ logits, int64_t ld, int V,
+                                                     int64_t* __restrict__ out) {
+  __shared__ float sval[32];
+  __shared__ int sidx[32];
+  const T* row = logits + static_cast<int64_t>(blockIdx.x) * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = to_f32<T>(row[i]);
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { sval[warp] = best; sidx[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < (blockDim.x >> 5) ? sval[lane] : -INFINITY;
+    bi = lane < (blockDim.x >> 5) ? sidx[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) out[blockIdx.x] = bi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// log-prob of the label and entropy per row (roll/utils/functionals.py:193-205):
+//   logp = x[label] - logsumexp(x);  H = logsumexp(x) - sum softmax(x) * x.      fp32 math.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) logprob_entropy_kernel(const T* __restrict__ logits, int64_t ld, int V,
+                                                              const int64_t* __restrict__ labels,
+                                                              float* __restrict__ logprob, float* __restrict__ entropy) {
+  __shared__ float red[32];
+  const T* row = logits + static_cast<int64_t>(blockIdx.x) * ld;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, to_f32<T>(row[i]));
+  mx = block_max(mx, red);
+  float se = 0.f, sxe = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float x = to_f32<T>(row[i]);
+    const float e = __expf(x - mx);
+    se += e;
+    sxe += e * x;
+  }
+  se = block_sum(se, red);
+  sxe = block_sum(sxe, red);
+  if (threadIdx.x == 0) {
+    const float lse = mx + logf(se);
+    if (entropy) entropy[blockIdx.x] = lse - sxe / se;
+    if (logprob) {
+      const int64_t lb = labels ? labels[blockIdx.x] : 0;
+      logprob[blockIdx.x] = to_f32<T>(row[lb]) - lse;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mask epilogue (roll/distributed/strategy/seg_strategy.py:47-65 + the tail of SAM2's predict()):
+//   per object: best = argmax(scores[o]) ; bilinear up-sample low-res logits[o,best] (h x w -> image^2,
+//   align_corners=False) ; > 0 ; OR over objects ; nearest resize image -> out (cv2.INTER_NEAREST) ; uint8.
+// Fused: one thread per OUTPUT pixel evaluates the bilinear sample at its nearest-source pixel.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_epilogue_kernel(const float* __restrict__ logits, const float* __restrict__ scores,
+                                                           int n_obj, int h, int w, int image, int out_size,
+                                                           uint8_t* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= out_size) return;
+  // cv2 INTER_NEAREST: sx = min(floor(x * (src/dst)), src-1) with the ratio in double
+  const double inv = static_cast<double>(image) / static_cast<double>(out_size);
+  int sx = static_cast<int>(floor(x * inv));
+  int sy = static_cast<int>(floor(y * inv));
+  sx = sx < image - 1 ? sx : image - 1;
+  sy = sy < image - 1 ? sy : image - 1;
+  // torch upsample_bilinear2d, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0; scale = in/out in fp32
+  const float scale_h = static_cast<float>(h) / static_cast<float>(image);
+  const float scale_w = static_cast<float>(w) / static_cast<float>(image);
+  float fy = scale_h * (static_cast<float>(sy) + 0.5f) - 0.5f;
+  float fx = scale_w * (static_cast<float>(sx) + 0.5f) - 0.5f;
+  fy = fy < 0.f ? 0.f : fy;
+  fx = fx < 0.f ? 0.f : fx;
+  int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  y0 = y0 < h - 1 ? y0 : h - 1;
+  x0 = x0 < w - 1 ? x0 : w - 1;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  float ly = fy - static_cast<float>(y0), lx = fx - static_cast<float>(x0);
+  ly = fminf(fmaxf(ly, 0.f), 1.f);
+  lx = fminf(fmaxf(lx, 0.f), 1.f);
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  uint8_t m = 0;
+  for (int o = 0; o < n_obj; ++o) {
+    const float s0 = __ldg(scores + o * 3), s1 = __ldg(scores + o * 3 + 1), s2 = __ldg(scores + o * 3 + 2);
+    int best = 0;
+    float bs = s0;
+    if (s1 > bs) { bs = s1; best = 1; }
+    if (s2 > bs) { bs = s2; best = 2; }
+    const float* p = logits + (static_cast<int64_t>(o) * 3 + best) * h * w;
+    const float v = hy * (hx * __ldg(p + y0 * w + x0) + lx * __ldg(p + y0 * w + x1)) +
+                    ly * (hx * __ldg(p + y1 * w + x0) + lx * __ldg(p + y1 * w + x1));
+    m |= (v > 0.f) ? 1 : 0;
+  }
+  out[static_cast<int64_t>(y) * out_size + x] = m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mask IoU (rlvr_socioseg_vlm_pipeline_infer.py:45-58): sum(p&g)/sum(p|g) on >0 masks, both empty -> empty_value
+// (1.0 in the infer pipeline, 0.0 in the reward worker, socioseg_rule_reward_worker.py:181-199).
+// One CTA per mask pair, 16-byte loads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) mask_iou_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt,
+                                                       int64_t n_pix, float empty_value, float* __restrict__ iou,
+                                                       int* __restrict__ counts) {
+  __shared__ float red[32];
+  const uint8_t* p = pred + static_cast<int64_t>(blockIdx.x) * n_pix;
+  const uint8_t* g = gt + static_cast<int64_t>(blockIdx.x) * n_pix;
+  int inter = 0, uni = 0;
+  const int64_t nvec = n_pix / 16;
+  for (int64_t i = threadIdx.x; i < nvec; i += blockDim.x) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p) + i);
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(g) + i);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // per-byte non-zero -> 0x01 flags
+      uint32_t pa = aw[j], pb = bw[j];
+      pa = ((pa | (pa >> 4)) & 0x0f0f0f0fu); pa = ((pa | (pa >> 2)) & 0x03030303u); pa = ((pa | (pa >> 1)) & 0x01010101u);
+      pb = ((pb | (pb >> 4)) & 0x0f0f0f0fu); pb = ((pb | (pb >> 2)) & 0x03030303u); pb = ((pb | (pb >> 1)) & 0x01010101u);
+      inter += __popc(pa & pb);
+      uni += __popc(pa | pb);
+    }
+  }
+  for (int64_t i = nvec * 16 + threadIdx.x; i < n_pix; i += blockDim.x) {
+    const int a = p[i] > 0, b = g[i] > 0;
+    inter += a & b;
+    uni += a | b;
+  }
+  const float fi = block_sum(static_cast<float>(inter), red);
+  const float fu = block_sum(static_cast<float>(uni), red);
+  if (threadIdx.x == 0) {
+    iou[blockIdx.x] = fu > 0.f ? fi / fu : empty_value;
+    if (counts) {
+      counts[blockIdx.x * 2] = static_cast<int>(fi);
+      counts[blockIdx.x * 2 + 1] = static_cast<int>(fu);
+    }
+  }
+}
+
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" int sr_decode_attention(const void* q, int64_t ldq, const void* Kc, const void* Vt, int64_t ldvt,
+                                   const int32_t* kv_start, const int32_t* kv_len, int max_len, void* out, int64_t ldo,
+                                   int batch, int n_q_heads, int n_kv_heads, float scale, void* stream) {
+  SR_REQUIRE(q && Kc && Vt && kv_start && kv_len && out, "sr_decode_attention: null pointer");
+  SR_REQUIRE(batch > 0 && n_q_heads % n_kv_heads == 0 && max_len > 0, "sr_decode_attention: bad shape");
+  const size_t smem = static_cast<size_t>(max_len) * sizeof(float);
+  SR_REQUIRE(smem <= 200 * 1024, "sr_decode_attention: max_len %d too long for the single-pass kernel", max_len);
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    SR_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_smem = 200 * 1024;
+  }
+  dim3 grid(batch, n_q_heads);
+  decode_attn_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(Kc),
+      reinterpret_cast<const __nv_bfloat16*>(Vt), ldvt, kv_start, kv_len, reinterpret_cast<__nv_bfloat16*>(out), ldo,
+      n_q_heads, n_kv_heads, scale * 1.4426950408889634f);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+extern "C" int sr_argmax_rows(const void* logits, int64_t ld, int dtype, int rows, int V, int64_t* out, void* stream) {
+  SR_REQUIRE(logits && out && rows >= 0 && V > 0, "sr_argmax_rows: bad args");
+  if (rows == 0) return SR_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SR_DTYPE_F32) argmax_kernel<float><<<rows, 1024, 0, s>>>(reinterpret_cast<const float*>(logits), ld, V, out);
+  else argmax_kernel<__nv_bfloat16><<<rows, 1024, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, V, out);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+extern "C" int sr_logprob_entropy(const void* logits, int64_t ld, int dtype, int rows, int V, const int64_t* labels,
+                                  float* logprob, float* entropy, void* stream) {
+  SR_REQUIRE(logits && rows >= 0 && V > 0 && (logprob == nullptr || labels != nullptr), "sr_logprob_entropy: bad args");
+  if (rows == 0) return SR_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == SR_DTYPE_F32)
+    logprob_entropy_kernel<float><<<rows, 1024, 0, s>>>(reinterpret_cast<const float*>(logits), ld, V, labels, logprob, entropy);
+  else
+    logprob_entropy_kernel<__nv_bfloat16><<<rows, 1024, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, V, labels,
+                                                                logprob, entropy);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+extern "C" int sr_mask_epilogue(const float* low_res_logits, const float* scores, int n_obj, int h, int w, int image_size,
+                                int out_size, uint8_t* out_mask, void* stream) {
+  SR_REQUIRE(out_mask && n_obj >= 0 && (n_obj == 0 || (low_res_logits && scores)) && h > 0 && w > 0 && image_size > 0 && out_size > 0,
+             "sr_mask_epilogue: bad args");
+  dim3 grid((out_size + 255) / 256, out_size);
+  mask_epilogue_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(low_res_logits, scores, n_obj, h, w,
+                                                                                image_size, out_size, out_mask);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+extern "C" int sr_mask_iou(const uint8_t* pred, const uint8_t* gt, int n_masks, int64_t n_pix, float empty_value, float* iou,
+                           int32_t* counts, void* stream) {
+  SR_REQUIRE(pred && gt && iou && n_masks >= 0 && n_pix > 0, "sr_mask_iou: bad args");
+  SR_REQUIRE(((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(gt)) & 15) == 0 && n_pix % 16 == 0,
+             "sr_mask_iou: masks must be 16B aligned with n_pix %% 16 == 0");
+  if (n_masks == 0) return SR_OK;
+  mask_iou_kernel<<<n_masks, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pred, gt, n_pix, empty_value, iou, counts);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}

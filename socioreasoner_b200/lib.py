@@ -1,0 +1,281 @@
+"""ctypes binding of libsocioreasoner_b200.so (the C ABI in include/socioreasoner_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every op below hands raw device pointers and the
+current CUDA stream to the hand-written sm_100a kernels.  There is NO fallback: if the shared library is missing
+or the device is not a B200 the import / first call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p, POINTER
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsocioreasoner_b200.so")
+
+EPI_NONE, EPI_RESIDUAL, EPI_SWIGLU, EPI_GELU = 0, 1, 2, 3
+DT_BF16, DT_F32 = 0, 1
+
+# every symbol include/socioreasoner_b200.h declares: name -> (restype, argtypes)
+_P = c_void_p
+SYMBOLS = {
+    "sr_last_error": (c_char_p, []),
+    "sr_abi_version": (c_int, []),
+    "sr_device_check": (c_int, []),
+    "sr_gemm_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sr_attention_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int,
+                                 _P, c_int64, c_int64, _P, c_int, _P, _P, c_float, c_int, _P]),
+    "sr_decode_attention": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int, _P, c_int64, c_int, c_int, c_int, c_float, _P]),
+    "sr_rmsnorm_bf16": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_float, _P]),
+    "sr_gather_rows": (c_int, [_P, c_int64, c_int, _P, _P, c_int64, c_int, c_int, _P]),
+    "sr_embed_scatter": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, _P]),
+    "sr_vit_rope_table": (c_int, [_P, _P, _P, _P, _P, c_int, _P]),
+    "sr_mrope_table": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "sr_vit_rope_split": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
+    "sr_mrope_kv": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
+    "sr_argmax_rows": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "sr_logprob_entropy": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "sr_mask_iou": (c_int, [_P, _P, c_int, c_int64, c_float, _P, _P, _P]),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library and bind every declared symbol.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C socioreasoner_b200/csrc).  There is no CPU / eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return (load().sr_last_error() or b"").decode()
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.stride(-1) != 1:
+        raise RuntimeError(f"{name}: innermost dimension must be contiguous")
+
+
+def device_check() -> None:
+    _check(load().sr_device_check(), "sr_device_check")
+
+
+# ---------------------------------------------------------------------------------------------------
+# ops
+# ---------------------------------------------------------------------------------------------------
+def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE, out_dtype=torch.bfloat16,
+         block_n: int = 0) -> torch.Tensor:
+    """out[M, n_out] = epilogue(a[M,K] @ w[N,K]^T (+bias)).  a, w bf16 row-major (row stride arbitrary % 8)."""
+    global launch_count
+    _req(a, torch.bfloat16, "gemm.a"); _req(w, torch.bfloat16, "gemm.w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (a.shape, w.shape)
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
+    assert out.shape == (M, n_out) and out.stride(-1) == 1
+    if bias is not None:
+        _req(bias, torch.float32, "gemm.bias")
+    if residual is not None:
+        _req(residual, torch.bfloat16, "gemm.residual")
+        epilogue = EPI_RESIDUAL if epilogue == EPI_NONE else epilogue
+    rc = load().sr_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+                             _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, M, N, K,
+                             epilogue, DT_F32 if out.dtype == torch.float32 else DT_BF16, block_n, _stream())
+    _check(rc, "sr_gemm_bf16")
+    launch_count += 1
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Tensor, tiles: torch.Tensor,
+              row_lo: torch.Tensor, row_hi: torch.Tensor, scale: float, head_dim_v: int) -> torch.Tensor:
+    """q [Rq,Hq,128], k [Rk,Hkv,128] (views with arbitrary row/head strides), vt [Hkv*hdv, cols], out [Rq,Hq,hdv]."""
+    global launch_count
+    for t, n in ((q, "q"), (k, "k"), (vt, "vt"), (out, "out")):
+        _req(t, torch.bfloat16, "attention." + n)
+    _req(tiles, torch.int32, "attention.tiles"); _req(row_lo, torch.int32, "row_lo"); _req(row_hi, torch.int32, "row_hi")
+    assert q.shape[2] == 128 and k.shape[2] == 128 and tiles.dim() == 2 and tiles.shape[1] == 4 and tiles.is_contiguous()
+    rc = load().sr_attention_fwd(q.data_ptr(), q.stride(0), q.stride(1), q.shape[0], q.shape[1],
+                                 k.data_ptr(), k.stride(0), k.stride(1), k.shape[0], k.shape[1],
+                                 vt.data_ptr(), vt.stride(0), vt.shape[1], out.data_ptr(), out.stride(0), out.stride(1),
+                                 tiles.data_ptr(), tiles.shape[0], row_lo.data_ptr(), row_hi.data_ptr(), float(scale),
+                                 head_dim_v, _stream())
+    _check(rc, "sr_attention_fwd")
+    launch_count += 1
+    return out
+
+
+def decode_attention(q, kc, vt, kv_start, kv_len, max_len, out, n_q_heads, n_kv_heads, scale):
+    global launch_count
+    rc = load().sr_decode_attention(q.data_ptr(), q.stride(0), kc.data_ptr(), vt.data_ptr(), vt.stride(0),
+                                    kv_start.data_ptr(), kv_len.data_ptr(), int(max_len), out.data_ptr(), out.stride(0),
+                                    q.shape[0], n_q_heads, n_kv_heads, float(scale), _stream())
+    _check(rc, "sr_decode_attention")
+    launch_count += 1
+    return out
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launch_count
+    _req(x, torch.bfloat16, "rmsnorm.x"); _req(weight, torch.float32, "rmsnorm.weight")
+    rows, dim = x.shape
+    if out is None:
+        out = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device)
+    rc = load().sr_rmsnorm_bf16(x.data_ptr(), x.stride(0), weight.data_ptr(), out.data_ptr(), out.stride(0), rows, dim,
+                                float(eps), _stream())
+    _check(rc, "sr_rmsnorm_bf16")
+    launch_count += 1
+    return out
+
+
+def gather_rows(src: torch.Tensor, idx: Optional[torch.Tensor], out: Optional[torch.Tensor] = None, rows: Optional[int] = None):
+    global launch_count
+    assert src.dtype in (torch.bfloat16, torch.float32) and src.is_cuda
+    n = idx.shape[0] if idx is not None else (rows if rows is not None else src.shape[0])
+    if idx is not None:
+        _req(idx, torch.int32, "gather.idx")
+    if out is None:
+        out = torch.empty((n, src.shape[1]), dtype=torch.bfloat16, device=src.device)
+    rc = load().sr_gather_rows(src.data_ptr(), src.stride(0), DT_F32 if src.dtype == torch.float32 else DT_BF16, _ptr(idx),
+                               out.data_ptr(), out.stride(0), n, src.shape[1], _stream())
+    _check(rc, "sr_gather_rows")
+    launch_count += 1
+    return out
+
+
+def embed_scatter(table, ids, vis, vis_idx, out=None):
+    global launch_count
+    _req(table, torch.bfloat16, "embed.table"); _req(ids, torch.int64, "embed.ids")
+    rows, cols = ids.shape[0], table.shape[1]
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.bfloat16, device=table.device)
+    rc = load().sr_embed_scatter(table.data_ptr(), table.stride(0), ids.data_ptr(), _ptr(vis),
+                                 vis.stride(0) if vis is not None else 0, _ptr(vis_idx), out.data_ptr(), out.stride(0),
+                                 rows, cols, _stream())
+    _check(rc, "sr_embed_scatter")
+    launch_count += 1
+    return out
+
+
+def vit_rope_table(hpos, wpos, inv_freq):
+    global launch_count
+    n = hpos.shape[0]
+    cos = torch.empty((n, 40), dtype=torch.float32, device=hpos.device)
+    sin = torch.empty_like(cos)
+    _check(load().sr_vit_rope_table(hpos.data_ptr(), wpos.data_ptr(), inv_freq.data_ptr(), cos.data_ptr(), sin.data_ptr(),
+                                    n, _stream()), "sr_vit_rope_table")
+    launch_count += 1
+    return cos, sin
+
+
+def mrope_table(pos3: torch.Tensor, inv_freq: torch.Tensor, sections=(16, 24, 24)):
+    global launch_count
+    _req(pos3, torch.int64, "mrope.pos3")
+    assert pos3.dim() == 2 and pos3.shape[0] == 3 and pos3.is_contiguous()
+    S = pos3.shape[1]
+    cos = torch.empty((S, 64), dtype=torch.float32, device=pos3.device)
+    sin = torch.empty_like(cos)
+    _check(load().sr_mrope_table(pos3.data_ptr(), inv_freq.data_ptr(), cos.data_ptr(), sin.data_ptr(), S, *sections,
+                                 _stream()), "sr_mrope_table")
+    launch_count += 1
+    return cos, sin
+
+
+def vit_rope_split(qkv, cos, sin, qp, kp, vt):
+    global launch_count
+    n = qkv.shape[0]
+    _check(load().sr_vit_rope_split(qkv.data_ptr(), qkv.stride(0), cos.data_ptr(), sin.data_ptr(), qp.data_ptr(),
+                                    kp.data_ptr(), vt.data_ptr(), vt.stride(0), n, _stream()), "sr_vit_rope_split")
+    launch_count += 1
+
+
+def mrope_kv(qkv, cos, sin, cache_row, kc, vt, n_q_heads, n_kv_heads):
+    global launch_count
+    _req(cache_row, torch.int32, "mrope_kv.cache_row")
+    _check(load().sr_mrope_kv(qkv.data_ptr(), qkv.stride(0), cos.data_ptr(), sin.data_ptr(), cache_row.data_ptr(),
+                              kc.data_ptr(), vt.data_ptr(), vt.stride(0), qkv.shape[0], n_q_heads, n_kv_heads, _stream()),
+           "sr_mrope_kv")
+    launch_count += 1
+
+
+def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launch_count
+    rows, V = logits.shape
+    if out is None:
+        out = torch.empty((rows,), dtype=torch.int64, device=logits.device)
+    _check(load().sr_argmax_rows(logits.data_ptr(), logits.stride(0), DT_F32 if logits.dtype == torch.float32 else DT_BF16,
+                                 rows, V, out.data_ptr(), _stream()), "sr_argmax_rows")
+    launch_count += 1
+    return out
+
+
+def logprob_entropy(logits: torch.Tensor, labels: Optional[torch.Tensor], want_entropy: bool = True):
+    global launch_count
+    rows, V = logits.shape
+    lp = torch.empty((rows,), dtype=torch.float32, device=logits.device) if labels is not None else None
+    ent = torch.empty((rows,), dtype=torch.float32, device=logits.device) if want_entropy else None
+    _check(load().sr_logprob_entropy(logits.data_ptr(), logits.stride(0), DT_F32 if logits.dtype == torch.float32 else DT_BF16,
+                                     rows, V, _ptr(labels), _ptr(lp), _ptr(ent), _stream()), "sr_logprob_entropy")
+    launch_count += 1
+    return lp, ent
+
+
+def mask_epilogue(low_res_logits: torch.Tensor, scores: torch.Tensor, image_size: int = 756, out_size: int = 768,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launch_count
+    n_obj = low_res_logits.shape[0]
+    if out is None:
+        out = torch.empty((out_size, out_size), dtype=torch.uint8, device=low_res_logits.device)
+    h, w = (low_res_logits.shape[2], low_res_logits.shape[3]) if n_obj else (1, 1)
+    _check(load().sr_mask_epilogue(low_res_logits.data_ptr() if n_obj else None, scores.data_ptr() if n_obj else None, n_obj,
+                                   h, w, image_size, out_size, out.data_ptr(), _stream()), "sr_mask_epilogue")
+    launch_count += 1
+    return out
+
+
+def mask_iou(pred: torch.Tensor, gt: torch.Tensor, empty_value: float = 1.0, want_counts: bool = False):
+    global launch_count
+    n = pred.shape[0]
+    n_pix = pred[0].numel()
+    iou = torch.empty((n,), dtype=torch.float32, device=pred.device)
+    counts = torch.empty((n, 2), dtype=torch.int32, device=pred.device) if want_counts else None
+    _check(load().sr_mask_iou(pred.data_ptr(), gt.data_ptr(), n, n_pix, float(empty_value), iou.data_ptr(), _ptr(counts),
+                              _stream()), "sr_mask_iou")
+    launch_count += 1
+    return (iou, counts) if want_counts else iou

@@ -61,7 +61,7 @@ def make_config(name: str):
     )
 
 
-def build_model(name: str = "tiny", seed: int = 42, dtype=torch.float32, perturb: bool = True):
+def build_model(name: str = "tiny", seed: int = 42, dtype=torch.float32, perturb: bool = True, round_bf16: bool = True):
     """Seeded random-init HF model (eager attention).  HF default init = N(0, 0.02) weights, unit norms,
     zero biases; with ``perturb`` the biases and norm weights are additionally randomised (seeded) so that
     the bias / norm-weight code paths are actually exercised by parity tests."""
@@ -78,6 +78,12 @@ def build_model(name: str = "tiny", seed: int = 42, dtype=torch.float32, perturb
                     p.copy_(torch.randn(p.shape, generator=g) * 0.02)
                 elif p.dim() == 1:  # RMSNorm weights
                     p.copy_(1.0 + torch.randn(p.shape, generator=g) * 0.1)
+    if round_bf16:
+        # A real checkpoint (Qwen2.5-VL / SocioReasoner-3B) stores bf16 values; round the random init to bf16-representable
+        # numbers so the fp32 oracle and the bf16-storage CUDA path see the SAME weights (differences are then arithmetic only).
+        with torch.no_grad():
+            for p in model.parameters():
+                p.copy_(p.to(torch.bfloat16).to(torch.float32))
     model = model.to(dtype).eval()
     return model
 

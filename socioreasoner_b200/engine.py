@@ -1,0 +1,325 @@
+"""Qwen2.5-VL forward on the hand-written sm_100a kernels: ViT -> patch merger -> embed scatter -> decoder -> logits,
+greedy KV-cache decode, mask epilogue + IoU.
+
+Follows (arithmetic only; nothing is imported from there) HF ``transformers/models/qwen2_5_vl/modeling_qwen2_5_vl.py``
+-- ``Qwen2_5_VisionTransformerPretrainedModel.forward`` (:455-518), ``Qwen2_5_VLVisionBlock`` (:290-321),
+``Qwen2_5_VLPatchMerger`` (:133-146), ``Qwen2_5_VLModel.forward`` (:1270-1345), ``Qwen2_5_VLDecoderLayer`` (:762-827) --
+which is what the reference's eager strategy executes (``roll/distributed/strategy/hf_strategy.py:84-90``).
+
+Internally sequences are PACKED (padding dropped, varlen attention); the padded [B,S] API of the reference is kept at
+the surface.  All device work goes through ``lib`` (C ABI); torch only allocates buffers and moves bytes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import lib, plan
+from .config import SocioReasonerConfig
+from .weights import PackedWeights
+
+
+def _dev(a: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
+
+
+@dataclass
+class DevAttnPlan:
+    tiles: torch.Tensor
+    row_lo: torch.Tensor
+    row_hi: torch.Tensor
+
+    @staticmethod
+    def make(p: plan.AttnPlan, device) -> "DevAttnPlan":
+        return DevAttnPlan(_dev(p.tiles, device), _dev(p.row_lo, device), _dev(p.row_hi, device))
+
+
+@dataclass
+class DevVitPlan:
+    host: plan.VitPlan
+    row_perm: torch.Tensor
+    hpos: torch.Tensor
+    wpos: torch.Tensor
+    window: DevAttnPlan
+    full: DevAttnPlan
+    cos: Optional[torch.Tensor] = None
+    sin: Optional[torch.Tensor] = None
+
+
+@dataclass
+class SeqPlan:
+    """Packed view of a padded [B,S] batch."""
+    B: int
+    S: int
+    lengths: np.ndarray          # [B]
+    q_starts: np.ndarray         # [B] packed row of each sample's first token
+    flat_index: np.ndarray       # [T] index into the flattened [B*S] grid of each packed token
+    total: int
+    last_pos: Optional[np.ndarray] = None  # [B] max M-RoPE position over the valid tokens of each sample
+
+
+class KVCache:
+    def __init__(self, n_layers: int, batch: int, l_max: int, n_kv: int, head_dim: int, device):
+        self.batch, self.l_max, self.n_kv, self.head_dim = batch, l_max, n_kv, head_dim
+        rows = batch * l_max
+        self.k = torch.zeros((n_layers, rows, n_kv, head_dim), dtype=torch.bfloat16, device=device)
+        self.vt = torch.zeros((n_layers, n_kv * head_dim, rows), dtype=torch.bfloat16, device=device)
+        self.lengths = np.zeros(batch, dtype=np.int64)
+
+    @property
+    def kv_starts(self) -> np.ndarray:
+        return np.arange(self.batch, dtype=np.int64) * self.l_max
+
+
+class Engine:
+    def __init__(self, cfg: SocioReasonerConfig, weights: PackedWeights, device="cuda"):
+        cfg.validate()
+        lib.load()
+        self.cfg, self.w, self.device = cfg, weights, torch.device(device)
+        v, t = cfg.vision, cfg.text
+        # inv_freq with the reference's exact fp32 expressions (HF:122, mcore_adapter .../modeling_qwen2_5_vl.py:62)
+        d = v.head_dim // 2
+        self.vit_inv_freq = (1.0 / (v.rope_theta ** (torch.arange(0, d, 2, dtype=torch.float) / d))).to(self.device)
+        self.txt_inv_freq = (1.0 / (t.rope_theta ** (torch.arange(0, t.head_dim, 2, dtype=torch.float32) / t.head_dim))).to(self.device)
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self._vit_plans: Dict[bytes, DevVitPlan] = {}
+
+    # ------------------------------------------------------------------ buffers
+    def _buf(self, name: str, shape, dtype=torch.bfloat16, zero: bool = False) -> torch.Tensor:
+        n = int(np.prod(shape))
+        cur = self._bufs.get(name)
+        if cur is None or cur.dtype != dtype or cur.numel() < n:
+            cur = (torch.zeros if zero else torch.empty)(max(n, 1), dtype=dtype, device=self.device)
+            self._bufs[name] = cur
+        return cur[:n].view(*shape)
+
+    def free_buffers(self) -> None:
+        self._bufs.clear()
+        self._vit_plans.clear()
+
+    # ------------------------------------------------------------------ ViT
+    def vit_plan(self, grid_thw) -> DevVitPlan:
+        g = np.ascontiguousarray(np.asarray(grid_thw.cpu() if torch.is_tensor(grid_thw) else grid_thw, dtype=np.int64))
+        key = g.tobytes()
+        p = self._vit_plans.get(key)
+        if p is None:
+            v = self.cfg.vision
+            hp = plan.vit_plan(g, v.spatial_merge_size, v.window_size, v.patch_size)
+            p = DevVitPlan(hp, _dev(hp.row_perm, self.device), _dev(hp.hpos, self.device), _dev(hp.wpos, self.device),
+                           DevAttnPlan.make(hp.window_plan, self.device), DevAttnPlan.make(hp.full_plan, self.device))
+            p.cos, p.sin = lib.vit_rope_table(p.hpos, p.wpos, self.vit_inv_freq)
+            if len(self._vit_plans) > 64:
+                self._vit_plans.clear()
+            self._vit_plans[key] = p
+        return p
+
+    def vit(self, pixel_values: torch.Tensor, grid_thw, capture: Optional[List[torch.Tensor]] = None
+            ) -> Tuple[torch.Tensor, DevVitPlan]:
+        """pixel_values [N,1176] (fp32 or bf16, processor row order) -> merged embeddings [M, 2048] in WINDOW order
+        (``vp.host.merged_reverse`` maps original order -> window order) and the plan."""
+        v, W = self.cfg.vision, self.w
+        vp = self.vit_plan(grid_thw)
+        n = vp.host.n
+        assert pixel_values.shape == (n, v.patch_dim), (pixel_values.shape, n)
+        D, H, hd = v.hidden_size, v.num_heads, v.head_dim
+        x0 = lib.gather_rows(pixel_values, vp.row_perm, out=self._buf("vit_x0", (n, v.patch_dim)))
+        h = lib.gemm(x0, W.patch_w, out=self._buf("vit_h", (n, D)))
+        y = self._buf("vit_y", (n, D))
+        qkv = self._buf("vit_qkv", (n, 3 * D))
+        qp = self._buf("vit_qp", (n, H, 128))
+        kp = self._buf("vit_kp", (n, H, 128))
+        npad = (n + 7) // 8 * 8
+        vt = self._buf("vit_vt", (H * hd, npad), zero=True)
+        ao = self._buf("vit_ao", (n, H, hd))
+        act = self._buf("vit_act", (n, v.intermediate_padded))
+        scale = hd ** -0.5
+        for i, b in enumerate(W.vit_blocks):
+            lib.rmsnorm(h, b.norm1, v.rms_norm_eps, out=y)
+            lib.gemm(y, b.qkv_w, out=qkv, bias=b.qkv_b)
+            lib.vit_rope_split(qkv, vp.cos, vp.sin, qp, kp, vt)
+            ap = vp.full if i in v.fullatt_block_indexes else vp.window
+            lib.attention(qp, kp, vt, ao, ap.tiles, ap.row_lo, ap.row_hi, scale, hd)
+            lib.gemm(ao.view(n, D), b.proj_w, out=h, bias=b.proj_b, residual=h)
+            lib.rmsnorm(h, b.norm2, v.rms_norm_eps, out=y)
+            lib.gemm(y, b.gu_w, out=act, bias=b.gu_b, epilogue=lib.EPI_SWIGLU)
+            lib.gemm(act, b.down_w, out=h, bias=b.down_b, residual=h)
+            if capture is not None:
+                capture.append(h.clone())
+        lib.rmsnorm(h, W.merger_ln, v.rms_norm_eps, out=y)
+        m = vp.host.m
+        hm = D * v.spatial_merge_size ** 2
+        z = lib.gemm(y.view(m, hm), W.merger_w0, out=self._buf("vit_z", (m, hm)), bias=W.merger_b0, epilogue=lib.EPI_GELU)
+        merged = lib.gemm(z, W.merger_w2, out=self._buf("vit_merged", (m, v.out_hidden_size)), bias=W.merger_b2)
+        return merged, vp
+
+    def image_features(self, pixel_values, grid_thw) -> torch.Tensor:
+        """Merged embeddings in ORIGINAL order (what HF's visual(...).pooler_output returns, HF:511-518)."""
+        merged, vp = self.vit(pixel_values, grid_thw)
+        rev = _dev(vp.host.merged_reverse, self.device)
+        return lib.gather_rows(merged, rev)
+
+    # ------------------------------------------------------------------ sequence packing
+    @staticmethod
+    def seq_plan(attention_mask: np.ndarray) -> SeqPlan:
+        B, S = attention_mask.shape
+        keep = attention_mask.reshape(-1) != 0
+        flat = np.nonzero(keep)[0]
+        lengths = (attention_mask != 0).sum(axis=1).astype(np.int64)
+        q_starts = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64)
+        return SeqPlan(B, S, lengths, q_starts, flat, int(lengths.sum()))
+
+    # ------------------------------------------------------------------ decoder
+    def _decoder_layers(self, x: torch.Tensor, cos, sin, cache: KVCache, cache_row: torch.Tensor,
+                        attn_plan: Optional[DevAttnPlan], decode: Optional[Tuple[torch.Tensor, torch.Tensor, int]],
+                        capture: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+        t, W = self.cfg.text, self.w
+        S = x.shape[0]
+        Hq, Hkv, hd = t.num_attention_heads, t.num_key_value_heads, t.head_dim
+        qkv_dim = (Hq + 2 * Hkv) * hd
+        tag = "d" if decode is not None else "p"
+        y = self._buf(tag + "_y", (S, t.hidden_size))
+        qkv = self._buf(tag + "_qkv", (S, qkv_dim))
+        ao = self._buf(tag + "_ao", (S, Hq * hd))
+        act = self._buf(tag + "_act", (S, t.intermediate_size))
+        scale = hd ** -0.5
+        for li, L in enumerate(W.layers):
+            lib.rmsnorm(x, L.ln1, t.rms_norm_eps, out=y)
+            lib.gemm(y, L.qkv_w, out=qkv, bias=L.qkv_b)
+            lib.mrope_kv(qkv, cos, sin, cache_row, cache.k[li], cache.vt[li], Hq, Hkv)
+            if decode is None:
+                q = qkv[:, : Hq * hd].view(S, Hq, hd)
+                lib.attention(q, cache.k[li], cache.vt[li], ao.view(S, Hq, hd), attn_plan.tiles, attn_plan.row_lo,
+                              attn_plan.row_hi, scale, hd)
+            else:
+                kv_start, kv_len, max_len = decode
+                lib.decode_attention(qkv, cache.k[li], cache.vt[li], kv_start, kv_len, max_len, ao, Hq, Hkv, scale)
+            lib.gemm(ao, L.o_w, out=x, residual=x)
+            lib.rmsnorm(x, L.ln2, t.rms_norm_eps, out=y)
+            lib.gemm(y, L.gu_w, out=act, epilogue=lib.EPI_SWIGLU)
+            lib.gemm(act, L.down_w, out=x, residual=x)
+            if capture is not None:
+                capture.append(x.clone())
+        return x
+
+    def prefill(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, position_ids: Optional[torch.Tensor],
+                pixel_values: Optional[torch.Tensor], image_grid_thw, cache: Optional[KVCache] = None,
+                reserve_new_tokens: int = 0, capture: Optional[List[torch.Tensor]] = None):
+        """Runs ViT + embed/scatter + all decoder layers over the packed tokens.
+        Returns (hidden [T, 2048] packed (pre final-norm), SeqPlan, KVCache, position_ids [3,B,S] numpy)."""
+        cfg, t = self.cfg, self.cfg.text
+        ids_cpu = input_ids.detach().cpu().numpy() if torch.is_tensor(input_ids) else np.asarray(input_ids)
+        mask_cpu = (attention_mask.detach().cpu().numpy() if torch.is_tensor(attention_mask) else np.asarray(attention_mask)) \
+            if attention_mask is not None else np.ones_like(ids_cpu)
+        grid_cpu = None
+        if image_grid_thw is not None:
+            grid_cpu = image_grid_thw.detach().cpu().numpy() if torch.is_tensor(image_grid_thw) else np.asarray(image_grid_thw)
+        sp = self.seq_plan(mask_cpu)
+        if position_ids is None:
+            pos3, _ = plan.rope_index(ids_cpu, grid_cpu, mask_cpu, cfg.image_token_id, cfg.vision_start_token_id,
+                                      cfg.vision.spatial_merge_size)
+        else:
+            pos3 = position_ids.detach().cpu().numpy() if torch.is_tensor(position_ids) else np.asarray(position_ids)
+            if pos3.shape[0] != 3:  # [B,3,S] as stored in DataProto (hf_strategy.py:65-67 transposes it)
+                pos3 = pos3.transpose(1, 0, 2)
+        sp.last_pos = np.where(mask_cpu[None] != 0, pos3, np.iinfo(np.int64).min).max(axis=(0, 2)).astype(np.int64)
+        ids_packed = ids_cpu.reshape(-1)[sp.flat_index].astype(np.int64)
+        pos_packed = np.ascontiguousarray(pos3.reshape(3, -1)[:, sp.flat_index]).astype(np.int64)
+        # vision
+        merged, vis_idx = None, None
+        if pixel_values is not None:
+            pv = pixel_values if pixel_values.is_cuda else pixel_values.to(self.device, non_blocking=True)
+            merged, vp = self.vit(pv, grid_cpu)
+            is_img = ids_packed == cfg.image_token_id
+            n_img_tok = int(is_img.sum())
+            if n_img_tok != vp.host.m:  # same check as HF get_placeholder_mask (HF:1179-1218)
+                raise ValueError(f"Image features and image tokens do not match: tokens: {n_img_tok}, features {vp.host.m}")
+            vi = np.full(sp.total, -1, dtype=np.int32)
+            vi[is_img] = vp.host.merged_reverse
+            vis_idx = _dev(vi, self.device)
+        # KV cache
+        if cache is None:
+            l_max = int((sp.lengths.max() + reserve_new_tokens + 127) // 128 * 128)
+            cache = KVCache(t.num_hidden_layers, sp.B, l_max, t.num_key_value_heads, t.head_dim, self.device)
+        assert cache.batch == sp.B and sp.lengths.max() + reserve_new_tokens <= cache.l_max
+        cache.lengths = sp.lengths.copy()
+        kv_starts = cache.kv_starts
+        cache_row_np = np.concatenate([kv_starts[b] + np.arange(sp.lengths[b]) for b in range(sp.B)]).astype(np.int32)
+        ap = DevAttnPlan.make(plan.plan_causal(sp.lengths, sp.q_starts, kv_starts), self.device)
+        ids_d = _dev(ids_packed, self.device)
+        pos_d = _dev(pos_packed, self.device)
+        cache_row = _dev(cache_row_np, self.device)
+        x = lib.embed_scatter(self.w.embed, ids_d, merged, vis_idx, out=self._buf("p_x", (sp.total, t.hidden_size)))
+        cos, sin = lib.mrope_table(pos_d, self.txt_inv_freq, t.mrope_section)
+        x = self._decoder_layers(x, cos, sin, cache, cache_row, ap, None, capture)
+        return x, sp, cache, pos3
+
+    def final_logits(self, hidden_rows: torch.Tensor, out_dtype=torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """final RMSNorm + LM head on the given rows (HF:1385)."""
+        t = self.cfg.text
+        y = lib.rmsnorm(hidden_rows, self.w.final_norm, t.rms_norm_eps)
+        return lib.gemm(y, self.w.lm_head, out=out, out_dtype=out_dtype)
+
+    # ------------------------------------------------------------------ public forwards
+    def forward_logits(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw,
+                       out_dtype=torch.float32) -> torch.Tensor:
+        """Padded-API forward: logits [B,S,V]; rows at padded positions are zero."""
+        x, sp, _, _ = self.prefill(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw)
+        V = self.cfg.text.vocab_size
+        packed = self.final_logits(x, out_dtype)
+        if sp.total == sp.B * sp.S:
+            return packed.view(sp.B, sp.S, V)
+        full = torch.zeros((sp.B * sp.S, V), dtype=out_dtype, device=self.device)
+        full[_dev(sp.flat_index, self.device)] = packed
+        return full.view(sp.B, sp.S, V)
+
+    def last_token_rows(self, x: torch.Tensor, sp: SeqPlan) -> torch.Tensor:
+        idx = _dev((sp.q_starts + sp.lengths - 1).astype(np.int32), self.device)
+        return lib.gather_rows(x, idx)
+
+    def generate_greedy(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens: int,
+                        return_logits: bool = False):
+        """Greedy decode, EOS ignored, fixed ``max_new_tokens``.  Response positions continue from the
+        last prompt position + 1 on all three axes (roll/utils/functionals.py:838-852).
+        Returns new tokens [B, T] (int64, device) and optionally fp32 logits [B, T, V]."""
+        t = self.cfg.text
+        x, sp, cache, pos3 = self.prefill(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw,
+                                          reserve_new_tokens=max_new_tokens)
+        B = sp.B
+        V = t.vocab_size
+        tokens = torch.empty((B, max_new_tokens), dtype=torch.int64, device=self.device)
+        all_logits = torch.empty((B, max_new_tokens, V), dtype=torch.float32, device=self.device) if return_logits else None
+        logits = self.final_logits(self.last_token_rows(x, sp), torch.float32, out=self._buf("g_logits", (B, V), torch.float32))
+        kv_start = _dev(cache.kv_starts.astype(np.int32), self.device)
+        lens0 = torch.from_numpy(sp.lengths.astype(np.int32)).to(self.device)
+        pos0 = torch.from_numpy(sp.last_pos).to(self.device)
+        nxt = torch.empty((B,), dtype=torch.int64, device=self.device)
+        xd = self._buf("d_x", (B, t.hidden_size))
+        max_len = int(sp.lengths.max()) + max_new_tokens
+        for step in range(max_new_tokens):
+            lib.argmax_rows(logits, out=nxt)
+            tokens[:, step] = nxt
+            if return_logits:
+                all_logits[:, step] = logits
+            if step == max_new_tokens - 1:
+                break
+            # one decode step for token `nxt` at cache slot len0 + step, position last_pos + 1 + step
+            kv_len = lens0 + (step + 1)
+            cache_row = (kv_start + lens0 + step).to(torch.int32)
+            pos = (pos0 + 1 + step).view(1, B).expand(3, B).contiguous()
+            cos, sin = lib.mrope_table(pos, self.txt_inv_freq, t.mrope_section)
+            lib.embed_scatter(self.w.embed, nxt, None, None, out=xd)
+            xo = self._decoder_layers(xd, cos, sin, cache, cache_row, None, (kv_start, kv_len, max_len))
+            logits = self.final_logits(xo, torch.float32, out=logits)
+        cache.lengths = sp.lengths + max_new_tokens - 1
+        return (tokens, all_logits) if return_logits else tokens
+
+    # ------------------------------------------------------------------ mask epilogue
+    def mask_epilogue(self, low_res_logits: torch.Tensor, scores: torch.Tensor, image_size: int = 756, out_size: int = 768,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return lib.mask_epilogue(low_res_logits, scores, image_size, out_size, out=out)
+
+    def mask_iou(self, pred: torch.Tensor, gt: torch.Tensor, empty_value: float = 1.0) -> torch.Tensor:
+        return lib.mask_iou(pred, gt, empty_value)

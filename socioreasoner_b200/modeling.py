@@ -1,0 +1,152 @@
+"""HF-style module surface over the B200 engine -- what the reference's strategies and model providers touch.
+
+The reference builds its actor through the HF Auto surface (``roll/models/model_providers.py:106-127``:
+``AutoConfig.from_pretrained`` + ``AutoModelForVision2Seq.from_pretrained``) and then only ever calls
+
+    model(input_ids=[b,S], attention_mask=[b,S], position_ids=[3,b,S], use_cache=False,
+          pixel_values=[sum N,1176], image_grid_thw=[k,3], force_vit_image=True).logits     (hf_strategy.py:84-91)
+    model.generate(input_ids=, attention_mask=, use_cache=True, pixel_values=, image_grid_thw=, **generation_config)
+                                                                                             (hf_strategy.py:123-126)
+
+This class answers exactly those calls (same argument names / meaning / error behaviour) on the hand-written
+kernels.  It is inference-only (``requires_grad`` nowhere); ``state_dict`` key names follow the checkpoint contract
+(SURVEY.md Appendix A).
+"""
+from __future__ import annotations
+
+import json
+import os
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Union
+
+import numpy as np
+import torch
+
+from . import lib
+from .config import SocioReasonerConfig
+from .engine import Engine
+from .weights import PackedWeights, pack, random_state_dict
+
+
+class CausalLMOutput(SimpleNamespace):
+    """Minimal stand-in for HF's ``Qwen2_5_VLCausalLMOutputWithPast`` (only ``.logits`` is read by the reference,
+    ``hf_strategy.py:91``; ``rope_deltas`` kept for API familiarity)."""
+
+
+class SocioReasonerB200ForConditionalGeneration:
+    """Drop-in for ``Qwen2_5_VLForConditionalGeneration`` on the reference's inference path."""
+
+    def __init__(self, config: SocioReasonerConfig, weights: PackedWeights, device="cuda", logits_dtype=torch.float32):
+        self.config = config
+        self.device = torch.device(device)
+        self.engine = Engine(config, weights, device)
+        self.logits_dtype = logits_dtype
+        self.training = False
+
+    # ---- construction -------------------------------------------------------------------------------
+    @classmethod
+    def from_state_dict(cls, state_dict: Dict[str, torch.Tensor], config, device="cuda", **kw):
+        cfg = config if isinstance(config, SocioReasonerConfig) else SocioReasonerConfig.from_hf(config)
+        return cls(cfg, pack(state_dict, cfg, device), device, **kw)
+
+    @classmethod
+    def from_hf_model(cls, hf_model, device="cuda", **kw):
+        return cls.from_state_dict(hf_model.state_dict(), hf_model.config, device, **kw)
+
+    @classmethod
+    def random_init(cls, config: SocioReasonerConfig, seed: int = 42, device="cuda", **kw):
+        sd = random_state_dict(config, seed, device)
+        w = pack(sd, config, device)
+        del sd
+        torch.cuda.empty_cache()
+        return cls(config, w, device, **kw)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, device="cuda", **kw):
+        """Loads an HF checkpoint directory (config.json + *.safetensors), the surface
+        ``model_providers.py:123-127`` uses.  Unknown HF kwargs (torch_dtype, attn_implementation, ...) are ignored:
+        there is exactly one implementation here (bf16 storage, fp32 accumulate, tcgen05 kernels)."""
+        path = pretrained_model_name_or_path
+        cfg = SocioReasonerConfig.from_pretrained(path)
+        from safetensors import safe_open  # transformers dependency, present wherever HF checkpoints are
+
+        sd: Dict[str, torch.Tensor] = {}
+        files = sorted(f for f in os.listdir(path) if f.endswith(".safetensors"))
+        if not files:
+            raise FileNotFoundError(f"no *.safetensors under {path}")
+        for f in files:
+            with safe_open(os.path.join(path, f), framework="pt", device="cpu") as fh:
+                for k in fh.keys():
+                    sd[k] = fh.get_tensor(k)
+        return cls.from_state_dict(sd, cfg, device, **{k: v for k, v in kw.items() if k in ("logits_dtype",)})
+
+    # ---- nn.Module-ish surface ------------------------------------------------------------------------
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("inference-only hot path (training backward is out of scope, SURVEY.md 8f)")
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @property
+    def dtype(self):
+        return torch.bfloat16
+
+    def __call__(self, *a, **k):
+        return self.forward(*a, **k)
+
+    # ---- forward ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor = None, attention_mask: Optional[torch.Tensor] = None,
+                position_ids: Optional[torch.Tensor] = None, use_cache: bool = False,
+                pixel_values: Optional[torch.Tensor] = None, image_grid_thw: Optional[torch.Tensor] = None,
+                force_vit_image: bool = False, **unused) -> CausalLMOutput:
+        if input_ids is None:
+            raise ValueError("You must specify input_ids")
+        if pixel_values is not None and image_grid_thw is None:
+            raise ValueError("pixel_values requires image_grid_thw")
+        # `force_vit_image` (roll/models/model_providers.py:251-320): on a text-only micro-batch the reference runs the
+        # ViT on a 4x1176 zero "mock image" and adds mean()*0 to keep ranks in collective lock-step.  The result is
+        # numerically a no-op; there is no in-forward collective here, so the flag is accepted and ignored.
+        logits = self.engine.forward_logits(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw,
+                                            out_dtype=self.logits_dtype)
+        return CausalLMOutput(logits=logits, past_key_values=None, rope_deltas=None)
+
+    @torch.no_grad()
+    def get_image_features(self, pixel_values: torch.Tensor, image_grid_thw: torch.Tensor) -> torch.Tensor:
+        return self.engine.image_features(pixel_values.to(self.device), image_grid_thw)
+
+    # ---- generate -----------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor = None, attention_mask: Optional[torch.Tensor] = None, use_cache: bool = True,
+                 pixel_values: Optional[torch.Tensor] = None, image_grid_thw: Optional[torch.Tensor] = None,
+                 position_ids: Optional[torch.Tensor] = None, max_new_tokens: int = 32, do_sample: bool = False,
+                 temperature: float = 1.0, top_p: float = 1.0, top_k: int = 0, num_beams: int = 1,
+                 repetition_penalty: float = 1.0, num_return_sequences: int = 1,
+                 eos_token_id: Union[int, List[int], None] = None, pad_token_id: Optional[int] = None,
+                 ignore_eos: bool = False, **unused) -> torch.Tensor:
+        """Returns [b * num_return_sequences, S_in + max_new_tokens] like HF generate (prompt included).  Greedy
+        only: sampling (T=1, top-p 0.8, top-k 100 in the reference yaml) is the ranked "next" row."""
+        if num_beams != 1 or repetition_penalty != 1.0:
+            raise NotImplementedError("beam search / repetition penalty are not on the SocioSeg path")
+        if do_sample and not (temperature == 0 or top_k == 1):
+            raise NotImplementedError("sampling decode is not built yet (SURVEY.md 8f rank 2); use greedy")
+        new = self.engine.generate_greedy(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens)
+        new = new.to(input_ids.device)
+        if not ignore_eos and eos_token_id is not None:
+            eos = [eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id)
+            pad = pad_token_id if pad_token_id is not None else eos[0]
+            is_eos = torch.zeros_like(new, dtype=torch.bool)
+            for e in eos:
+                is_eos |= new == e
+            after = (is_eos.cumsum(1) - is_eos.long()) > 0  # strictly after the first EOS
+            new = torch.where(after, torch.full_like(new, pad), new)
+        out = torch.cat([input_ids, new], dim=1)
+        if num_return_sequences > 1:
+            out = out.repeat_interleave(num_return_sequences, dim=0)
+        return out

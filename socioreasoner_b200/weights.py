@@ -1,0 +1,188 @@
+"""Checkpoint layout -> kernel layout.
+
+The checkpoint contract is the transformers-4.x key layout the reference's converter maps
+(``mcore_adapter/src/mcore_adapter/models/converter/template.py`` ``register_template("qwen2_5_vl", ...)``;
+SURVEY.md Appendix A): ``visual.*``, ``model.layers.*``, ``model.embed_tokens.weight``, ``model.norm.weight``,
+``lm_head.weight``.  The 5.x in-memory names (``model.visual.*``, ``model.language_model.*``) are accepted too.
+
+Kernel layout (all bf16 matrices are nn.Linear-style [N, K], K contiguous; norms / biases fp32):
+  * patch embed Conv3d weight flattened to [1280, 1176] (columns (C,T,Ph,Pw) = pixel_values column order)
+  * ViT MLP gate/up fused to one [2*Ipad, 1280] matrix, rows interleaved in groups of 16 gate / 16 up (SwiGLU is
+    evaluated in the GEMM epilogue on 32-column TMEM chunks); I = 3420 zero-padded to Ipad = 3456 so every row is a
+    multiple of 16 bytes (TMA) -- down_proj K is padded with zero columns to match
+  * decoder q/k/v fused to [2560, 2048]; gate/up fused + interleaved to [22016, 2048]
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, Iterator, List, Optional, Tuple
+
+import torch
+
+from .config import SocioReasonerConfig
+
+GROUP = 16  # SwiGLU interleave granularity (rows)
+
+
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor, pad_to: int) -> torch.Tensor:
+    """[I, ...] x2 -> [2*pad_to, ...] with rows [16 gate | 16 up] repeating; zero rows beyond I."""
+    I = gate.shape[0]
+    rest = gate.shape[1:]
+    g = torch.zeros((pad_to,) + tuple(rest), dtype=gate.dtype, device=gate.device)
+    u = torch.zeros_like(g)
+    g[:I] = gate
+    u[:I] = up
+    g = g.view(pad_to // GROUP, 1, GROUP, *rest)
+    u = u.view(pad_to // GROUP, 1, GROUP, *rest)
+    return torch.cat([g, u], dim=1).reshape(2 * pad_to, *rest).contiguous()
+
+
+def normalize_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    out = {}
+    for k, v in sd.items():
+        if k.startswith("model.visual."):
+            k = "visual." + k[len("model.visual."):]
+        elif k.startswith("model.language_model."):
+            k = "model." + k[len("model.language_model."):]
+        out[k] = v
+    return out
+
+
+@dataclass
+class VitBlockW:
+    norm1: torch.Tensor
+    norm2: torch.Tensor
+    qkv_w: torch.Tensor
+    qkv_b: torch.Tensor
+    proj_w: torch.Tensor
+    proj_b: torch.Tensor
+    gu_w: torch.Tensor
+    gu_b: torch.Tensor
+    down_w: torch.Tensor
+    down_b: torch.Tensor
+
+
+@dataclass
+class DecLayerW:
+    ln1: torch.Tensor
+    ln2: torch.Tensor
+    qkv_w: torch.Tensor
+    qkv_b: torch.Tensor
+    o_w: torch.Tensor
+    gu_w: torch.Tensor
+    down_w: torch.Tensor
+
+
+@dataclass
+class PackedWeights:
+    patch_w: torch.Tensor = None
+    vit_blocks: List[VitBlockW] = field(default_factory=list)
+    merger_ln: torch.Tensor = None
+    merger_w0: torch.Tensor = None
+    merger_b0: torch.Tensor = None
+    merger_w2: torch.Tensor = None
+    merger_b2: torch.Tensor = None
+    embed: torch.Tensor = None
+    layers: List[DecLayerW] = field(default_factory=list)
+    final_norm: torch.Tensor = None
+    lm_head: torch.Tensor = None  # == embed when tied
+
+    def nbytes(self) -> int:
+        seen, tot = set(), 0
+        def add(t):
+            nonlocal tot
+            if t is not None and t.data_ptr() not in seen:
+                seen.add(t.data_ptr()); tot += t.numel() * t.element_size()
+        for t in (self.patch_w, self.merger_ln, self.merger_w0, self.merger_b0, self.merger_w2, self.merger_b2, self.embed,
+                  self.final_norm, self.lm_head):
+            add(t)
+        for b in self.vit_blocks:
+            for t in vars(b).values():
+                add(t)
+        for l in self.layers:
+            for t in vars(l).values():
+                add(t)
+        return tot
+
+
+def pack(sd: Dict[str, torch.Tensor], cfg: SocioReasonerConfig, device="cuda") -> PackedWeights:
+    cfg.validate()
+    sd = normalize_keys(sd)
+    v, t = cfg.vision, cfg.text
+    bf = lambda x: x.to(device=device, dtype=torch.bfloat16).contiguous()
+    f32 = lambda x: x.to(device=device, dtype=torch.float32).contiguous()
+    W = PackedWeights()
+    W.patch_w = bf(sd["visual.patch_embed.proj.weight"].reshape(v.hidden_size, -1))
+    Ip = v.intermediate_padded
+    for i in range(v.depth):
+        p = f"visual.blocks.{i}."
+        gate_w, up_w = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
+        gate_b, up_b = sd[p + "mlp.gate_proj.bias"], sd[p + "mlp.up_proj.bias"]
+        down = sd[p + "mlp.down_proj.weight"]
+        down_p = torch.zeros((down.shape[0], Ip), dtype=down.dtype, device=down.device)
+        down_p[:, : v.intermediate_size] = down
+        W.vit_blocks.append(VitBlockW(
+            norm1=f32(sd[p + "norm1.weight"]), norm2=f32(sd[p + "norm2.weight"]),
+            qkv_w=bf(sd[p + "attn.qkv.weight"]), qkv_b=f32(sd[p + "attn.qkv.bias"]),
+            proj_w=bf(sd[p + "attn.proj.weight"]), proj_b=f32(sd[p + "attn.proj.bias"]),
+            gu_w=bf(interleave_gate_up(gate_w, up_w, Ip)), gu_b=f32(interleave_gate_up(gate_b, up_b, Ip)),
+            down_w=bf(down_p), down_b=f32(sd[p + "mlp.down_proj.bias"]),
+        ))
+    W.merger_ln = f32(sd["visual.merger.ln_q.weight"])
+    W.merger_w0, W.merger_b0 = bf(sd["visual.merger.mlp.0.weight"]), f32(sd["visual.merger.mlp.0.bias"])
+    W.merger_w2, W.merger_b2 = bf(sd["visual.merger.mlp.2.weight"]), f32(sd["visual.merger.mlp.2.bias"])
+    W.embed = bf(sd["model.embed_tokens.weight"])
+    for i in range(t.num_hidden_layers):
+        p = f"model.layers.{i}."
+        qkv_w = torch.cat([sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.v_proj.weight"]], 0)
+        qkv_b = torch.cat([sd[p + "self_attn.q_proj.bias"], sd[p + "self_attn.k_proj.bias"], sd[p + "self_attn.v_proj.bias"]], 0)
+        W.layers.append(DecLayerW(
+            ln1=f32(sd[p + "input_layernorm.weight"]), ln2=f32(sd[p + "post_attention_layernorm.weight"]),
+            qkv_w=bf(qkv_w), qkv_b=f32(qkv_b), o_w=bf(sd[p + "self_attn.o_proj.weight"]),
+            gu_w=bf(interleave_gate_up(sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"], t.intermediate_size)),
+            down_w=bf(sd[p + "mlp.down_proj.weight"]),
+        ))
+    W.final_norm = f32(sd["model.norm.weight"])
+    if t.tie_word_embeddings or "lm_head.weight" not in sd:
+        W.lm_head = W.embed
+    else:
+        lh = sd["lm_head.weight"]
+        W.lm_head = W.embed if lh.data_ptr() == sd["model.embed_tokens.weight"].data_ptr() else bf(lh)
+    return W
+
+
+def random_state_dict(cfg: SocioReasonerConfig, seed: int = 42, device="cuda", std: float = 0.02,
+                      dtype=torch.bfloat16) -> Dict[str, torch.Tensor]:
+    """Random-init weights of the architecture in checkpoint (4.x) layout, generated on ``device``
+    (N(0, 0.02) matrices; norm weights ~ 1, small random biases so every code path carries signal)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    v, t = cfg.vision, cfg.text
+    rn = lambda *s: (torch.randn(*s, generator=g, device=device, dtype=torch.float32) * std).to(dtype)
+    nw = lambda n: (1.0 + 0.1 * torch.randn(n, generator=g, device=device, dtype=torch.float32)).to(dtype)
+    sd: Dict[str, torch.Tensor] = {}
+    sd["visual.patch_embed.proj.weight"] = rn(v.hidden_size, v.in_channels, v.temporal_patch_size, v.patch_size, v.patch_size)
+    for i in range(v.depth):
+        p = f"visual.blocks.{i}."
+        sd[p + "norm1.weight"], sd[p + "norm2.weight"] = nw(v.hidden_size), nw(v.hidden_size)
+        sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"] = rn(3 * v.hidden_size, v.hidden_size), rn(3 * v.hidden_size)
+        sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"] = rn(v.hidden_size, v.hidden_size), rn(v.hidden_size)
+        for n in ("gate_proj", "up_proj"):
+            sd[p + f"mlp.{n}.weight"], sd[p + f"mlp.{n}.bias"] = rn(v.intermediate_size, v.hidden_size), rn(v.intermediate_size)
+        sd[p + "mlp.down_proj.weight"], sd[p + "mlp.down_proj.bias"] = rn(v.hidden_size, v.intermediate_size), rn(v.hidden_size)
+    hm = v.hidden_size * v.spatial_merge_size ** 2
+    sd["visual.merger.ln_q.weight"] = nw(v.hidden_size)
+    sd["visual.merger.mlp.0.weight"], sd["visual.merger.mlp.0.bias"] = rn(hm, hm), rn(hm)
+    sd["visual.merger.mlp.2.weight"], sd["visual.merger.mlp.2.bias"] = rn(v.out_hidden_size, hm), rn(v.out_hidden_size)
+    sd["model.embed_tokens.weight"] = rn(t.vocab_size, t.hidden_size)
+    kvd = t.num_key_value_heads * t.head_dim
+    for i in range(t.num_hidden_layers):
+        p = f"model.layers.{i}."
+        sd[p + "input_layernorm.weight"], sd[p + "post_attention_layernorm.weight"] = nw(t.hidden_size), nw(t.hidden_size)
+        sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.q_proj.bias"] = rn(t.hidden_size, t.hidden_size), rn(t.hidden_size)
+        sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.k_proj.bias"] = rn(kvd, t.hidden_size), rn(kvd)
+        sd[p + "self_attn.v_proj.weight"], sd[p + "self_attn.v_proj.bias"] = rn(kvd, t.hidden_size), rn(kvd)
+        sd[p + "self_attn.o_proj.weight"] = rn(t.hidden_size, t.hidden_size)
+        sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"] = rn(t.intermediate_size, t.hidden_size), rn(t.intermediate_size, t.hidden_size)
+        sd[p + "mlp.down_proj.weight"] = rn(t.hidden_size, t.intermediate_size)
+    sd["model.norm.weight"] = nw(t.hidden_size)
+    return sd

@@ -88,6 +88,40 @@ def build_model(name: str = "tiny", seed: int = 42, dtype=torch.float32, perturb
     return model
 
 
+def build_model_fast(name: str = "3b", seed: int = 42, dtype=torch.float32):
+    """Same architecture, weights tiled from one seeded N(0,0.02) chunk (norm weights 1): constructs the 3B model in
+    seconds instead of minutes.  ONLY for timing the CPU baseline (values do not affect CPU time); parity tests use
+    ``build_model``."""
+    from transformers import Qwen2_5_VLForConditionalGeneration
+
+    cfg = make_config(name)
+    with torch.device("meta"):
+        model = Qwen2_5_VLForConditionalGeneration._from_config(cfg, attn_implementation="eager", dtype=dtype)
+    model = model.to_empty(device="cpu")
+    g = torch.Generator().manual_seed(seed)
+    chunk = (torch.randn(1 << 22, generator=g) * 0.02).to(dtype)
+    with torch.no_grad():
+        for pname, p in model.named_parameters():
+            if p.dim() == 1 and not pname.endswith(".bias"):
+                p.fill_(1.0)
+            else:
+                flat = p.view(-1)
+                n = flat.numel()
+                reps = (n + chunk.numel() - 1) // chunk.numel()
+                flat.copy_(chunk.repeat(reps)[:n] if reps > 1 else chunk[:n])
+        vc, tc = cfg.vision_config, cfg.text_config
+        hd = vc.hidden_size // vc.num_heads // 2
+        model.model.visual.rotary_pos_emb.inv_freq.copy_(1.0 / (10000.0 ** (torch.arange(0, hd, 2, dtype=torch.float) / hd)))
+        thd = tc.hidden_size // tc.num_attention_heads
+        theta = tc.rope_parameters["rope_theta"]
+        inv = 1.0 / (theta ** (torch.arange(0, thd, 2, dtype=torch.float) / thd))
+        model.model.language_model.rotary_emb.inv_freq.copy_(inv)
+        if hasattr(model.model.language_model.rotary_emb, "original_inv_freq"):
+            model.model.language_model.rotary_emb.original_inv_freq.copy_(inv)
+    model.tie_weights()
+    return model.eval()
+
+
 def state_dict_4x_names(model) -> Dict[str, torch.Tensor]:
     """State dict renamed to the transformers-4.x checkpoint layout, which is the
     reference's checkpoint contract: ``visual.*``, ``model.layers.*``, ``model.embed_tokens``, ``lm_head``."""
@@ -203,16 +237,22 @@ def forward_logits(model, batch: Batch, output_hidden_states: bool = False):
 
 
 @torch.no_grad()
-def greedy_decode(model, batch: Batch, steps: int) -> Tuple[torch.Tensor, torch.Tensor]:
+def greedy_decode(model, batch: Batch, steps: int, timers: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Greedy, EOS ignored, fixed ``steps`` new tokens.  Response positions follow the
     last prompt position + 1.. on all three axes (roll/utils/functionals.py:838-852).  Implemented as
     explicit KV-cache steps so the positions are the reference's, not HF-5.x generate()'s.
     Returns (new_tokens [B,steps], per-step fp32 logits of the chosen row [B,steps,V])."""
+    import time as _time
+
     B, S = batch.input_ids.shape
+    _t = _time.time()
     out = model(
         input_ids=batch.input_ids, attention_mask=batch.attention_mask, position_ids=batch.position_ids,
         use_cache=True, pixel_values=batch.pixel_values.to(model.dtype), image_grid_thw=batch.image_grid_thw,
     )
+    if timers is not None:
+        timers["prefill_s"] = _time.time() - _t
+        timers["decode_s"] = []
     past = out.past_key_values
     logits = out.logits[:, -1].float()
     last_pos = batch.position_ids.max(dim=0)[0].max(dim=-1)[0]  # [B]
@@ -226,8 +266,11 @@ def greedy_decode(model, batch: Batch, steps: int) -> Tuple[torch.Tensor, torch.
             break
         mask = torch.cat([mask, torch.ones(B, 1, dtype=mask.dtype)], 1)
         pos = (last_pos + 1 + t).view(1, B, 1).expand(3, B, 1)
+        _t = _time.time()
         out = model(input_ids=nxt.view(B, 1), attention_mask=mask, position_ids=pos, use_cache=True,
                     past_key_values=past)
+        if timers is not None:
+            timers["decode_s"].append(_time.time() - _t)
         past = out.past_key_values
         logits = out.logits[:, -1].float()
     return torch.stack(toks, 1), torch.stack(all_logits, 1)

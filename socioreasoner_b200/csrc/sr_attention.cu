@@ -72,7 +72,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int4 tile = p.tiles[blockIdx.x];
-  const int q_row0 = tile.x, q_nrows = tile.y, kv_lo = tile.z, kv_hi = tile.w;
+  // TMA needs 16-byte-aligned box origins: the key axis is the INNER dimension of the V^T map, so the key range is
+  // widened down to a multiple of 8 keys (the extra keys are masked by row_lo like any other out-of-range key).
+  const int q_row0 = tile.x, q_nrows = tile.y, kv_lo = tile.z & ~7, kv_hi = tile.w;
   const int head = blockIdx.y;
   const int kv_head = head / p.group;
   const int nblk = (kv_hi - kv_lo + ATT_BN - 1) / ATT_BN;

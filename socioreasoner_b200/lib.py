@@ -45,6 +45,30 @@ SYMBOLS = {
 _lib: Optional[ctypes.CDLL] = None
 launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
 
+# Optional per-launch timing (bench.py roofline): when `timeline` is a list, gemm()/attention() bracket their launch
+# with CUDA events on the launching stream and append (kind, tag, work, start_event, end_event).
+timeline = None
+
+
+class _Timed:
+    __slots__ = ("kind", "tag", "work", "e0")
+
+    def __init__(self, kind, tag, work):
+        self.kind, self.tag, self.work = kind, tag, work
+
+    def __enter__(self):
+        if timeline is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        if timeline is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream())
+            timeline.append((self.kind, self.tag, self.work, self.e0, e1))
+        return False
+
 
 def load() -> ctypes.CDLL:
     """Load the shared library and bind every declared symbol.  Raises if the library is missing."""
@@ -68,9 +92,17 @@ def last_error() -> str:
     return (load().sr_last_error() or b"").decode()
 
 
+_SYNC_DEBUG = os.environ.get("SR_SYNC_DEBUG", "0") == "1"
+
+
 def _check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")
+    if _SYNC_DEBUG:  # bring-up aid: surface asynchronous kernel faults at the launch that caused them
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(f"{what}: kernel fault surfaced at synchronize: {e}") from e
 
 
 def _stream() -> int:
@@ -115,9 +147,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, b
     if residual is not None:
         _req(residual, torch.bfloat16, "gemm.residual")
         epilogue = EPI_RESIDUAL if epilogue == EPI_NONE else epilogue
-    rc = load().sr_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
-                             _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, M, N, K,
-                             epilogue, DT_F32 if out.dtype == torch.float32 else DT_BF16, block_n, _stream())
+    with _Timed("gemm", (M, N, K, epilogue), 2.0 * M * N * K):
+        rc = load().sr_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
+                                 _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, M, N, K,
+                                 epilogue, DT_F32 if out.dtype == torch.float32 else DT_BF16, block_n, _stream())
     _check(rc, "sr_gemm_bf16")
     launch_count += 1
     return out
@@ -131,11 +164,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
         _req(t, torch.bfloat16, "attention." + n)
     _req(tiles, torch.int32, "attention.tiles"); _req(row_lo, torch.int32, "row_lo"); _req(row_hi, torch.int32, "row_hi")
     assert q.shape[2] == 128 and k.shape[2] == 128 and tiles.dim() == 2 and tiles.shape[1] == 4 and tiles.is_contiguous()
-    rc = load().sr_attention_fwd(q.data_ptr(), q.stride(0), q.stride(1), q.shape[0], q.shape[1],
-                                 k.data_ptr(), k.stride(0), k.stride(1), k.shape[0], k.shape[1],
-                                 vt.data_ptr(), vt.stride(0), vt.shape[1], out.data_ptr(), out.stride(0), out.stride(1),
-                                 tiles.data_ptr(), tiles.shape[0], row_lo.data_ptr(), row_hi.data_ptr(), float(scale),
-                                 head_dim_v, _stream())
+    with _Timed("attention", (q.shape[0], q.shape[1], head_dim_v, tiles.shape[0]), 0.0):
+        rc = load().sr_attention_fwd(q.data_ptr(), q.stride(0), q.stride(1), q.shape[0], q.shape[1],
+                                     k.data_ptr(), k.stride(0), k.stride(1), k.shape[0], k.shape[1],
+                                     vt.data_ptr(), vt.stride(0), vt.shape[1], out.data_ptr(), out.stride(0), out.stride(1),
+                                     tiles.data_ptr(), tiles.shape[0], row_lo.data_ptr(), row_hi.data_ptr(), float(scale),
+                                     head_dim_v, _stream())
     _check(rc, "sr_attention_fwd")
     launch_count += 1
     return out

@@ -1,0 +1,119 @@
+"""Data-parallel rollout over whole tiles + the single result exchange.
+
+Reference behaviour being replaced:
+  * ``dispatch_dp_mp_compute`` splits the batch along dim 0 into ``dp_size`` chunks with ``np.array_split`` sizes
+    (``roll/distributed/scheduler/decorator.py:106-148``, ``protocol.py:550-617``), one chunk per GPU worker, every worker
+    holding a full weight replica; there is no communication inside the forward.
+  * ``collect_dp_mp_compute`` + ``DataProto.concat`` bring the per-rank results back through the Ray object store
+    (pickled ``torch.save``; ``decorator.py:151-180``, ``protocol.py:718-732``).
+Here: one process per GPU (torch.distributed, NCCL over NVLink/NVSwitch).  Each rank runs its shard through the engine;
+the mask epilogue writes straight into this rank's slot of one registered gather buffer and ONE ``ncclAllGather``
+moves masks + IoU + generated tokens of all ranks (rank order == chunk order == the reference's concat order).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import lib
+
+
+def shard_indices(batch: int, world: int) -> List[np.ndarray]:
+    """Chunk sizes/order of ``DataProto.chunk`` (``np.array_split`` semantics, protocol.py:562-566)."""
+    return [np.asarray(c, dtype=np.int64) for c in np.array_split(np.arange(batch), world)]
+
+
+@dataclass
+class TileBatch:
+    """One rank's shard (host or device tensors)."""
+    input_ids: torch.Tensor          # [b,S] int64 (left padded)
+    attention_mask: torch.Tensor     # [b,S]
+    position_ids: Optional[torch.Tensor]  # [3,b,S] or None (-> reference get_rope_index semantics)
+    pixel_values: torch.Tensor       # [sum N, 1176] fp32
+    image_grid_thw: torch.Tensor     # [b,3] (cpu)
+    mask_logits: torch.Tensor        # [b, n_obj, 3, h, w] fp32  (SAM-style low-res logits)
+    mask_scores: torch.Tensor        # [b, n_obj, 3] fp32
+    gt_masks: torch.Tensor           # [b, out, out] uint8
+
+    def pin(self) -> "TileBatch":
+        f = lambda t: t.pin_memory() if (t is not None and not t.is_cuda and torch.cuda.is_available()) else t
+        return TileBatch(f(self.input_ids), f(self.attention_mask), f(self.position_ids), f(self.pixel_values),
+                         self.image_grid_thw, f(self.mask_logits), f(self.mask_scores), f(self.gt_masks))
+
+    def h2d_bytes(self) -> int:
+        ts = [self.input_ids, self.attention_mask, self.position_ids, self.pixel_values, self.mask_logits, self.mask_scores, self.gt_masks]
+        return int(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
+@dataclass
+class RolloutResult:
+    tokens: torch.Tensor  # [B,T] int64
+    masks: torch.Tensor   # [B,out,out] uint8
+    iou: torch.Tensor     # [B] fp32
+
+
+class DataParallelRollout:
+    def __init__(self, model, max_new_tokens: int = 32, image_size: int = 756, out_size: int = 768, group=None):
+        self.model, self.engine = model, model.engine
+        self.T, self.image_size, self.out_size = max_new_tokens, image_size, out_size
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self._gbuf = None
+        self._slot_bytes = 0
+
+    # layout of one rank's slot in the gather buffer: [b_max masks][b_max iou f32][b_max*T tokens i64][count i64]
+    def _slot_layout(self, b_max: int):
+        mask_b = b_max * self.out_size * self.out_size
+        iou_off = (mask_b + 15) // 16 * 16
+        tok_off = iou_off + (b_max * 4 + 15) // 16 * 16
+        cnt_off = tok_off + b_max * self.T * 8
+        total = (cnt_off + 8 + 15) // 16 * 16
+        return mask_b, iou_off, tok_off, cnt_off, total
+
+    def _ensure_gbuf(self, b_max: int, device):
+        *_, total = self._slot_layout(b_max)
+        if self._gbuf is None or self._slot_bytes != total:
+            self._gbuf = torch.zeros((self.world, total), dtype=torch.uint8, device=device)
+            self._slot_bytes = total
+        return self._gbuf
+
+    def step(self, batch: TileBatch, b_max: Optional[int] = None) -> RolloutResult:
+        """Runs this rank's shard.  Host tensors are copied to the device here (pinned -> async H2D)."""
+        dev = self.engine.device
+        b = batch.input_ids.shape[0]
+        b_max = b_max or b
+        gbuf = self._ensure_gbuf(b_max, dev)
+        mask_b, iou_off, tok_off, cnt_off, _ = self._slot_layout(b_max)
+        slot = gbuf[self.rank]
+        masks = slot[:mask_b].view(b_max, self.out_size, self.out_size)
+        to = lambda t: t if (t is None or t.is_cuda) else t.to(dev, non_blocking=True)
+        pv, ml, ms, gt = to(batch.pixel_values), to(batch.mask_logits), to(batch.mask_scores), to(batch.gt_masks)
+        tokens = self.engine.generate_greedy(batch.input_ids, batch.attention_mask, batch.position_ids, pv,
+                                             batch.image_grid_thw, self.T)
+        for i in range(b):
+            lib.mask_epilogue(ml[i], ms[i], self.image_size, self.out_size, out=masks[i])
+        iou = lib.mask_iou(masks[:b], gt, 1.0)
+        slot[iou_off:iou_off + b * 4].view(torch.float32).copy_(iou)
+        slot[tok_off:tok_off + b * self.T * 8].view(torch.int64).copy_(tokens.reshape(-1))
+        slot[cnt_off:cnt_off + 8].view(torch.int64).fill_(b)
+        return RolloutResult(tokens, masks[:b], iou)
+
+    def gather(self, b_max: int) -> RolloutResult:
+        """ONE all-gather of every rank's slot; returns the concatenation in rank order (= reference concat order)."""
+        gbuf = self._gbuf
+        if self.world > 1:
+            dist.all_gather_into_tensor(gbuf.view(-1), gbuf[self.rank], group=self.group)
+        mask_b, iou_off, tok_off, cnt_off, _ = self._slot_layout(b_max)
+        counts = gbuf[:, cnt_off:cnt_off + 8].contiguous().view(torch.int64).view(-1).tolist()
+        toks, masks, ious = [], [], []
+        for r, c in enumerate(counts):
+            c = int(c)
+            masks.append(gbuf[r, :mask_b].view(b_max, self.out_size, self.out_size)[:c])
+            ious.append(gbuf[r, iou_off:iou_off + b_max * 4].view(torch.float32)[:c])
+            toks.append(gbuf[r, tok_off:tok_off + b_max * self.T * 8].view(torch.int64).view(b_max, self.T)[:c])
+        return RolloutResult(torch.cat(toks), torch.cat(masks), torch.cat(ious))

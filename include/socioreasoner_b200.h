@@ -53,10 +53,17 @@ int sr_device_check(void);
  * proj), HF:77-88 (ViT MLP), HF:133-146 (merger), HF:704-707 (decoder q/k/v/o), HF:611-624 (decoder MLP),
  * HF:1385 (lm_head).  lda/ldw/ldc/ldr are row strides in ELEMENTS (multiples of 8).  bias: fp32[N] or NULL.
  * SR_EPI_SWIGLU: W/bias rows are packed in groups of 32 = [16 gate rows | 16 up rows]; n_out = N/2.
- * block_n: 0 = auto (256 for M > 64, else 32), or 32 / 128 / 256. */
+ * block_n: 0 = auto (M <= 32 -> sr_gemm_skinny_bf16; 256 for M > 64, else 32), or 32 / 128 / 256 to force a tcgen05 tile. */
 int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, const float* bias,
                  const void* residual, int64_t ldr, int M, int N, int K, int epilogue, int out_dtype, int block_n,
                  void* stream);
+
+/* Skinny variant for the decode step (M <= 32 live sequences, K % 32 == 0): HBM-bound weight streaming
+ * (16-byte ld.global.nc vectors -> mma.sync m16n8k16 fragments, in-CTA split-K), same epilogues.  The decode-time
+ * nn.Linear calls of HF:704-707,611-624,1385 that the reference runs inside vLLM (vllm_strategy.py:114-141).
+ * sr_gemm_bf16 dispatches here automatically when block_n == 0 and the shape qualifies. */
+int sr_gemm_skinny_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, const float* bias,
+                        const void* residual, int64_t ldr, int M, int N, int K, int epilogue, int out_dtype, void* stream);
 
 /* ---- attention (tcgen05 + TMA) --------------------------------------------------------------
  * Variable-length softmax(Q K^T * scale) V; query row r attends key rows k with row_lo[r] <= k < row_hi[r].
@@ -111,6 +118,13 @@ int sr_argmax_rows(const void* logits, int64_t ld, int dtype, int rows, int V, i
 /* log_probs_from_logits / entropy_from_logits (roll/utils/functionals.py:193-205). Either output may be NULL. */
 int sr_logprob_entropy(const void* logits, int64_t ld, int dtype, int rows, int V, const int64_t* labels, float* logprob,
                        float* entropy, void* stream);
+
+/* Decode-loop bookkeeping on the device (makes one decode step a replayable CUDA graph): tokens[:, *step] = next_tokens;
+ * cache_row = row0 + *step; kv_len = len0 + *step + 1; pos3[3,batch] = pos0 + 1 + *step; (*step)++.
+ * Response positions follow roll/utils/functionals.py:838-852. */
+int sr_decode_advance(const int64_t* next_tokens, int64_t* tokens, int T, int32_t* step, const int32_t* row0,
+                      const int32_t* len0, const int64_t* pos0, int32_t* cache_row, int32_t* kv_len, int64_t* pos3,
+                      int batch, void* stream);
 
 /* ---- mask epilogue + IoU -------------------------------------------------------------------- */
 /* seg_strategy.py:47-65: per object pick argmax(scores) of 3 candidates, bilinear up-sample h x w -> image_size^2

@@ -277,6 +277,10 @@ static int dispatch_epi(int epi, int out_f32, const CUtensorMap& a, const CUtens
 
 }  // namespace sr
 
+extern "C" int sr_gemm_skinny_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                                   const float* bias, const void* residual, int64_t ldr, int M, int N, int K, int epilogue,
+                                   int out_dtype, void* stream);
+
 extern "C" int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
                             const float* bias, const void* residual, int64_t ldr, int M, int N, int K, int epilogue,
                             int out_dtype, int block_n, void* stream) {
@@ -292,6 +296,8 @@ extern "C" int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   SR_REQUIRE((reinterpret_cast<uintptr_t>(C) & 15) == 0, "sr_gemm_bf16: C not 16B aligned");
   SR_REQUIRE(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "sr_gemm_bf16: bias not 16B aligned");
 
+  if (block_n == 0 && M <= 32 && K % 32 == 0)  // decode-step shapes: weight-streaming kernel (sr_gemv.cu), HBM-bound
+    return sr_gemm_skinny_bf16(A, lda, W, ldw, C, ldc, bias, residual, ldr, M, N, K, epilogue, out_dtype, stream);
   int bn = block_n;
   if (bn == 0) bn = (M <= 64) ? 32 : 256;
   SR_REQUIRE(bn == 32 || bn == 128 || bn == 256, "sr_gemm_bf16: block_n must be 0/32/128/256");

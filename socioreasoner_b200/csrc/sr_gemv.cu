@@ -1,0 +1,205 @@
+// sr_gemv.cu -- skinny GEMM for the decode step: C[M<=32, N] = epilogue(A[M,K] . W[N,K]^T), M = live sequences.
+//
+// One new token per sequence makes every linear layer of the decoder (HF modeling_qwen2_5_vl.py:704-707, 611-624,
+// 1385; the reference runs them inside vLLM's decode loop, roll/distributed/strategy/vllm_strategy.py:114-141) a
+// weight-streaming problem: 2 bytes of W per 2*M flops -> HBM-bound for M <= ~150.  The job of this kernel is to keep
+// ~6 TB/s of weight bytes in flight, not to feed tcgen05 (a 128-row UMMA tile would be 94% padding):
+//   * CTA = 16 output features (32 packed rows for SwiGLU) x the whole K; its 8 warps split K in interleaved
+//     64-byte chunks, so the CTA reads 512 contiguous bytes per weight row per iteration;
+//   * every thread streams 16-byte vectors of W straight into registers (ld.global.nc, L1 no-allocate), 4 chunks
+//     (8..16 independent 16 B loads) in flight, and feeds them to mma.sync.m16n8k16 (bf16 -> fp32) as the A operand
+//     with the k index permuted so that one 16 B load IS an A fragment (the activation fragment uses the same
+//     permutation, so no shuffles / shared-memory staging of W);
+//   * the activations (M x K bf16, L2-resident) are read with the same 16 B pattern as the B operand;
+//   * cross-warp K reduction through 4 KB of shared memory, then the fused epilogue (bias / residual / SwiGLU).
+// Reported against the HBM roofline (algorithmic bytes = N*K*2).
+#include "sr_host.h"
+
+namespace sr {
+
+constexpr int GV_WARPS = 8;
+constexpr int GV_THREADS = GV_WARPS * 32;
+constexpr int GV_UNROLL = 4;
+
+SR_DEVINL uint4 ld_stream_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+SR_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct GemvParams {
+  const __nv_bfloat16* A;
+  const __nv_bfloat16* W;
+  void* C;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int64_t lda, ldw, ldc, ldr;
+  int M, N, K;
+};
+
+// RG = row groups of 16 weight rows per CTA (1, or 2 for SwiGLU: gate group + up group); NB = batch tiles of 8.
+template <int RG, int NB, int EPI, bool OUT_F32>
+__global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvParams p) {
+  __shared__ float red[GV_WARPS][RG][NB][16 * 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = blockIdx.x * (16 * RG);
+  float acc[RG][NB][4];
+#pragma unroll
+  for (int r = 0; r < RG; ++r)
+#pragma unroll
+    for (int n = 0; n < NB; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[r][n][i] = 0.f;
+
+  // row pointers (clamped: rows >= N are read but never stored)
+  const __nv_bfloat16* wrow[RG][2];
+#pragma unroll
+  for (int r = 0; r < RG; ++r) {
+    int ra = row0 + r * 16 + g, rb = ra + 8;
+    ra = ra < p.N ? ra : p.N - 1;
+    rb = rb < p.N ? rb : p.N - 1;
+    wrow[r][0] = p.W + static_cast<int64_t>(ra) * p.ldw + t * 8;
+    wrow[r][1] = p.W + static_cast<int64_t>(rb) * p.ldw + t * 8;
+  }
+  const __nv_bfloat16* xrow[NB];
+  bool xok[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) {
+    const int m = n * 8 + g;
+    xok[n] = m < p.M;
+    xrow[n] = p.A + static_cast<int64_t>(xok[n] ? m : 0) * p.lda + t * 8;
+  }
+
+  const int nchunks = p.K >> 5;  // 32 k per chunk
+  for (int c0 = warp; c0 < nchunks; c0 += GV_WARPS * GV_UNROLL) {
+    uint4 w[GV_UNROLL][RG][2];
+    uint4 x[GV_UNROLL][NB];
+#pragma unroll
+    for (int u = 0; u < GV_UNROLL; ++u) {
+      const int c = c0 + u * GV_WARPS;
+      if (c < nchunks) {
+#pragma unroll
+        for (int r = 0; r < RG; ++r) {
+          w[u][r][0] = ld_stream_v4(wrow[r][0] + c * 32);
+          w[u][r][1] = ld_stream_v4(wrow[r][1] + c * 32);
+        }
+#pragma unroll
+        for (int n = 0; n < NB; ++n) x[u][n] = xok[n] ? *reinterpret_cast<const uint4*>(xrow[n] + c * 32) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < GV_UNROLL; ++u) {
+      const int c = c0 + u * GV_WARPS;
+      if (c < nchunks) {
+#pragma unroll
+        for (int r = 0; r < RG; ++r)
+#pragma unroll
+          for (int n = 0; n < NB; ++n) {
+            // slots (2t,2t+1 | 2t+8,2t+9) <-> actual k = c*32 + t*8 + {0,1 | 2,3}, then {4,5 | 6,7}
+            mma_bf16_16816(acc[r][n], w[u][r][0].x, w[u][r][1].x, w[u][r][0].y, w[u][r][1].y, x[u][n].x, x[u][n].y);
+            mma_bf16_16816(acc[r][n], w[u][r][0].z, w[u][r][1].z, w[u][r][0].w, w[u][r][1].w, x[u][n].z, x[u][n].w);
+          }
+      }
+    }
+  }
+  // cross-warp reduction: C fragment (feature g | g+8, batch 2t | 2t+1) -> red[warp][r][n][feature*8 + batch]
+#pragma unroll
+  for (int r = 0; r < RG; ++r)
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+      red[warp][r][n][g * 8 + 2 * t] = acc[r][n][0];
+      red[warp][r][n][g * 8 + 2 * t + 1] = acc[r][n][1];
+      red[warp][r][n][(g + 8) * 8 + 2 * t] = acc[r][n][2];
+      red[warp][r][n][(g + 8) * 8 + 2 * t + 1] = acc[r][n][3];
+    }
+  __syncthreads();
+  // epilogue: thread -> (batch tile n, feature f, batch b); 128 outputs per batch tile
+  for (int idx = threadIdx.x; idx < NB * 128; idx += GV_THREADS) {
+    const int n = idx >> 7, e = idx & 127;
+    const int b = e >> 4, f = e & 15;  // consecutive threads -> consecutive features (contiguous stores)
+    const int m = n * 8 + b;
+    float v[RG];
+#pragma unroll
+    for (int r = 0; r < RG; ++r) {
+      float s = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < GV_WARPS; ++w8) s += red[w8][r][n][f * 8 + b];
+      v[r] = s;
+    }
+    if (m >= p.M) continue;
+    if (EPI == SR_EPI_SWIGLU) {
+      const int prow = row0 + f;  // packed gate row; up row = prow + 16
+      if (prow + 16 >= p.N) continue;
+      float gate = v[0], up = v[RG - 1];
+      if (p.bias) { gate += __ldg(p.bias + prow); up += __ldg(p.bias + prow + 16); }
+      const float o = (gate / (1.0f + __expf(-gate))) * up;
+      const int oc = (row0 >> 1) + f;
+      reinterpret_cast<__nv_bfloat16*>(p.C)[static_cast<int64_t>(m) * p.ldc + oc] = __float2bfloat16(o);
+    } else {
+      const int col = row0 + f;
+      if (col >= p.N) continue;
+      float o = v[0];
+      if (p.bias) o += __ldg(p.bias + col);
+      if (EPI == SR_EPI_GELU) o = 0.5f * o * (1.0f + erff(o * 0.70710678118654752440f));
+      if (EPI == SR_EPI_RESIDUAL) o += __bfloat162float(p.residual[static_cast<int64_t>(m) * p.ldr + col]);
+      if (OUT_F32) reinterpret_cast<float*>(p.C)[static_cast<int64_t>(m) * p.ldc + col] = o;
+      else reinterpret_cast<__nv_bfloat16*>(p.C)[static_cast<int64_t>(m) * p.ldc + col] = __float2bfloat16(o);
+    }
+  }
+}
+
+template <int NB>
+static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s) {
+  if (epi == SR_EPI_SWIGLU) {
+    const int grid = (p.N + 31) / 32;
+    gemv_kernel<2, NB, SR_EPI_SWIGLU, false><<<grid, GV_THREADS, 0, s>>>(p);
+  } else {
+    const int grid = (p.N + 15) / 16;
+    if (out_f32) gemv_kernel<1, NB, SR_EPI_NONE, true><<<grid, GV_THREADS, 0, s>>>(p);
+    else if (epi == SR_EPI_NONE) gemv_kernel<1, NB, SR_EPI_NONE, false><<<grid, GV_THREADS, 0, s>>>(p);
+    else if (epi == SR_EPI_RESIDUAL) gemv_kernel<1, NB, SR_EPI_RESIDUAL, false><<<grid, GV_THREADS, 0, s>>>(p);
+    else if (epi == SR_EPI_GELU) gemv_kernel<1, NB, SR_EPI_GELU, false><<<grid, GV_THREADS, 0, s>>>(p);
+    else {
+      set_last_error("sr_gemm_skinny_bf16: unknown epilogue %d", epi);
+      return SR_ERR_INVALID;
+    }
+  }
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+}  // namespace sr
+
+extern "C" int sr_gemm_skinny_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                                   const float* bias, const void* residual, int64_t ldr, int M, int N, int K, int epilogue,
+                                   int out_dtype, void* stream) {
+  using namespace sr;
+  SR_REQUIRE(A && W && C, "sr_gemm_skinny_bf16: null operand");
+  SR_REQUIRE(M > 0 && M <= 32 && N > 0 && K > 0 && K % 32 == 0, "sr_gemm_skinny_bf16: need 0 < M <= 32, K %% 32 == 0 (M=%d K=%d)", M, K);
+  SR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "sr_gemm_skinny_bf16: lda/ldw must be multiples of 8");
+  SR_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "sr_gemm_skinny_bf16: A/W not 16B aligned");
+  SR_REQUIRE(epilogue != SR_EPI_RESIDUAL || residual, "sr_gemm_skinny_bf16: residual epilogue needs residual");
+  SR_REQUIRE(epilogue != SR_EPI_SWIGLU || (N % 32 == 0 && out_dtype == SR_DTYPE_BF16), "sr_gemm_skinny_bf16: SwiGLU needs N %% 32 == 0, bf16 out");
+  SR_REQUIRE(out_dtype == SR_DTYPE_BF16 || epilogue == SR_EPI_NONE, "sr_gemm_skinny_bf16: fp32 output supports SR_EPI_NONE only");
+  GemvParams p;
+  p.A = reinterpret_cast<const __nv_bfloat16*>(A);
+  p.W = reinterpret_cast<const __nv_bfloat16*>(W);
+  p.C = C;
+  p.bias = bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.lda = lda; p.ldw = ldw; p.ldc = ldc; p.ldr = ldr;
+  p.M = M; p.N = N; p.K = K;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int f32 = out_dtype == SR_DTYPE_F32;
+  if (M <= 8) return launch_gemv<1>(p, epilogue, f32, s);
+  if (M <= 16) return launch_gemv<2>(p, epilogue, f32, s);
+  return launch_gemv<4>(p, epilogue, f32, s);
+}

@@ -244,9 +244,43 @@ __global__ void __launch_bounds__(1024) mask_iou_kernel(const uint8_t* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Decode-loop bookkeeping on the device (so that one decode step is a replayable CUDA graph): append the token chosen
+// by argmax to tokens[:, step] and derive this step's KV-cache slot, KV length and M-RoPE position
+// (response positions = last prompt position + 1 + step on all three axes, roll/utils/functionals.py:838-852).
+// ------------------------------------------------------------------------------------------------
+__global__ void decode_advance_kernel(const int64_t* __restrict__ nxt, int64_t* __restrict__ tokens, int T,
+                                      int* __restrict__ step, const int* __restrict__ row0, const int* __restrict__ len0,
+                                      const int64_t* __restrict__ pos0, int* __restrict__ cache_row, int* __restrict__ kv_len,
+                                      int64_t* __restrict__ pos3, int B) {
+  const int s = *step;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    if (s < T) tokens[static_cast<int64_t>(b) * T + s] = nxt[b];
+    cache_row[b] = row0[b] + s;
+    kv_len[b] = len0[b] + s + 1;
+    const int64_t p = pos0[b] + 1 + s;
+    pos3[b] = p;
+    pos3[B + b] = p;
+    pos3[2 * B + b] = p;
+  }
+  if (threadIdx.x == 0) *step = s + 1;
+}
+
 }  // namespace sr
 
 using namespace sr;
+
+extern "C" int sr_decode_advance(const int64_t* next_tokens, int64_t* tokens, int T, int32_t* step, const int32_t* row0,
+                                 const int32_t* len0, const int64_t* pos0, int32_t* cache_row, int32_t* kv_len,
+                                 int64_t* pos3, int batch, void* stream) {
+  SR_REQUIRE(next_tokens && tokens && step && row0 && len0 && pos0 && cache_row && kv_len && pos3 && batch > 0 && T > 0,
+             "sr_decode_advance: bad args");
+  decode_advance_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(next_tokens, tokens, T, step, row0, len0, pos0,
+                                                                             cache_row, kv_len, pos3, batch);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}
 
 extern "C" int sr_decode_attention(const void* q, int64_t ldq, const void* Kc, const void* Vt, int64_t ldvt,
                                    const int32_t* kv_start, const int32_t* kv_len, int max_len, void* out, int64_t ldo,

@@ -86,6 +86,11 @@ class Engine:
         self.txt_inv_freq = (1.0 / (t.rope_theta ** (torch.arange(0, t.head_dim, 2, dtype=torch.float32) / t.head_dim))).to(self.device)
         self._bufs: Dict[str, torch.Tensor] = {}
         self._vit_plans: Dict[bytes, DevVitPlan] = {}
+        self._caches: Dict[Tuple[int, int], KVCache] = {}
+        self._graphs: Dict[Tuple[int, int, int], "torch.cuda.CUDAGraph"] = {}
+        self._dstate: Dict[Tuple[int, int], dict] = {}
+        self._decode_launches = 0
+        self.use_cuda_graph = True
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, name: str, shape, dtype=torch.bfloat16, zero: bool = False) -> torch.Tensor:
@@ -97,8 +102,11 @@ class Engine:
         return cur[:n].view(*shape)
 
     def free_buffers(self) -> None:
+        self._graphs.clear()
         self._bufs.clear()
         self._vit_plans.clear()
+        self._caches.clear()
+        self._dstate.clear()
 
     # ------------------------------------------------------------------ ViT
     def vit_plan(self, grid_thw) -> DevVitPlan:
@@ -179,7 +187,7 @@ class Engine:
         S = x.shape[0]
         Hq, Hkv, hd = t.num_attention_heads, t.num_key_value_heads, t.head_dim
         qkv_dim = (Hq + 2 * Hkv) * hd
-        tag = "d" if decode is not None else "p"
+        tag = f"d{S}" if decode is not None else "p"  # decode buffers are baked into CUDA graphs: never resized
         y = self._buf(tag + "_y", (S, t.hidden_size))
         qkv = self._buf(tag + "_qkv", (S, qkv_dim))
         ao = self._buf(tag + "_ao", (S, Hq * hd))
@@ -279,41 +287,113 @@ class Engine:
         idx = _dev((sp.q_starts + sp.lengths - 1).astype(np.int32), self.device)
         return lib.gather_rows(x, idx)
 
+    def _get_cache(self, batch: int, l_max: int) -> KVCache:
+        """KV caches are kept per (batch, l_max) so their addresses stay valid for captured decode graphs."""
+        t = self.cfg.text
+        key = (batch, l_max)
+        c = self._caches.get(key)
+        if c is None:
+            if len(self._caches) >= 2:  # bounded: two shapes alive at most (180 GB HBM, ~40 MB / sequence-k-token)
+                self._caches.clear()
+                self._graphs.clear()
+            c = KVCache(t.num_hidden_layers, batch, l_max, t.num_key_value_heads, t.head_dim, self.device)
+            self._caches[key] = c
+        return c
+
+    def _decode_state(self, B: int, T: int):
+        key = (B, T)
+        st = self._dstate.get(key)
+        if st is None:
+            dev = self.device
+            st = dict(
+                tokens=torch.zeros((B, T), dtype=torch.int64, device=dev), step=torch.zeros((1,), dtype=torch.int32, device=dev),
+                nxt=torch.zeros((B,), dtype=torch.int64, device=dev), row0=torch.zeros((B,), dtype=torch.int32, device=dev),
+                len0=torch.zeros((B,), dtype=torch.int32, device=dev), pos0=torch.zeros((B,), dtype=torch.int64, device=dev),
+                cache_row=torch.zeros((B,), dtype=torch.int32, device=dev), kv_len=torch.zeros((B,), dtype=torch.int32, device=dev),
+                pos3=torch.zeros((3, B), dtype=torch.int64, device=dev), kv_start=torch.zeros((B,), dtype=torch.int32, device=dev),
+                logits=torch.zeros((B, self.cfg.text.vocab_size), dtype=torch.float32, device=dev),
+                x=torch.zeros((B, self.cfg.text.hidden_size), dtype=torch.bfloat16, device=dev),
+            )
+            self._dstate[key] = st
+        return st
+
+    def _decode_step(self, st, cache: KVCache) -> None:
+        """One decode step, entirely on the device (graph-capturable): argmax -> append/advance -> embed -> 36 layers ->
+        final norm + LM head -> st['logits']."""
+        t = self.cfg.text
+        lib.argmax_rows(st["logits"], out=st["nxt"])
+        lib.decode_advance(st["nxt"], st["tokens"], st["step"], st["row0"], st["len0"], st["pos0"], st["cache_row"],
+                           st["kv_len"], st["pos3"])
+        cos, sin = lib.mrope_table(st["pos3"], self.txt_inv_freq, t.mrope_section)
+        lib.embed_scatter(self.w.embed, st["nxt"], None, None, out=st["x"])
+        xo = self._decoder_layers(st["x"], cos, sin, cache, st["cache_row"], None, (st["kv_start"], st["kv_len"], cache.l_max))
+        self.final_logits(xo, torch.float32, out=st["logits"])
+
     def generate_greedy(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens: int,
-                        return_logits: bool = False):
+                        return_logits: bool = False, use_graph: Optional[bool] = None):
         """Greedy decode, EOS ignored, fixed ``max_new_tokens``.  Response positions continue from the
-        last prompt position + 1 on all three axes (roll/utils/functionals.py:838-852).
+        last prompt position + 1 on all three axes (roll/utils/functionals.py:838-852).  The decode step is captured
+        once per (batch, cache) into a CUDA graph and replayed (launch-bound loop, ~300 kernels per token).
         Returns new tokens [B, T] (int64, device) and optionally fp32 logits [B, T, V]."""
         t = self.cfg.text
-        x, sp, cache, pos3 = self.prefill(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw,
-                                          reserve_new_tokens=max_new_tokens)
-        B = sp.B
+        T = max_new_tokens
+        mask_np = attention_mask.detach().cpu().numpy() if torch.is_tensor(attention_mask) else np.asarray(attention_mask)
+        lens = (mask_np != 0).sum(axis=1)
+        B = mask_np.shape[0]
+        l_max = int((lens.max() + T + 127) // 128 * 128)
+        cache = self._get_cache(B, l_max)
+        x, sp, cache, pos3 = self.prefill(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, cache=cache,
+                                          reserve_new_tokens=T)
         V = t.vocab_size
-        tokens = torch.empty((B, max_new_tokens), dtype=torch.int64, device=self.device)
-        all_logits = torch.empty((B, max_new_tokens, V), dtype=torch.float32, device=self.device) if return_logits else None
-        logits = self.final_logits(self.last_token_rows(x, sp), torch.float32, out=self._buf("g_logits", (B, V), torch.float32))
-        kv_start = _dev(cache.kv_starts.astype(np.int32), self.device)
-        lens0 = torch.from_numpy(sp.lengths.astype(np.int32)).to(self.device)
-        pos0 = torch.from_numpy(sp.last_pos).to(self.device)
-        nxt = torch.empty((B,), dtype=torch.int64, device=self.device)
-        xd = self._buf("d_x", (B, t.hidden_size))
-        max_len = int(sp.lengths.max()) + max_new_tokens
-        for step in range(max_new_tokens):
-            lib.argmax_rows(logits, out=nxt)
-            tokens[:, step] = nxt
-            if return_logits:
-                all_logits[:, step] = logits
-            if step == max_new_tokens - 1:
-                break
-            # one decode step for token `nxt` at cache slot len0 + step, position last_pos + 1 + step
-            kv_len = lens0 + (step + 1)
-            cache_row = (kv_start + lens0 + step).to(torch.int32)
-            pos = (pos0 + 1 + step).view(1, B).expand(3, B).contiguous()
-            cos, sin = lib.mrope_table(pos, self.txt_inv_freq, t.mrope_section)
-            lib.embed_scatter(self.w.embed, nxt, None, None, out=xd)
-            xo = self._decoder_layers(xd, cos, sin, cache, cache_row, None, (kv_start, kv_len, max_len))
-            logits = self.final_logits(xo, torch.float32, out=logits)
-        cache.lengths = sp.lengths + max_new_tokens - 1
+        st = self._decode_state(B, T)
+        st["step"].zero_()
+        st["kv_start"].copy_(torch.from_numpy(cache.kv_starts.astype(np.int32)), non_blocking=True)
+        st["row0"].copy_(torch.from_numpy((cache.kv_starts + sp.lengths).astype(np.int32)), non_blocking=True)
+        st["len0"].copy_(torch.from_numpy(sp.lengths.astype(np.int32)), non_blocking=True)
+        st["pos0"].copy_(torch.from_numpy(sp.last_pos.astype(np.int64)), non_blocking=True)
+        self.final_logits(self.last_token_rows(x, sp), torch.float32, out=st["logits"])
+        all_logits = torch.empty((B, T, V), dtype=torch.float32, device=self.device) if return_logits else None
+        if use_graph is None:
+            use_graph = self.use_cuda_graph and not return_logits and lib.timeline is None
+        if use_graph and T > 1:
+            gkey = (B, T, l_max)
+            g = self._graphs.get(gkey)
+            if g is None:
+                # warm-up outside capture (buffer allocation, function attributes), then restore the state it advanced
+                keep = {k: st[k].clone() for k in ("logits", "step")}
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                l0 = lib.launch_count
+                with torch.cuda.stream(side):
+                    self._decode_step(st, cache)
+                self._decode_launches = lib.launch_count - l0
+                torch.cuda.current_stream().wait_stream(side)
+                st["logits"].copy_(keep["logits"]); st["step"].copy_(keep["step"])
+                g = torch.cuda.CUDAGraph()
+                l0 = lib.launch_count
+                with torch.cuda.graph(g):
+                    self._decode_step(st, cache)
+                lib.launch_count = l0  # capture launches nothing
+                st["logits"].copy_(keep["logits"]); st["step"].copy_(keep["step"])
+                self._graphs[gkey] = g
+            for _ in range(T - 1):
+                g.replay()
+            lib.launch_count += (T - 1) * self._decode_launches
+        else:
+            for step in range(T - 1):
+                if return_logits:
+                    all_logits[:, step] = st["logits"]
+                l0 = lib.launch_count
+                self._decode_step(st, cache)
+                self._decode_launches = lib.launch_count - l0
+        if return_logits:
+            all_logits[:, T - 1] = st["logits"]
+        # the last token: argmax + append (no further forward needed)
+        lib.argmax_rows(st["logits"], out=st["nxt"])
+        lib.decode_advance(st["nxt"], st["tokens"], st["step"], st["row0"], st["len0"], st["pos0"], st["cache_row"],
+                           st["kv_len"], st["pos3"])
+        cache.lengths = sp.lengths + T - 1
+        tokens = st["tokens"].clone()
         return (tokens, all_logits) if return_logits else tokens
 
     # ------------------------------------------------------------------ mask epilogue

@@ -26,6 +26,7 @@ SYMBOLS = {
     "sr_abi_version": (c_int, []),
     "sr_device_check": (c_int, []),
     "sr_gemm_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sr_gemm_skinny_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_attention_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int,
                                  _P, c_int64, c_int64, _P, c_int, _P, _P, c_float, c_int, _P]),
     "sr_decode_attention": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int, _P, c_int64, c_int, c_int, c_int, c_float, _P]),
@@ -38,6 +39,7 @@ SYMBOLS = {
     "sr_mrope_kv": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "sr_argmax_rows": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
     "sr_logprob_entropy": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "sr_decode_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "sr_mask_iou": (c_int, [_P, _P, c_int, c_int64, c_float, _P, _P, _P]),
 }
@@ -277,6 +279,14 @@ def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> tor
                                  rows, V, out.data_ptr(), _stream()), "sr_argmax_rows")
     launch_count += 1
     return out
+
+
+def decode_advance(nxt, tokens, step, row0, len0, pos0, cache_row, kv_len, pos3):
+    global launch_count
+    _check(load().sr_decode_advance(nxt.data_ptr(), tokens.data_ptr(), tokens.shape[1], step.data_ptr(), row0.data_ptr(),
+                                    len0.data_ptr(), pos0.data_ptr(), cache_row.data_ptr(), kv_len.data_ptr(), pos3.data_ptr(),
+                                    tokens.shape[0], _stream()), "sr_decode_advance")
+    launch_count += 1
 
 
 def logprob_entropy(logits: torch.Tensor, labels: Optional[torch.Tensor], want_entropy: bool = True):

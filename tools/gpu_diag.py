@@ -97,6 +97,15 @@ def diag_gemm():
     run("gemm swiglu bn32", lambda: one(8, 22016, 2048, epi=lib.EPI_SWIGLU))
     run("gemm f32 out ragged N", lambda: one(8, 151936, 2048, out_dtype=torch.float32))
     run("gemm f32 out bn256 ragged N", lambda: one(200, 151936 // 8, 2048, out_dtype=torch.float32, block_n=256))
+    for M_ in (1, 8, 13, 16, 32):
+        run(f"skinny M={M_} qkv", lambda M_=M_: one(M_, 2560, 2048, bias=True))
+    run("skinny residual", lambda: one(8, 2048, 2048, res=True))
+    run("skinny down", lambda: one(8, 2048, 11008, res=True, time_it=True))
+    run("skinny swiglu", lambda: one(8, 22016, 2048, epi=lib.EPI_SWIGLU, time_it=True))
+    run("skinny swiglu bias M=5", lambda: one(5, 6912, 1280, epi=lib.EPI_SWIGLU, bias=True))
+    run("skinny lm head f32", lambda: one(8, 151936, 2048, out_dtype=torch.float32, time_it=True))
+    run("skinny qkv perf", lambda: one(8, 2560, 2048, bias=True, time_it=True))
+    run("skinny gelu M=20", lambda: one(20, 5120, 5120, epi=lib.EPI_GELU, bias=True))
     run("gemm perf vit qkv", lambda: one(23328, 3840, 1280, bias=True, time_it=True))
     run("gemm perf vit swiglu", lambda: one(23328, 6912, 1280, epi=lib.EPI_SWIGLU, bias=True, time_it=True))
     run("gemm perf vit down", lambda: one(23328, 1280, 3456, bias=True, res=True, time_it=True))

@@ -113,8 +113,9 @@ int sr_mrope_kv(void* qkv, int64_t ldqkv, const float* cosb, const float* sinb, 
                 void* Vt, int64_t ldvt, int S, int n_q_heads, int n_kv_heads, void* stream);
 
 /* ---- LM-head tail --------------------------------------------------------------------------- */
-/* Greedy token: argmax over V per row (first index on ties). logits bf16 or fp32. */
-int sr_argmax_rows(const void* logits, int64_t ld, int dtype, int rows, int V, int64_t* out, void* stream);
+/* Greedy token: argmax over V per row (first index on ties). logits bf16 or fp32.  Two-stage (64 slices per row);
+ * workspace: rows * 512 bytes of device scratch. */
+int sr_argmax_rows(const void* logits, int64_t ld, int dtype, int rows, int V, int64_t* out, void* workspace, void* stream);
 /* log_probs_from_logits / entropy_from_logits (roll/utils/functionals.py:193-205). Either output may be NULL. */
 int sr_logprob_entropy(const void* logits, int64_t ld, int dtype, int rows, int V, const int64_t* labels, float* logprob,
                        float* entropy, void* stream);

@@ -226,43 +226,51 @@ __global__ void __launch_bounds__(256) mrope_kv_kernel(__nv_bfloat16* __restrict
                                                       const float* __restrict__ cosb, const float* __restrict__ sinb,
                                                       const int* __restrict__ cache_row, __nv_bfloat16* __restrict__ Kc,
                                                       __nv_bfloat16* __restrict__ Vt, int64_t ldvt, int S, int nq, int nkv) {
+  // grid = (token blocks of 32, nq + nkv rotary heads + nkv value heads): one (token block, head) per CTA so that the
+  // decode step (S = live sequences) spreads over ~20 CTAs instead of serialising 18 heads in one warp.
   constexpr int TOK = 32;
-  extern __shared__ __nv_bfloat16 sv[];  // [TOK][nkv*128 + 2]
-  const int vw = nkv * 128 + 2;
+  __shared__ __nv_bfloat16 sv[TOK][128 + 2];
   const int t0 = blockIdx.x * TOK;
+  const int hh = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int tt = warp; tt < TOK; tt += 8) {
-    const int t = t0 + tt;
-    if (t >= S) break;
-    const float c0 = __ldg(cosb + static_cast<int64_t>(t) * 64 + lane * 2), c1 = __ldg(cosb + static_cast<int64_t>(t) * 64 + lane * 2 + 1);
-    const float s0 = __ldg(sinb + static_cast<int64_t>(t) * 64 + lane * 2), s1 = __ldg(sinb + static_cast<int64_t>(t) * 64 + lane * 2 + 1);
-    __nv_bfloat16* row = qkv + static_cast<int64_t>(t) * ldqkv;
-    const int crow = __ldg(cache_row + t);
-    for (int hh = 0; hh < nq + nkv; ++hh) {
-      uint32_t* lo = reinterpret_cast<uint32_t*>(row + hh * 128) + lane;
-      uint32_t* hi = reinterpret_cast<uint32_t*>(row + hh * 128 + 64) + lane;
+  if (hh < nq + nkv) {
+    for (int tt = warp; tt < TOK; tt += 8) {
+      const int t = t0 + tt;
+      if (t >= S) break;
+      const float2 c = __ldg(reinterpret_cast<const float2*>(cosb + static_cast<int64_t>(t) * 64) + lane);
+      const float2 sn = __ldg(reinterpret_cast<const float2*>(sinb + static_cast<int64_t>(t) * 64) + lane);
+      __nv_bfloat16* row = qkv + static_cast<int64_t>(t) * ldqkv + hh * 128;
+      uint32_t* lo = reinterpret_cast<uint32_t*>(row) + lane;
+      uint32_t* hi = reinterpret_cast<uint32_t*>(row + 64) + lane;
       const uint32_t a = *lo, b = *hi;
       const float x1a = bf16_lo(a), x1b = bf16_hi(a), x2a = bf16_lo(b), x2b = bf16_hi(b);
-      const uint32_t olo = pack_bf16x2(x1a * c0 - x2a * s0, x1b * c1 - x2b * s1);
-      const uint32_t ohi = pack_bf16x2(x2a * c0 + x1a * s0, x2b * c1 + x1b * s1);
+      const uint32_t olo = pack_bf16x2(x1a * c.x - x2a * sn.x, x1b * c.y - x2b * sn.y);
+      const uint32_t ohi = pack_bf16x2(x2a * c.x + x1a * sn.x, x2b * c.y + x1b * sn.y);
       if (hh < nq) {
         *lo = olo;
         *hi = ohi;
       } else {
+        const int crow = __ldg(cache_row + t);
         uint32_t* kd = reinterpret_cast<uint32_t*>(Kc + (static_cast<int64_t>(crow) * nkv + (hh - nq)) * 128);
         kd[lane] = olo;
         kd[32 + lane] = ohi;
       }
     }
-    // stage v for the transpose
-    const uint32_t* vsrc = reinterpret_cast<const uint32_t*>(row + (nq + nkv) * 128);
-    for (int i = lane; i < nkv * 64; i += 32) *reinterpret_cast<uint32_t*>(&sv[tt * vw + i * 2]) = vsrc[i];
-  }
-  __syncthreads();
-  const bool ok = t0 + lane < S;
-  const int crow = ok ? __ldg(cache_row + t0 + lane) : 0;
-  for (int d = warp; d < nkv * 128; d += 8) {
-    if (ok) Vt[static_cast<int64_t>(d) * ldvt + crow] = sv[lane * vw + d];
+  } else {
+    const int vh = hh - nq - nkv;
+    for (int tt = warp; tt < TOK; tt += 8) {
+      const int t = t0 + tt;
+      if (t >= S) break;
+      const uint32_t* vsrc = reinterpret_cast<const uint32_t*>(qkv + static_cast<int64_t>(t) * ldqkv + (nq + nkv + vh) * 128);
+      *reinterpret_cast<uint32_t*>(&sv[tt][lane * 2]) = vsrc[lane];
+      *reinterpret_cast<uint32_t*>(&sv[tt][64 + lane * 2]) = vsrc[32 + lane];
+    }
+    __syncthreads();
+    const bool ok = t0 + lane < S;
+    const int crow = ok ? __ldg(cache_row + t0 + lane) : 0;
+    for (int d = warp; d < 128; d += 8) {
+      if (ok) Vt[static_cast<int64_t>(vh * 128 + d) * ldvt + crow] = sv[lane][d];
+    }
   }
 }
 
@@ -365,15 +373,10 @@ extern "C" int sr_mrope_kv(void* qkv, int64_t ldqkv, const float* cosb, const fl
   SR_REQUIRE(ldqkv % 8 == 0 && n_q_heads > 0 && n_kv_heads > 0 && n_kv_heads <= 8, "sr_mrope_kv: bad shape");
   if (S <= 0) return SR_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const size_t smem = 32 * (n_kv_heads * 128 + 2) * sizeof(__nv_bfloat16);
-  static bool attr_done = false;
-  if (!attr_done && smem > 48 * 1024) {
-    SR_CHECK_CUDA(cudaFuncSetAttribute(mrope_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 8 + 256));
-    attr_done = true;
-  }
-  mrope_kv_kernel<<<(S + 31) / 32, 256, smem, s>>>(reinterpret_cast<__nv_bfloat16*>(qkv), ldqkv, cosb, sinb, cache_row,
-                                                  reinterpret_cast<__nv_bfloat16*>(Kc),
-                                                  reinterpret_cast<__nv_bfloat16*>(Vt), ldvt, S, n_q_heads, n_kv_heads);
+  dim3 grid((S + 31) / 32, n_q_heads + 2 * n_kv_heads);
+  mrope_kv_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(qkv), ldqkv, cosb, sinb, cache_row,
+                                      reinterpret_cast<__nv_bfloat16*>(Kc), reinterpret_cast<__nv_bfloat16*>(Vt), ldvt, S,
+                                      n_q_heads, n_kv_heads);
   SR_CHECK_CUDA(cudaGetLastError());
   return SR_OK;
 }

@@ -17,8 +17,6 @@
 
 namespace sr {
 
-constexpr int GV_WARPS = 8;
-constexpr int GV_THREADS = GV_WARPS * 32;
 constexpr int GV_UNROLL = 4;
 
 SR_DEVINL uint4 ld_stream_v4(const void* p) {
@@ -45,8 +43,9 @@ struct GemvParams {
 };
 
 // RG = row groups of 16 weight rows per CTA (1, or 2 for SwiGLU: gate group + up group); NB = batch tiles of 8.
-template <int RG, int NB, int EPI, bool OUT_F32>
-__global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvParams p) {
+template <int RG, int NB, int EPI, bool OUT_F32, int GV_WARPS>
+__global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p) {
+  constexpr int GV_THREADS = GV_WARPS * 32;
   __shared__ float red[GV_WARPS][RG][NB][16 * 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -158,15 +157,19 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_kernel(const GemvParams p) {
 
 template <int NB>
 static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s) {
+  // 16 warps split K when one batch tile is live (the decode case): every warp then has <= 3 unrolled iterations even for
+  // K = 11008, i.e. (almost) all of a CTA's weight bytes are in flight at once.  Shared-memory budget caps NB >= 2 at 8.
+  constexpr int W = (NB == 1) ? 16 : 8;
+  constexpr int GV_THREADS = W * 32;
   if (epi == SR_EPI_SWIGLU) {
     const int grid = (p.N + 31) / 32;
-    gemv_kernel<2, NB, SR_EPI_SWIGLU, false><<<grid, GV_THREADS, 0, s>>>(p);
+    gemv_kernel<2, NB, SR_EPI_SWIGLU, false, W><<<grid, GV_THREADS, 0, s>>>(p);
   } else {
     const int grid = (p.N + 15) / 16;
-    if (out_f32) gemv_kernel<1, NB, SR_EPI_NONE, true><<<grid, GV_THREADS, 0, s>>>(p);
-    else if (epi == SR_EPI_NONE) gemv_kernel<1, NB, SR_EPI_NONE, false><<<grid, GV_THREADS, 0, s>>>(p);
-    else if (epi == SR_EPI_RESIDUAL) gemv_kernel<1, NB, SR_EPI_RESIDUAL, false><<<grid, GV_THREADS, 0, s>>>(p);
-    else if (epi == SR_EPI_GELU) gemv_kernel<1, NB, SR_EPI_GELU, false><<<grid, GV_THREADS, 0, s>>>(p);
+    if (out_f32) gemv_kernel<1, NB, SR_EPI_NONE, true, W><<<grid, GV_THREADS, 0, s>>>(p);
+    else if (epi == SR_EPI_NONE) gemv_kernel<1, NB, SR_EPI_NONE, false, W><<<grid, GV_THREADS, 0, s>>>(p);
+    else if (epi == SR_EPI_RESIDUAL) gemv_kernel<1, NB, SR_EPI_RESIDUAL, false, W><<<grid, GV_THREADS, 0, s>>>(p);
+    else if (epi == SR_EPI_GELU) gemv_kernel<1, NB, SR_EPI_GELU, false, W><<<grid, GV_THREADS, 0, s>>>(p);
     else {
       set_last_error("sr_gemm_skinny_bf16: unknown epilogue %d", epi);
       return SR_ERR_INVALID;

@@ -34,47 +34,70 @@ SR_DEVINL float block_sum(float v, float* sbuf) {
 // use_cache).  q [B, nq, 128] (row stride ldq), Kc [rows, nkv, 128], Vt [nkv*128, ldvt]; sample b attends cache
 // rows [kv_start[b], kv_start[b] + kv_len[b]).  One CTA per (sample, q head).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
-                                                         const __nv_bfloat16* __restrict__ Kc,
-                                                         const __nv_bfloat16* __restrict__ Vt, int64_t ldvt,
-                                                         const int* __restrict__ kv_start, const int* __restrict__ kv_len,
-                                                         __nv_bfloat16* __restrict__ out, int64_t ldo, int nq, int nkv,
-                                                         float scale_log2) {
-  extern __shared__ float sc[];  // [max_len] scores / probabilities
-  __shared__ float sq[128];
+constexpr int DA_THREADS = 512;
+__global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
+                                                                const __nv_bfloat16* __restrict__ Kc,
+                                                                const __nv_bfloat16* __restrict__ Vt, int64_t ldvt,
+                                                                const int* __restrict__ kv_start, const int* __restrict__ kv_len,
+                                                                __nv_bfloat16* __restrict__ out, int64_t ldo, int nq, int nkv,
+                                                                float scale_log2) {
+  extern __shared__ float sc[];  // [max_len rounded up to 32] scores / probabilities
+  __shared__ __align__(16) float sq[128];
   __shared__ float red[32];
   const int b = blockIdx.x, h = blockIdx.y, kvh = h / (nq / nkv);
   const int start = __ldg(kv_start + b), len = __ldg(kv_len + b);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   if (tid < 128) sq[tid] = __bfloat162float(q[static_cast<int64_t>(b) * ldq + h * 128 + tid]) * scale_log2;
   __syncthreads();
-  // scores: each warp owns keys warp, warp+8, ...; lanes split the 128-dim dot product (8 B per lane, coalesced 256 B row)
+  // scores: ONE KEY PER THREAD -- 16 independent 16-byte loads of the key row in flight per thread (memory-level
+  // parallelism instead of a serial per-key loop); q is broadcast from shared memory.
   float lmax = -INFINITY;
-  for (int k = warp; k < len; k += 8) {
-    const uint2 u = __ldg(reinterpret_cast<const uint2*>(Kc + (static_cast<int64_t>(start + k) * nkv + kvh) * 128) + lane);
-    float d = bf16_lo(u.x) * sq[lane * 4] + bf16_hi(u.x) * sq[lane * 4 + 1] + bf16_lo(u.y) * sq[lane * 4 + 2] +
-              bf16_hi(u.y) * sq[lane * 4 + 3];
-    d = warp_sum(d);
-    if (lane == 0) sc[k] = d;
+  for (int k = tid; k < len; k += DA_THREADS) {
+    const uint4* kr = reinterpret_cast<const uint4*>(Kc + (static_cast<int64_t>(start + k) * nkv + kvh) * 128);
+    uint4 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __ldg(kr + i);
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 q0 = *reinterpret_cast<const float4*>(&sq[i * 8]);
+      const float4 q1 = *reinterpret_cast<const float4*>(&sq[i * 8 + 4]);
+      d += bf16_lo(v[i].x) * q0.x + bf16_hi(v[i].x) * q0.y + bf16_lo(v[i].y) * q0.z + bf16_hi(v[i].y) * q0.w +
+           bf16_lo(v[i].z) * q1.x + bf16_hi(v[i].z) * q1.y + bf16_lo(v[i].w) * q1.z + bf16_hi(v[i].w) * q1.w;
+    }
+    sc[k] = d;
     lmax = fmaxf(lmax, d);
   }
   const float mx = block_max(lmax, red);
   float lsum = 0.f;
-  for (int k = tid; k < len; k += 256) {
+  for (int k = tid; k < len; k += DA_THREADS) {
     const float pv = exp2f(sc[k] - mx);
     sc[k] = pv;
     lsum += pv;
   }
+  const int len8 = (len + 7) & ~7;
+  for (int k = len + tid; k < len8; k += DA_THREADS) sc[k] = 0.f;  // zero tail so the 8-key vectors below can over-read
   const float tot = block_sum(lsum, red);  // also orders the sc[] writes before the reads below
   const float inv = tot > 0.f ? 1.f / tot : 0.f;
-  // o[d] = sum_k p[k] * Vt[kvh*128 + d, start + k]: warp per d, lanes stride the (contiguous) key axis
-  for (int d = warp; d < 128; d += 8) {
-    const __nv_bfloat16* vrow = Vt + static_cast<int64_t>(kvh * 128 + d) * ldvt + start;
-    float acc = 0.f;
-    for (int k = lane; k < len; k += 32) acc += sc[k] * __bfloat162float(__ldg(vrow + k));
-    acc = warp_sum(acc);
-    if (lane == 0) out[static_cast<int64_t>(b) * ldo + h * 128 + d] = __float2bfloat16(acc * inv);
+  // o[d] = sum_k p[k] * Vt[kvh*128 + d, start + k]: 4 threads per d row, each streams a contiguous quarter of the keys
+  // with 16-byte loads (start is a multiple of 8 keys: cache rows are l_max-aligned).
+  const int d = tid >> 2, part = tid & 3;
+  const int nvec = len8 >> 3;
+  const int per = (nvec + 3) >> 2;
+  const int v0 = part * per, v1 = min(nvec, v0 + per);
+  const uint4* vrow = reinterpret_cast<const uint4*>(Vt + static_cast<int64_t>(kvh * 128 + d) * ldvt + start);
+  float acc = 0.f;
+#pragma unroll 4
+  for (int i = v0; i < v1; ++i) {
+    const uint4 u = __ldg(vrow + i);
+    const float4 p0 = *reinterpret_cast<const float4*>(&sc[i * 8]);
+    const float4 p1 = *reinterpret_cast<const float4*>(&sc[i * 8 + 4]);
+    acc += bf16_lo(u.x) * p0.x + bf16_hi(u.x) * p0.y + bf16_lo(u.y) * p0.z + bf16_hi(u.y) * p0.w +
+           bf16_lo(u.z) * p1.x + bf16_hi(u.z) * p1.y + bf16_lo(u.w) * p1.z + bf16_hi(u.w) * p1.w;
   }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (part == 0) out[static_cast<int64_t>(b) * ldo + h * 128 + d] = __float2bfloat16(acc * inv);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -87,24 +110,13 @@ SR_DEVINL float to_f32<float>(float v) { return v; }
 template <>
 SR_DEVINL float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-template <typename T>
-__global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ logits, int64_t ld, int V,
-                                                     int64_t* __restrict__ out) {
-  __shared__ float sval[32];
-  __shared__ int sidx[32];
-  const T* row = logits + static_cast<int64_t>(blockIdx.x) * ld;
-  float best = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float v = to_f32<T>(row[i]);
-    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
-  }
+constexpr int AM_SPLIT = 64;
+SR_DEVINL void argmax_combine(float& best, int& bi, float ov, int oi) {
+  if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+}
+SR_DEVINL void argmax_block(float& best, int& bi, float* sval, int* sidx) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-  }
+  for (int o = 16; o > 0; o >>= 1) argmax_combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) { sval[warp] = best; sidx[warp] = bi; }
   __syncthreads();
@@ -112,13 +124,35 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ logi
     best = lane < (blockDim.x >> 5) ? sval[lane] : -INFINITY;
     bi = lane < (blockDim.x >> 5) ? sidx[lane] : 0x7fffffff;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-    }
-    if (lane == 0) out[blockIdx.x] = bi;
+    for (int o = 16; o > 0; o >>= 1) argmax_combine(best, bi, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, bi, o));
   }
+}
+// stage 1: grid (rows, AM_SPLIT) -> partial (value, index) per slice; stage 2: grid rows -> final index.
+template <typename T>
+__global__ void __launch_bounds__(256) argmax_partial_kernel(const T* __restrict__ logits, int64_t ld, int V,
+                                                            float* __restrict__ pval, int* __restrict__ pidx) {
+  __shared__ float sval[32];
+  __shared__ int sidx[32];
+  const T* row = logits + static_cast<int64_t>(blockIdx.x) * ld;
+  const int per = (V + AM_SPLIT - 1) / AM_SPLIT;
+  const int i0 = blockIdx.y * per, i1 = min(V, i0 + per);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) argmax_combine(best, bi, to_f32<T>(row[i]), i);
+  argmax_block(best, bi, sval, sidx);
+  if (threadIdx.x == 0) {
+    pval[blockIdx.x * AM_SPLIT + blockIdx.y] = best;
+    pidx[blockIdx.x * AM_SPLIT + blockIdx.y] = bi;
+  }
+}
+__global__ void __launch_bounds__(AM_SPLIT) argmax_final_kernel(const float* __restrict__ pval, const int* __restrict__ pidx,
+                                                               int64_t* __restrict__ out) {
+  __shared__ float sval[32];
+  __shared__ int sidx[32];
+  float best = pval[blockIdx.x * AM_SPLIT + threadIdx.x];
+  int bi = pidx[blockIdx.x * AM_SPLIT + threadIdx.x];
+  argmax_block(best, bi, sval, sidx);
+  if (threadIdx.x == 0) out[blockIdx.x] = bi;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -287,7 +321,7 @@ extern "C" int sr_decode_attention(const void* q, int64_t ldq, const void* Kc, c
                                    int batch, int n_q_heads, int n_kv_heads, float scale, void* stream) {
   SR_REQUIRE(q && Kc && Vt && kv_start && kv_len && out, "sr_decode_attention: null pointer");
   SR_REQUIRE(batch > 0 && n_q_heads % n_kv_heads == 0 && max_len > 0, "sr_decode_attention: bad shape");
-  const size_t smem = static_cast<size_t>(max_len) * sizeof(float);
+  const size_t smem = static_cast<size_t>((max_len + 31) / 32 * 32 + 8) * sizeof(float);
   SR_REQUIRE(smem <= 200 * 1024, "sr_decode_attention: max_len %d too long for the single-pass kernel", max_len);
   static size_t attr_smem = 48 * 1024;
   if (smem > attr_smem) {
@@ -295,7 +329,7 @@ extern "C" int sr_decode_attention(const void* q, int64_t ldq, const void* Kc, c
     attr_smem = 200 * 1024;
   }
   dim3 grid(batch, n_q_heads);
-  decode_attn_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  decode_attn_kernel<<<grid, DA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(Kc),
       reinterpret_cast<const __nv_bfloat16*>(Vt), ldvt, kv_start, kv_len, reinterpret_cast<__nv_bfloat16*>(out), ldo,
       n_q_heads, n_kv_heads, scale * 1.4426950408889634f);
@@ -303,12 +337,19 @@ extern "C" int sr_decode_attention(const void* q, int64_t ldq, const void* Kc, c
   return SR_OK;
 }
 
-extern "C" int sr_argmax_rows(const void* logits, int64_t ld, int dtype, int rows, int V, int64_t* out, void* stream) {
-  SR_REQUIRE(logits && out && rows >= 0 && V > 0, "sr_argmax_rows: bad args");
+extern "C" int sr_argmax_rows(const void* logits, int64_t ld, int dtype, int rows, int V, int64_t* out, void* workspace,
+                              void* stream) {
+  SR_REQUIRE(logits && out && workspace && rows >= 0 && V > 0, "sr_argmax_rows: bad args (workspace = rows*512 bytes)");
   if (rows == 0) return SR_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == SR_DTYPE_F32) argmax_kernel<float><<<rows, 1024, 0, s>>>(reinterpret_cast<const float*>(logits), ld, V, out);
-  else argmax_kernel<__nv_bfloat16><<<rows, 1024, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, V, out);
+  float* pval = reinterpret_cast<float*>(workspace);
+  int* pidx = reinterpret_cast<int*>(pval + static_cast<size_t>(rows) * AM_SPLIT);
+  dim3 grid(rows, AM_SPLIT);
+  if (dtype == SR_DTYPE_F32)
+    argmax_partial_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(logits), ld, V, pval, pidx);
+  else
+    argmax_partial_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, V, pval, pidx);
+  argmax_final_kernel<<<rows, AM_SPLIT, 0, s>>>(pval, pidx, out);
   SR_CHECK_CUDA(cudaGetLastError());
   return SR_OK;
 }

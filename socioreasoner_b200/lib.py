@@ -37,7 +37,7 @@ SYMBOLS = {
     "sr_mrope_table": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "sr_vit_rope_split": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "sr_mrope_kv": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
-    "sr_argmax_rows": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "sr_argmax_rows": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
     "sr_logprob_entropy": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sr_decode_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
@@ -270,14 +270,21 @@ def mrope_kv(qkv, cos, sin, cache_row, kc, vt, n_q_heads, n_kv_heads):
     launch_count += 1
 
 
+_argmax_ws = {}
+
+
 def argmax_rows(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     global launch_count
     rows, V = logits.shape
     if out is None:
         out = torch.empty((rows,), dtype=torch.int64, device=logits.device)
+    key = (logits.device, rows)
+    ws = _argmax_ws.get(key)
+    if ws is None:
+        ws = _argmax_ws[key] = torch.empty((rows * 512,), dtype=torch.uint8, device=logits.device)
     _check(load().sr_argmax_rows(logits.data_ptr(), logits.stride(0), DT_F32 if logits.dtype == torch.float32 else DT_BF16,
-                                 rows, V, out.data_ptr(), _stream()), "sr_argmax_rows")
-    launch_count += 1
+                                 rows, V, out.data_ptr(), ws.data_ptr(), _stream()), "sr_argmax_rows")
+    launch_count += 2
     return out
 
 

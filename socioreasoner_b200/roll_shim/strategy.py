@@ -1,0 +1,193 @@
+"""B200 strategies behind the reference's ``InferenceStrategy`` surface.
+
+``B200InferStrategy`` answers to what ``HfInferStrategy`` (``roll/distributed/strategy/hf_strategy.py:26-129``) and the
+rollout side of ``VllmStrategy`` (``vllm_strategy.py:114-141``) answer to; ``B200SegStrategy`` to ``SegInferStrategy``
+(``seg_strategy.py:12-79``).  The micro-batch loop, the multi-modal input concatenation and the result collation follow
+the reference line by line (cited inline) so that swapping the strategy does not change what the workers see.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .protocol import DataProto, collate_fn_to_dict_list
+
+
+class InferenceStrategy:
+    """``roll/distributed/strategy/strategy.py:16-138`` (the members the hot path touches)."""
+    strategy_name = None
+
+    def __init__(self, worker):
+        self.worker = worker
+        self.model = None
+        self.tokenizer = None
+        self.worker_config = getattr(worker, "worker_config", None)
+        self.model_update_comm_plan = {}
+
+    def initialize(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def forward_step(self, batch, forward_func):
+        raise NotImplementedError
+
+    def get_data_input(self, batch):
+        return batch
+
+    def generate(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def unwrap_model(self):
+        return self.model
+
+    # offload / reload around every RPC (context_managers.py:126-128,175-177).  On a 180 GB B200 the 7.5 GB replica stays
+    # resident: both are no-ops that keep the call contract.
+    def load_states(self, include=None, non_blocking=False):
+        return None
+
+    def offload_states(self, include=None, non_blocking=False):
+        return None
+
+    # weight-sync hooks (megatron_strategy.py:411-448 -> strategy.py broadcast_*/update_*): ranked "next" row
+    def broadcast_parameter(self, *a, **k):
+        raise NotImplementedError("weight sync over NVLink is a ranked next row (SURVEY.md 8f-4)")
+
+    broadcast_bucket = update_parameter = update_parameter_in_bucket = broadcast_parameter
+
+    # ---- distributed ops (strategy.py:123-138) on the fused device kernel ----
+    def op_compute_log_probs(self, logits: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor):
+        """logits [b,S,V], input_ids [b,S], attention_mask(response_mask) [b,S] -> [b,S-1] (strategy.py:123-133)."""
+        from .. import lib
+        b, S, V = logits.shape
+        labels = input_ids[:, 1:].clone()
+        labels[attention_mask[:, 1:] == 0] = 0  # avoid invalid token id
+        lg = logits[:, :-1].reshape(-1, V)
+        lp, _ = lib.logprob_entropy(lg, labels.reshape(-1).to(lg.device).contiguous(), want_entropy=False)
+        return lp.view(b, S - 1) * attention_mask[:, 1:].to(lp.device)
+
+    def op_compute_entropy(self, logits: torch.Tensor, attention_mask: torch.Tensor):
+        from .. import lib
+        b, S, V = logits.shape
+        _, ent = lib.logprob_entropy(logits.reshape(-1, V), None, want_entropy=True)
+        return ent.view(b, S)[:, :-1] * attention_mask[:, 1:].to(ent.device)
+
+
+def _concat_multi_modal(data: DataProto, forward_args: dict, device) -> dict:
+    """hf_strategy.py:68-79: per-sample dicts -> concatenated pixel_values / image_grid_thw."""
+    if "multi_modal_inputs" in data.non_tensor_batch:
+        mm = defaultdict(list)
+        for sample in data.non_tensor_batch["multi_modal_inputs"]:  # samples may be empty (text + mm mixed data)
+            for key in sample.keys():
+                mm[key].append(sample[key])
+        for key in mm.keys():
+            assert key not in forward_args
+            forward_args[key] = torch.concat(mm[key], dim=0).to(device)
+    return forward_args
+
+
+class B200InferStrategy(InferenceStrategy):
+    strategy_name = "b200_infer"
+
+    def initialize(self, model_provider):
+        """Sets ``self.model`` / ``self.tokenizer`` and the worker's rank_info (dispatch depends on it,
+        decorator.py:113-121).  One process per GPU; torch.distributed (NCCL) is initialised by the launcher."""
+        import torch.distributed as dist
+        wc = self.worker_config
+        model_args = getattr(wc, "model_args", None)
+        self.model = model_provider(tokenizer=self.tokenizer, model_args=model_args, is_trainable=False)
+        ri = getattr(self.worker, "rank_info", None)
+        if ri is not None:
+            ri.dp_rank = dist.get_rank() if dist.is_initialized() else 0
+            ri.dp_size = dist.get_world_size() if dist.is_initialized() else 1
+        return self
+
+    def forward_step(self, batch: DataProto, forward_func: Callable[[DataProto, torch.Tensor], Tuple[torch.Tensor, Dict[str, torch.Tensor]]]
+                     ) -> Dict[str, torch.Tensor]:
+        """hf_strategy.py:49-94."""
+        batch_size = batch.batch.batch_size[0]
+        micro_batch_size = batch.meta_info["micro_batch_size"]
+        num_microbatches = max(batch_size // micro_batch_size, 1)
+        losses_reduced = []
+        for data in batch.chunk(chunks=num_microbatches):
+            input_ids = data.batch["input_ids"]
+            attention_mask = data.batch["attention_mask"]
+            position_ids = data.batch["position_ids"]
+            forward_args = dict(data.meta_info.get("forward_args", {}))
+            if position_ids.dim() == 3:
+                position_ids = position_ids.transpose(0, 1)  # (bsz, 3, seqlen) -> (3, bsz, seqlen)
+            forward_args = _concat_multi_modal(data, forward_args, input_ids.device)
+            output = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids, use_cache=False,
+                                **forward_args)
+            loss, loss_reduced = forward_func(data, output.logits)
+            losses_reduced.append(loss_reduced)
+        return collate_fn_to_dict_list(losses_reduced)
+
+    def generate(self, batch: DataProto, generation_config: dict) -> torch.Tensor:
+        """hf_strategy.py:96-129: micro-batched ``model.generate`` then pad_sequence with pad_token_id."""
+        from torch.nn.utils.rnn import pad_sequence
+        batch_size = batch.batch.batch_size[0]
+        micro_batch_size = batch.meta_info["micro_batch_size"]
+        num_microbatches = max(batch_size // micro_batch_size, 1)
+        output_list: List[torch.Tensor] = []
+        for data in batch.chunk(chunks=num_microbatches):
+            forward_args = dict(data.meta_info.get("forward_args", {}))
+            forward_args = _concat_multi_modal(data, forward_args, data.batch["input_ids"].device)
+            output = self.model.generate(input_ids=data.batch["input_ids"], attention_mask=data.batch["attention_mask"],
+                                         use_cache=True, **forward_args, **generation_config)
+            output_list.extend(list(output))
+        return pad_sequence(output_list, batch_first=True, padding_value=generation_config["pad_token_id"])
+
+
+class B200SegStrategy(InferenceStrategy):
+    """Mask side (seg_strategy.py:26-72).  The SAM2 network itself is the ranked next component; this
+    strategy owns the epilogue the reference runs on the CPU: argmax-score candidate pick, OR over objects, nearest resize
+    to 768, uint8.  ``predictor(image, prompt) -> (low_res_logits [3,h,w], scores [3])`` is injected (a SAM2 wrapper in
+    production, synthetic logits in tests / bench)."""
+    strategy_name = "seg_infer"
+
+    def __init__(self, worker, image_size: int = 756, out_size: int = 768):
+        super().__init__(worker)
+        self.image_size, self.out_size = image_size, out_size
+        self.predictor = None
+
+    def initialize(self, model_provider):
+        self.predictor = model_provider(model_args=getattr(self.worker_config, "model_args", None), is_trainable=False)
+        return self
+
+    def segment(self, batch: DataProto) -> dict:
+        from .. import lib
+        masks = []
+        for i in range(len(batch)):
+            image = batch.non_tensor_batch["seg_image"][i]
+            visual_prompt = batch.non_tensor_batch["visual_prompt"][i]
+            if len(visual_prompt) == 0:  # seg_strategy.py:40-45: zero mask, model untouched
+                masks.append({"mask": np.zeros((self.out_size, self.out_size), dtype=np.uint8)})
+                continue
+            logits, scores = [], []
+            for single_vp in visual_prompt:
+                try:
+                    l, s = self.predictor(image, single_vp)
+                    logits.append(torch.as_tensor(l, dtype=torch.float32))
+                    scores.append(torch.as_tensor(s, dtype=torch.float32))
+                except Exception:  # seg_strategy.py:62-63: a failing object is skipped
+                    continue
+            if not logits:
+                # every object failed: the reference still resizes its zero 756 mask -> zero 768 mask
+                masks.append({"mask": np.zeros((self.out_size, self.out_size), dtype=np.uint8)})
+                continue
+            m = lib.mask_epilogue(torch.stack(logits).cuda(), torch.stack(scores).cuda(), self.image_size, self.out_size)
+            masks.append({"mask": m.cpu().numpy()})
+        return collate_fn_to_dict_list(masks)
+
+
+def create_strategy(worker):
+    """``roll/distributed/strategy/factory.py:7-30`` with the B200 backends answering to the existing names, so the
+    entry script and the yaml stay unchanged: rollout (`vllm`, `hf_infer`) and mask (`seg_infer`)."""
+    name = worker.worker_config.strategy_args.strategy_name
+    if name in ("b200_infer", "hf_infer", "vllm"):
+        return B200InferStrategy(worker)
+    if name in ("b200_seg", "seg_infer"):
+        return B200SegStrategy(worker)
+    raise ValueError(f"Unknown strategy name: {name}")

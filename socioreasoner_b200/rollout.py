@@ -58,7 +58,7 @@ class RolloutResult:
 
 class DataParallelRollout:
     def __init__(self, model, max_new_tokens: int = 32, image_size: int = 756, out_size: int = 768, group=None):
-        self.model, self.engine = model, model.engine
+        self.model, self.engine = model, (model.engine if model is not None else None)
         self.T, self.image_size, self.out_size = max_new_tokens, image_size, out_size
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
@@ -98,16 +98,34 @@ class DataParallelRollout:
         for i in range(b):
             lib.mask_epilogue(ml[i], ms[i], self.image_size, self.out_size, out=masks[i])
         iou = lib.mask_iou(masks[:b], gt, 1.0)
+        self.pack_slot(b_max, tokens, iou)
+        return RolloutResult(tokens, masks[:b], iou)
+
+    def slot_masks(self, b_max: int, device=None) -> torch.Tensor:
+        """This rank's mask region of the gather buffer ([b_max, out, out] uint8 view): the epilogue's output target."""
+        gbuf = self._ensure_gbuf(b_max, device if device is not None else self.engine.device)
+        mask_b = self._slot_layout(b_max)[0]
+        return gbuf[self.rank][:mask_b].view(b_max, self.out_size, self.out_size)
+
+    def pack_slot(self, b_max: int, tokens: torch.Tensor, iou: torch.Tensor) -> None:
+        """Write IoU, tokens and the valid-count next to the masks in this rank's slot."""
+        b = tokens.shape[0]
+        _, iou_off, tok_off, cnt_off, _ = self._slot_layout(b_max)
+        slot = self._gbuf[self.rank]
         slot[iou_off:iou_off + b * 4].view(torch.float32).copy_(iou)
         slot[tok_off:tok_off + b * self.T * 8].view(torch.int64).copy_(tokens.reshape(-1))
         slot[cnt_off:cnt_off + 8].view(torch.int64).fill_(b)
-        return RolloutResult(tokens, masks[:b], iou)
 
     def gather(self, b_max: int) -> RolloutResult:
         """ONE all-gather of every rank's slot; returns the concatenation in rank order (= reference concat order)."""
         gbuf = self._gbuf
         if self.world > 1:
-            dist.all_gather_into_tensor(gbuf.view(-1), gbuf[self.rank], group=self.group)
+            if gbuf.is_cuda:  # NCCL in-place all-gather (send buffer = this rank's slot of the receive buffer)
+                dist.all_gather_into_tensor(gbuf.view(-1), gbuf[self.rank], group=self.group)
+            else:             # gloo (CPU tests of the host logic)
+                parts = [torch.empty_like(gbuf[0]) for _ in range(self.world)]
+                dist.all_gather(parts, gbuf[self.rank].clone(), group=self.group)
+                gbuf.copy_(torch.stack(parts))
         mask_b, iou_off, tok_off, cnt_off, _ = self._slot_layout(b_max)
         counts = gbuf[:, cnt_off:cnt_off + 8].contiguous().view(torch.int64).view(-1).tolist()
         toks, masks, ious = [], [], []

@@ -1,0 +1,158 @@
+"""CPU: the mirrored reference surface (DataProto subset, strategy micro-batch loop, factory) with a fake model, and the
+world_size-2 (gloo) data-parallel shard + gather logic."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import host_ref
+from socioreasoner_b200.roll_shim import B200InferStrategy, B200SegStrategy, DataProto, collate_fn_to_dict_list, create_strategy
+from socioreasoner_b200.rollout import DataParallelRollout, shard_indices
+
+
+def make_proto(n=7, S=5):
+    ids = torch.arange(n * S).view(n, S)
+    mm = [dict(pixel_values=torch.full((4 * (i + 1), 1176), float(i)), image_grid_thw=torch.tensor([[1, 2, 2 * (i + 1)]])) for i in range(n)]
+    return DataProto.from_dict(
+        tensors=dict(input_ids=ids, attention_mask=torch.ones_like(ids), position_ids=torch.arange(n * 3 * S).view(n, 3, S),
+                     response_mask=torch.ones_like(ids)),
+        non_tensors=dict(multi_modal_inputs=mm), meta_info=dict(micro_batch_size=2))
+
+
+def test_dataproto_chunk_concat_follow_array_split():
+    d = make_proto(7)
+    for chunks in (1, 2, 3, 4, 7):
+        parts = d.chunk(chunks)
+        assert [len(p) for p in parts] == [len(c) for c in np.array_split(np.arange(7), chunks)]
+        back = DataProto.concat(parts)
+        assert torch.equal(back.batch["input_ids"], d.batch["input_ids"])
+        assert [m["image_grid_thw"].tolist() for m in back.non_tensor_batch["multi_modal_inputs"]] == \
+               [m["image_grid_thw"].tolist() for m in d.non_tensor_batch["multi_modal_inputs"]]
+        assert all(p.meta_info is d.meta_info for p in parts)
+    with pytest.raises(AssertionError):
+        d.chunk(8)
+
+
+def test_collate_fn_to_dict_list():
+    out = collate_fn_to_dict_list([{"a": torch.ones(2, 3), "m": np.zeros(2)}, {"a": torch.zeros(1, 3), "m": np.ones(2)}])
+    assert out["a"].shape == (3, 3) and out["m"].dtype == object and len(out["m"]) == 2
+
+
+class FakeModel:
+    """Records what the strategy passes (the contract of hf_strategy.py:84-90) and returns logits that encode the ids."""
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, input_ids, attention_mask, position_ids, use_cache, **kw):
+        self.calls.append(dict(ids=input_ids.clone(), pos_shape=tuple(position_ids.shape), use_cache=use_cache,
+                               pv_rows=kw["pixel_values"].shape[0], grid=kw["image_grid_thw"].clone(), extra=sorted(kw)))
+        V = 64
+        logits = torch.zeros(*input_ids.shape, V)
+        logits.scatter_(-1, (input_ids % V).unsqueeze(-1), 5.0)
+        return SimpleNamespace(logits=logits)
+
+    def generate(self, input_ids, attention_mask, use_cache, **kw):
+        n = kw["max_new_tokens"] - (1 if int(input_ids[0, 0]) % 2 else 0)  # ragged outputs across micro-batches
+        return torch.cat([input_ids, torch.full((input_ids.shape[0], n), 9)], 1)
+
+
+def worker(name):
+    return SimpleNamespace(worker_config=SimpleNamespace(strategy_args=SimpleNamespace(strategy_name=name), model_args=None),
+                           rank_info=SimpleNamespace(dp_rank=None, dp_size=None))
+
+
+def test_forward_step_micro_batching_and_multimodal_concat():
+    st = create_strategy(worker("hf_infer"))
+    assert isinstance(st, B200InferStrategy)
+    st.model = FakeModel()
+    d = make_proto(7)
+
+    def forward_func(data, logits):
+        lp = host_ref.op_compute_log_probs(logits, data.batch["input_ids"], data.batch["response_mask"])
+        return lp, {"log_probs": lp.clone(), "tag": "x"}
+
+    res = st.forward_step(d, forward_func)
+    # 7 // 2 = 3 micro-batches with array_split sizes 3,2,2; results concatenated in order
+    assert [c["ids"].shape[0] for c in st.model.calls] == [3, 2, 2]
+    assert res["log_probs"].shape == (7, 4) and len(res["tag"]) == 3
+    ref = host_ref.op_compute_log_probs(FakeModel()(d.batch["input_ids"], None, d.batch["position_ids"], False,
+                                                    pixel_values=torch.zeros(1, 1), image_grid_thw=torch.zeros(1, 3)).logits,
+                                        d.batch["input_ids"], d.batch["response_mask"])
+    assert torch.allclose(res["log_probs"], ref)
+    c0 = st.model.calls[0]
+    assert c0["pos_shape"] == (3, 3, 5) and c0["use_cache"] is False          # (bsz,3,S) -> (3,bsz,S)
+    assert c0["pv_rows"] == 4 + 8 + 12 and c0["grid"].shape == (3, 3)          # per-sample mm inputs concatenated
+    assert c0["extra"] == ["image_grid_thw", "pixel_values"]
+
+
+def test_generate_pads_ragged_micro_batches():
+    st = create_strategy(worker("vllm"))
+    st.model = FakeModel()
+    d = make_proto(4)
+    d.meta_info["micro_batch_size"] = 2
+    out = st.generate(d, dict(max_new_tokens=3, pad_token_id=0))
+    assert out.shape == (4, 5 + 3)
+    assert (out[:, :5] == d.batch["input_ids"]).all()
+
+
+def test_factory_names_and_seg_empty_prompt():
+    assert isinstance(create_strategy(worker("seg_infer")), B200SegStrategy)
+    with pytest.raises(ValueError, match="Unknown strategy name"):
+        create_strategy(worker("deepspeed_train"))
+    seg = create_strategy(worker("seg_infer"))
+    seg.predictor = lambda image, vp: (_ for _ in ()).throw(RuntimeError("must not be called"))
+    d = DataProto.from_dict(tensors=dict(x=torch.zeros(2, 1)), non_tensors=dict(seg_image=[None, None], visual_prompt=[[], []]))
+    out = seg.segment(d)
+    assert out["mask"].shape == (2,) and out["mask"][0].shape == (768, 768) and out["mask"][0].sum() == 0
+
+
+def test_offload_hooks_are_noops_and_weight_sync_is_declared_next():
+    st = B200InferStrategy(worker("b200_infer"))
+    assert st.load_states(include=None, non_blocking=True) is None and st.offload_states() is None
+    with pytest.raises(NotImplementedError):
+        st.update_parameter_in_bucket({}, None, [0])
+
+
+# ---------------------------------------------------------------------------------------------- world_size 2, gloo
+def _dp_worker(rank, world, port, total, T, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shards = shard_indices(total, world)
+        mine = shards[rank]
+        b_max = max(len(s) for s in shards)
+        ro = DataParallelRollout(None, max_new_tokens=T, out_size=8)
+        masks = ro.slot_masks(b_max, device="cpu")
+        for j, i in enumerate(mine):
+            masks[j].fill_(int(i) + 1)                              # "epilogue" writes straight into the gather slot
+        toks = torch.stack([torch.arange(T) + 100 * int(i) for i in mine]) if len(mine) else torch.zeros(0, T, dtype=torch.int64)
+        ro.pack_slot(b_max, toks, torch.tensor([float(i) / 10 for i in mine]))
+        res = ro.gather(b_max)
+        out_q.put((rank, res.tokens.clone(), res.masks.clone(), res.iou.clone()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [5, 4])
+def test_dp_shard_and_gather_world2_gloo(total):
+    world, T = 2, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + total
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, total, T, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, toks, masks, iou in results:
+        # every rank sees the whole batch in rank order == np.array_split order == the reference's DataProto.concat order
+        assert toks.shape == (total, T) and masks.shape == (total, 8, 8)
+        assert toks[:, 0].tolist() == [100 * i for i in range(total)]
+        assert masks[:, 0, 0].tolist() == [i + 1 for i in range(total)]
+        assert torch.allclose(iou, torch.arange(total).float() / 10)

@@ -39,7 +39,8 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kBiasBytes = 2 * BLOCK_N * 4;  // double-buffered per-tile bias slice (epilogue warps)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
 };
 
 SR_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -59,6 +60,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tmem_full_bar = empty_bar + kStages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + 256);  // [2][BLOCK_N]
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,23 +140,59 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else {
     // ---------------- epilogue warps (2..5) ----------------
+    // Global-memory operands of the epilogue are kept off the critical path: the tile's bias slice is staged once in
+    // shared memory (a per-use __ldg costs one L2 round trip per 8 columns -- ncu showed 60% of all stall samples
+    // there), and the residual rows of chunk c+1 are prefetched while chunk c is converted and stored.
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;   // 0..127 within the epilogue group
     int acc = 0;
     uint32_t acc_phase = 0;
+    int tile_par = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile % p.num_m_blocks;
       const int n_blk = tile / p.num_m_blocks;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
+      float* sb = s_bias + tile_par * BLOCK_N;
+      if (p.bias != nullptr) {
+        for (int j = et; j < BLOCK_N; j += 128) {
+          const int col = n_blk * BLOCK_N + j;
+          sb[j] = col < p.N ? __ldg(p.bias + col) : 0.f;
+        }
+      }
       const int row = m_blk * GEMM_BLOCK_M + quarter * 32 + lane;
       const bool row_ok = row < p.M;
+      uint4 rnext[4];
+      const __nv_bfloat16* rrow = nullptr;
+      if (EPI == SR_EPI_RESIDUAL) {
+        rrow = reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<int64_t>(row_ok ? row : 0) * p.ldr;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int col = n_blk * BLOCK_N + g8 * 8;
+          rnext[g8] = (row_ok && col < p.N) ? *reinterpret_cast<const uint4*>(rrow + col) : make_uint4(0, 0, 0, 0);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // bias slice visible to the 4 epilogue warps
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(chunk * 32), v);
-        tmem_ld_wait();
         const int col0 = n_blk * BLOCK_N + chunk * 32;
+        uint4 rcur[4];
+        if (EPI == SR_EPI_RESIDUAL) {
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) rcur[g8] = rnext[g8];
+          if (chunk + 1 < BLOCK_N / 32) {
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const int col = col0 + 32 + g8 * 8;
+              rnext[g8] = (row_ok && col < p.N) ? *reinterpret_cast<const uint4*>(rrow + col) : make_uint4(0, 0, 0, 0);
+            }
+          }
+        }
+        tmem_ld_wait();
+        const float* sbc = sb + chunk * 32;
         if (EPI == SR_EPI_SWIGLU) {
           // packed weight rows: [16 gate | 16 up] per 32 columns -> 16 outputs at col0/2
           const int oc0 = col0 >> 1;
@@ -163,11 +201,11 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 16; ++j) {
             float g = __uint_as_float(v[j]);
             float u = __uint_as_float(v[16 + j]);
-            if (p.bias != nullptr && col0 + 31 < p.N) {
-              g += __ldg(p.bias + col0 + j);
-              u += __ldg(p.bias + col0 + 16 + j);
+            if (p.bias != nullptr) {
+              g += sbc[j];
+              u += sbc[16 + j];
             }
-            o[j] = silu(g) * u;
+            o[j] = __fdividef(g, 1.0f + __expf(-g)) * u;
           }
           if (row_ok && oc0 < (p.N >> 1)) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + oc0;
@@ -190,10 +228,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g8 * 8 + j]);
             if (p.bias != nullptr) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] += sbc[g8 * 8 + j];
             }
             if (EPI == SR_EPI_GELU) {
 #pragma unroll
@@ -201,8 +237,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if (row_ok) {
               if (EPI == SR_EPI_RESIDUAL) {
-                const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) +
-                                                                static_cast<int64_t>(row) * p.ldr + col);
+                const uint4 r = rcur[g8];
                 x[0] += bf16_lo(r.x); x[1] += bf16_hi(r.x); x[2] += bf16_lo(r.y); x[3] += bf16_hi(r.y);
                 x[4] += bf16_lo(r.z); x[5] += bf16_hi(r.z); x[6] += bf16_lo(r.w); x[7] += bf16_hi(r.w);
               }
@@ -228,6 +263,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+      tile_par ^= 1;
     }
   }
 

@@ -46,6 +46,8 @@ const char* sr_last_error(void);
 int sr_abi_version(void);
 /* 0 if the current CUDA device is compute capability 10.x (B200), else SR_ERR_UNSUPPORTED. */
 int sr_device_check(void);
+/* Programmatic dependent launch for the decode-step kernels (default on; env SR_PDL=0 disables). */
+int sr_set_pdl(int enabled);
 
 /* ---- dense contraction (tcgen05 + TMA) ------------------------------------------------------
  * C[M, n_out] = epilogue(A[M,K] . W[N,K]^T), bf16 inputs, fp32 accumulate in TMEM.
@@ -64,6 +66,13 @@ int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C
  * sr_gemm_bf16 dispatches here automatically when block_n == 0 and the shape qualifies. */
 int sr_gemm_skinny_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, const float* bias,
                         const void* residual, int64_t ldr, int M, int N, int K, int epilogue, int out_dtype, void* stream);
+
+/* Same with RMSNorm fused into the operand load: C = epilogue(rmsnorm(A; norm_weight, eps) . W^T).  Replaces the
+ * input_layernorm / post_attention_layernorm / final norm + following nn.Linear pairs of the decode step
+ * (HF:57-71 + HF:704-707 / 611-624 / 1385) with one launch. */
+int sr_gemm_skinny_norm_bf16(const void* A, int64_t lda, const float* norm_weight, float norm_eps, const void* W, int64_t ldw,
+                             void* C, int64_t ldc, const float* bias, const void* residual, int64_t ldr, int M, int N, int K,
+                             int epilogue, int out_dtype, void* stream);
 
 /* ---- attention (tcgen05 + TMA) --------------------------------------------------------------
  * Variable-length softmax(Q K^T * scale) V; query row r attends key rows k with row_lo[r] <= k < row_hi[r].

@@ -172,6 +172,15 @@ SR_DEVINL void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
 SR_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may become
+// resident while its predecessor is still running; pdl_wait() blocks until the predecessor grid has completed and its
+// memory is visible, pdl_trigger() lets the NEXT kernel start becoming resident.  Both are no-ops for plain launches.
+// Used by the ~220 small kernels of a decode step to hide launch/ramp latency (they are captured into one CUDA graph).
+// ------------------------------------------------------------------------------------------------
+SR_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+SR_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
 // numeric helpers
 // ------------------------------------------------------------------------------------------------
 SR_DEVINL uint32_t pack_bf16x2(float lo, float hi) {

@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(256) mrope_kv_kernel(__nv_bfloat16* __restrict
   const int t0 = blockIdx.x * TOK;
   const int hh = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_wait();
+  pdl_trigger();
   if (hh < nq + nkv) {
     for (int tt = warp; tt < TOK; tt += 8) {
       const int t = t0 + tt;
@@ -374,9 +376,9 @@ extern "C" int sr_mrope_kv(void* qkv, int64_t ldqkv, const float* cosb, const fl
   if (S <= 0) return SR_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid((S + 31) / 32, n_q_heads + 2 * n_kv_heads);
-  mrope_kv_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(qkv), ldqkv, cosb, sinb, cache_row,
-                                      reinterpret_cast<__nv_bfloat16*>(Kc), reinterpret_cast<__nv_bfloat16*>(Vt), ldvt, S,
-                                      n_q_heads, n_kv_heads);
+  SR_CHECK_CUDA(launch_pdl(mrope_kv_kernel, grid, dim3(256), 0, s, reinterpret_cast<__nv_bfloat16*>(qkv), ldqkv, cosb, sinb,
+                           cache_row, reinterpret_cast<__nv_bfloat16*>(Kc), reinterpret_cast<__nv_bfloat16*>(Vt), ldvt, S,
+                           n_q_heads, n_kv_heads));
   SR_CHECK_CUDA(cudaGetLastError());
   return SR_OK;
 }

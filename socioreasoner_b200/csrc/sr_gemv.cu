@@ -40,13 +40,24 @@ struct GemvParams {
   const __nv_bfloat16* residual;
   int64_t lda, ldw, ldc, ldr;
   int M, N, K;
+  const float* norm_w;  // optional fused RMSNorm on A rows: A'[m,k] = A[m,k] * rsqrt(mean_k A^2 + eps) * norm_w[k]
+  float norm_eps;
 };
 
 // RG = row groups of 16 weight rows per CTA (1, or 2 for SwiGLU: gate group + up group); NB = batch tiles of 8.
-template <int RG, int NB, int EPI, bool OUT_F32, int GV_WARPS>
+SR_DEVINL uint32_t scale_bf16x2(uint32_t x, float w0, float w1) { return pack_bf16x2(bf16_lo(x) * w0, bf16_hi(x) * w1); }
+
+template <int RG, int NB, int EPI, bool OUT_F32, int GV_WARPS, bool NORM>
 __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p) {
   constexpr int GV_THREADS = GV_WARPS * 32;
   __shared__ float red[GV_WARPS][RG][NB][16 * 8];
+  __shared__ float ssq_red[GV_WARPS][NB][8];
+  __shared__ float inv_rms[NB][8];
+  float ssq[NB];
+#pragma unroll
+  for (int n = 0; n < NB; ++n) ssq[n] = 0.f;
+  pdl_wait();
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * (16 * RG);
@@ -92,6 +103,23 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
         }
 #pragma unroll
         for (int n = 0; n < NB; ++n) x[u][n] = xok[n] ? *reinterpret_cast<const uint4*>(xrow[n] + c * 32) : make_uint4(0, 0, 0, 0);
+        if (NORM) {
+          // fused RMSNorm (HF:57-71): the activation fragment is multiplied by the norm weight here; sum(x^2) is
+          // accumulated on the side and 1/rms is applied to the fp32 result (every CTA reads all of A anyway)
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.norm_w + c * 32 + t * 8));
+          const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.norm_w + c * 32 + t * 8 + 4));
+#pragma unroll
+          for (int n = 0; n < NB; ++n) {
+            const uint4 xv = x[u][n];
+            const float a0 = bf16_lo(xv.x), a1 = bf16_hi(xv.x), a2 = bf16_lo(xv.y), a3 = bf16_hi(xv.y);
+            const float a4 = bf16_lo(xv.z), a5 = bf16_hi(xv.z), a6 = bf16_lo(xv.w), a7 = bf16_hi(xv.w);
+            ssq[n] += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+            x[u][n].x = pack_bf16x2(a0 * w0.x, a1 * w0.y);
+            x[u][n].y = pack_bf16x2(a2 * w0.z, a3 * w0.w);
+            x[u][n].z = pack_bf16x2(a4 * w1.x, a5 * w1.y);
+            x[u][n].w = pack_bf16x2(a6 * w1.z, a7 * w1.w);
+          }
+        }
       }
     }
 #pragma unroll
@@ -119,7 +147,26 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
       red[warp][r][n][(g + 8) * 8 + 2 * t] = acc[r][n][2];
       red[warp][r][n][(g + 8) * 8 + 2 * t + 1] = acc[r][n][3];
     }
+  if (NORM) {
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+      float v = ssq[n];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (t == 0) ssq_red[warp][n][g] = v;
+    }
+  }
   __syncthreads();
+  if (NORM) {
+    if (threadIdx.x < NB * 8) {
+      const int n = threadIdx.x >> 3, r = threadIdx.x & 7;
+      float v = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < GV_WARPS; ++w8) v += ssq_red[w8][n][r];
+      inv_rms[n][r] = rsqrtf(v / static_cast<float>(p.K) + p.norm_eps);
+    }
+    __syncthreads();
+  }
   // epilogue: thread -> (batch tile n, feature f, batch b); 128 outputs per batch tile
   for (int idx = threadIdx.x; idx < NB * 128; idx += GV_THREADS) {
     const int n = idx >> 7, e = idx & 127;
@@ -131,7 +178,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
       float s = 0.f;
 #pragma unroll
       for (int w8 = 0; w8 < GV_WARPS; ++w8) s += red[w8][r][n][f * 8 + b];
-      v[r] = s;
+      v[r] = NORM ? s * inv_rms[n][b] : s;
     }
     if (m >= p.M) continue;
     if (EPI == SR_EPI_SWIGLU) {
@@ -155,7 +202,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   }
 }
 
-template <int NB>
+template <int NB, bool NORM>
 static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s) {
   // 16 warps split K when one batch tile is live (the decode case): every warp then has <= 3 unrolled iterations even for
   // K = 11008, i.e. (almost) all of a CTA's weight bytes are in flight at once.  Shared-memory budget caps NB >= 2 at 8.
@@ -163,13 +210,13 @@ static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s
   constexpr int GV_THREADS = W * 32;
   if (epi == SR_EPI_SWIGLU) {
     const int grid = (p.N + 31) / 32;
-    gemv_kernel<2, NB, SR_EPI_SWIGLU, false, W><<<grid, GV_THREADS, 0, s>>>(p);
+    SR_CHECK_CUDA(launch_pdl(gemv_kernel<2, NB, SR_EPI_SWIGLU, false, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
   } else {
     const int grid = (p.N + 15) / 16;
-    if (out_f32) gemv_kernel<1, NB, SR_EPI_NONE, true, W><<<grid, GV_THREADS, 0, s>>>(p);
-    else if (epi == SR_EPI_NONE) gemv_kernel<1, NB, SR_EPI_NONE, false, W><<<grid, GV_THREADS, 0, s>>>(p);
-    else if (epi == SR_EPI_RESIDUAL) gemv_kernel<1, NB, SR_EPI_RESIDUAL, false, W><<<grid, GV_THREADS, 0, s>>>(p);
-    else if (epi == SR_EPI_GELU) gemv_kernel<1, NB, SR_EPI_GELU, false, W><<<grid, GV_THREADS, 0, s>>>(p);
+    if (out_f32) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, true, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    else if (epi == SR_EPI_NONE) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, false, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    else if (epi == SR_EPI_RESIDUAL) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_RESIDUAL, false, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    else if (epi == SR_EPI_GELU) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_GELU, false, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
     else {
       set_last_error("sr_gemm_skinny_bf16: unknown epilogue %d", epi);
       return SR_ERR_INVALID;
@@ -181,9 +228,9 @@ static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s
 
 }  // namespace sr
 
-extern "C" int sr_gemm_skinny_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
-                                   const float* bias, const void* residual, int64_t ldr, int M, int N, int K, int epilogue,
-                                   int out_dtype, void* stream) {
+static int gemm_skinny_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, const float* bias,
+                            const void* residual, int64_t ldr, int M, int N, int K, int epilogue, int out_dtype,
+                            const float* norm_weight, float norm_eps, void* stream) {
   using namespace sr;
   SR_REQUIRE(A && W && C, "sr_gemm_skinny_bf16: null operand");
   SR_REQUIRE(M > 0 && M <= 32 && N > 0 && K > 0 && K % 32 == 0, "sr_gemm_skinny_bf16: need 0 < M <= 32, K %% 32 == 0 (M=%d K=%d)", M, K);
@@ -200,9 +247,31 @@ extern "C" int sr_gemm_skinny_bf16(const void* A, int64_t lda, const void* W, in
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.lda = lda; p.ldw = ldw; p.ldc = ldc; p.ldr = ldr;
   p.M = M; p.N = N; p.K = K;
+  p.norm_w = norm_weight;
+  p.norm_eps = norm_eps;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int f32 = out_dtype == SR_DTYPE_F32;
-  if (M <= 8) return launch_gemv<1>(p, epilogue, f32, s);
-  if (M <= 16) return launch_gemv<2>(p, epilogue, f32, s);
-  return launch_gemv<4>(p, epilogue, f32, s);
+  if (norm_weight != nullptr) {
+    SR_REQUIRE((reinterpret_cast<uintptr_t>(norm_weight) & 15) == 0, "sr_gemm_skinny_norm_bf16: norm_weight not 16B aligned");
+    if (M <= 8) return launch_gemv<1, true>(p, epilogue, f32, s);
+    if (M <= 16) return launch_gemv<2, true>(p, epilogue, f32, s);
+    return launch_gemv<4, true>(p, epilogue, f32, s);
+  }
+  if (M <= 8) return launch_gemv<1, false>(p, epilogue, f32, s);
+  if (M <= 16) return launch_gemv<2, false>(p, epilogue, f32, s);
+  return launch_gemv<4, false>(p, epilogue, f32, s);
+}
+
+extern "C" int sr_gemm_skinny_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
+                                   const float* bias, const void* residual, int64_t ldr, int M, int N, int K, int epilogue,
+                                   int out_dtype, void* stream) {
+  return gemm_skinny_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, M, N, K, epilogue, out_dtype, nullptr, 0.f, stream);
+}
+
+extern "C" int sr_gemm_skinny_norm_bf16(const void* A, int64_t lda, const float* norm_weight, float norm_eps, const void* W,
+                                        int64_t ldw, void* C, int64_t ldc, const float* bias, const void* residual,
+                                        int64_t ldr, int M, int N, int K, int epilogue, int out_dtype, void* stream) {
+  using namespace sr;
+  SR_REQUIRE(norm_weight != nullptr, "sr_gemm_skinny_norm_bf16: norm_weight is null");
+  return gemm_skinny_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, M, N, K, epilogue, out_dtype, norm_weight, norm_eps, stream);
 }

@@ -2,11 +2,14 @@
 #include "sr_host.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/socioreasoner_b200.h"
 
 namespace sr {
+
+void set_pdl(int on);
 
 static thread_local char g_err[1024] = "";
 
@@ -36,6 +39,16 @@ int max_smem_optin() {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) n = 0;
   return n;
 }
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("SR_PDL");
+    g_pdl = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return g_pdl != 0;
+}
+void set_pdl(int on) { g_pdl = on ? 1 : 0; }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -101,6 +114,11 @@ extern "C" {
 const char* sr_last_error(void) { return sr::get_last_error(); }
 
 int sr_abi_version(void) { return SR_ABI_VERSION; }
+
+int sr_set_pdl(int enabled) {
+  sr::set_pdl(enabled);
+  return SR_OK;
+}
 
 int sr_device_check(void) {
   int dev = 0;

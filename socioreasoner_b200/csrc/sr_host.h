@@ -22,6 +22,24 @@ int max_smem_optin();      // max dynamic shared memory per block (opt-in)
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle_bytes);
 
+bool pdl_enabled();  // SR_PDL env (default 1) / sr_set_pdl()
+
+// Launch with the programmatic-dependent-launch attribute (kernels must call pdl_wait() before touching global memory).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define SR_CHECK_CUDA(expr)                                                                  \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \

@@ -45,6 +45,8 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const __nv_bflo
   __shared__ __align__(16) float sq[128];
   __shared__ float red[32];
   const int b = blockIdx.x, h = blockIdx.y, kvh = h / (nq / nkv);
+  pdl_wait();
+  pdl_trigger();
   const int start = __ldg(kv_start + b), len = __ldg(kv_len + b);
   const int tid = threadIdx.x;
   if (tid < 128) sq[tid] = __bfloat162float(q[static_cast<int64_t>(b) * ldq + h * 128 + tid]) * scale_log2;
@@ -329,10 +331,11 @@ extern "C" int sr_decode_attention(const void* q, int64_t ldq, const void* Kc, c
     attr_smem = 200 * 1024;
   }
   dim3 grid(batch, n_q_heads);
-  decode_attn_kernel<<<grid, DA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(Kc),
-      reinterpret_cast<const __nv_bfloat16*>(Vt), ldvt, kv_start, kv_len, reinterpret_cast<__nv_bfloat16*>(out), ldo,
-      n_q_heads, n_kv_heads, scale * 1.4426950408889634f);
+  SR_CHECK_CUDA(launch_pdl(decode_attn_kernel, grid, dim3(DA_THREADS), smem, reinterpret_cast<cudaStream_t>(stream),
+                           reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(Kc),
+                           reinterpret_cast<const __nv_bfloat16*>(Vt), ldvt, kv_start, kv_len,
+                           reinterpret_cast<__nv_bfloat16*>(out), ldo, n_q_heads, n_kv_heads,
+                           scale * 1.4426950408889634f));
   SR_CHECK_CUDA(cudaGetLastError());
   return SR_OK;
 }

@@ -193,9 +193,13 @@ class Engine:
         ao = self._buf(tag + "_ao", (S, Hq * hd))
         act = self._buf(tag + "_act", (S, t.intermediate_size))
         scale = hd ** -0.5
+        fuse_norm = decode is not None and S <= 32  # decode: RMSNorm folded into the weight-streaming GEMM (2 launches/layer less)
         for li, L in enumerate(W.layers):
-            lib.rmsnorm(x, L.ln1, t.rms_norm_eps, out=y)
-            lib.gemm(y, L.qkv_w, out=qkv, bias=L.qkv_b)
+            if fuse_norm:
+                lib.gemm(x, L.qkv_w, out=qkv, bias=L.qkv_b, norm_weight=L.ln1, norm_eps=t.rms_norm_eps)
+            else:
+                lib.rmsnorm(x, L.ln1, t.rms_norm_eps, out=y)
+                lib.gemm(y, L.qkv_w, out=qkv, bias=L.qkv_b)
             lib.mrope_kv(qkv, cos, sin, cache_row, cache.k[li], cache.vt[li], Hq, Hkv)
             if decode is None:
                 q = qkv[:, : Hq * hd].view(S, Hq, hd)
@@ -205,8 +209,11 @@ class Engine:
                 kv_start, kv_len, max_len = decode
                 lib.decode_attention(qkv, cache.k[li], cache.vt[li], kv_start, kv_len, max_len, ao, Hq, Hkv, scale)
             lib.gemm(ao, L.o_w, out=x, residual=x)
-            lib.rmsnorm(x, L.ln2, t.rms_norm_eps, out=y)
-            lib.gemm(y, L.gu_w, out=act, epilogue=lib.EPI_SWIGLU)
+            if fuse_norm:
+                lib.gemm(x, L.gu_w, out=act, epilogue=lib.EPI_SWIGLU, norm_weight=L.ln2, norm_eps=t.rms_norm_eps)
+            else:
+                lib.rmsnorm(x, L.ln2, t.rms_norm_eps, out=y)
+                lib.gemm(y, L.gu_w, out=act, epilogue=lib.EPI_SWIGLU)
             lib.gemm(act, L.down_w, out=x, residual=x)
             if capture is not None:
                 capture.append(x.clone())
@@ -267,6 +274,9 @@ class Engine:
     def final_logits(self, hidden_rows: torch.Tensor, out_dtype=torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """final RMSNorm + LM head on the given rows (HF:1385)."""
         t = self.cfg.text
+        if hidden_rows.shape[0] <= 32:
+            return lib.gemm(hidden_rows, self.w.lm_head, out=out, out_dtype=out_dtype, norm_weight=self.w.final_norm,
+                            norm_eps=t.rms_norm_eps)
         y = lib.rmsnorm(hidden_rows, self.w.final_norm, t.rms_norm_eps)
         return lib.gemm(y, self.w.lm_head, out=out, out_dtype=out_dtype)
 

@@ -25,8 +25,10 @@ SYMBOLS = {
     "sr_last_error": (c_char_p, []),
     "sr_abi_version": (c_int, []),
     "sr_device_check": (c_int, []),
+    "sr_set_pdl": (c_int, [c_int]),
     "sr_gemm_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_gemm_skinny_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sr_gemm_skinny_norm_bf16": (c_int, [_P, c_int64, _P, c_float, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_attention_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int,
                                  _P, c_int64, c_int64, _P, c_int, _P, _P, c_float, c_int, _P]),
     "sr_decode_attention": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int, _P, c_int64, c_int, c_int, c_int, c_float, _P]),
@@ -133,8 +135,9 @@ def device_check() -> None:
 # ---------------------------------------------------------------------------------------------------
 def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE, out_dtype=torch.bfloat16,
-         block_n: int = 0) -> torch.Tensor:
-    """out[M, n_out] = epilogue(a[M,K] @ w[N,K]^T (+bias)).  a, w bf16 row-major (row stride arbitrary % 8)."""
+         block_n: int = 0, norm_weight: Optional[torch.Tensor] = None, norm_eps: float = 1e-6) -> torch.Tensor:
+    """out[M, n_out] = epilogue(a[M,K] @ w[N,K]^T (+bias)).  a, w bf16 row-major (row stride arbitrary % 8).
+    ``norm_weight``: RMSNorm of ``a`` fused into the operand load (skinny/decode shapes only: M <= 32, K % 32 == 0)."""
     global launch_count
     _req(a, torch.bfloat16, "gemm.a"); _req(w, torch.bfloat16, "gemm.w")
     M, K = a.shape
@@ -149,6 +152,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, b
     if residual is not None:
         _req(residual, torch.bfloat16, "gemm.residual")
         epilogue = EPI_RESIDUAL if epilogue == EPI_NONE else epilogue
+    if norm_weight is not None:
+        _req(norm_weight, torch.float32, "gemm.norm_weight")
+        with _Timed("gemm", (M, N, K, epilogue), 2.0 * M * N * K):
+            rc = load().sr_gemm_skinny_norm_bf16(a.data_ptr(), a.stride(0), norm_weight.data_ptr(), float(norm_eps), w.data_ptr(),
+                                                 w.stride(0), out.data_ptr(), out.stride(0), _ptr(bias), _ptr(residual),
+                                                 residual.stride(0) if residual is not None else 0, M, N, K, epilogue,
+                                                 DT_F32 if out.dtype == torch.float32 else DT_BF16, _stream())
+        _check(rc, "sr_gemm_skinny_norm_bf16")
+        launch_count += 1
+        return out
     with _Timed("gemm", (M, N, K, epilogue), 2.0 * M * N * K):
         rc = load().sr_gemm_bf16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), out.data_ptr(), out.stride(0),
                                  _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, M, N, K,

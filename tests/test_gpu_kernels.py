@@ -83,6 +83,22 @@ def test_gemm(M, N, K, epi, bias, res, f32, bn):
     assert rel_max(out, ref) < (2e-5 if f32 else 6e-3)
 
 
+@pytest.mark.parametrize("M,N,K,epi,f32", [(8, 2560, 2048, 0, False), (8, 22016, 2048, 2, False), (3, 151936, 2048, 0, True),
+                                             (16, 2048, 2048, 0, False), (29, 2560, 2048, 0, False)])
+def test_skinny_gemm_with_fused_rmsnorm(M, N, K, epi, f32):
+    """Decode step: RMSNorm (HF:57-71) folded into the weight-streaming GEMM == rmsnorm followed by the linear layer."""
+    a = rnd(M, K, scale=1.5).bfloat16()
+    w = rnd(N, K, scale=0.05, seed=1).bfloat16()
+    nw = 1 + 0.1 * rnd(K, seed=2)
+    b = rnd(N, scale=0.1, seed=3) if epi == 0 and not f32 else None
+    out = lib.gemm(a.to(DEV), w.to(DEV), bias=b.to(DEV) if b is not None else None, epilogue=epi,
+                   out_dtype=torch.float32 if f32 else torch.bfloat16, norm_weight=nw.to(DEV), norm_eps=1e-6)
+    af = a.float()
+    normed = nw * (af * torch.rsqrt(af.pow(2).mean(-1, keepdim=True) + 1e-6))
+    ref = gemm_ref(normed, w, b, None, epi)
+    assert rel_max(out, ref) < 8e-3   # one extra bf16 rounding of (x * w_norm) before the MMA
+
+
 def test_gemm_linearity_and_row_independence():
     """Size-independent properties at a production shape: rows are independent (batch invariance is bit-exact because
     every output element sees the same k-block order) and f(2a) == 2 f(a) exactly for a power-of-two scale."""

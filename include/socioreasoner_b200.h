@@ -114,7 +114,8 @@ int sr_vit_rope_table(const int32_t* hpos, const int32_t* wpos, const float* inv
  * (mcore_adapter/.../qwen2_5_vl/modeling_qwen2_5_vl.py:21-75; HF:595-608,627-669). inv_freq fp32[64]. */
 int sr_mrope_table(const int64_t* pos3, const float* inv_freq, float* cos_out, float* sin_out, int S, int sec_t,
                    int sec_h, int sec_w, void* stream);
-/* ViT: split qkv [n, 3*16*80], apply 2-D RoPE (HF:156-167), write Qp/Kp [n,16,128] (zero-padded) and Vt [16*80, ldvt]. */
+/* ViT: split qkv [n, 3*16*80], apply 2-D RoPE (HF:156-167), write Qp/Kp [n,16,128] columns 0..79 (the caller zero-fills the
+ * padding columns 80..127 once; they are never written here) and Vt [16*80, ldvt]. */
 int sr_vit_rope_split(const void* qkv, int64_t ldqkv, const float* cosb, const float* sinb, void* Qp, void* Kp, void* Vt,
                       int64_t ldvt, int n, void* stream);
 /* Decoder: M-RoPE on q (in place) and k; append k -> Kc[cache_row[s]], v -> Vt[:, cache_row[s]] (KV cache). */

@@ -146,74 +146,71 @@ __global__ void mrope_table_kernel(const int64_t* __restrict__ pos /*[3,S]*/, co
 
 // ------------------------------------------------------------------------------------------------
 // ViT: split qkv, apply 2-D RoPE (HF:156-167 apply_rotary_pos_emb_vision, fp32), re-layout for attention:
-//   qkv [N, 3*16*80] -> Qp, Kp [N,16,128] (cols 80..127 = 0) and Vt [16*80, ldvt] (transposed).
-// Block = 32 tokens x 1 head, 256 threads.
+//   qkv [N, 3*16*80] -> Qp, Kp [N,16,128] (columns 0..79; 80..127 are zero padding that the caller zero-fills ONCE --
+//   this kernel never writes them) and Vt [16*80, ldvt] (transposed).
+// Block = 32 tokens x all heads, 256 threads.  rotate_half pairs element d with d+40, i.e. 16-byte group j (j < 5)
+// with group j+5: one work item = (token, q|k, head, j) = 2 vector loads -> 2 vector stores, no staging of q/k;
+// cos/sin of the 32 tokens are staged in shared memory once (each value is reused 32x), V goes through a padded
+// shared-memory tile for the transpose.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) vit_rope_split_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ldqkv,
                                                             const float* __restrict__ cosb, const float* __restrict__ sinb,
                                                             __nv_bfloat16* __restrict__ Qp, __nv_bfloat16* __restrict__ Kp,
                                                             __nv_bfloat16* __restrict__ Vt, int64_t ldvt, int n) {
-  constexpr int HD = 80, NH = 16, TOK = 32;
-  __shared__ float sq[TOK][HD + 1];
-  __shared__ float sk[TOK][HD + 1];
-  __shared__ __nv_bfloat16 sv[TOK][HD + 2];
+  constexpr int HD = 80, NH = 16, TOK = 32, VH = 4;  // VH heads of V per transpose pass
+  __shared__ __align__(16) float sc[TOK][40];
+  __shared__ __align__(16) float ss[TOK][40];
+  __shared__ __nv_bfloat16 sv[TOK][VH * HD + 2];
   const int t0 = blockIdx.x * TOK;
-  const int h = blockIdx.y;
   const int tid = threadIdx.x;
-  // load q, k, v head slices: 32 tokens x 3 x 10 uint4
-  for (int i = tid; i < TOK * 30; i += 256) {
-    const int t = i / 30, r = i % 30;
-    const int which = r / 10, c = r % 10;
-    if (t0 + t < n) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(qkv + static_cast<int64_t>(t0 + t) * ldqkv + which * NH * HD + h * HD) + c);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-      if (which == 2) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint32_t*>(&sv[t][c * 8 + j * 2]) = w[j];
-      } else {
-        float(*dst)[HD + 1] = which == 0 ? sq : sk;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          dst[t][c * 8 + j * 2] = bf16_lo(w[j]);
-          dst[t][c * 8 + j * 2 + 1] = bf16_hi(w[j]);
-        }
-      }
-    }
+  const int ntok = min(TOK, n - t0);
+  for (int i = tid; i < ntok * 10; i += 256) {  // 40 floats = 10 float4 per token
+    const int t = i / 10, c = i % 10;
+    reinterpret_cast<float4*>(&sc[t][0])[c] = __ldg(reinterpret_cast<const float4*>(cosb + static_cast<int64_t>(t0 + t) * 40) + c);
+    reinterpret_cast<float4*>(&ss[t][0])[c] = __ldg(reinterpret_cast<const float4*>(sinb + static_cast<int64_t>(t0 + t) * 40) + c);
   }
   __syncthreads();
-  // rotate + write Q/K rows: 32 tokens x 2 tensors x 16 uint4 (8 elements each)
-  for (int i = tid; i < TOK * 2 * 16; i += 256) {
-    const int t = i / 32, r = i % 32;
-    const int which = r / 16, c = r % 16;
-    if (t0 + t >= n) continue;
-    float(*src)[HD + 1] = which == 0 ? sq : sk;
-    float o[8];
+  // q / k rotation: items = ntok * 2 * 16 * 5
+  const int items = ntok * 160;
+#pragma unroll 2
+  for (int i = tid; i < items; i += 256) {
+    const int t = i / 160, r = i % 160;
+    const int which = r / 80, hj = r % 80;
+    const int h = hj / 5, j = hj % 5;
+    const __nv_bfloat16* src = qkv + static_cast<int64_t>(t0 + t) * ldqkv + which * NH * HD + h * HD + j * 8;
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(src));
+    const uint4 hi = __ldg(reinterpret_cast<const uint4*>(src + 40));
+    const float4 c0 = *reinterpret_cast<const float4*>(&sc[t][j * 8]), c1 = *reinterpret_cast<const float4*>(&sc[t][j * 8 + 4]);
+    const float4 s0 = *reinterpret_cast<const float4*>(&ss[t][j * 8]), s1 = *reinterpret_cast<const float4*>(&ss[t][j * 8 + 4]);
+    const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+    uint32_t ol[4], oh[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int d = c * 8 + j;
-      float val = 0.f;
-      if (d < HD) {
-        const int f = d < 40 ? d : d - 40;
-        const float cs = __ldg(cosb + static_cast<int64_t>(t0 + t) * 40 + f);
-        const float sn = __ldg(sinb + static_cast<int64_t>(t0 + t) * 40 + f);
-        const float x = src[t][d];
-        const float xr = d < 40 ? -src[t][d + 40] : src[t][d - 40];  // rotate_half
-        val = x * cs + xr * sn;
-      }
-      o[j] = val;
+    for (int e = 0; e < 4; ++e) {
+      const float x1a = bf16_lo(lw[e]), x1b = bf16_hi(lw[e]), x2a = bf16_lo(hw[e]), x2b = bf16_hi(hw[e]);
+      // out[d] = x[d] cos - x[d+40] sin ; out[d+40] = x[d+40] cos + x[d] sin   (cos/sin of d and d+40 are identical)
+      ol[e] = pack_bf16x2(x1a * cs[2 * e] - x2a * sn[2 * e], x1b * cs[2 * e + 1] - x2b * sn[2 * e + 1]);
+      oh[e] = pack_bf16x2(x2a * cs[2 * e] + x1a * sn[2 * e], x2b * cs[2 * e + 1] + x1b * sn[2 * e + 1]);
     }
-    uint4 pk;
-    pk.x = pack_bf16x2(o[0], o[1]);
-    pk.y = pack_bf16x2(o[2], o[3]);
-    pk.z = pack_bf16x2(o[4], o[5]);
-    pk.w = pack_bf16x2(o[6], o[7]);
-    __nv_bfloat16* base = (which == 0 ? Qp : Kp) + (static_cast<int64_t>(t0 + t) * NH + h) * 128;
-    reinterpret_cast<uint4*>(base)[c] = pk;
+    __nv_bfloat16* dst = (which == 0 ? Qp : Kp) + (static_cast<int64_t>(t0 + t) * NH + h) * 128 + j * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    *reinterpret_cast<uint4*>(dst + 40) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
   }
-  // transposed V: row (h*80 + d), 32 consecutive token columns per warp store
+  // transposed V, VH heads per pass: row (h*80 + d) of Vt gets 32 consecutive token columns per warp store
   const int lane = tid & 31, warp = tid >> 5;
-  for (int d = warp; d < HD; d += 8) {
-    if (t0 + lane < n) Vt[static_cast<int64_t>(h * HD + d) * ldvt + t0 + lane] = sv[lane][d];
+  for (int h0 = 0; h0 < NH; h0 += VH) {
+    __syncthreads();
+    for (int i = tid; i < ntok * (VH * HD / 8); i += 256) {
+      const int t = i / (VH * HD / 8), c = i % (VH * HD / 8);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(qkv + static_cast<int64_t>(t0 + t) * ldqkv + 2 * NH * HD + h0 * HD) + c);
+      uint32_t* d = reinterpret_cast<uint32_t*>(&sv[t][c * 8]);
+      d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+    }
+    __syncthreads();
+    for (int d = warp; d < VH * HD; d += 8) {
+      if (lane < ntok) Vt[static_cast<int64_t>(h0 * HD + d) * ldvt + t0 + lane] = sv[lane][d];
+    }
   }
 }
 
@@ -361,7 +358,7 @@ extern "C" int sr_vit_rope_split(const void* qkv, int64_t ldqkv, const float* co
   SR_REQUIRE(ldqkv % 8 == 0 && ldvt >= n, "sr_vit_rope_split: bad strides");
   if (n <= 0) return SR_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  dim3 grid((n + 31) / 32, 16);
+  dim3 grid((n + 31) / 32);
   vit_rope_split_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv), ldqkv, cosb, sinb,
                                              reinterpret_cast<__nv_bfloat16*>(Qp), reinterpret_cast<__nv_bfloat16*>(Kp),
                                              reinterpret_cast<__nv_bfloat16*>(Vt), ldvt, n);

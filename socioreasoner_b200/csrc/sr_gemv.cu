@@ -17,7 +17,7 @@
 
 namespace sr {
 
-constexpr int GV_UNROLL = 4;
+
 
 SR_DEVINL uint4 ld_stream_v4(const void* p) {
   uint4 r;
@@ -47,7 +47,7 @@ struct GemvParams {
 // RG = row groups of 16 weight rows per CTA (1, or 2 for SwiGLU: gate group + up group); NB = batch tiles of 8.
 SR_DEVINL uint32_t scale_bf16x2(uint32_t x, float w0, float w1) { return pack_bf16x2(bf16_lo(x) * w0, bf16_hi(x) * w1); }
 
-template <int RG, int NB, int EPI, bool OUT_F32, int GV_WARPS, bool NORM>
+template <int RG, int NB, int EPI, bool OUT_F32, int GV_WARPS, bool NORM, int GV_UNROLL>
 __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p) {
   constexpr int GV_THREADS = GV_WARPS * 32;
   __shared__ float red[GV_WARPS][RG][NB][16 * 8];
@@ -89,51 +89,63 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   }
 
   const int nchunks = p.K >> 5;  // 32 k per chunk
-  for (int c0 = warp; c0 < nchunks; c0 += GV_WARPS * GV_UNROLL) {
-    uint4 w[GV_UNROLL][RG][2];
-    uint4 x[GV_UNROLL][NB];
+  // Rolling software pipeline over GV_UNROLL register slots: slot u is consumed (MMA) and immediately re-armed with the
+  // chunk GV_WARPS*GV_UNROLL further on, so GV_UNROLL-1 chunk loads per thread stay in flight across iterations
+  // (without this the kernel paid one full HBM latency per batch of loads).
+  uint4 w[GV_UNROLL][RG][2];
+  uint4 x[GV_UNROLL][NB];
+  float4 nw0[GV_UNROLL], nw1[GV_UNROLL];
+  auto load_slot = [&](int u, int c) {
 #pragma unroll
-    for (int u = 0; u < GV_UNROLL; ++u) {
-      const int c = c0 + u * GV_WARPS;
-      if (c < nchunks) {
+    for (int r = 0; r < RG; ++r) {
+      w[u][r][0] = ld_stream_v4(wrow[r][0] + c * 32);
+      w[u][r][1] = ld_stream_v4(wrow[r][1] + c * 32);
+    }
 #pragma unroll
-        for (int r = 0; r < RG; ++r) {
-          w[u][r][0] = ld_stream_v4(wrow[r][0] + c * 32);
-          w[u][r][1] = ld_stream_v4(wrow[r][1] + c * 32);
-        }
+    for (int n = 0; n < NB; ++n) x[u][n] = xok[n] ? *reinterpret_cast<const uint4*>(xrow[n] + c * 32) : make_uint4(0, 0, 0, 0);
+    if (NORM) {
+      nw0[u] = __ldg(reinterpret_cast<const float4*>(p.norm_w + c * 32 + t * 8));
+      nw1[u] = __ldg(reinterpret_cast<const float4*>(p.norm_w + c * 32 + t * 8 + 4));
+    }
+  };
+  auto compute_slot = [&](int u) {
+    if (NORM) {
+      // fused RMSNorm (HF:57-71): the activation fragment is multiplied by the norm weight here; sum(x^2) is
+      // accumulated on the side and 1/rms is applied to the fp32 result (every CTA reads all of A anyway)
 #pragma unroll
-        for (int n = 0; n < NB; ++n) x[u][n] = xok[n] ? *reinterpret_cast<const uint4*>(xrow[n] + c * 32) : make_uint4(0, 0, 0, 0);
-        if (NORM) {
-          // fused RMSNorm (HF:57-71): the activation fragment is multiplied by the norm weight here; sum(x^2) is
-          // accumulated on the side and 1/rms is applied to the fp32 result (every CTA reads all of A anyway)
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.norm_w + c * 32 + t * 8));
-          const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.norm_w + c * 32 + t * 8 + 4));
-#pragma unroll
-          for (int n = 0; n < NB; ++n) {
-            const uint4 xv = x[u][n];
-            const float a0 = bf16_lo(xv.x), a1 = bf16_hi(xv.x), a2 = bf16_lo(xv.y), a3 = bf16_hi(xv.y);
-            const float a4 = bf16_lo(xv.z), a5 = bf16_hi(xv.z), a6 = bf16_lo(xv.w), a7 = bf16_hi(xv.w);
-            ssq[n] += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
-            x[u][n].x = pack_bf16x2(a0 * w0.x, a1 * w0.y);
-            x[u][n].y = pack_bf16x2(a2 * w0.z, a3 * w0.w);
-            x[u][n].z = pack_bf16x2(a4 * w1.x, a5 * w1.y);
-            x[u][n].w = pack_bf16x2(a6 * w1.z, a7 * w1.w);
-          }
-        }
+      for (int n = 0; n < NB; ++n) {
+        const uint4 xv = x[u][n];
+        const float a0 = bf16_lo(xv.x), a1 = bf16_hi(xv.x), a2 = bf16_lo(xv.y), a3 = bf16_hi(xv.y);
+        const float a4 = bf16_lo(xv.z), a5 = bf16_hi(xv.z), a6 = bf16_lo(xv.w), a7 = bf16_hi(xv.w);
+        ssq[n] += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 + a4 * a4 + a5 * a5 + a6 * a6 + a7 * a7;
+        x[u][n].x = pack_bf16x2(a0 * nw0[u].x, a1 * nw0[u].y);
+        x[u][n].y = pack_bf16x2(a2 * nw0[u].z, a3 * nw0[u].w);
+        x[u][n].z = pack_bf16x2(a4 * nw1[u].x, a5 * nw1[u].y);
+        x[u][n].w = pack_bf16x2(a6 * nw1[u].z, a7 * nw1[u].w);
       }
     }
 #pragma unroll
+    for (int r = 0; r < RG; ++r)
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        // slots (2t,2t+1 | 2t+8,2t+9) <-> actual k = c*32 + t*8 + {0,1 | 2,3}, then {4,5 | 6,7}
+        mma_bf16_16816(acc[r][n], w[u][r][0].x, w[u][r][1].x, w[u][r][0].y, w[u][r][1].y, x[u][n].x, x[u][n].y);
+        mma_bf16_16816(acc[r][n], w[u][r][0].z, w[u][r][1].z, w[u][r][0].w, w[u][r][1].w, x[u][n].z, x[u][n].w);
+      }
+  };
+#pragma unroll
+  for (int u = 0; u < GV_UNROLL; ++u) {
+    const int c = warp + u * GV_WARPS;
+    if (c < nchunks) load_slot(u, c);
+  }
+  for (int base = warp; base < nchunks; base += GV_WARPS * GV_UNROLL) {
+#pragma unroll
     for (int u = 0; u < GV_UNROLL; ++u) {
-      const int c = c0 + u * GV_WARPS;
+      const int c = base + u * GV_WARPS;
       if (c < nchunks) {
-#pragma unroll
-        for (int r = 0; r < RG; ++r)
-#pragma unroll
-          for (int n = 0; n < NB; ++n) {
-            // slots (2t,2t+1 | 2t+8,2t+9) <-> actual k = c*32 + t*8 + {0,1 | 2,3}, then {4,5 | 6,7}
-            mma_bf16_16816(acc[r][n], w[u][r][0].x, w[u][r][1].x, w[u][r][0].y, w[u][r][1].y, x[u][n].x, x[u][n].y);
-            mma_bf16_16816(acc[r][n], w[u][r][0].z, w[u][r][1].z, w[u][r][0].w, w[u][r][1].w, x[u][n].z, x[u][n].w);
-          }
+        compute_slot(u);
+        const int cn = c + GV_WARPS * GV_UNROLL;
+        if (cn < nchunks) load_slot(u, cn);
       }
     }
   }
@@ -208,15 +220,17 @@ static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s
   // K = 11008, i.e. (almost) all of a CTA's weight bytes are in flight at once.  Shared-memory budget caps NB >= 2 at 8.
   constexpr int W = (NB == 1) ? 16 : 8;
   constexpr int GV_THREADS = W * 32;
+  constexpr int U1 = (NB == 1) ? (NORM ? 4 : 6) : 4;  // register slots (chunks in flight + 1) per thread, 1 row group
+  constexpr int U2 = (NB == 1) ? 3 : 2;  // 2 row groups (SwiGLU) load twice the weight bytes per slot
   if (epi == SR_EPI_SWIGLU) {
     const int grid = (p.N + 31) / 32;
-    SR_CHECK_CUDA(launch_pdl(gemv_kernel<2, NB, SR_EPI_SWIGLU, false, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    SR_CHECK_CUDA(launch_pdl(gemv_kernel<2, NB, SR_EPI_SWIGLU, false, W, NORM, U2>, dim3(grid), dim3(GV_THREADS), 0, s, p));
   } else {
     const int grid = (p.N + 15) / 16;
-    if (out_f32) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, true, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
-    else if (epi == SR_EPI_NONE) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, false, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
-    else if (epi == SR_EPI_RESIDUAL) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_RESIDUAL, false, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
-    else if (epi == SR_EPI_GELU) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_GELU, false, W, NORM>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    if (out_f32) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, true, W, NORM, U1>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    else if (epi == SR_EPI_NONE) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, false, W, NORM, U1>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    else if (epi == SR_EPI_RESIDUAL) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_RESIDUAL, false, W, NORM, U1>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    else if (epi == SR_EPI_GELU) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_GELU, false, W, NORM, U1>, dim3(grid), dim3(GV_THREADS), 0, s, p));
     else {
       set_last_error("sr_gemm_skinny_bf16: unknown epilogue %d", epi);
       return SR_ERR_INVALID;

@@ -137,8 +137,8 @@ class Engine:
         h = lib.gemm(x0, W.patch_w, out=self._buf("vit_h", (n, D)))
         y = self._buf("vit_y", (n, D))
         qkv = self._buf("vit_qkv", (n, 3 * D))
-        qp = self._buf("vit_qp", (n, H, 128))
-        kp = self._buf("vit_kp", (n, H, 128))
+        qp = self._buf("vit_qp", (n, H, 128), zero=True)  # head_dim 80 -> 128: padding columns stay zero (never written)
+        kp = self._buf("vit_kp", (n, H, 128), zero=True)
         npad = (n + 7) // 8 * 8
         vt = self._buf("vit_vt", (H * hd, npad), zero=True)
         ao = self._buf("vit_ao", (n, H, hd))

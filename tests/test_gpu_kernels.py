@@ -223,8 +223,8 @@ def test_vit_rope_tables_and_split():
     fr = torch.cat([hp.float()[:, None] * inv[None], wp.float()[:, None] * inv[None]], 1)
     assert (cos.cpu() - fr.cos()).abs().max() < 2e-6 and (sin.cpu() - fr.sin()).abs().max() < 2e-6
     qkv = rnd(n, 3840).bfloat16()
-    qp = torch.full((n, 16, 128), 7.0, dtype=torch.bfloat16, device=DEV)
-    kp = torch.full((n, 16, 128), 7.0, dtype=torch.bfloat16, device=DEV)
+    qp = torch.zeros((n, 16, 128), dtype=torch.bfloat16, device=DEV)   # caller zero-fills the 80..127 padding once
+    kp = torch.zeros((n, 16, 128), dtype=torch.bfloat16, device=DEV)
     vt = torch.zeros(1280, (n + 7) // 8 * 8, dtype=torch.bfloat16, device=DEV)
     lib.vit_rope_split(qkv.to(DEV), cos, sin, qp, kp, vt)
     q, k, v = qkv.float().view(n, 3, 16, 80).unbind(1)

@@ -230,8 +230,8 @@ def diag_elem():
         stats("vit rope cos", cos, fr.cos(), tol=1e-5)
         stats("vit rope sin", sin, fr.sin(), tol=1e-5)
         qkv = torch.randn(n, 3840, device=dev).bfloat16()
-        qp = torch.full((n, 16, 128), 7.0, device=dev, dtype=torch.bfloat16)
-        kp = torch.full((n, 16, 128), 7.0, device=dev, dtype=torch.bfloat16)
+        qp = torch.zeros((n, 16, 128), device=dev, dtype=torch.bfloat16)
+        kp = torch.zeros((n, 16, 128), device=dev, dtype=torch.bfloat16)
         npad = (n + 7) // 8 * 8
         vt = torch.zeros(16 * 80, npad, device=dev, dtype=torch.bfloat16)
         lib.vit_rope_split(qkv, cos, sin, qp, kp, vt)

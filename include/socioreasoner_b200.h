@@ -90,10 +90,14 @@ int sr_attention_fwd(const void* Q, int64_t q_row_stride, int64_t q_head_stride,
 
 /* Decode-step attention: one query token per sample against its KV cache (the reference's vLLM decode step,
  * roll/distributed/strategy/vllm_strategy.py:114-141; HF:740-756 with use_cache).  q [batch, n_q_heads*128] (ldq),
- * Kc [rows, n_kv_heads, 128], Vt [n_kv_heads*128, ldvt]; sample b attends cache rows [kv_start[b], +kv_len[b]). */
+ * Kc [rows, n_kv_heads, 128], Vt [n_kv_heads*128, ldvt]; sample b attends cache rows [kv_start[b], +kv_len[b]), kv_start
+ * a multiple of 8.  Split-KV: grid = (batch, kv head, ceil(max_len/128) splits); workspace = device scratch of
+ * sr_decode_attention_workspace_bytes() bytes whose first batch*n_kv_heads int32 must be ZERO before the first call
+ * (the kernel re-arms them). */
+int64_t sr_decode_attention_workspace_bytes(int batch, int n_kv_heads, int max_len);
 int sr_decode_attention(const void* q, int64_t ldq, const void* Kc, const void* Vt, int64_t ldvt, const int32_t* kv_start,
                         const int32_t* kv_len, int max_len, void* out, int64_t ldo, int batch, int n_q_heads,
-                        int n_kv_heads, float scale, void* stream);
+                        int n_kv_heads, float scale, void* workspace, void* stream);
 
 /* ---- HBM-bound element-wise / gather kernels ------------------------------------------------ */
 /* RMSNorm, fp32 math (HF:57-71; mcore_adapter/src/mcore_adapter/models/model_utils.py:91-106). dim in {256,1280,2048}. */

@@ -34,72 +34,171 @@ SR_DEVINL float block_sum(float v, float* sbuf) {
 // use_cache).  q [B, nq, 128] (row stride ldq), Kc [rows, nkv, 128], Vt [nkv*128, ldvt]; sample b attends cache
 // rows [kv_start[b], kv_start[b] + kv_len[b]).  One CTA per (sample, q head).
 // ------------------------------------------------------------------------------------------------
-constexpr int DA_THREADS = 512;
+// Split-KV ("flash-decoding") formulation: CTA = (sample, kv head, key split).  The G = n_q/n_kv query heads that share a
+// kv head are processed together, so K and V^T are read ONCE per (sample, kv head) instead of once per query head, and the
+// key axis is split across CTAs so that ~all SMs pull cache bytes concurrently.  Per 128-key pass: thread = (key, head
+// half) for the scores (16 independent 16-byte loads of the key row in flight), block softmax statistics per head,
+// thread = (output dim, head half) for P.V with 16-byte V^T loads; running (max, sum, out) are rescaled between passes.
+// Each split writes its un-normalised partial (m, l, o) to the workspace; the last CTA to finish a (sample, kv head)
+// (atomic ticket) merges the splits and writes the bf16 output, then re-arms the ticket.
+constexpr int DA_THREADS = 256;
+constexpr int DA_KEYS = 128;   // keys per pass
+constexpr int DA_GMAX = 8;     // max query heads per kv head
 __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
                                                                 const __nv_bfloat16* __restrict__ Kc,
                                                                 const __nv_bfloat16* __restrict__ Vt, int64_t ldvt,
                                                                 const int* __restrict__ kv_start, const int* __restrict__ kv_len,
                                                                 __nv_bfloat16* __restrict__ out, int64_t ldo, int nq, int nkv,
-                                                                float scale_log2) {
-  extern __shared__ float sc[];  // [max_len rounded up to 32] scores / probabilities
-  __shared__ __align__(16) float sq[128];
-  __shared__ float red[32];
-  const int b = blockIdx.x, h = blockIdx.y, kvh = h / (nq / nkv);
+                                                                float scale_log2, float* __restrict__ ws, int* __restrict__ tickets) {
+  __shared__ __align__(16) float sq[DA_GMAX][128];
+  __shared__ __align__(16) float sp[DA_GMAX][DA_KEYS];   // scores, then probabilities of the current pass
+  __shared__ float s_red[8][DA_GMAX];
+  __shared__ float s_m[DA_GMAX], s_l[DA_GMAX], s_alpha[DA_GMAX];
+  __shared__ int s_last;
+  const int b = blockIdx.x, kvh = blockIdx.y, split = blockIdx.z, ns = gridDim.z;
+  const int G = nq / nkv;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();
   pdl_trigger();
   const int start = __ldg(kv_start + b), len = __ldg(kv_len + b);
-  const int tid = threadIdx.x;
-  if (tid < 128) sq[tid] = __bfloat162float(q[static_cast<int64_t>(b) * ldq + h * 128 + tid]) * scale_log2;
+  int per = (len + ns - 1) / ns;
+  per = (per + 7) & ~7;                      // V^T vectors are 8 keys wide
+  const int k_begin = split * per, k_end = min(len, k_begin + per);
+  for (int i = tid; i < G * 128; i += DA_THREADS)
+    sq[i >> 7][i & 127] = __bfloat162float(q[static_cast<int64_t>(b) * ldq + (kvh * G + (i >> 7)) * 128 + (i & 127)]) * scale_log2;
+  if (tid < DA_GMAX) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; }
+  const int half = tid >> 7;                 // heads [half*4, half*4+4) (scores) / (P.V)
+  const int kk = tid & 127;                  // key within the pass / output dim
+  float o_acc[4] = {0.f, 0.f, 0.f, 0.f};
   __syncthreads();
-  // scores: ONE KEY PER THREAD -- 16 independent 16-byte loads of the key row in flight per thread (memory-level
-  // parallelism instead of a serial per-key loop); q is broadcast from shared memory.
-  float lmax = -INFINITY;
-  for (int k = tid; k < len; k += DA_THREADS) {
-    const uint4* kr = reinterpret_cast<const uint4*>(Kc + (static_cast<int64_t>(start + k) * nkv + kvh) * 128);
-    uint4 v[16];
+  for (int p0 = k_begin; p0 < k_end; p0 += DA_KEYS) {
+    const int nk = min(DA_KEYS, k_end - p0);
+    // ---- scores for (key kk, 4 heads) ----
+    float sc4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (kk < nk) {
+      const uint4* kr = reinterpret_cast<const uint4*>(Kc + (static_cast<int64_t>(start + p0 + kk) * nkv + kvh) * 128);
+      uint4 v[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __ldg(kr + i);
-    float d = 0.f;
+      for (int i = 0; i < 16; ++i) v[i] = __ldg(kr + i);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4 q0 = *reinterpret_cast<const float4*>(&sq[i * 8]);
-      const float4 q1 = *reinterpret_cast<const float4*>(&sq[i * 8 + 4]);
-      d += bf16_lo(v[i].x) * q0.x + bf16_hi(v[i].x) * q0.y + bf16_lo(v[i].y) * q0.z + bf16_hi(v[i].y) * q0.w +
-           bf16_lo(v[i].z) * q1.x + bf16_hi(v[i].z) * q1.y + bf16_lo(v[i].w) * q1.z + bf16_hi(v[i].w) * q1.w;
+      for (int hh = 0; hh < 4; ++hh) {
+        const int h = half * 4 + hh;
+        if (h < G) {
+          float d = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 q0 = *reinterpret_cast<const float4*>(&sq[h][i * 8]);
+            const float4 q1 = *reinterpret_cast<const float4*>(&sq[h][i * 8 + 4]);
+            d += bf16_lo(v[i].x) * q0.x + bf16_hi(v[i].x) * q0.y + bf16_lo(v[i].y) * q0.z + bf16_hi(v[i].y) * q0.w +
+                 bf16_lo(v[i].z) * q1.x + bf16_hi(v[i].z) * q1.y + bf16_lo(v[i].w) * q1.z + bf16_hi(v[i].w) * q1.w;
+          }
+          sc4[hh] = d;
+        }
+      }
     }
-    sc[k] = d;
-    lmax = fmaxf(lmax, d);
-  }
-  const float mx = block_max(lmax, red);
-  float lsum = 0.f;
-  for (int k = tid; k < len; k += DA_THREADS) {
-    const float pv = exp2f(sc[k] - mx);
-    sc[k] = pv;
-    lsum += pv;
-  }
-  const int len8 = (len + 7) & ~7;
-  for (int k = len + tid; k < len8; k += DA_THREADS) sc[k] = 0.f;  // zero tail so the 8-key vectors below can over-read
-  const float tot = block_sum(lsum, red);  // also orders the sc[] writes before the reads below
-  const float inv = tot > 0.f ? 1.f / tot : 0.f;
-  // o[d] = sum_k p[k] * Vt[kvh*128 + d, start + k]: 4 threads per d row, each streams a contiguous quarter of the keys
-  // with 16-byte loads (start is a multiple of 8 keys: cache rows are l_max-aligned).
-  const int d = tid >> 2, part = tid & 3;
-  const int nvec = len8 >> 3;
-  const int per = (nvec + 3) >> 2;
-  const int v0 = part * per, v1 = min(nvec, v0 + per);
-  const uint4* vrow = reinterpret_cast<const uint4*>(Vt + static_cast<int64_t>(kvh * 128 + d) * ldvt + start);
-  float acc = 0.f;
+    // ---- per-head max over the pass ----
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+      const float m = warp_max(sc4[hh]);
+      if (lane == 0) s_red[warp][hh] = m;    // warps 0-3 hold half 0, warps 4-7 half 1
+    }
+    __syncthreads();
+    if (tid < G) {
+      const int hf = tid >> 2, hh = tid & 3;
+      float m = s_m[tid];
+      for (int w = 0; w < 4; ++w) m = fmaxf(m, s_red[hf * 4 + w][hh]);
+      const float m_use = (m == -INFINITY) ? 0.f : m;
+      s_alpha[tid] = exp2f(s_m[tid] - m_use);   // rescale of the running sum / output (0 on the first pass)
+      s_m[tid] = m;
+    }
+    __syncthreads();
+    // ---- probabilities ----
+    float ps[4];
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = half * 4 + hh;
+      float pv = 0.f;
+      if (h < G && kk < nk) {
+        const float m = s_m[h];
+        pv = exp2f(sc4[hh] - ((m == -INFINITY) ? 0.f : m));
+      }
+      if (h < G) sp[h][kk] = pv;             // zero beyond nk: the 8-key vectors below may over-read the tail
+      ps[hh] = warp_sum(pv);
+      if (lane == 0) s_red[warp][hh] = ps[hh];
+    }
+    __syncthreads();
+    if (tid < G) {
+      const int hf = tid >> 2, hh = tid & 3;
+      float l = 0.f;
+      for (int w = 0; w < 4; ++w) l += s_red[hf * 4 + w][hh];
+      s_l[tid] = s_l[tid] * s_alpha[tid] + l;
+    }
+    // ---- partial O for (dim kk, 4 heads): o = o * alpha + sum_k p[h][k] * Vt[kvh*128 + kk, start + p0 + k] ----
+    const uint4* vrow = reinterpret_cast<const uint4*>(Vt + static_cast<int64_t>(kvh * 128 + kk) * ldvt + start + p0);
+    const int nvec = (nk + 7) >> 3;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-  for (int i = v0; i < v1; ++i) {
-    const uint4 u = __ldg(vrow + i);
-    const float4 p0 = *reinterpret_cast<const float4*>(&sc[i * 8]);
-    const float4 p1 = *reinterpret_cast<const float4*>(&sc[i * 8 + 4]);
-    acc += bf16_lo(u.x) * p0.x + bf16_hi(u.x) * p0.y + bf16_lo(u.y) * p0.z + bf16_hi(u.y) * p0.w +
-           bf16_lo(u.z) * p1.x + bf16_hi(u.z) * p1.y + bf16_lo(u.w) * p1.z + bf16_hi(u.w) * p1.w;
+    for (int i = 0; i < nvec; ++i) {
+      const uint4 u = __ldg(vrow + i);
+      const float vv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const int h = half * 4 + hh;
+        if (h < G) {
+          const float4 p0v = *reinterpret_cast<const float4*>(&sp[h][i * 8]);
+          const float4 p1v = *reinterpret_cast<const float4*>(&sp[h][i * 8 + 4]);
+          acc[hh] += vv[0] * p0v.x + vv[1] * p0v.y + vv[2] * p0v.z + vv[3] * p0v.w + vv[4] * p1v.x + vv[5] * p1v.y +
+                     vv[6] * p1v.z + vv[7] * p1v.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = half * 4 + hh;
+      if (h < G) o_acc[hh] = o_acc[hh] * s_alpha[h] + acc[hh];
+    }
+    __syncthreads();   // sp / s_red / s_alpha are reused by the next pass
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  if (part == 0) out[static_cast<int64_t>(b) * ldo + h * 128 + d] = __float2bfloat16(acc * inv);
+  // ---- publish this split's partial ----
+  const int64_t slot = (static_cast<int64_t>(b) * nkv + kvh) * ns + split;
+  float* wo = ws + slot * (DA_GMAX * 128 + 2 * DA_GMAX);
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+    const int h = half * 4 + hh;
+    if (h < G) wo[h * 128 + kk] = o_acc[hh];
+  }
+  if (tid < G) {
+    wo[DA_GMAX * 128 + tid] = s_m[tid];
+    wo[DA_GMAX * 128 + DA_GMAX + tid] = s_l[tid];
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int ticket = atomicAdd(tickets + b * nkv + kvh, 1);
+    s_last = (ticket == ns - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- merge the splits (last CTA of this (sample, kv head)) ----
+  const float* wb = ws + (static_cast<int64_t>(b) * nkv + kvh) * ns * (DA_GMAX * 128 + 2 * DA_GMAX);
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+    const int h = half * 4 + hh;
+    if (h >= G) continue;
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < ns; ++s2) M = fmaxf(M, __ldcg(wb + s2 * (DA_GMAX * 128 + 2 * DA_GMAX) + DA_GMAX * 128 + h));
+    const float Mu = (M == -INFINITY) ? 0.f : M;
+    float L = 0.f, O = 0.f;
+    for (int s2 = 0; s2 < ns; ++s2) {
+      const float* w2 = wb + s2 * (DA_GMAX * 128 + 2 * DA_GMAX);
+      const float f = exp2f(__ldcg(w2 + DA_GMAX * 128 + h) - Mu);
+      L += __ldcg(w2 + DA_GMAX * 128 + DA_GMAX + h) * f;
+      O += __ldcg(w2 + h * 128 + kk) * f;
+    }
+    out[static_cast<int64_t>(b) * ldo + (kvh * G + h) * 128 + kk] = __float2bfloat16(L > 0.f ? O / L : 0.f);
+  }
+  if (tid == 0) tickets[b * nkv + kvh] = 0;   // re-arm for the next launch
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -318,25 +417,29 @@ extern "C" int sr_decode_advance(const int64_t* next_tokens, int64_t* tokens, in
   return SR_OK;
 }
 
+extern "C" int64_t sr_decode_attention_workspace_bytes(int batch, int n_kv_heads, int max_len) {
+  const int ns = (max_len + DA_KEYS - 1) / DA_KEYS < 1 ? 1 : ((max_len + DA_KEYS - 1) / DA_KEYS > 32 ? 32 : (max_len + DA_KEYS - 1) / DA_KEYS);
+  return static_cast<int64_t>(batch) * n_kv_heads * (static_cast<int64_t>(ns) * (DA_GMAX * 128 + 2 * DA_GMAX) * 4 + 16);
+}
+
 extern "C" int sr_decode_attention(const void* q, int64_t ldq, const void* Kc, const void* Vt, int64_t ldvt,
                                    const int32_t* kv_start, const int32_t* kv_len, int max_len, void* out, int64_t ldo,
-                                   int batch, int n_q_heads, int n_kv_heads, float scale, void* stream) {
-  SR_REQUIRE(q && Kc && Vt && kv_start && kv_len && out, "sr_decode_attention: null pointer");
-  SR_REQUIRE(batch > 0 && n_q_heads % n_kv_heads == 0 && max_len > 0, "sr_decode_attention: bad shape");
-  const size_t smem = static_cast<size_t>((max_len + 31) / 32 * 32 + 8) * sizeof(float);
-  SR_REQUIRE(smem <= 200 * 1024, "sr_decode_attention: max_len %d too long for the single-pass kernel", max_len);
-  static size_t attr_smem = 48 * 1024;
-  if (smem > attr_smem) {
-    SR_CHECK_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_smem = 200 * 1024;
-  }
-  dim3 grid(batch, n_q_heads);
-  SR_CHECK_CUDA(launch_pdl(decode_attn_kernel, grid, dim3(DA_THREADS), smem, reinterpret_cast<cudaStream_t>(stream),
+                                   int batch, int n_q_heads, int n_kv_heads, float scale, void* workspace, void* stream) {
+  SR_REQUIRE(q && Kc && Vt && kv_start && kv_len && out && workspace, "sr_decode_attention: null pointer");
+  SR_REQUIRE(batch > 0 && n_q_heads % n_kv_heads == 0 && n_q_heads / n_kv_heads <= DA_GMAX && max_len > 0,
+             "sr_decode_attention: bad shape (query heads per kv head must be <= 8)");
+  SR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && ldvt % 8 == 0, "sr_decode_attention: workspace/ldvt alignment");
+  int ns = (max_len + DA_KEYS - 1) / DA_KEYS;
+  ns = ns < 1 ? 1 : (ns > 32 ? 32 : ns);
+  // workspace layout: [batch*n_kv] int32 tickets (zeroed once by the caller, re-armed by the kernel), then partials
+  int* tickets = reinterpret_cast<int*>(workspace);
+  float* ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((static_cast<size_t>(batch) * n_kv_heads * 4 + 15) / 16) * 16);
+  dim3 grid(batch, n_kv_heads, ns);
+  SR_CHECK_CUDA(launch_pdl(decode_attn_kernel, grid, dim3(DA_THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
                            reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(Kc),
                            reinterpret_cast<const __nv_bfloat16*>(Vt), ldvt, kv_start, kv_len,
                            reinterpret_cast<__nv_bfloat16*>(out), ldo, n_q_heads, n_kv_heads,
-                           scale * 1.4426950408889634f));
-  SR_CHECK_CUDA(cudaGetLastError());
+                           scale * 1.4426950408889634f, ws, tickets));
   return SR_OK;
 }
 

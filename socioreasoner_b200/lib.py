@@ -31,7 +31,8 @@ SYMBOLS = {
     "sr_gemm_skinny_norm_bf16": (c_int, [_P, c_int64, _P, c_float, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_attention_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int,
                                  _P, c_int64, c_int64, _P, c_int, _P, _P, c_float, c_int, _P]),
-    "sr_decode_attention": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int, _P, c_int64, c_int, c_int, c_int, c_float, _P]),
+    "sr_decode_attention_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "sr_decode_attention": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int, _P, c_int64, c_int, c_int, c_int, c_float, _P, _P]),
     "sr_rmsnorm_bf16": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, c_float, _P]),
     "sr_gather_rows": (c_int, [_P, c_int64, c_int, _P, _P, c_int64, c_int, c_int, _P]),
     "sr_embed_scatter": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, _P]),
@@ -190,11 +191,19 @@ def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, out: torch.Ten
     return out
 
 
+_dattn_ws = {}
+
+
 def decode_attention(q, kc, vt, kv_start, kv_len, max_len, out, n_q_heads, n_kv_heads, scale):
     global launch_count
+    key = (q.device, q.shape[0], n_kv_heads, int(max_len))
+    ws = _dattn_ws.get(key)
+    if ws is None:  # zero-initialised once: the leading int32 tickets must start at 0, the kernel re-arms them
+        nbytes = load().sr_decode_attention_workspace_bytes(q.shape[0], n_kv_heads, int(max_len))
+        ws = _dattn_ws[key] = torch.zeros((nbytes,), dtype=torch.uint8, device=q.device)
     rc = load().sr_decode_attention(q.data_ptr(), q.stride(0), kc.data_ptr(), vt.data_ptr(), vt.stride(0),
                                     kv_start.data_ptr(), kv_len.data_ptr(), int(max_len), out.data_ptr(), out.stride(0),
-                                    q.shape[0], n_q_heads, n_kv_heads, float(scale), _stream())
+                                    q.shape[0], n_q_heads, n_kv_heads, float(scale), ws.data_ptr(), _stream())
     _check(rc, "sr_decode_attention")
     launch_count += 1
     return out

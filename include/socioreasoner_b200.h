@@ -74,6 +74,13 @@ int sr_gemm_skinny_norm_bf16(const void* A, int64_t lda, const float* norm_weigh
                              void* C, int64_t ldc, const float* bias, const void* residual, int64_t ldr, int M, int N, int K,
                              int epilogue, int out_dtype, void* stream);
 
+/* Same on weights pre-packed for streaming: Wpacked[N/16][K/32][16][32] (block (g,c) holds rows 16g..16g+15, columns
+ * 32c..32c+31, 1 KB contiguous; N % 16 == 0, K % 32 == 0).  A warp-wide 16-byte load then covers 512 contiguous bytes and a
+ * CTA streams one linear region of HBM.  norm_weight may be NULL (no fused RMSNorm). */
+int sr_gemm_skinny_packed_bf16(const void* A, int64_t lda, const float* norm_weight, float norm_eps, const void* Wpacked, void* C,
+                               int64_t ldc, const float* bias, const void* residual, int64_t ldr, int M, int N, int K,
+                               int epilogue, int out_dtype, void* stream);
+
 /* ---- attention (tcgen05 + TMA) --------------------------------------------------------------
  * Variable-length softmax(Q K^T * scale) V; query row r attends key rows k with row_lo[r] <= k < row_hi[r].
  * Replaces flash_attn_varlen_func / eager per-window attention at HF:244-283 (ViT windowed + full attention,

@@ -40,6 +40,7 @@ struct GemvParams {
   const __nv_bfloat16* residual;
   int64_t lda, ldw, ldc, ldr;
   int M, N, K;
+  int packed;           // 1: W is in the streaming layout [N/16][K/32][16 rows][32 k] (1 KB blocks, see sr_pack_skinny_weights)
   const float* norm_w;  // optional fused RMSNorm on A rows: A'[m,k] = A[m,k] * rsqrt(mean_k A^2 + eps) * norm_w[k]
   float norm_eps;
 };
@@ -76,8 +77,16 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
     int ra = row0 + r * 16 + g, rb = ra + 8;
     ra = ra < p.N ? ra : p.N - 1;
     rb = rb < p.N ? rb : p.N - 1;
-    wrow[r][0] = p.W + static_cast<int64_t>(ra) * p.ldw + t * 8;
-    wrow[r][1] = p.W + static_cast<int64_t>(rb) * p.ldw + t * 8;
+    if (p.packed) {
+      // block (row group, chunk) = 16 rows x 32 k contiguous (1 KB): a warp-wide 16 B load covers 8 rows x 64 B = 512
+      // contiguous bytes (4 full 128 B lines instead of 8 half-used ones) and the CTA streams one linear region
+      const int64_t grp = static_cast<int64_t>(row0 / 16 + r) * (p.K >> 5) * 512;
+      wrow[r][0] = p.W + grp + g * 32 + t * 8;
+      wrow[r][1] = p.W + grp + (g + 8) * 32 + t * 8;
+    } else {
+      wrow[r][0] = p.W + static_cast<int64_t>(ra) * p.ldw + t * 8;
+      wrow[r][1] = p.W + static_cast<int64_t>(rb) * p.ldw + t * 8;
+    }
   }
   const __nv_bfloat16* xrow[NB];
   bool xok[NB];
@@ -89,6 +98,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   }
 
   const int nchunks = p.K >> 5;  // 32 k per chunk
+  const int wstep = p.packed ? 512 : 32;  // elements between consecutive chunks of one row group
   // Rolling software pipeline over GV_UNROLL register slots: slot u is consumed (MMA) and immediately re-armed with the
   // chunk GV_WARPS*GV_UNROLL further on, so GV_UNROLL-1 chunk loads per thread stay in flight across iterations
   // (without this the kernel paid one full HBM latency per batch of loads).
@@ -98,8 +108,8 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   auto load_slot = [&](int u, int c) {
 #pragma unroll
     for (int r = 0; r < RG; ++r) {
-      w[u][r][0] = ld_stream_v4(wrow[r][0] + c * 32);
-      w[u][r][1] = ld_stream_v4(wrow[r][1] + c * 32);
+      w[u][r][0] = ld_stream_v4(wrow[r][0] + static_cast<int64_t>(c) * wstep);
+      w[u][r][1] = ld_stream_v4(wrow[r][1] + static_cast<int64_t>(c) * wstep);
     }
 #pragma unroll
     for (int n = 0; n < NB; ++n) x[u][n] = xok[n] ? *reinterpret_cast<const uint4*>(xrow[n] + c * 32) : make_uint4(0, 0, 0, 0);
@@ -244,11 +254,11 @@ static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s
 
 static int gemm_skinny_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, const float* bias,
                             const void* residual, int64_t ldr, int M, int N, int K, int epilogue, int out_dtype,
-                            const float* norm_weight, float norm_eps, void* stream) {
+                            const float* norm_weight, float norm_eps, void* stream, int packed = 0) {
   using namespace sr;
   SR_REQUIRE(A && W && C, "sr_gemm_skinny_bf16: null operand");
   SR_REQUIRE(M > 0 && M <= 32 && N > 0 && K > 0 && K % 32 == 0, "sr_gemm_skinny_bf16: need 0 < M <= 32, K %% 32 == 0 (M=%d K=%d)", M, K);
-  SR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0, "sr_gemm_skinny_bf16: lda/ldw must be multiples of 8");
+  SR_REQUIRE(lda % 8 == 0 && (packed || ldw % 8 == 0), "sr_gemm_skinny_bf16: lda/ldw must be multiples of 8");
   SR_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, "sr_gemm_skinny_bf16: A/W not 16B aligned");
   SR_REQUIRE(epilogue != SR_EPI_RESIDUAL || residual, "sr_gemm_skinny_bf16: residual epilogue needs residual");
   SR_REQUIRE(epilogue != SR_EPI_SWIGLU || (N % 32 == 0 && out_dtype == SR_DTYPE_BF16), "sr_gemm_skinny_bf16: SwiGLU needs N %% 32 == 0, bf16 out");
@@ -263,6 +273,8 @@ static int gemm_skinny_impl(const void* A, int64_t lda, const void* W, int64_t l
   p.M = M; p.N = N; p.K = K;
   p.norm_w = norm_weight;
   p.norm_eps = norm_eps;
+  p.packed = packed;
+  SR_REQUIRE(!packed || N % 16 == 0, "sr_gemm_skinny_packed_bf16: N must be a multiple of 16");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int f32 = out_dtype == SR_DTYPE_F32;
   if (norm_weight != nullptr) {
@@ -288,4 +300,10 @@ extern "C" int sr_gemm_skinny_norm_bf16(const void* A, int64_t lda, const float*
   using namespace sr;
   SR_REQUIRE(norm_weight != nullptr, "sr_gemm_skinny_norm_bf16: norm_weight is null");
   return gemm_skinny_impl(A, lda, W, ldw, C, ldc, bias, residual, ldr, M, N, K, epilogue, out_dtype, norm_weight, norm_eps, stream);
+}
+
+extern "C" int sr_gemm_skinny_packed_bf16(const void* A, int64_t lda, const float* norm_weight, float norm_eps, const void* Wpacked,
+                                          void* C, int64_t ldc, const float* bias, const void* residual, int64_t ldr, int M,
+                                          int N, int K, int epilogue, int out_dtype, void* stream) {
+  return gemm_skinny_impl(A, lda, Wpacked, K, C, ldc, bias, residual, ldr, M, N, K, epilogue, out_dtype, norm_weight, norm_eps, stream, 1);
 }

@@ -29,6 +29,7 @@ SYMBOLS = {
     "sr_gemm_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_gemm_skinny_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_gemm_skinny_norm_bf16": (c_int, [_P, c_int64, _P, c_float, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sr_gemm_skinny_packed_bf16": (c_int, [_P, c_int64, _P, c_float, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_attention_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int,
                                  _P, c_int64, c_int64, _P, c_int, _P, _P, c_float, c_int, _P]),
     "sr_decode_attention_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
@@ -168,6 +169,36 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor] = None, b
                                  _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0, M, N, K,
                                  epilogue, DT_F32 if out.dtype == torch.float32 else DT_BF16, block_n, _stream())
     _check(rc, "sr_gemm_bf16")
+    launch_count += 1
+    return out
+
+
+def pack_skinny(w: torch.Tensor) -> torch.Tensor:
+    """[N,K] -> streaming layout [N/16][K/32][16][32] for ``gemm_skinny_packed`` (pure re-layout, done once at load)."""
+    N, K = w.shape
+    assert N % 16 == 0 and K % 32 == 0
+    return w.view(N // 16, 16, K // 32, 32).permute(0, 2, 1, 3).contiguous()
+
+
+def gemm_skinny_packed(a: torch.Tensor, wp: torch.Tensor, N: int, K: int, out: Optional[torch.Tensor] = None,
+                       bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE,
+                       out_dtype=torch.bfloat16, norm_weight: Optional[torch.Tensor] = None, norm_eps: float = 1e-6) -> torch.Tensor:
+    """Decode-step linear on pre-packed weights (see ``pack_skinny``); M = a.shape[0] <= 32."""
+    global launch_count
+    _req(a, torch.bfloat16, "gemm_skinny_packed.a"); _req(wp, torch.bfloat16, "gemm_skinny_packed.w")
+    M = a.shape[0]
+    assert a.shape[1] == K and wp.numel() == N * K and wp.is_contiguous()
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
+    if residual is not None:
+        epilogue = EPI_RESIDUAL if epilogue == EPI_NONE else epilogue
+    with _Timed("gemm", (M, N, K, epilogue), 2.0 * M * N * K):
+        rc = load().sr_gemm_skinny_packed_bf16(a.data_ptr(), a.stride(0), _ptr(norm_weight), float(norm_eps), wp.data_ptr(),
+                                               out.data_ptr(), out.stride(0), _ptr(bias), _ptr(residual),
+                                               residual.stride(0) if residual is not None else 0, M, N, K, epilogue,
+                                               DT_F32 if out.dtype == torch.float32 else DT_BF16, _stream())
+    _check(rc, "sr_gemm_skinny_packed_bf16")
     launch_count += 1
     return out
 

@@ -99,6 +99,17 @@ def test_skinny_gemm_with_fused_rmsnorm(M, N, K, epi, f32):
     assert rel_max(out, ref) < 8e-3   # one extra bf16 rounding of (x * w_norm) before the MMA
 
 
+@pytest.mark.parametrize("M,N,K,epi,norm", [(8, 2048, 11008, 0, False), (8, 22016, 2048, 2, True), (5, 2560, 2048, 0, True)])
+def test_skinny_gemm_packed_layout_is_bit_identical(M, N, K, epi, norm):
+    """The streaming weight layout is a pure re-layout: same products in the same order => identical bits."""
+    a = rnd(M, K, scale=0.7).bfloat16().to(DEV)
+    w = rnd(N, K, scale=0.05, seed=1).bfloat16().to(DEV)
+    nw = (1 + 0.1 * rnd(K, seed=2)).to(DEV) if norm else None
+    ref = lib.gemm(a, w, epilogue=epi, norm_weight=nw)
+    got = lib.gemm_skinny_packed(a, lib.pack_skinny(w), N, K, epilogue=epi, norm_weight=nw)
+    assert torch.equal(ref, got)
+
+
 def test_gemm_linearity_and_row_independence():
     """Size-independent properties at a production shape: rows are independent (batch invariance is bit-exact because
     every output element sees the same k-block order) and f(2a) == 2 f(a) exactly for a power-of-two scale."""

@@ -81,6 +81,9 @@ int sr_gemm_skinny_packed_bf16(const void* A, int64_t lda, const float* norm_wei
                                int64_t ldc, const float* bias, const void* residual, int64_t ldr, int M, int N, int K,
                                int epilogue, int out_dtype, void* stream);
 
+/* Tuning knob: warps per CTA of the skinny GEMM at M <= 8 (0 = default, 4 / 8 / 16). */
+int sr_set_gemv_warps(int warps);
+
 /* ---- attention (tcgen05 + TMA) --------------------------------------------------------------
  * Variable-length softmax(Q K^T * scale) V; query row r attends key rows k with row_lo[r] <= k < row_hi[r].
  * Replaces flash_attn_varlen_func / eager per-window attention at HF:244-283 (ViT windowed + full attention,

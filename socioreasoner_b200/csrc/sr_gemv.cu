@@ -224,14 +224,13 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   }
 }
 
-template <int NB, bool NORM>
-static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s) {
-  // 16 warps split K when one batch tile is live (the decode case): every warp then has <= 3 unrolled iterations even for
-  // K = 11008, i.e. (almost) all of a CTA's weight bytes are in flight at once.  Shared-memory budget caps NB >= 2 at 8.
-  constexpr int W = (NB == 1) ? 16 : 8;
+static int g_gemv_warps = 0;  // 0 = default policy; 4 / 8 / 16 force (tuning knob, see sr_set_gemv_warps)
+
+template <int NB, bool NORM, int W>
+static int launch_gemv_w(const GemvParams& p, int epi, int out_f32, cudaStream_t s) {
   constexpr int GV_THREADS = W * 32;
   constexpr int U1 = (NB == 1) ? (NORM ? 4 : 6) : 4;  // register slots (chunks in flight + 1) per thread, 1 row group
-  constexpr int U2 = (NB == 1) ? 3 : 2;  // 2 row groups (SwiGLU) load twice the weight bytes per slot
+  constexpr int U2 = (NB == 1) ? 3 : 2;               // 2 row groups (SwiGLU) load twice the weight bytes per slot
   if (epi == SR_EPI_SWIGLU) {
     const int grid = (p.N + 31) / 32;
     SR_CHECK_CUDA(launch_pdl(gemv_kernel<2, NB, SR_EPI_SWIGLU, false, W, NORM, U2>, dim3(grid), dim3(GV_THREADS), 0, s, p));
@@ -246,8 +245,21 @@ static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s
       return SR_ERR_INVALID;
     }
   }
-  SR_CHECK_CUDA(cudaGetLastError());
   return SR_OK;
+}
+
+template <int NB, bool NORM>
+static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s) {
+  // Warps per CTA split K.  Fewer warps per CTA = more CTAs co-resident per SM, so one CTA's reduction/epilogue (no loads
+  // in flight) overlaps another CTA's streaming; more warps = shorter per-CTA chains.  Shared-memory budget caps NB >= 2 at 8.
+  if constexpr (NB == 1) {
+    const int w = g_gemv_warps ? g_gemv_warps : 8;
+    if (w == 4) return launch_gemv_w<NB, NORM, 4>(p, epi, out_f32, s);
+    if (w == 16) return launch_gemv_w<NB, NORM, 16>(p, epi, out_f32, s);
+    return launch_gemv_w<NB, NORM, 8>(p, epi, out_f32, s);
+  } else {
+    return launch_gemv_w<NB, NORM, 8>(p, epi, out_f32, s);
+  }
 }
 
 }  // namespace sr
@@ -306,4 +318,10 @@ extern "C" int sr_gemm_skinny_packed_bf16(const void* A, int64_t lda, const floa
                                           void* C, int64_t ldc, const float* bias, const void* residual, int64_t ldr, int M,
                                           int N, int K, int epilogue, int out_dtype, void* stream) {
   return gemm_skinny_impl(A, lda, Wpacked, K, C, ldc, bias, residual, ldr, M, N, K, epilogue, out_dtype, norm_weight, norm_eps, stream, 1);
+}
+
+extern "C" int sr_set_gemv_warps(int warps) {
+  if (warps != 0 && warps != 4 && warps != 8 && warps != 16) return SR_ERR_INVALID;
+  sr::g_gemv_warps = warps;
+  return SR_OK;
 }

@@ -253,7 +253,9 @@ static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s
   // Warps per CTA split K.  Fewer warps per CTA = more CTAs co-resident per SM, so one CTA's reduction/epilogue (no loads
   // in flight) overlaps another CTA's streaming; more warps = shorter per-CTA chains.  Shared-memory budget caps NB >= 2 at 8.
   if constexpr (NB == 1) {
-    const int w = g_gemv_warps ? g_gemv_warps : 8;
+    // measured on B200 (tools/gemv_bench.py, cold weights): 16 warps for the 16-row groups (N = 2048 gives only 128 CTAs:
+    // long K needs the wide K split), 8 warps for SwiGLU pairs (688+ CTAs: two co-resident CTAs overlap epilogue and streaming)
+    const int w = g_gemv_warps ? g_gemv_warps : (epi == SR_EPI_SWIGLU ? 8 : 16);
     if (w == 4) return launch_gemv_w<NB, NORM, 4>(p, epi, out_f32, s);
     if (w == 16) return launch_gemv_w<NB, NORM, 16>(p, epi, out_f32, s);
     return launch_gemv_w<NB, NORM, 8>(p, epi, out_f32, s);

@@ -195,7 +195,10 @@ class Engine:
         scale = hd ** -0.5
         fuse_norm = decode is not None and S <= 32  # decode: RMSNorm folded into the weight-streaming GEMM (2 launches/layer less)
         for li, L in enumerate(W.layers):
-            if fuse_norm:
+            if fuse_norm and L.qkv_wp is not None:
+                lib.gemm_skinny_packed(x, L.qkv_wp, qkv_dim, t.hidden_size, out=qkv, bias=L.qkv_b, norm_weight=L.ln1,
+                                       norm_eps=t.rms_norm_eps)
+            elif fuse_norm:
                 lib.gemm(x, L.qkv_w, out=qkv, bias=L.qkv_b, norm_weight=L.ln1, norm_eps=t.rms_norm_eps)
             else:
                 lib.rmsnorm(x, L.ln1, t.rms_norm_eps, out=y)
@@ -208,6 +211,14 @@ class Engine:
             else:
                 kv_start, kv_len, max_len = decode
                 lib.decode_attention(qkv, cache.k[li], cache.vt[li], kv_start, kv_len, max_len, ao, Hq, Hkv, scale)
+            if fuse_norm and L.o_wp is not None:
+                lib.gemm_skinny_packed(ao, L.o_wp, t.hidden_size, Hq * hd, out=x, residual=x)
+                lib.gemm_skinny_packed(x, L.gu_wp, 2 * t.intermediate_size, t.hidden_size, out=act, epilogue=lib.EPI_SWIGLU,
+                                       norm_weight=L.ln2, norm_eps=t.rms_norm_eps)
+                lib.gemm_skinny_packed(act, L.down_wp, t.hidden_size, t.intermediate_size, out=x, residual=x)
+                if capture is not None:
+                    capture.append(x.clone())
+                continue
             lib.gemm(ao, L.o_w, out=x, residual=x)
             if fuse_norm:
                 lib.gemm(x, L.gu_w, out=act, epilogue=lib.EPI_SWIGLU, norm_weight=L.ln2, norm_eps=t.rms_norm_eps)
@@ -275,6 +286,9 @@ class Engine:
         """final RMSNorm + LM head on the given rows (HF:1385)."""
         t = self.cfg.text
         if hidden_rows.shape[0] <= 32:
+            if self.w.lm_head_p is not None:  # separate norm: the fused-norm variant is slower on the 622 MB LM head
+                y = lib.rmsnorm(hidden_rows, self.w.final_norm, t.rms_norm_eps, out=self._buf(f"ln_y{hidden_rows.shape[0]}", tuple(hidden_rows.shape)))
+                return lib.gemm_skinny_packed(y, self.w.lm_head_p, t.vocab_size, t.hidden_size, out=out, out_dtype=out_dtype)
             return lib.gemm(hidden_rows, self.w.lm_head, out=out, out_dtype=out_dtype, norm_weight=self.w.final_norm,
                             norm_eps=t.rms_norm_eps)
         y = lib.rmsnorm(hidden_rows, self.w.final_norm, t.rms_norm_eps)

@@ -101,13 +101,37 @@ def test_skinny_gemm_with_fused_rmsnorm(M, N, K, epi, f32):
 
 @pytest.mark.parametrize("M,N,K,epi,norm", [(8, 2048, 11008, 0, False), (8, 22016, 2048, 2, True), (5, 2560, 2048, 0, True)])
 def test_skinny_gemm_packed_layout_is_bit_identical(M, N, K, epi, norm):
-    """The streaming weight layout is a pure re-layout: same products in the same order => identical bits."""
+    """The streaming weight layout is a pure re-layout: same products in the same order => identical bits (LDG kernel);
+    the bulk-copy variant splits K over 8 instead of 16 warps => equal up to fp32 re-association + one bf16 rounding."""
     a = rnd(M, K, scale=0.7).bfloat16().to(DEV)
     w = rnd(N, K, scale=0.05, seed=1).bfloat16().to(DEV)
     nw = (1 + 0.1 * rnd(K, seed=2)).to(DEV) if norm else None
     ref = lib.gemm(a, w, epilogue=epi, norm_weight=nw)
-    got = lib.gemm_skinny_packed(a, lib.pack_skinny(w), N, K, epilogue=epi, norm_weight=nw)
+    wp = lib.pack_skinny(w)
+    lib.load().sr_set_gemv_bulk(0)
+    try:
+        got = lib.gemm_skinny_packed(a, wp, N, K, epilogue=epi, norm_weight=nw)
+    finally:
+        lib.load().sr_set_gemv_bulk(1)
     assert torch.equal(ref, got)
+    bulk = lib.gemm_skinny_packed(a, wp, N, K, epilogue=epi, norm_weight=nw)
+    assert rel_max(bulk, ref) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K,epi,f32,bias,res", [(8, 2560, 2048, 0, False, True, False), (1, 2048, 2048, 0, False, False, True),
+                                                  (8, 2048, 11008, 0, False, False, True), (7, 22016, 2048, 2, False, False, False),
+                                                  (8, 151936, 2048, 0, True, False, False), (3, 5120, 5120, 3, False, True, False),
+                                                  (8, 2048, 2080, 0, False, False, False)])
+def test_skinny_gemm_bulk_engine(M, N, K, epi, f32, bias, res):
+    """cp.async.bulk streaming variant vs the fp32 reference (ragged last stage: K = 2080 = 65 chunks)."""
+    a = rnd(M, K, scale=0.5).bfloat16()
+    w = rnd(N, K, scale=0.05, seed=1).bfloat16()
+    b = rnd(N, scale=0.1, seed=2) if bias else None
+    n_out = N // 2 if epi == lib.EPI_SWIGLU else N
+    r = rnd(M, n_out, seed=3).bfloat16() if res else None
+    out = lib.gemm_skinny_packed(a.to(DEV), lib.pack_skinny(w.to(DEV)), N, K, bias=b.to(DEV) if bias else None,
+                                 residual=r.to(DEV) if res else None, epilogue=epi, out_dtype=torch.float32 if f32 else torch.bfloat16)
+    assert rel_max(out, gemm_ref(a, w, b, r, epi)) < (2e-5 if f32 else 6e-3)
 
 
 def test_gemm_linearity_and_row_independence():

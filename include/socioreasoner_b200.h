@@ -82,8 +82,9 @@ int sr_gemm_skinny_packed_bf16(const void* A, int64_t lda, const float* norm_wei
                                int epilogue, int out_dtype, void* stream);
 
 /* Variant of sr_gemm_skinny_packed_bf16 for M <= 8 that streams the packed weights with the bulk-copy engine
- * (cp.async.bulk into a 96-128 KB shared-memory ring, producer/consumer mbarriers); sr_gemm_skinny_packed_bf16 dispatches
- * here unless sr_set_gemv_bulk(0) / env SR_GEMV_BULK=0. */
+ * (cp.async.bulk into a 96-128 KB shared-memory ring, producer/consumer mbarriers).  Measured on B200 it is NOT faster than
+ * the register-streaming kernel (tools/gemv_bench.py: 2.5-4.1 vs 3.0-4.7 TB/s), so sr_gemm_skinny_packed_bf16 uses it only
+ * after sr_set_gemv_bulk(1) / env SR_GEMV_BULK=1. */
 int sr_gemm_skinny_bulk_bf16(const void* A, int64_t lda, const float* norm_weight, float norm_eps, const void* Wpacked, void* C,
                              int64_t ldc, const float* bias, const void* residual, int64_t ldr, int M, int N, int K,
                              int epilogue, int out_dtype, void* stream);

@@ -321,7 +321,7 @@ extern "C" int sr_gemm_skinny_norm_bf16(const void* A, int64_t lda, const float*
 extern "C" int sr_gemm_skinny_bulk_bf16(const void* A, int64_t lda, const float* norm_weight, float norm_eps, const void* Wpacked,
                                         void* C, int64_t ldc, const float* bias, const void* residual, int64_t ldr, int M, int N,
                                         int K, int epilogue, int out_dtype, void* stream);
-static int g_gemv_bulk = -1;  // -1: env SR_GEMV_BULK (default 1)
+static int g_gemv_bulk = -1;  // -1: env SR_GEMV_BULK (default 0: measured slower than the LDG kernel on B200 except at K >= 8192)
 extern "C" int sr_set_gemv_bulk(int on) {
   g_gemv_bulk = on ? 1 : 0;
   return SR_OK;
@@ -332,7 +332,7 @@ extern "C" int sr_gemm_skinny_packed_bf16(const void* A, int64_t lda, const floa
                                           int N, int K, int epilogue, int out_dtype, void* stream) {
   if (g_gemv_bulk < 0) {
     const char* e = getenv("SR_GEMV_BULK");
-    g_gemv_bulk = (e == nullptr || e[0] != '0') ? 1 : 0;
+    g_gemv_bulk = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
   if (g_gemv_bulk && M <= 8)  // bulk-copy-engine streaming variant (sr_gemv_bulk.cu)
     return sr_gemm_skinny_bulk_bf16(A, lda, norm_weight, norm_eps, Wpacked, C, ldc, bias, residual, ldr, M, N, K, epilogue,

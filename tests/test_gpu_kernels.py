@@ -109,13 +109,14 @@ def test_skinny_gemm_packed_layout_is_bit_identical(M, N, K, epi, norm):
     ref = lib.gemm(a, w, epilogue=epi, norm_weight=nw)
     wp = lib.pack_skinny(w)
     lib.load().sr_set_gemv_bulk(0)
-    try:
-        got = lib.gemm_skinny_packed(a, wp, N, K, epilogue=epi, norm_weight=nw)
-    finally:
-        lib.load().sr_set_gemv_bulk(1)
+    got = lib.gemm_skinny_packed(a, wp, N, K, epilogue=epi, norm_weight=nw)
     assert torch.equal(ref, got)
-    bulk = lib.gemm_skinny_packed(a, wp, N, K, epilogue=epi, norm_weight=nw)
-    assert rel_max(bulk, ref) < 4e-3
+    lib.load().sr_set_gemv_bulk(1)
+    try:
+        bulk = lib.gemm_skinny_packed(a, wp, N, K, epilogue=epi, norm_weight=nw)
+    finally:
+        lib.load().sr_set_gemv_bulk(0)
+    assert rel_max(bulk, ref) < 8e-3   # one bf16 ulp of the largest element = 3.9e-3
 
 
 @pytest.mark.parametrize("M,N,K,epi,f32,bias,res", [(8, 2560, 2048, 0, False, True, False), (1, 2048, 2048, 0, False, False, True),
@@ -129,8 +130,12 @@ def test_skinny_gemm_bulk_engine(M, N, K, epi, f32, bias, res):
     b = rnd(N, scale=0.1, seed=2) if bias else None
     n_out = N // 2 if epi == lib.EPI_SWIGLU else N
     r = rnd(M, n_out, seed=3).bfloat16() if res else None
-    out = lib.gemm_skinny_packed(a.to(DEV), lib.pack_skinny(w.to(DEV)), N, K, bias=b.to(DEV) if bias else None,
-                                 residual=r.to(DEV) if res else None, epilogue=epi, out_dtype=torch.float32 if f32 else torch.bfloat16)
+    lib.load().sr_set_gemv_bulk(1)
+    try:
+        out = lib.gemm_skinny_packed(a.to(DEV), lib.pack_skinny(w.to(DEV)), N, K, bias=b.to(DEV) if bias else None,
+                                     residual=r.to(DEV) if res else None, epilogue=epi, out_dtype=torch.float32 if f32 else torch.bfloat16)
+    finally:
+        lib.load().sr_set_gemv_bulk(0)
     assert rel_max(out, gemm_ref(a, w, b, r, epi)) < (2e-5 if f32 else 6e-3)
 
 

@@ -247,11 +247,30 @@ def run_ours(args):
 # ---------------------------------------------------------------------------------------------------
 # reference arm: HF eager fp32 on the host cores (oracle/), bounded sample
 # ---------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """Threads the CPU arm may use: CPU affinity and cgroup quota respected (os.cpu_count() on a shared GPU host counts
+    cores the container does not own; 128 oversubscribed threads ran HF eager ~70x SLOWER than 8 real cores), capped at 32
+    where HF eager fp32 stops scaling."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return int(os.environ.get("SR_CPU_THREADS", min(n, 32)))
+
+
 def cpu_reference(steps: int, warmup: int, budget_s: float = 150.0):
     from oracle import hf_oracle as O
     from oracle import host_ref
 
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     torch.set_num_threads(cores)
     t0 = time.time()
     hf = O.build_model_fast("3b")

@@ -181,21 +181,44 @@ __global__ void __launch_bounds__(DA_THREADS) decode_attn_kernel(const __nv_bflo
   if (!s_last) return;
   __threadfence();
   // ---- merge the splits (last CTA of this (sample, kv head)) ----
-  const float* wb = ws + (static_cast<int64_t>(b) * nkv + kvh) * ns * (DA_GMAX * 128 + 2 * DA_GMAX);
+  // All loads of the merge are issued in parallel: first the per-split (max, sum) pairs into shared memory, then every
+  // thread gathers its ns partial outputs with independent L2 loads (a serial loop here cost ~16 us of L2 round trips).
+  constexpr int kStride = DA_GMAX * 128 + 2 * DA_GMAX;
+  __shared__ float m_ms[32][DA_GMAX], m_ls[32][DA_GMAX], m_f[32][DA_GMAX];
+  __shared__ float m_L[DA_GMAX];
+  const float* wb = ws + (static_cast<int64_t>(b) * nkv + kvh) * ns * kStride;
+  for (int i = tid; i < ns * G; i += DA_THREADS) {
+    const int s2 = i / G, h = i % G;
+    m_ms[s2][h] = __ldcg(wb + s2 * kStride + DA_GMAX * 128 + h);
+    m_ls[s2][h] = __ldcg(wb + s2 * kStride + DA_GMAX * 128 + DA_GMAX + h);
+  }
+  __syncthreads();
+  if (tid < G) {
+    float M = -INFINITY;
+    for (int s2 = 0; s2 < ns; ++s2) M = fmaxf(M, m_ms[s2][tid]);
+    const float Mu = (M == -INFINITY) ? 0.f : M;
+    float L = 0.f;
+    for (int s2 = 0; s2 < ns; ++s2) {
+      const float f = exp2f(m_ms[s2][tid] - Mu);
+      m_f[s2][tid] = f;
+      L += m_ls[s2][tid] * f;
+    }
+    m_L[tid] = L;
+  }
+  __syncthreads();
 #pragma unroll
   for (int hh = 0; hh < 4; ++hh) {
     const int h = half * 4 + hh;
     if (h >= G) continue;
-    float M = -INFINITY;
-    for (int s2 = 0; s2 < ns; ++s2) M = fmaxf(M, __ldcg(wb + s2 * (DA_GMAX * 128 + 2 * DA_GMAX) + DA_GMAX * 128 + h));
-    const float Mu = (M == -INFINITY) ? 0.f : M;
-    float L = 0.f, O = 0.f;
-    for (int s2 = 0; s2 < ns; ++s2) {
-      const float* w2 = wb + s2 * (DA_GMAX * 128 + 2 * DA_GMAX);
-      const float f = exp2f(__ldcg(w2 + DA_GMAX * 128 + h) - Mu);
-      L += __ldcg(w2 + DA_GMAX * 128 + DA_GMAX + h) * f;
-      O += __ldcg(w2 + h * 128 + kk) * f;
+    float O = 0.f;
+    for (int s0 = 0; s0 < ns; s0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (s0 + j < ns) ? __ldcg(wb + (s0 + j) * kStride + h * 128 + kk) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) O += (s0 + j < ns) ? v[j] * m_f[s0 + j][h] : 0.f;
     }
+    const float L = m_L[h];
     out[static_cast<int64_t>(b) * ldo + (kvh * G + h) * 128 + kk] = __float2bfloat16(L > 0.f ? O / L : 0.f);
   }
   if (tid == 0) tickets[b * nkv + kvh] = 0;   // re-arm for the next launch

@@ -174,6 +174,15 @@ def run_ours(args):
     ms_dev, res = timed(step_device, args.steps)
     launches = (lib.launch_count - l0) // max(args.steps, 1)
     clk = clocks.stop() if rank == 0 else None
+    # stage split of one more (un-instrumented, graph-replaying) step: CUDA events at the stage boundaries
+    model.engine.stage_events = []
+    torch.cuda.synchronize()
+    step_device()
+    torch.cuda.synchronize()
+    evs, model.engine.stage_events = model.engine.stage_events, None
+    stages = {evs[i + 1][0] + "_ms": round(evs[i][1].elapsed_time(evs[i + 1][1]), 2) for i in range(len(evs) - 1)}
+    if "decode_ms" in stages:
+        stages["decode_ms_per_token"] = round(stages["decode_ms"] / max(NEW_TOKENS - 1, 1), 3)
 
     # roofline of the dominant kernel: per-launch CUDA events around every tensor-core GEMM, measured during one more
     # pass of the same step (events on the launching stream; the aggregate over the BLOCK_N=256 instantiations = the
@@ -230,7 +239,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "tiles_per_gpu": TILES_PER_GPU, "global_batch": TILES_PER_GPU * world,
                    "patches_per_tile": n_patches, "prompt_tokens": S, "new_tokens": NEW_TOKENS, "objects_per_tile": N_OBJ,
                    "parallelism": f"dp{world}", "l2": "7.5 GB of weights are streamed every step (>> 126 MB L2); no explicit flush",
-                   "mean_iou": round(float(res.iou.float().mean().item()), 6)},
+                   "mean_iou": round(float(res.iou.float().mean().item()), 6), "stage_split": stages},
         "e2e": {"value": round(total_imgs / (ms_e2e * 1e-3), 3), "unit": "images/s", "h2d_bytes_per_step": host.h2d_bytes(),
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": int(launches) * args.steps,

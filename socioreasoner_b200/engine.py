@@ -91,6 +91,13 @@ class Engine:
         self._dstate: Dict[Tuple[int, int], dict] = {}
         self._decode_launches = 0
         self.use_cuda_graph = True
+        self.stage_events = None  # optional list: generate_greedy appends (stage, cuda event) pairs (bench.py stage split)
+
+    @staticmethod
+    def _event():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        return e
 
     # ------------------------------------------------------------------ buffers
     def _buf(self, name: str, shape, dtype=torch.bfloat16, zero: bool = False) -> torch.Tensor:
@@ -366,8 +373,13 @@ class Engine:
         B = mask_np.shape[0]
         l_max = int((lens.max() + T + 127) // 128 * 128)
         cache = self._get_cache(B, l_max)
+        ev = self.stage_events
+        if ev is not None:
+            ev.append(("start", self._event()))
         x, sp, cache, pos3 = self.prefill(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, cache=cache,
                                           reserve_new_tokens=T)
+        if ev is not None:
+            ev.append(("vit+prefill", self._event()))
         V = t.vocab_size
         st = self._decode_state(B, T)
         st["step"].zero_()
@@ -417,6 +429,8 @@ class Engine:
         lib.decode_advance(st["nxt"], st["tokens"], st["step"], st["row0"], st["len0"], st["pos0"], st["cache_row"],
                            st["kv_len"], st["pos3"])
         cache.lengths = sp.lengths + T - 1
+        if ev is not None:
+            ev.append(("decode", self._event()))
         tokens = st["tokens"].clone()
         return (tokens, all_logits) if return_logits else tokens
 

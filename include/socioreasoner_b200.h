@@ -91,6 +91,8 @@ int sr_gemm_skinny_bulk_bf16(const void* A, int64_t lda, const float* norm_weigh
 int sr_set_gemv_bulk(int enabled);
 /* Tuning knob: warps per CTA of the skinny GEMM at M <= 8 (0 = default, 4 / 8 / 16). */
 int sr_set_gemv_warps(int warps);
+/* Tuning knob: weight-load instruction flavour of the skinny GEMM at M <= 8 (0 nc/no-allocate, 1 + L2::256B, 2 plain). */
+int sr_set_gemv_load(int flavour);
 
 /* ---- attention (tcgen05 + TMA) --------------------------------------------------------------
  * Variable-length softmax(Q K^T * scale) V; query row r attends key rows k with row_lo[r] <= k < row_hi[r].

@@ -21,9 +21,17 @@ namespace sr {
 
 
 
+// weight-stream load flavours (tuning knob sr_set_gemv_load): 0 = nc + L1 no-allocate, 1 = the same with a 256-byte L2
+// prefetch granule (bigger DRAM bursts on the linear streaming layout), 2 = plain cached load
+template <int LDV>
 SR_DEVINL uint4 ld_stream_v4(const void* p) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  if (LDV == 1)
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  else if (LDV == 2)
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  else
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
 
@@ -50,7 +58,7 @@ struct GemvParams {
 // RG = row groups of 16 weight rows per CTA (1, or 2 for SwiGLU: gate group + up group); NB = batch tiles of 8.
 SR_DEVINL uint32_t scale_bf16x2(uint32_t x, float w0, float w1) { return pack_bf16x2(bf16_lo(x) * w0, bf16_hi(x) * w1); }
 
-template <int RG, int NB, int EPI, bool OUT_F32, int GV_WARPS, bool NORM, int GV_UNROLL>
+template <int RG, int NB, int EPI, bool OUT_F32, int GV_WARPS, bool NORM, int GV_UNROLL, int LDV>
 __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p) {
   constexpr int GV_THREADS = GV_WARPS * 32;
   __shared__ float red[GV_WARPS][RG][NB][16 * 8];
@@ -110,8 +118,8 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   auto load_slot = [&](int u, int c) {
 #pragma unroll
     for (int r = 0; r < RG; ++r) {
-      w[u][r][0] = ld_stream_v4(wrow[r][0] + static_cast<int64_t>(c) * wstep);
-      w[u][r][1] = ld_stream_v4(wrow[r][1] + static_cast<int64_t>(c) * wstep);
+      w[u][r][0] = ld_stream_v4<LDV>(wrow[r][0] + static_cast<int64_t>(c) * wstep);
+      w[u][r][1] = ld_stream_v4<LDV>(wrow[r][1] + static_cast<int64_t>(c) * wstep);
     }
 #pragma unroll
     for (int n = 0; n < NB; ++n) x[u][n] = xok[n] ? *reinterpret_cast<const uint4*>(xrow[n] + c * 32) : make_uint4(0, 0, 0, 0);
@@ -226,22 +234,23 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   }
 }
 
+static int g_gemv_load = 0;   // weight-load flavour for M <= 8 (see ld_stream_v4)
 static int g_gemv_warps = 0;  // 0 = default policy; 4 / 8 / 16 force (tuning knob, see sr_set_gemv_warps)
 
-template <int NB, bool NORM, int W>
+template <int NB, bool NORM, int W, int LDV>
 static int launch_gemv_w(const GemvParams& p, int epi, int out_f32, cudaStream_t s) {
   constexpr int GV_THREADS = W * 32;
   constexpr int U1 = (NB == 1) ? (NORM ? 4 : 6) : 4;  // register slots (chunks in flight + 1) per thread, 1 row group
   constexpr int U2 = (NB == 1) ? 3 : 2;               // 2 row groups (SwiGLU) load twice the weight bytes per slot
   if (epi == SR_EPI_SWIGLU) {
     const int grid = (p.N + 31) / 32;
-    SR_CHECK_CUDA(launch_pdl(gemv_kernel<2, NB, SR_EPI_SWIGLU, false, W, NORM, U2>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    SR_CHECK_CUDA(launch_pdl(gemv_kernel<2, NB, SR_EPI_SWIGLU, false, W, NORM, U2, LDV>, dim3(grid), dim3(GV_THREADS), 0, s, p));
   } else {
     const int grid = (p.N + 15) / 16;
-    if (out_f32) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, true, W, NORM, U1>, dim3(grid), dim3(GV_THREADS), 0, s, p));
-    else if (epi == SR_EPI_NONE) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, false, W, NORM, U1>, dim3(grid), dim3(GV_THREADS), 0, s, p));
-    else if (epi == SR_EPI_RESIDUAL) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_RESIDUAL, false, W, NORM, U1>, dim3(grid), dim3(GV_THREADS), 0, s, p));
-    else if (epi == SR_EPI_GELU) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_GELU, false, W, NORM, U1>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    if (out_f32) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, true, W, NORM, U1, LDV>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    else if (epi == SR_EPI_NONE) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, false, W, NORM, U1, LDV>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    else if (epi == SR_EPI_RESIDUAL) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_RESIDUAL, false, W, NORM, U1, LDV>, dim3(grid), dim3(GV_THREADS), 0, s, p));
+    else if (epi == SR_EPI_GELU) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_GELU, false, W, NORM, U1, LDV>, dim3(grid), dim3(GV_THREADS), 0, s, p));
     else {
       set_last_error("sr_gemm_skinny_bf16: unknown epilogue %d", epi);
       return SR_ERR_INVALID;
@@ -258,11 +267,19 @@ static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s
     // measured on B200 (tools/gemv_bench.py, cold weights): 16 warps for the 16-row groups (N = 2048 gives only 128 CTAs:
     // long K needs the wide K split), 8 warps for SwiGLU pairs (688+ CTAs: two co-resident CTAs overlap epilogue and streaming)
     const int w = g_gemv_warps ? g_gemv_warps : (epi == SR_EPI_SWIGLU ? 8 : 16);
-    if (w == 4) return launch_gemv_w<NB, NORM, 4>(p, epi, out_f32, s);
-    if (w == 16) return launch_gemv_w<NB, NORM, 16>(p, epi, out_f32, s);
-    return launch_gemv_w<NB, NORM, 8>(p, epi, out_f32, s);
+    if (g_gemv_load == 1) {
+      if (w == 16) return launch_gemv_w<NB, NORM, 16, 1>(p, epi, out_f32, s);
+      return launch_gemv_w<NB, NORM, 8, 1>(p, epi, out_f32, s);
+    }
+    if (g_gemv_load == 2) {
+      if (w == 16) return launch_gemv_w<NB, NORM, 16, 2>(p, epi, out_f32, s);
+      return launch_gemv_w<NB, NORM, 8, 2>(p, epi, out_f32, s);
+    }
+    if (w == 4) return launch_gemv_w<NB, NORM, 4, 0>(p, epi, out_f32, s);
+    if (w == 16) return launch_gemv_w<NB, NORM, 16, 0>(p, epi, out_f32, s);
+    return launch_gemv_w<NB, NORM, 8, 0>(p, epi, out_f32, s);
   } else {
-    return launch_gemv_w<NB, NORM, 8>(p, epi, out_f32, s);
+    return launch_gemv_w<NB, NORM, 8, 0>(p, epi, out_f32, s);
   }
 }
 
@@ -338,6 +355,12 @@ extern "C" int sr_gemm_skinny_packed_bf16(const void* A, int64_t lda, const floa
     return sr_gemm_skinny_bulk_bf16(A, lda, norm_weight, norm_eps, Wpacked, C, ldc, bias, residual, ldr, M, N, K, epilogue,
                                     out_dtype, stream);
   return gemm_skinny_impl(A, lda, Wpacked, K, C, ldc, bias, residual, ldr, M, N, K, epilogue, out_dtype, norm_weight, norm_eps, stream, 1);
+}
+
+extern "C" int sr_set_gemv_load(int flavour) {
+  if (flavour < 0 || flavour > 2) return SR_ERR_INVALID;
+  sr::g_gemv_load = flavour;
+  return SR_OK;
 }
 
 extern "C" int sr_set_gemv_warps(int warps) {

@@ -31,6 +31,7 @@ SYMBOLS = {
     "sr_gemm_skinny_norm_bf16": (c_int, [_P, c_int64, _P, c_float, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_gemm_skinny_packed_bf16": (c_int, [_P, c_int64, _P, c_float, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_set_gemv_warps": (c_int, [c_int]),
+    "sr_set_gemv_load": (c_int, [c_int]),
     "sr_set_gemv_bulk": (c_int, [c_int]),
     "sr_gemm_skinny_bulk_bf16": (c_int, [_P, c_int64, _P, c_float, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_attention_fwd": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int64, c_int, c_int, _P, c_int64, c_int,

@@ -25,14 +25,11 @@ def run(name, N, K, epi=lib.EPI_NONE, f32=False, norm=False, M=8, packed=False):
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (iters * copies)
     print(f"{name:28s} N={N:6d} K={K:5d} copies={copies:3d}: {us:7.2f} us  {nbytes / us / 1e6:6.2f} TB/s", flush=True)
-for bulk in (1, 0):
-    lib.load().sr_set_gemv_bulk(bulk)
-    print(f"=== packed layout, bulk engine = {bulk}")
-    run("qkv+norm", 2560, 2048, norm=True, packed=True)
-    run("o", 2048, 2048, packed=True)
+for ld in (0, 1, 2):
+    lib.load().sr_set_gemv_load(ld)
+    print(f"=== packed layout, load flavour = {ld}")
     run("down", 2048, 11008, packed=True)
     run("gate-up swiglu+norm", 22016, 2048, epi=lib.EPI_SWIGLU, norm=True, packed=True)
-    run("gate-up plain", 22016, 2048, packed=True)
     run("lm head f32", 151936, 2048, f32=True, packed=True)
-    run("lm head f32 norm", 151936, 2048, f32=True, norm=True, packed=True)
     run("K8192", 2752, 8192, packed=True)
+    run("down unpacked", 2048, 11008)

@@ -150,6 +150,12 @@ int sr_mrope_kv(void* qkv, int64_t ldqkv, const float* cosb, const float* sinb, 
 /* Greedy token: argmax over V per row (first index on ties). logits bf16 or fp32.  Two-stage (64 slices per row);
  * workspace: rows * 512 bytes of device scratch. */
 int sr_argmax_rows(const void* logits, int64_t ld, int dtype, int rows, int V, int64_t* out, void* workspace, void* stream);
+/* Sampling decode with the reference's rollout parameters (temperature -> top-k -> top-p; examples/infer/rlvr_megatron.yaml:89-95,
+ * roll/distributed/strategy/vllm_strategy.py:289-309): exact top-k (1 <= top_k <= 1024) by radix select, candidates ordered
+ * (value desc, index asc), nucleus keeps j iff the exclusive prefix mass < top_p, inverse-CDF pick with the caller's uniform
+ * uniforms[row*u_ld + *step] in [0,1) (step may be NULL = 0).  fp32 logits. */
+int sr_sample_topk_topp(const float* logits, int64_t ld, int rows, int V, const float* uniforms, int u_ld, const int32_t* step,
+                        float temperature, int top_k, float top_p, int64_t* out, void* stream);
 /* log_probs_from_logits / entropy_from_logits (roll/utils/functionals.py:193-205). Either output may be NULL. */
 int sr_logprob_entropy(const void* logits, int64_t ld, int dtype, int rows, int V, const int64_t* labels, float* logprob,
                        float* entropy, void* stream);

@@ -168,3 +168,27 @@ def pad_generate_output(output: torch.Tensor, sequence_length: int, pad_token_id
     if output.shape[1] >= sequence_length:
         return output[:, :sequence_length]
     return F.pad(output, (0, sequence_length - output.shape[1]), value=pad_token_id)
+
+
+# ----------------------------------------------------------------------------------------------
+# Sampling decode -- the reference's rollout parameters (examples/infer/rlvr_megatron.yaml:89-95: temperature 1.0,
+# top_p 0.8, top_k 100 -> vLLM SamplingParams, roll/distributed/strategy/vllm_strategy.py:289-309).  Restated with the HF
+# warper order temperature -> top-k -> top-p (TopPLogitsWarper removes tokens whose ASCENDING cumulative probability is
+# <= 1 - top_p, i.e. keeps descending token j iff the mass strictly before it is < top_p) and an inverse-CDF pick from a
+# given uniform so the result is deterministic.  float64.
+# ----------------------------------------------------------------------------------------------
+def sample_topk_topp_ref(logits: torch.Tensor, u: float, temperature: float, top_k: int, top_p: float):
+    """logits [V] -> (token, (cdf_lo, cdf_hi) of that token in the renormalised kept distribution, kept token ids)."""
+    x = logits.double().numpy()
+    order = np.lexsort((np.arange(len(x)), -x))[: min(top_k, len(x))]     # value desc, index asc
+    z = x[order] / temperature
+    p = np.exp(z - z.max())
+    p /= p.sum()
+    excl = np.cumsum(p) - p
+    keep = excl < top_p
+    keep[0] = True
+    q = p[keep] / p[keep].sum()
+    cdf = np.cumsum(q)
+    j = int(np.searchsorted(cdf, u, side="right"))
+    j = min(j, len(q) - 1)
+    return int(order[keep][j]), (float(cdf[j] - q[j]), float(cdf[j])), order[keep]

@@ -518,3 +518,157 @@ extern "C" int sr_mask_iou(const uint8_t* pred, const uint8_t* gt, int n_masks, 
   SR_CHECK_CUDA(cudaGetLastError());
   return SR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Sampling decode (the reference's rollout config: temperature 1.0, top-p 0.8, top-k 100,
+// examples/infer/rlvr_megatron.yaml:89-95 -> vLLM SamplingParams, roll/distributed/strategy/vllm_strategy.py:289-309;
+// HF order of warpers: temperature -> top-k -> top-p).  One CTA per row:
+//   1. exact top-k selection by a 3-round radix select over order-preserving keys (histograms in shared memory),
+//   2. candidates (value desc, index asc) bitonic-sorted in shared memory,
+//   3. softmax(value / T) over the candidates, nucleus cut: keep j iff exclusive prefix mass < top_p (>= 1 token),
+//   4. inverse-CDF pick with the caller-provided uniform u[row, *step]  (deterministic, graph-replayable).
+// ------------------------------------------------------------------------------------------------
+namespace sr {
+constexpr int SMP_THREADS = 1024;
+constexpr int SMP_MAXK = 1024;
+
+SR_DEVINL uint32_t order_key(float x) {  // larger float -> larger key
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(SMP_THREADS) sample_topk_topp_kernel(const float* __restrict__ logits, int64_t ld, int V,
+                                                                      const float* __restrict__ uniforms, int u_ld,
+                                                                      const int* __restrict__ step_ptr, float inv_temperature,
+                                                                      int top_k, float top_p, int64_t* __restrict__ out) {
+  __shared__ int hist[2048];
+  __shared__ float cval[SMP_MAXK];
+  __shared__ int cidx[SMP_MAXK];
+  __shared__ float cprob[SMP_MAXK];
+  __shared__ int s_bin, s_need, s_cnt;
+  __shared__ float s_red[32];
+  const float* row = logits + static_cast<int64_t>(blockIdx.x) * ld;
+  const int tid = threadIdx.x;
+  const int k = min(top_k, min(V, SMP_MAXK));
+  // ---- radix select: find the key of the k-th largest element ----
+  uint32_t prefix = 0, prefix_mask = 0;
+  int need = k;  // how many elements with (key & mask) == prefix we still need from the current bucket
+  const int shifts[3] = {21, 10, 0};
+  const int bits[3] = {11, 11, 10};
+  for (int r = 0; r < 3; ++r) {
+    const int nb = 1 << bits[r];
+    for (int i = tid; i < nb; i += SMP_THREADS) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < V; i += SMP_THREADS) {
+      const uint32_t key = order_key(row[i]);
+      if ((key & prefix_mask) == prefix) atomicAdd(&hist[(key >> shifts[r]) & (nb - 1)], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int acc = 0, b = nb - 1;
+      for (; b >= 0; --b) {
+        if (acc + hist[b] >= need) break;
+        acc += hist[b];
+      }
+      s_bin = b;
+      s_need = need - acc;
+    }
+    __syncthreads();
+    prefix |= static_cast<uint32_t>(s_bin) << shifts[r];
+    prefix_mask |= static_cast<uint32_t>(nb - 1) << shifts[r];
+    need = s_need;
+    __syncthreads();
+  }
+  const uint32_t kth_key = prefix;  // exact key of the k-th largest; `need` of the elements equal to it are taken (lowest index first)
+  // ---- collect candidates: all keys > kth_key, plus the `need` lowest-index elements equal to it ----
+  __shared__ int tie_idx[SMP_MAXK];
+  __shared__ int s_ties;
+  if (tid == 0) { s_cnt = 0; s_ties = 0; }
+  for (int i = tid; i < SMP_MAXK; i += SMP_THREADS) { cval[i] = -INFINITY; cidx[i] = 0x7fffffff; }
+  __syncthreads();
+  for (int i = tid; i < V; i += SMP_THREADS) {
+    const float x = row[i];
+    const uint32_t key = order_key(x);
+    if (key > kth_key) {
+      const int slot = atomicAdd(&s_cnt, 1);
+      cval[slot] = x;
+      cidx[slot] = i;
+    } else if (key == kth_key) {
+      const int slot = atomicAdd(&s_ties, 1);
+      if (slot < SMP_MAXK) tie_idx[slot] = i;  // > 1024 exact ties at the threshold: any 1024 of them (degenerate logits)
+    }
+  }
+  __syncthreads();
+  const int n_gt = s_cnt;
+  if (tid == 0) {
+    const int nt = min(s_ties, SMP_MAXK);
+    for (int t2 = 0; t2 < need; ++t2) {  // `need` smallest indices among the ties (nt is 1-2 in practice)
+      int best = -1;
+      for (int j = 0; j < nt; ++j)
+        if (tie_idx[j] != 0x7fffffff && (best < 0 || tie_idx[j] < tie_idx[best])) best = j;
+      if (best < 0) break;
+      cval[n_gt + t2] = row[tie_idx[best]];
+      cidx[n_gt + t2] = tie_idx[best];
+      tie_idx[best] = 0x7fffffff;
+    }
+  }
+  __syncthreads();
+  // ---- bitonic sort of SMP_MAXK (value desc, index asc); padding = (-inf, INT_MAX) sinks to the end ----
+  for (int size = 2; size <= SMP_MAXK; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int i = tid, j = i ^ stride;
+      if (j > i) {
+        const bool desc = (i & size) == 0;
+        const float vi = cval[i], vj = cval[j];
+        const int ii = cidx[i], ij = cidx[j];
+        const bool i_before_j = (vi > vj) || (vi == vj && ii < ij);
+        if (desc ? !i_before_j : i_before_j) {
+          cval[i] = vj; cval[j] = vi;
+          cidx[i] = ij; cidx[j] = ii;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- softmax over the k candidates at temperature T ----
+  const float vmax = cval[0];
+  const float e = (tid < k) ? __expf((cval[tid] - vmax) * inv_temperature) : 0.f;
+  const float tot = block_sum(e, s_red);
+  cprob[tid] = e / tot;
+  __syncthreads();
+  // inclusive prefix sum (Hillis-Steele over 1024 entries)
+  for (int off = 1; off < SMP_MAXK; off <<= 1) {
+    const float add = (tid >= off) ? cprob[tid - off] : 0.f;
+    __syncthreads();
+    cprob[tid] += add;
+    __syncthreads();
+  }
+  // nucleus: keep j iff exclusive prefix < top_p  (j = 0 always kept)
+  const float incl = cprob[tid];
+  const float p_j = e / tot;
+  const bool keep = (tid < k) && (tid == 0 || (incl - p_j) < top_p);
+  // kept set is a prefix [0, n_keep)
+  const float kept_mass = block_sum(keep ? p_j : 0.f, s_red);
+  const int n_keep = static_cast<int>(block_sum(keep ? 1.f : 0.f, s_red) + 0.5f);
+  const float u = uniforms[static_cast<int64_t>(blockIdx.x) * u_ld + (step_ptr ? *step_ptr : 0)] * kept_mass;
+  // pick the first kept j with inclusive prefix > u  (u == kept mass numerically -> last kept)
+  __shared__ int s_pick;
+  if (tid == 0) s_pick = 0x7fffffff;
+  __syncthreads();
+  if (keep && incl > u) atomicMin(&s_pick, tid);
+  __syncthreads();
+  if (tid == 0) out[blockIdx.x] = cidx[min(s_pick, n_keep - 1)];
+}
+}  // namespace sr
+
+extern "C" int sr_sample_topk_topp(const float* logits, int64_t ld, int rows, int V, const float* uniforms, int u_ld,
+                                   const int32_t* step, float temperature, int top_k, float top_p, int64_t* out, void* stream) {
+  SR_REQUIRE(logits && uniforms && out && rows >= 0 && V > 0, "sr_sample_topk_topp: bad args");
+  SR_REQUIRE(temperature > 0.f && top_k >= 1 && top_k <= sr::SMP_MAXK && top_p > 0.f && top_p <= 1.f,
+             "sr_sample_topk_topp: need temperature > 0, 1 <= top_k <= 1024, 0 < top_p <= 1");
+  if (rows == 0) return SR_OK;
+  sr::sample_topk_topp_kernel<<<rows, sr::SMP_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      logits, ld, V, uniforms, u_ld, step, 1.0f / temperature, top_k, top_p, out);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}

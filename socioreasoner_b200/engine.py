@@ -343,16 +343,23 @@ class Engine:
                 cache_row=torch.zeros((B,), dtype=torch.int32, device=dev), kv_len=torch.zeros((B,), dtype=torch.int32, device=dev),
                 pos3=torch.zeros((3, B), dtype=torch.int64, device=dev), kv_start=torch.zeros((B,), dtype=torch.int32, device=dev),
                 logits=torch.zeros((B, self.cfg.text.vocab_size), dtype=torch.float32, device=dev),
+                u=torch.zeros((B, T), dtype=torch.float32, device=dev),
                 x=torch.zeros((B, self.cfg.text.hidden_size), dtype=torch.bfloat16, device=dev),
             )
             self._dstate[key] = st
         return st
 
-    def _decode_step(self, st, cache: KVCache) -> None:
-        """One decode step, entirely on the device (graph-capturable): argmax -> append/advance -> embed -> 36 layers ->
+    def _pick_token(self, st, sampling) -> None:
+        if sampling is None:
+            lib.argmax_rows(st["logits"], out=st["nxt"])
+        else:  # (temperature, top_k, top_p): uniforms[b, step] drive the inverse-CDF pick
+            lib.sample_topk_topp(st["logits"], st["u"], sampling[0], sampling[1], sampling[2], step=st["step"], out=st["nxt"])
+
+    def _decode_step(self, st, cache: KVCache, sampling=None) -> None:
+        """One decode step, entirely on the device (graph-capturable): pick token -> append/advance -> embed -> 36 layers ->
         final norm + LM head -> st['logits']."""
         t = self.cfg.text
-        lib.argmax_rows(st["logits"], out=st["nxt"])
+        self._pick_token(st, sampling)
         lib.decode_advance(st["nxt"], st["tokens"], st["step"], st["row0"], st["len0"], st["pos0"], st["cache_row"],
                            st["kv_len"], st["pos3"])
         cos, sin = lib.mrope_table(st["pos3"], self.txt_inv_freq, t.mrope_section)
@@ -361,10 +368,12 @@ class Engine:
         self.final_logits(xo, torch.float32, out=st["logits"])
 
     def generate_greedy(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens: int,
-                        return_logits: bool = False, use_graph: Optional[bool] = None):
+                        return_logits: bool = False, use_graph: Optional[bool] = None, sampling=None, uniforms=None):
         """Greedy decode, EOS ignored, fixed ``max_new_tokens``.  Response positions continue from the
         last prompt position + 1 on all three axes (roll/utils/functionals.py:838-852).  The decode step is captured
         once per (batch, cache) into a CUDA graph and replayed (launch-bound loop, ~300 kernels per token).
+        ``sampling`` = (temperature, top_k, top_p) switches the per-step pick from argmax to the reference's sampling
+        config; ``uniforms`` [B, T] in [0,1) are the random numbers consumed (one per sample and step).
         Returns new tokens [B, T] (int64, device) and optionally fp32 logits [B, T, V]."""
         t = self.cfg.text
         T = max_new_tokens
@@ -383,6 +392,10 @@ class Engine:
         V = t.vocab_size
         st = self._decode_state(B, T)
         st["step"].zero_()
+        if sampling is not None:
+            sampling = (float(sampling[0]), int(sampling[1]), float(sampling[2]))
+            assert uniforms is not None and tuple(uniforms.shape) == (B, T)
+            st["u"].copy_(uniforms.to(self.device, torch.float32), non_blocking=True)
         st["kv_start"].copy_(torch.from_numpy(cache.kv_starts.astype(np.int32)), non_blocking=True)
         st["row0"].copy_(torch.from_numpy((cache.kv_starts + sp.lengths).astype(np.int32)), non_blocking=True)
         st["len0"].copy_(torch.from_numpy(sp.lengths.astype(np.int32)), non_blocking=True)
@@ -392,7 +405,7 @@ class Engine:
         if use_graph is None:
             use_graph = self.use_cuda_graph and not return_logits and lib.timeline is None
         if use_graph and T > 1:
-            gkey = (B, T, l_max)
+            gkey = (B, T, l_max, sampling)
             g = self._graphs.get(gkey)
             if g is None:
                 # warm-up outside capture (buffer allocation, function attributes), then restore the state it advanced
@@ -401,14 +414,14 @@ class Engine:
                 side.wait_stream(torch.cuda.current_stream())
                 l0 = lib.launch_count
                 with torch.cuda.stream(side):
-                    self._decode_step(st, cache)
+                    self._decode_step(st, cache, sampling)
                 self._decode_launches = lib.launch_count - l0
                 torch.cuda.current_stream().wait_stream(side)
                 st["logits"].copy_(keep["logits"]); st["step"].copy_(keep["step"])
                 g = torch.cuda.CUDAGraph()
                 l0 = lib.launch_count
                 with torch.cuda.graph(g):
-                    self._decode_step(st, cache)
+                    self._decode_step(st, cache, sampling)
                 lib.launch_count = l0  # capture launches nothing
                 st["logits"].copy_(keep["logits"]); st["step"].copy_(keep["step"])
                 self._graphs[gkey] = g
@@ -420,12 +433,12 @@ class Engine:
                 if return_logits:
                     all_logits[:, step] = st["logits"]
                 l0 = lib.launch_count
-                self._decode_step(st, cache)
+                self._decode_step(st, cache, sampling)
                 self._decode_launches = lib.launch_count - l0
         if return_logits:
             all_logits[:, T - 1] = st["logits"]
-        # the last token: argmax + append (no further forward needed)
-        lib.argmax_rows(st["logits"], out=st["nxt"])
+        # the last token: pick + append (no further forward needed)
+        self._pick_token(st, sampling)
         lib.decode_advance(st["nxt"], st["tokens"], st["step"], st["row0"], st["len0"], st["pos0"], st["cache_row"],
                            st["kv_len"], st["pos3"])
         cache.lengths = sp.lengths + T - 1

@@ -46,6 +46,7 @@ SYMBOLS = {
     "sr_vit_rope_split": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, _P]),
     "sr_mrope_kv": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, _P]),
     "sr_argmax_rows": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    "sr_sample_topk_topp": (c_int, [_P, c_int64, c_int, c_int, _P, c_int, _P, c_float, c_int, c_float, _P, _P]),
     "sr_logprob_entropy": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sr_decode_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
@@ -351,6 +352,21 @@ def decode_advance(nxt, tokens, step, row0, len0, pos0, cache_row, kv_len, pos3)
                                     len0.data_ptr(), pos0.data_ptr(), cache_row.data_ptr(), kv_len.data_ptr(), pos3.data_ptr(),
                                     tokens.shape[0], _stream()), "sr_decode_advance")
     launch_count += 1
+
+
+def sample_topk_topp(logits: torch.Tensor, uniforms: torch.Tensor, temperature: float, top_k: int, top_p: float,
+                     step: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """logits fp32 [rows, V]; uniforms fp32 [rows, T] (column *step, or 0) -> sampled token ids [rows]."""
+    global launch_count
+    _req(logits, torch.float32, "sample.logits"); _req(uniforms, torch.float32, "sample.uniforms")
+    rows, V = logits.shape
+    if out is None:
+        out = torch.empty((rows,), dtype=torch.int64, device=logits.device)
+    u2 = uniforms if uniforms.dim() == 2 else uniforms.view(rows, 1)
+    _check(load().sr_sample_topk_topp(logits.data_ptr(), logits.stride(0), rows, V, u2.data_ptr(), u2.stride(0), _ptr(step),
+                                      float(temperature), int(top_k), float(top_p), out.data_ptr(), _stream()), "sr_sample_topk_topp")
+    launch_count += 1
+    return out
 
 
 def logprob_entropy(logits: torch.Tensor, labels: Optional[torch.Tensor], want_entropy: bool = True):

@@ -129,14 +129,36 @@ class SocioReasonerB200ForConditionalGeneration:
                  temperature: float = 1.0, top_p: float = 1.0, top_k: int = 0, num_beams: int = 1,
                  repetition_penalty: float = 1.0, num_return_sequences: int = 1,
                  eos_token_id: Union[int, List[int], None] = None, pad_token_id: Optional[int] = None,
-                 ignore_eos: bool = False, **unused) -> torch.Tensor:
-        """Returns [b * num_return_sequences, S_in + max_new_tokens] like HF generate (prompt included).  Greedy
-        only: sampling (T=1, top-p 0.8, top-k 100 in the reference yaml) is the ranked "next" row."""
+                 ignore_eos: bool = False, seed: Optional[int] = None, **unused) -> torch.Tensor:
+        """Returns [b * num_return_sequences, S_in + max_new_tokens] like HF generate (prompt included).
+        ``do_sample=False`` (or temperature 0 / top_k 1): greedy.  ``do_sample=True``: temperature -> top-k -> top-p sampling
+        on the device (the reference's rollout config is T=1, top-p 0.8, top-k 100, examples/infer/rlvr_megatron.yaml:89-95);
+        1 <= top_k <= 1024 (top_k 0 = "disabled" is mapped to 1024).  ``num_return_sequences`` > 1 with sampling draws
+        independent continuations (the prompt batch is repeated, as HF does)."""
         if num_beams != 1 or repetition_penalty != 1.0:
             raise NotImplementedError("beam search / repetition penalty are not on the SocioSeg path")
-        if do_sample and not (temperature == 0 or top_k == 1):
-            raise NotImplementedError("sampling decode is not built yet (SURVEY.md 8f rank 2); use greedy")
-        new = self.engine.generate_greedy(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens)
+        sample = do_sample and not (temperature == 0 or top_k == 1)
+        if sample:
+            n = num_return_sequences
+            rep = lambda t_: t_.repeat_interleave(n, dim=0) if (t_ is not None and n > 1) else t_
+            ids_r, mask_r = rep(input_ids), rep(attention_mask)
+            pos_r = position_ids.repeat_interleave(n, dim=1 if position_ids.shape[0] == 3 else 0) if (position_ids is not None and n > 1) else position_ids
+            if n > 1 and pixel_values is not None:
+                per = (image_grid_thw[:, 0] * image_grid_thw[:, 1] * image_grid_thw[:, 2]).tolist()
+                if len(per) != input_ids.shape[0]:
+                    raise NotImplementedError("num_return_sequences > 1 needs exactly one image per prompt")
+                chunks = torch.split(pixel_values, per, dim=0)
+                pixel_values = torch.cat([c for c in chunks for _ in range(n)], 0)
+                image_grid_thw = image_grid_thw.repeat_interleave(n, dim=0)
+            g = torch.Generator(device=self.device)
+            g.manual_seed(int(seed) if seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
+            u = torch.rand((ids_r.shape[0], max_new_tokens), generator=g, device=self.device, dtype=torch.float32)
+            k = 1024 if top_k in (0, None) else min(int(top_k), 1024)
+            new = self.engine.generate_greedy(ids_r, mask_r, pos_r, pixel_values, image_grid_thw, max_new_tokens,
+                                              sampling=(float(temperature), k, float(top_p)), uniforms=u)
+            input_ids, num_return_sequences = ids_r, 1
+        else:
+            new = self.engine.generate_greedy(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens)
         new = new.to(input_ids.device)
         if not ignore_eos and eos_token_id is not None:
             eos = [eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id)

@@ -125,6 +125,27 @@ def test_generate_eos_padding(model, tiny_batch):
     assert torch.equal(out[0, :first + 1], raw[0, :first + 1]) and (out[0, first + 1:] == 3).all()
 
 
+def test_generate_sampling_reference_config(model, oracle_tiny, tiny_batch):
+    """do_sample with the reference's rollout parameters: reproducible for a seed, replays identically through the CUDA
+    graph, and every sampled token lies in the oracle's top-k / nucleus set of the teacher-forced oracle logits."""
+    b = tiny_batch
+    kw = dict(input_ids=b.input_ids, attention_mask=b.attention_mask, pixel_values=b.pixel_values, image_grid_thw=b.image_grid_thw,
+              max_new_tokens=5, do_sample=True, temperature=1.0, top_p=0.8, top_k=100, ignore_eos=True)
+    a = model.generate(seed=123, **kw)
+    c = model.generate(seed=123, **kw)
+    d = model.generate(seed=124, **kw)
+    assert torch.equal(a, c) and a.shape == (2, b.input_ids.shape[1] + 5)
+    assert not torch.equal(a, d)
+    # first sampled token vs the oracle's distribution at the last prompt position
+    ref = O.forward_logits(oracle_tiny, b).logits[:, -1].float()
+    for i in range(2):
+        _, _, kept = host_ref.sample_topk_topp_ref(ref[i], 0.5, 1.0, 100, 0.8)
+        wide = host_ref.sample_topk_topp_ref(ref[i], 0.5, 1.0, 130, 0.9)[2]   # bf16 logits may move a boundary candidate
+        assert int(a[i, b.input_ids.shape[1]]) in wide.tolist()
+    n2 = model.generate(seed=7, num_return_sequences=2, **kw)
+    assert n2.shape[0] == 4 and torch.equal(n2[0, :b.input_ids.shape[1]], n2[1, :b.input_ids.shape[1]])
+
+
 def test_ragged_left_padded_and_mixed_resolution_batch(model, oracle_tiny):
     """cfg-4 style mixed grids + ragged prompts, left padded like the reference collator; each sample must equal its
     single-sample run (padding / packing / window planning do not leak between samples)."""

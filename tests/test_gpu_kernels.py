@@ -318,6 +318,31 @@ def test_argmax_logprob_entropy():
     np.testing.assert_allclose(ent.cpu().numpy(), host_ref.entropy_from_logits(lg).numpy(), atol=2e-5)
 
 
+def test_sampling_topk_topp_against_oracle():
+    """temperature -> top-k -> top-p sampling (reference rollout config T=1, top-p 0.8, top-k 100) with given uniforms:
+    the picked token must be the oracle's inverse-CDF token (or, at an fp32 boundary, a neighbour whose CDF interval
+    touches u within 1e-5)."""
+    g = torch.Generator().manual_seed(0)
+    V, rows = 151936, 16
+    lg = torch.randn(rows, V, generator=g) * 2.0
+    lg[3, 100:110] = lg[3].max() + 0.5          # exact ties inside the top-k: lowest index first
+    lg[4] = torch.randn(V, generator=g) * 0.01  # flat row: nucleus keeps many candidates
+    u = torch.rand(rows, 3, generator=g)
+    u[5, :] = torch.tensor([0.0, 0.999999, 0.5])
+    for (T, k, p), col in (((1.0, 100, 0.8), 0), ((0.7, 50, 0.95), 1), ((1.3, 1024, 1.0), 2), ((1.0, 1, 0.8), 0)):
+        step = torch.tensor([col], dtype=torch.int32, device=DEV)
+        got = lib.sample_topk_topp(lg.to(DEV), u.to(DEV), T, k, p, step=step).cpu()
+        for r in range(rows):
+            ur = float(u[r, col])
+            tok, (lo, hi), kept = host_ref.sample_topk_topp_ref(lg[r], ur, T, k, p)
+            if int(got[r]) != tok:  # only legal at an fp32 rounding boundary of the CDF: a neighbouring kept candidate
+                kl = kept.tolist()
+                assert int(got[r]) in kl, (r, T, k, p)
+                assert abs(kl.index(int(got[r])) - kl.index(tok)) == 1 and min(abs(ur - lo), abs(ur - hi)) < 1e-4, (r, T, k, p, int(got[r]), tok)
+    # top_k = 1 is greedy
+    assert torch.equal(lib.sample_topk_topp(lg.to(DEV), u.to(DEV), 1.0, 1, 1.0).cpu(), lg.argmax(-1))
+
+
 # ---------------------------------------------------------------------------------------------------- mask epilogue / IoU
 @pytest.mark.parametrize("i,n_obj", [(0, 3), (1, 1), (2, 4)])
 def test_mask_epilogue_bit_exact_and_iou(i, n_obj):

@@ -89,6 +89,13 @@ int sr_gemm_skinny_bulk_bf16(const void* A, int64_t lda, const float* norm_weigh
                              int64_t ldc, const float* bias, const void* residual, int64_t ldr, int M, int N, int K,
                              int epilogue, int out_dtype, void* stream);
 int sr_set_gemv_bulk(int enabled);
+/* Split-K variant for long-K / narrow-N decode linears (down_proj: N=2048 gives only 128 CTAs): two CTAs per 16-row group
+ * each stream half of K, fp32 partials meet in `workspace` (sr_gemm_skinny_splitk_workspace_bytes(N) bytes, the leading
+ * ceil(N/16) int32 tickets zeroed once by the caller; the kernel re-arms them).  M <= 8, no fused norm, no SwiGLU. */
+int64_t sr_gemm_skinny_splitk_workspace_bytes(int N);
+int sr_gemm_skinny_packed_splitk_bf16(const void* A, int64_t lda, const void* Wpacked, void* C, int64_t ldc, const float* bias,
+                                      const void* residual, int64_t ldr, int M, int N, int K, int epilogue, int out_dtype,
+                                      void* workspace, void* stream);
 /* Tuning knob: warps per CTA of the skinny GEMM at M <= 8 (0 = default, 4 / 8 / 16). */
 int sr_set_gemv_warps(int warps);
 /* Tuning knob: weight-load instruction flavour of the skinny GEMM at M <= 8 (0 nc/no-allocate, 1 + L2::256B, 2 plain). */

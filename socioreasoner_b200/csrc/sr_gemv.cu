@@ -50,6 +50,9 @@ struct GemvParams {
   const __nv_bfloat16* residual;
   int64_t lda, ldw, ldc, ldr;
   int M, N, K;
+  int ksplit;           // 1, or 2: two CTAs per row group split K; partials meet in `ws` (ticket in `tickets`), NB=1 / no fused norm
+  float* ws;
+  int* tickets;
   int packed;           // 1: W is in the streaming layout [N/16][K/32][16 rows][32 k] (1 KB blocks, see sr_pack_skinny_weights)
   const float* norm_w;  // optional fused RMSNorm on A rows: A'[m,k] = A[m,k] * rsqrt(mean_k A^2 + eps) * norm_w[k]
   float norm_eps;
@@ -107,7 +110,10 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
     xrow[n] = p.A + static_cast<int64_t>(xok[n] ? m : 0) * p.lda + t * 8;
   }
 
-  const int nchunks = p.K >> 5;  // 32 k per chunk
+  const int nchunks_all = p.K >> 5;  // 32 k per chunk
+  const int cper = (nchunks_all + p.ksplit - 1) / p.ksplit;
+  const int c_begin = blockIdx.y * cper;
+  const int nchunks = min(nchunks_all, c_begin + cper);  // this CTA handles chunks [c_begin, nchunks)
   const int wstep = p.packed ? 512 : 32;  // elements between consecutive chunks of one row group
   // Rolling software pipeline over GV_UNROLL register slots: slot u is consumed (MMA) and immediately re-armed with the
   // chunk GV_WARPS*GV_UNROLL further on, so GV_UNROLL-1 chunk loads per thread stay in flight across iterations
@@ -155,10 +161,10 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   };
 #pragma unroll
   for (int u = 0; u < GV_UNROLL; ++u) {
-    const int c = warp + u * GV_WARPS;
+    const int c = c_begin + warp + u * GV_WARPS;
     if (c < nchunks) load_slot(u, c);
   }
-  for (int base = warp; base < nchunks; base += GV_WARPS * GV_UNROLL) {
+  for (int base = c_begin + warp; base < nchunks; base += GV_WARPS * GV_UNROLL) {
 #pragma unroll
     for (int u = 0; u < GV_UNROLL; ++u) {
       const int c = base + u * GV_WARPS;
@@ -199,6 +205,31 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
     }
     __syncthreads();
   }
+  // split-K: the two CTAs of a row group exchange fp32 partials through global memory; the second to arrive (ticket)
+  // adds its partner's partial and runs the epilogue, the first one leaves
+  const bool use_split = (NB == 1 && RG == 1 && !NORM && p.ksplit == 2);
+  float vsplit = 0.f;
+  if (use_split) {
+    __shared__ int s_ticket;
+    float* myws = p.ws + (static_cast<int64_t>(blockIdx.x) * 2 + blockIdx.y) * 128;
+    if (threadIdx.x < 128) {
+      const int b = threadIdx.x >> 4, f = threadIdx.x & 15;
+      float sacc = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < GV_WARPS; ++w8) sacc += red[w8][0][0][f * 8 + b];
+      vsplit = sacc;
+      myws[threadIdx.x] = sacc;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + blockIdx.x, 1);
+    __syncthreads();
+    if (s_ticket == 0) return;
+    __threadfence();
+    if (threadIdx.x < 128)
+      vsplit += __ldcg(p.ws + (static_cast<int64_t>(blockIdx.x) * 2 + (1 - blockIdx.y)) * 128 + threadIdx.x);
+    if (threadIdx.x == 0) p.tickets[blockIdx.x] = 0;  // re-arm
+  }
   // epilogue: thread -> (batch tile n, feature f, batch b); 128 outputs per batch tile
   for (int idx = threadIdx.x; idx < NB * 128; idx += GV_THREADS) {
     const int n = idx >> 7, e = idx & 127;
@@ -210,7 +241,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
       float s = 0.f;
 #pragma unroll
       for (int w8 = 0; w8 < GV_WARPS; ++w8) s += red[w8][r][n][f * 8 + b];
-      v[r] = NORM ? s * inv_rms[n][b] : s;
+      v[r] = use_split ? vsplit : (NORM ? s * inv_rms[n][b] : s);
     }
     if (m >= p.M) continue;
     if (EPI == SR_EPI_SWIGLU) {
@@ -246,7 +277,7 @@ static int launch_gemv_w(const GemvParams& p, int epi, int out_f32, cudaStream_t
     const int grid = (p.N + 31) / 32;
     SR_CHECK_CUDA(launch_pdl(gemv_kernel<2, NB, SR_EPI_SWIGLU, false, W, NORM, U2, LDV>, dim3(grid), dim3(GV_THREADS), 0, s, p));
   } else {
-    const int grid = (p.N + 15) / 16;
+    const dim3 grid((p.N + 15) / 16, p.ksplit);
     if (out_f32) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, true, W, NORM, U1, LDV>, dim3(grid), dim3(GV_THREADS), 0, s, p));
     else if (epi == SR_EPI_NONE) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_NONE, false, W, NORM, U1, LDV>, dim3(grid), dim3(GV_THREADS), 0, s, p));
     else if (epi == SR_EPI_RESIDUAL) SR_CHECK_CUDA(launch_pdl(gemv_kernel<1, NB, SR_EPI_RESIDUAL, false, W, NORM, U1, LDV>, dim3(grid), dim3(GV_THREADS), 0, s, p));
@@ -287,7 +318,8 @@ static int launch_gemv(const GemvParams& p, int epi, int out_f32, cudaStream_t s
 
 static int gemm_skinny_impl(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, const float* bias,
                             const void* residual, int64_t ldr, int M, int N, int K, int epilogue, int out_dtype,
-                            const float* norm_weight, float norm_eps, void* stream, int packed = 0) {
+                            const float* norm_weight, float norm_eps, void* stream, int packed = 0, int ksplit = 1,
+                            void* workspace = nullptr) {
   using namespace sr;
   SR_REQUIRE(A && W && C, "sr_gemm_skinny_bf16: null operand");
   SR_REQUIRE(M > 0 && M <= 32 && N > 0 && K > 0 && K % 32 == 0, "sr_gemm_skinny_bf16: need 0 < M <= 32, K %% 32 == 0 (M=%d K=%d)", M, K);
@@ -307,6 +339,16 @@ static int gemm_skinny_impl(const void* A, int64_t lda, const void* W, int64_t l
   p.norm_w = norm_weight;
   p.norm_eps = norm_eps;
   p.packed = packed;
+  p.ksplit = 1;
+  p.ws = nullptr;
+  p.tickets = nullptr;
+  if (ksplit == 2 && M <= 8 && norm_weight == nullptr && epilogue != SR_EPI_SWIGLU) {
+    SR_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sr_gemm_skinny split-K: workspace missing / unaligned");
+    const int groups = (N + 15) / 16;
+    p.ksplit = 2;
+    p.tickets = reinterpret_cast<int*>(workspace);
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((static_cast<size_t>(groups) * 4 + 15) / 16) * 16);
+  }
   SR_REQUIRE(!packed || N % 16 == 0, "sr_gemm_skinny_packed_bf16: N must be a multiple of 16");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int f32 = out_dtype == SR_DTYPE_F32;
@@ -367,4 +409,16 @@ extern "C" int sr_set_gemv_warps(int warps) {
   if (warps != 0 && warps != 4 && warps != 8 && warps != 16) return SR_ERR_INVALID;
   sr::g_gemv_warps = warps;
   return SR_OK;
+}
+
+extern "C" int64_t sr_gemm_skinny_splitk_workspace_bytes(int N) {
+  const int64_t groups = (N + 15) / 16;
+  return ((groups * 4 + 15) / 16) * 16 + groups * 2 * 128 * 4;
+}
+
+extern "C" int sr_gemm_skinny_packed_splitk_bf16(const void* A, int64_t lda, const void* Wpacked, void* C, int64_t ldc,
+                                                 const float* bias, const void* residual, int64_t ldr, int M, int N, int K,
+                                                 int epilogue, int out_dtype, void* workspace, void* stream) {
+  return gemm_skinny_impl(A, lda, Wpacked, K, C, ldc, bias, residual, ldr, M, N, K, epilogue, out_dtype, nullptr, 0.f, stream, 1, 2,
+                          workspace);
 }

@@ -30,6 +30,8 @@ SYMBOLS = {
     "sr_gemm_skinny_bf16": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_gemm_skinny_norm_bf16": (c_int, [_P, c_int64, _P, c_float, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "sr_gemm_skinny_packed_bf16": (c_int, [_P, c_int64, _P, c_float, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
+    "sr_gemm_skinny_splitk_workspace_bytes": (c_int64, [c_int]),
+    "sr_gemm_skinny_packed_splitk_bf16": (c_int, [_P, c_int64, _P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "sr_set_gemv_warps": (c_int, [c_int]),
     "sr_set_gemv_load": (c_int, [c_int]),
     "sr_set_gemv_bulk": (c_int, [c_int]),
@@ -185,10 +187,15 @@ def pack_skinny(w: torch.Tensor) -> torch.Tensor:
     return w.view(N // 16, 16, K // 32, 32).permute(0, 2, 1, 3).contiguous()
 
 
+_splitk_ws = {}
+
+
 def gemm_skinny_packed(a: torch.Tensor, wp: torch.Tensor, N: int, K: int, out: Optional[torch.Tensor] = None,
                        bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, epilogue: int = EPI_NONE,
-                       out_dtype=torch.bfloat16, norm_weight: Optional[torch.Tensor] = None, norm_eps: float = 1e-6) -> torch.Tensor:
-    """Decode-step linear on pre-packed weights (see ``pack_skinny``); M = a.shape[0] <= 32."""
+                       out_dtype=torch.bfloat16, norm_weight: Optional[torch.Tensor] = None, norm_eps: float = 1e-6,
+                       split_k: bool = False) -> torch.Tensor:
+    """Decode-step linear on pre-packed weights (see ``pack_skinny``); M = a.shape[0] <= 32.
+    ``split_k``: two CTAs per row group split K (long-K, narrow-N layers; M <= 8, no fused norm / SwiGLU)."""
     global launch_count
     _req(a, torch.bfloat16, "gemm_skinny_packed.a"); _req(wp, torch.bfloat16, "gemm_skinny_packed.w")
     M = a.shape[0]
@@ -198,6 +205,19 @@ def gemm_skinny_packed(a: torch.Tensor, wp: torch.Tensor, N: int, K: int, out: O
         out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
     if residual is not None:
         epilogue = EPI_RESIDUAL if epilogue == EPI_NONE else epilogue
+    if split_k and M <= 8 and norm_weight is None and epilogue != EPI_SWIGLU:
+        key = (a.device, N)
+        ws = _splitk_ws.get(key)
+        if ws is None:  # zeroed once (tickets); re-armed by the kernel
+            ws = _splitk_ws[key] = torch.zeros((load().sr_gemm_skinny_splitk_workspace_bytes(N),), dtype=torch.uint8, device=a.device)
+        with _Timed("gemm", (M, N, K, epilogue), 2.0 * M * N * K):
+            rc = load().sr_gemm_skinny_packed_splitk_bf16(a.data_ptr(), a.stride(0), wp.data_ptr(), out.data_ptr(), out.stride(0),
+                                                          _ptr(bias), _ptr(residual), residual.stride(0) if residual is not None else 0,
+                                                          M, N, K, epilogue, DT_F32 if out.dtype == torch.float32 else DT_BF16,
+                                                          ws.data_ptr(), _stream())
+        _check(rc, "sr_gemm_skinny_packed_splitk_bf16")
+        launch_count += 1
+        return out
     with _Timed("gemm", (M, N, K, epilogue), 2.0 * M * N * K):
         rc = load().sr_gemm_skinny_packed_bf16(a.data_ptr(), a.stride(0), _ptr(norm_weight), float(norm_eps), wp.data_ptr(),
                                                out.data_ptr(), out.stride(0), _ptr(bias), _ptr(residual),

@@ -3,7 +3,7 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from socioreasoner_b200 import lib
 dev = "cuda"
-def run(name, N, K, epi=lib.EPI_NONE, f32=False, norm=False, M=8, packed=False):
+def run(name, N, K, epi=lib.EPI_NONE, f32=False, norm=False, M=8, packed=False, split_k=False):
     nbytes = N * K * 2
     copies = max(2, int(400e6 // nbytes) + 1)
     Ws = [(torch.randn(N, K, device=dev) * 0.02).bfloat16() for _ in range(copies)]
@@ -13,7 +13,7 @@ def run(name, N, K, epi=lib.EPI_NONE, f32=False, norm=False, M=8, packed=False):
     nw = torch.ones(K, device=dev) if norm else None
     n_out = N // 2 if epi == lib.EPI_SWIGLU else N
     out = torch.empty(M, n_out, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
-    call = (lambda w: lib.gemm_skinny_packed(x, w, N, K, out=out, epilogue=epi, norm_weight=nw)) if packed else \
+    call = (lambda w: lib.gemm_skinny_packed(x, w, N, K, out=out, epilogue=epi, norm_weight=nw, split_k=split_k)) if packed else \
            (lambda w: lib.gemm(x, w, out=out, epilogue=epi, norm_weight=nw))
     for w in Ws: call(w)
     torch.cuda.synchronize()
@@ -25,11 +25,10 @@ def run(name, N, K, epi=lib.EPI_NONE, f32=False, norm=False, M=8, packed=False):
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (iters * copies)
     print(f"{name:28s} N={N:6d} K={K:5d} copies={copies:3d}: {us:7.2f} us  {nbytes / us / 1e6:6.2f} TB/s", flush=True)
-for ld in (0, 1, 2):
-    lib.load().sr_set_gemv_load(ld)
-    print(f"=== packed layout, load flavour = {ld}")
-    run("down", 2048, 11008, packed=True)
-    run("gate-up swiglu+norm", 22016, 2048, epi=lib.EPI_SWIGLU, norm=True, packed=True)
-    run("lm head f32", 151936, 2048, f32=True, packed=True)
-    run("K8192", 2752, 8192, packed=True)
-    run("down unpacked", 2048, 11008)
+print("=== split-K")
+run("down", 2048, 11008, packed=True)
+run("down split-K", 2048, 11008, packed=True, split_k=True)
+run("o", 2048, 2048, packed=True)
+run("o split-K", 2048, 2048, packed=True, split_k=True)
+run("K8192", 2752, 8192, packed=True)
+run("K8192 split-K", 2752, 8192, packed=True, split_k=True)

@@ -70,8 +70,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   float ssq[NB];
 #pragma unroll
   for (int n = 0; n < NB; ++n) ssq[n] = 0.f;
-  pdl_wait();
-  pdl_trigger();
+  pdl_trigger();  // let the next decode kernel become resident; it blocks in its own pdl_wait() until we are done
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int row0 = blockIdx.x * (16 * RG);
@@ -121,12 +120,14 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
   uint4 w[GV_UNROLL][RG][2];
   uint4 x[GV_UNROLL][NB];
   float4 nw0[GV_UNROLL], nw1[GV_UNROLL];
-  auto load_slot = [&](int u, int c) {
+  auto load_w = [&](int u, int c) {
 #pragma unroll
     for (int r = 0; r < RG; ++r) {
       w[u][r][0] = ld_stream_v4<LDV>(wrow[r][0] + static_cast<int64_t>(c) * wstep);
       w[u][r][1] = ld_stream_v4<LDV>(wrow[r][1] + static_cast<int64_t>(c) * wstep);
     }
+  };
+  auto load_x = [&](int u, int c) {
 #pragma unroll
     for (int n = 0; n < NB; ++n) x[u][n] = xok[n] ? *reinterpret_cast<const uint4*>(xrow[n] + c * 32) : make_uint4(0, 0, 0, 0);
     if (NORM) {
@@ -160,9 +161,17 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
       }
   };
 #pragma unroll
+  // The first wave of WEIGHT loads does not depend on the previous kernel: issue it before the programmatic-dependency
+  // wait so the HBM stream of this layer starts while the previous decode kernel is still draining.
   for (int u = 0; u < GV_UNROLL; ++u) {
     const int c = c_begin + warp + u * GV_WARPS;
-    if (c < nchunks) load_slot(u, c);
+    if (c < nchunks) load_w(u, c);
+  }
+  pdl_wait();  // activations / residual / output buffers belong to the previous kernel until here
+#pragma unroll
+  for (int u = 0; u < GV_UNROLL; ++u) {
+    const int c = c_begin + warp + u * GV_WARPS;
+    if (c < nchunks) load_x(u, c);
   }
   for (int base = c_begin + warp; base < nchunks; base += GV_WARPS * GV_UNROLL) {
 #pragma unroll
@@ -171,7 +180,7 @@ __global__ void __launch_bounds__(GV_WARPS * 32) gemv_kernel(const GemvParams p)
       if (c < nchunks) {
         compute_slot(u);
         const int cn = c + GV_WARPS * GV_UNROLL;
-        if (cn < nchunks) load_slot(u, cn);
+        if (cn < nchunks) { load_w(u, cn); load_x(u, cn); }
       }
     }
   }

@@ -11,6 +11,7 @@ the surface.  All device work goes through ``lib`` (C ABI); torch only allocates
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -91,6 +92,7 @@ class Engine:
         self._dstate: Dict[Tuple[int, int], dict] = {}
         self._decode_launches = 0
         self.use_cuda_graph = True
+        self.vit_narrow_block_n = int(os.environ.get("SR_VIT_N1280_BLOCK_N", "0"))  # 0 = auto (256)
         self.stage_events = None  # optional list: generate_greedy appends (stage, cuda event) pairs (bench.py stage split)
 
     @staticmethod
@@ -151,16 +153,17 @@ class Engine:
         ao = self._buf("vit_ao", (n, H, hd))
         act = self._buf("vit_act", (n, v.intermediate_padded))
         scale = hd ** -0.5
+        bn_narrow = self.vit_narrow_block_n  # tile width for the N = 1280 GEMMs (915 tiles of 128x256 = 6.2 waves on 148 SMs)
         for i, b in enumerate(W.vit_blocks):
             lib.rmsnorm(h, b.norm1, v.rms_norm_eps, out=y)
             lib.gemm(y, b.qkv_w, out=qkv, bias=b.qkv_b)
             lib.vit_rope_split(qkv, vp.cos, vp.sin, qp, kp, vt)
             ap = vp.full if i in v.fullatt_block_indexes else vp.window
             lib.attention(qp, kp, vt, ao, ap.tiles, ap.row_lo, ap.row_hi, scale, hd)
-            lib.gemm(ao.view(n, D), b.proj_w, out=h, bias=b.proj_b, residual=h)
+            lib.gemm(ao.view(n, D), b.proj_w, out=h, bias=b.proj_b, residual=h, block_n=bn_narrow)
             lib.rmsnorm(h, b.norm2, v.rms_norm_eps, out=y)
             lib.gemm(y, b.gu_w, out=act, bias=b.gu_b, epilogue=lib.EPI_SWIGLU)
-            lib.gemm(act, b.down_w, out=h, bias=b.down_b, residual=h)
+            lib.gemm(act, b.down_w, out=h, bias=b.down_b, residual=h, block_n=bn_narrow)
             if capture is not None:
                 capture.append(h.clone())
         lib.rmsnorm(h, W.merger_ln, v.rms_norm_eps, out=y)

@@ -164,6 +164,37 @@ def test_ragged_left_padded_and_mixed_resolution_batch(model, oracle_tiny):
         assert rel_rms(batched, single) < 4e-3   # not bit-exact: KV block boundaries of the varlen attention shift with packing
 
 
+def test_two_images_per_prompt_and_long_left_padding(model, oracle_tiny):
+    """The reference sends TWO images per prompt (map + satellite, rlvr_socioseg_vlm_pipeline_infer.py:74-81) and left-pads
+    prompts to prompt_length (collator.py:421-565); both must go through the packed / varlen internals unchanged."""
+    from oracle import host_ref
+    tok = O.CONFIGS["tiny"]["tokens"]
+    tiles = [O.synth_tile_uint8(20, 224), O.synth_tile_uint8(21, 336), O.synth_tile_uint8(22, 224), O.synth_tile_uint8(23, 224)]
+    pvs, thws = O.preprocess_tiles(tiles)
+    def prompt(a, b2, seed):
+        g = torch.Generator().manual_seed(seed)
+        m = lambda t: int(t[0, 0] * t[0, 1] * t[0, 2]) // 4
+        return torch.tensor([7001, 872, 198, tok["vision_start_token_id"]] + [tok["image_token_id"]] * m(thws[a]) + [tok["vision_end_token_id"]]
+                            + torch.randint(0, 7000, (5,), generator=g).tolist() + [tok["vision_start_token_id"]]
+                            + [tok["image_token_id"]] * m(thws[b2]) + [tok["vision_end_token_id"]] + torch.randint(0, 7000, (9,), generator=g).tolist() + [7002, 198])
+    prompts = [prompt(0, 1, 1), prompt(2, 3, 2)]
+    S = 512   # long left padding (a scaled-down prompt_length=4096)
+    ids = torch.zeros((2, S), dtype=torch.long); mask = torch.zeros((2, S), dtype=torch.long)
+    for i, pr in enumerate(prompts):
+        ids[i, S - len(pr):] = pr; mask[i, S - len(pr):] = 1
+    grid = torch.cat(thws, 0)
+    pos, _ = host_ref.get_rope_index(ids, grid, mask, image_token_id=tok["image_token_id"], vision_start_token_id=tok["vision_start_token_id"])
+    b = O.Batch(ids, mask, pos, torch.cat(pvs, 0), grid)
+    ref = O.forward_logits(oracle_tiny, b).logits
+    out = model(input_ids=ids, attention_mask=mask, position_ids=pos.transpose(0, 1).contiguous(), use_cache=False,
+                pixel_values=b.pixel_values, image_grid_thw=grid, force_vit_image=True).logits
+    keep = mask.bool()
+    assert out.shape == ref.shape and rel_rms(out[keep], ref[keep]) < 2e-2
+    assert out[~keep].abs().max().item() == 0
+    auto = model(input_ids=ids, attention_mask=mask, pixel_values=b.pixel_values, image_grid_thw=grid).logits   # positions derived internally
+    assert torch.equal(auto, out)
+
+
 def test_text_only_and_image_token_mismatch(model):
     ids = torch.randint(0, 7000, (2, 17))
     mask = torch.ones_like(ids)

@@ -132,7 +132,8 @@ def _dp_worker(rank, world, port, total, T, out_q):
         toks = torch.stack([torch.arange(T) + 100 * int(i) for i in mine]) if len(mine) else torch.zeros(0, T, dtype=torch.int64)
         ro.pack_slot(b_max, toks, torch.tensor([float(i) / 10 for i in mine]))
         res = ro.gather(b_max)
-        out_q.put((rank, res.tokens.clone(), res.masks.clone(), res.iou.clone()))
+        # plain numpy through the queue: torch tensors travel as shared-memory handles that die with the producer process
+        out_q.put((rank, res.tokens.numpy().copy(), res.masks.numpy().copy(), res.iou.numpy().copy()))
     finally:
         dist.destroy_process_group()
 
@@ -142,7 +143,7 @@ def test_dp_shard_and_gather_world2_gloo(total):
     world, T = 2, 3
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + total
+    port = 29600 + total + (os.getpid() % 200) * 10
     procs = [ctx.Process(target=_dp_worker, args=(r, world, port, total, T, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -151,6 +152,7 @@ def test_dp_shard_and_gather_world2_gloo(total):
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, toks, masks, iou in results:
+        toks, masks, iou = torch.from_numpy(toks), torch.from_numpy(masks), torch.from_numpy(iou)
         # every rank sees the whole batch in rank order == np.array_split order == the reference's DataProto.concat order
         assert toks.shape == (total, T) and masks.shape == (total, 8, 8)
         assert toks[:, 0].tolist() == [100 * i for i in range(total)]

@@ -174,6 +174,42 @@ int sr_decode_advance(const int64_t* next_tokens, int64_t* tokens, int T, int32_
                       const int32_t* len0, const int64_t* pos0, int32_t* cache_row, int32_t* kv_len, int64_t* pos3,
                       int batch, void* stream);
 
+/* ---- persistent decode step ------------------------------------------------------------------
+ * ONE launch for a whole decode step of M = batch <= 8 live sequences: all decoder layers (RMSNorm + q/k/v, M-RoPE + KV-cache
+ * append + attention over the cache, o-proj + residual, RMSNorm + gate/up + SwiGLU, down + residual; HF:762-827, 672-759,
+ * 611-624 with use_cache) + final norm + lm_head (HF:1385) -> fp32 logits.  Replaces the body of the reference's rollout
+ * decode loop (vLLM engine step, roll/distributed/strategy/vllm_strategy.py:114-141).  Persistent kernel, one CTA per SM
+ * (cooperative launch; env SR_DECODE_COOP=0 or sr_set_decode_persistent_coop(0) = plain launch): a producer warp streams
+ * the packed weights through a shared-memory ring with cp.async.bulk without ever draining between layers, consumer warps
+ * feed mma.sync and synchronise phases with a grid barrier.  HBM-bound (all decoder weights + LM head per launch).
+ *   layer_table: DEVICE array of n_layers sr_decode_layer (weights in the sr_gemm_skinny_packed_bf16 streaming layout).
+ *   x [batch, 2048] bf16 (ldx): residual stream, in = embedded tokens, out = last hidden state (pre final norm).
+ *   qkv/ao/act scratch: bf16 [batch, (n_q+2 n_kv)*128], [batch, n_q*128], [batch, intermediate] (dense rows).
+ *   cosb/sinb fp32 [batch, 64] (sr_mrope_table of this step's positions); cache_row/kv_start/kv_len as sr_decode_advance
+ *   writes them (kv_len INCLUDES the new token, cache_row = kv_start + kv_len - 1).
+ *   Kc [n_layers][rows, n_kv, 128], Vt [n_layers][n_kv*128, ldvt]: layer strides in ELEMENTS.
+ *   workspace: sr_decode_persistent_workspace_bytes() bytes, 16-byte aligned (barrier counter + tickets are reset by a
+ *   memset node enqueued by this call).  stop_after_phases: 0 = everything; k > 0 runs only the first k phases
+ *   (5 per layer: qkv, attention, o-proj, gate/up, down; then the LM head) -- bring-up / test aid.
+ * Hidden size is fixed at 2048 (= n_q_heads * 128); intermediate % 32 == 0; vocab % 16 == 0. */
+typedef struct sr_decode_layer {
+  const void* qkv_wp;   /* packed [ (n_q+2 n_kv)*128, 2048 ] */
+  const float* qkv_b;   /* [(n_q+2 n_kv)*128] or NULL */
+  const float* ln1;     /* input_layernorm weight [2048] */
+  const void* o_wp;     /* packed [2048, 2048] */
+  const float* ln2;     /* post_attention_layernorm weight [2048] */
+  const void* gu_wp;    /* packed [2*intermediate, 2048], rows interleaved 16 gate | 16 up */
+  const void* down_wp;  /* packed [2048, intermediate] */
+} sr_decode_layer;
+int64_t sr_decode_persistent_workspace_bytes(int batch, int n_kv_heads);
+int sr_set_decode_persistent_coop(int enabled);
+int sr_decode_step_persistent(const void* layer_table, int n_layers, const void* lm_head_packed, const float* final_norm,
+                              int vocab, void* x, int64_t ldx, void* qkv_scratch, void* ao_scratch, void* act_scratch,
+                              float* logits, int64_t ld_logits, const float* cosb, const float* sinb, const int32_t* cache_row,
+                              const int32_t* kv_start, const int32_t* kv_len, void* Kc, int64_t k_layer_stride, void* Vt,
+                              int64_t vt_layer_stride, int64_t ldvt, int batch, int n_q_heads, int n_kv_heads, int intermediate,
+                              float norm_eps, float scale, void* workspace, int stop_after_phases, void* stream);
+
 /* ---- mask epilogue + IoU -------------------------------------------------------------------- */
 /* seg_strategy.py:47-65: per object pick argmax(scores) of 3 candidates, bilinear up-sample h x w -> image_size^2
  * (align_corners=False), > 0, OR over objects, cv2.INTER_NEAREST resize to out_size^2, uint8 {0,1}. */

@@ -1,0 +1,777 @@
+// sr_decode_persistent.cu -- one decode step (all decoder layers + final norm + LM head) as ONE persistent kernel.
+//
+// What it replaces: the per-token body of the reference's rollout decode loop (vLLM engine step,
+// roll/distributed/strategy/vllm_strategy.py:114-141; HF eager equivalent: Qwen2_5_VLDecoderLayer x L with use_cache,
+// HF:762-827, 672-759, 611-624, final norm + lm_head HF:1385) -- here for M <= 8 live sequences.
+//
+// Why: at M = 8 the step is pure weight streaming (6.2 GB for the 3B model).  Launched as ~6 kernels per layer, every kernel
+// pays a ramp (first bytes arrive after one HBM latency) and a tail (cross-warp reduction + epilogue with no loads in flight)
+// -- measured 2.84 ms/token against ~1.0 ms of streaming at the measured HBM rate.  Here the HBM stream
+// never stops:
+//   * grid = one CTA per SM, resident for the whole step (cooperative launch);
+//   * warp 0 of every CTA is a PRODUCER: one thread walks the static schedule (layer -> {qkv, o, gate/up, down} -> this CTA's
+//     row groups -> 16 KB stages) and issues cp.async.bulk copies of the pre-packed weights ([N/16][K/32][16][32], 1 KB
+//     blocks) into a 10-stage / 160 KB shared-memory ring guarded by full/empty mbarriers.  Weights never depend on
+//     activations, so the producer runs AHEAD of the consumers across phase boundaries and grid barriers: while the CTAs
+//     synchronise, do attention or run an epilogue, ~24 MB of the next matrices are already in flight chip-wide;
+//   * warps 1-8 are CONSUMERS: per phase they stage the 8 activation rows in shared memory (RMSNorm fused in the staging,
+//     HF:57-71), read 16-byte weight fragments from the ring straight into mma.sync.m16n8k16 A operands (same k permutation
+//     as sr_gemv.cu: a 16 B load IS a fragment), reduce across warps, run the fused epilogue (bias / residual / SwiGLU);
+//   * phases are separated by a grid barrier (release-add + acquire-poll on one counter): qkv | rope + KV append + split-KV
+//     attention (flash-decoding, merge by the last CTA of a (sample, kv head)) | o-proj + residual | gate/up + SwiGLU |
+//     down + residual; then final norm + LM head (fp32 logits).
+// HBM-bound: algorithmic bytes per launch = all decoder weights + LM head (N*K*2 each) + KV cache of the live sequences.
+#include <stdlib.h>
+
+#include "sr_host.h"
+
+namespace sr {
+
+constexpr int DP_CONSUMERS = 8;
+constexpr int DP_CTHREADS = DP_CONSUMERS * 32;
+constexpr int DP_THREADS = DP_CTHREADS + 32;          // warp 0 = producer
+constexpr int DP_STAGE_BLOCKS = 16;                   // 1 KB weight blocks per ring stage
+constexpr int DP_STAGE_BYTES = DP_STAGE_BLOCKS * 1024;
+constexpr int DP_STAGES = 10;
+constexpr int DP_H = 2048;                            // staged activation width (hidden size = n_q_heads * 128)
+constexpr int DP_XS_STRIDE = DP_H * 2 + 64;           // bytes per staged row (+64 B: conflict-free 16 B fragment reads)
+constexpr int DP_XPF = 3;                             // activation prefetch distance (stages) on the L2 path
+constexpr int DP_GMAX = 8;                            // query heads per kv head (max)
+constexpr int DP_KEYS = 128;                          // keys per attention pass
+constexpr int DP_NS_MAX = 32;                         // max key splits
+constexpr int DP_PART = DP_GMAX * 128 + 2 * DP_GMAX;  // floats per attention partial (o, m, l)
+
+// shared-memory carve-up (bytes, from a 1024-aligned base)
+constexpr int DP_OFF_RING = 0;
+constexpr int DP_OFF_XS = DP_STAGES * DP_STAGE_BYTES;                 // staged activations; aliased by attention scratch
+constexpr int DP_XS_BYTES = 8 * DP_XS_STRIDE;                         // 33280
+constexpr int DP_OFF_RED = DP_OFF_XS + DP_XS_BYTES;                   // [2][8 warps][2 rg][128] fp32
+constexpr int DP_RED_BYTES = 2 * DP_CONSUMERS * 2 * 128 * 4;          // 16384
+constexpr int DP_OFF_BAR = DP_OFF_RED + DP_RED_BYTES;
+constexpr int DP_SMEM_BYTES = DP_OFF_BAR + 2 * DP_STAGES * 8 + 64 + 1024;  // + alignment slack
+
+// attention scratch inside the xs region (floats)
+constexpr int DPA_SQ = 0;                              // [8][128]
+constexpr int DPA_SP = DPA_SQ + DP_GMAX * 128;         // [8][128]
+constexpr int DPA_RED = DPA_SP + DP_GMAX * DP_KEYS;    // [8 warps][8]
+constexpr int DPA_M = DPA_RED + 8 * DP_GMAX;           // [8]
+constexpr int DPA_L = DPA_M + DP_GMAX;
+constexpr int DPA_ALPHA = DPA_L + DP_GMAX;
+constexpr int DPA_MS = DPA_ALPHA + DP_GMAX;            // [32][8]
+constexpr int DPA_LS = DPA_MS + DP_NS_MAX * DP_GMAX;
+constexpr int DPA_F = DPA_LS + DP_NS_MAX * DP_GMAX;
+constexpr int DPA_LL = DPA_F + DP_NS_MAX * DP_GMAX;    // [8]
+constexpr int DPA_FLAG = DPA_LL + DP_GMAX;             // 1 int
+constexpr int DPA_END = DPA_FLAG + 4;
+static_assert(DPA_END * 4 <= DP_XS_BYTES, "attention scratch must fit in the staged-activation region");
+
+struct DpLayer {  // == sr_decode_layer (include/socioreasoner_b200.h)
+  const __nv_bfloat16* qkv_wp;
+  const float* qkv_b;
+  const float* ln1;
+  const __nv_bfloat16* o_wp;
+  const float* ln2;
+  const __nv_bfloat16* gu_wp;
+  const __nv_bfloat16* down_wp;
+};
+
+struct DpParams {
+  const DpLayer* layers;
+  int n_layers;
+  const __nv_bfloat16* lm_head_p;
+  const float* final_norm;
+  int vocab;
+  __nv_bfloat16* x;
+  int64_t ldx;
+  __nv_bfloat16* qkv;      // [B, (nq + 2 nkv) * 128]
+  __nv_bfloat16* ao;       // [B, nq * 128]
+  __nv_bfloat16* act;      // [B, I]
+  float* logits;
+  int64_t ld_logits;
+  const float* cosb;       // [B, 64]
+  const float* sinb;
+  const int* cache_row;
+  const int* kv_start;
+  const int* kv_len;
+  __nv_bfloat16* Kc;       // [n_layers][rows, nkv, 128]
+  int64_t k_layer_stride;
+  __nv_bfloat16* Vt;       // [n_layers][nkv*128, ldvt]
+  int64_t vt_layer_stride;
+  int64_t ldvt;
+  int B, nq, nkv, I;
+  float eps, scale_log2;
+  float* attn_ws;
+  int* attn_tickets;
+  int ns;
+  unsigned int* grid_bar;  // zero before launch
+  int stop_after;          // debug: run only the first `stop_after` phases (<= 0: all)
+};
+
+SR_DEVINL void dp_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+SR_DEVINL void dp_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+SR_DEVINL void dp_cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // consumer warps only
+SR_DEVINL uint4 dp_ldcg(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+
+#ifndef SR_GRIDBAR_SPIN_LIMIT
+#define SR_GRIDBAR_SPIN_LIMIT (1u << 23)
+#endif
+// Grid barrier for the consumer threads of all CTAs: every thread's global stores are fenced, one thread per CTA does a
+// release-add and polls with acquire loads until all CTAs of this generation have arrived.  Bounded: a broken schedule
+// traps (CUDA error through the C ABI) instead of hanging the GPU.
+SR_DEVINL void dp_grid_barrier(unsigned int* ctr, unsigned int target) {
+  __threadfence();
+  dp_cbar();
+  if (threadIdx.x == 32) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+    unsigned int v = 0, spins = 0;
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (v >= target) break;
+      if (++spins > SR_GRIDBAR_SPIN_LIMIT) {
+        printf("sr: grid barrier timeout block=%d have=%u want=%u\n", blockIdx.x, v, target);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  dp_cbar();
+}
+
+struct DpRing {
+  uint8_t* data;
+  uint64_t* full;
+  uint64_t* empty;
+  int slot;
+  uint32_t phase;
+  SR_DEVINL void advance() {
+    if (++slot == DP_STAGES) { slot = 0; phase ^= 1; }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ producer
+// Streams this CTA's units of one packed matrix: unit u = RG consecutive 16-row groups; stage = 16 blocks of 1 KB
+// (RG = 1: 16 k-chunks of the group; RG = 2: 8 k-chunks of each of the two groups, second group at +8 KB).
+template <int RG>
+SR_DEVINL void dp_produce(DpRing& r, const __nv_bfloat16* Wp, int n_units, int nchunks) {
+  constexpr int CPS = DP_STAGE_BLOCKS / RG;
+  const int nst = (nchunks + CPS - 1) / CPS;
+  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    for (int st = 0; st < nst; ++st) {
+      mbar_wait(&r.empty[r.slot], r.phase ^ 1);
+      const int nch = min(CPS, nchunks - st * CPS);
+      mbar_arrive_expect_tx(&r.full[r.slot], static_cast<uint32_t>(RG * nch * 1024));
+#pragma unroll
+      for (int g = 0; g < RG; ++g) {
+        const __nv_bfloat16* src = Wp + (static_cast<int64_t>(u * RG + g) * nchunks + st * CPS) * 512;
+        dp_bulk_g2s(r.data + r.slot * DP_STAGE_BYTES + g * (CPS * 1024), src, static_cast<uint32_t>(nch * 1024), &r.full[r.slot]);
+      }
+      r.advance();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ consumers
+// Stage M (<= 8) rows of width DP_H into shared memory, warp cw <-> row cw, optional RMSNorm (y = w * x * rsqrt(mean x^2 + eps),
+// one rounding to bf16 -- the arithmetic of rmsnorm_kernel in sr_elementwise.cu).  Rows >= M are zero.
+template <bool NORM>
+SR_DEVINL void dp_stage_rows(uint8_t* xs, const __nv_bfloat16* src, int64_t ld, int M, const float* nw, float eps, int cw,
+                             int lane) {
+  constexpr int NV = DP_H / 256;  // 16 B vectors per lane
+  uint4 v[NV];
+  const bool ok = cw < M;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    v[i] = ok ? dp_ldcg(src + static_cast<int64_t>(cw) * ld + (lane + 32 * i) * 8) : make_uint4(0, 0, 0, 0);
+  if (NORM) {
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+        ss += a * a + b * b;
+      }
+    }
+    ss = warp_sum(ss);
+    const float inv = rsqrtf(ss / static_cast<float>(DP_H) + eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(nw + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(nw + c + 4));
+      uint4 o;
+      o.x = pack_bf16x2(bf16_lo(v[i].x) * inv * w0.x, bf16_hi(v[i].x) * inv * w0.y);
+      o.y = pack_bf16x2(bf16_lo(v[i].y) * inv * w0.z, bf16_hi(v[i].y) * inv * w0.w);
+      o.z = pack_bf16x2(bf16_lo(v[i].z) * inv * w1.x, bf16_hi(v[i].z) * inv * w1.y);
+      o.w = pack_bf16x2(bf16_lo(v[i].w) * inv * w1.z, bf16_hi(v[i].w) * inv * w1.w);
+      v[i] = o;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) *reinterpret_cast<uint4*>(xs + cw * DP_XS_STRIDE + (lane + 32 * i) * 16) = v[i];
+}
+
+// K loop of one unit with the activations staged in shared memory (K = DP_H).
+template <int RG>
+SR_DEVINL void dp_consume_staged(DpRing& r, int nchunks, const uint8_t* xs, float (&acc)[RG][4], int cw, int lane) {
+  constexpr int CPS = DP_STAGE_BLOCKS / RG;
+  const int g = lane >> 2, t = lane & 3;
+  const int nst = (nchunks + CPS - 1) / CPS;
+  const uint8_t* xrow = xs + g * DP_XS_STRIDE + t * 16;
+  for (int st = 0; st < nst; ++st) {
+    mbar_wait(&r.full[r.slot], r.phase);
+    const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
+    if (RG == 2) {
+      const int c = st * CPS + cw;
+      if (c < nchunks) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
+#pragma unroll
+        for (int q = 0; q < RG; ++q) {
+          const uint8_t* blk = stage + q * (CPS * 1024) + cw * 1024;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
+          dp_mma(acc[q], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
+          dp_mma(acc[q], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = st * CPS + cw + 8 * j;
+        if (c < nchunks) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
+          const uint8_t* blk = stage + (cw + 8 * j) * 1024;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
+          dp_mma(acc[0], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
+          dp_mma(acc[0], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&r.empty[r.slot]);
+    r.advance();
+  }
+}
+
+// K loop of one unit (RG = 1) with the activations read from global memory / L2 (long K: the down projection).
+SR_DEVINL void dp_consume_l2(DpRing& r, int nchunks, const __nv_bfloat16* xg, int64_t ldx, int M, float (&acc)[1][4], int cw,
+                             int lane) {
+  constexpr int CPS = DP_STAGE_BLOCKS;
+  const int g = lane >> 2, t = lane & 3;
+  const int nst = (nchunks + CPS - 1) / CPS;
+  const bool xok = g < M;
+  const __nv_bfloat16* xrow = xg + static_cast<int64_t>(xok ? g : 0) * ldx + t * 8;
+  uint4 xq[DP_XPF][2];
+  auto load_x = [&](int i, int st) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = st * CPS + cw + 8 * j;
+      xq[i][j] = (xok && c < nchunks) ? dp_ldcg(xrow + c * 32) : make_uint4(0, 0, 0, 0);
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < DP_XPF; ++i) load_x(i, i);
+  for (int st0 = 0; st0 < nst; st0 += DP_XPF) {
+#pragma unroll
+    for (int i = 0; i < DP_XPF; ++i) {
+      const int st = st0 + i;
+      if (st < nst) {
+        mbar_wait(&r.full[r.slot], r.phase);
+        const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = st * CPS + cw + 8 * j;
+          if (c < nchunks) {
+            const uint4 xv = xq[i][j];
+            const uint8_t* blk = stage + (cw + 8 * j) * 1024;
+            const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
+            const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
+            dp_mma(acc[0], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
+            dp_mma(acc[0], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&r.empty[r.slot]);
+        load_x(i, st + DP_XPF);
+        r.advance();
+      }
+    }
+  }
+}
+
+enum { DP_EPI_BIAS = 0, DP_EPI_RESIDUAL = 1, DP_EPI_SWIGLU = 2, DP_EPI_F32 = 3 };
+
+// One GEMV phase: all units of this CTA.  `staged`: activations come from xs (K = DP_H), else from xg (L2).
+template <int RG, int EPI, bool STAGED>
+SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t* xs, const __nv_bfloat16* xg, int64_t ldxg,
+                             int M, float* red, int& red_par, const float* bias, __nv_bfloat16* out_bf, float* out_f32,
+                             int64_t ldo, int cw, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int ct = threadIdx.x - 32;
+  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    float acc[RG][4];
+#pragma unroll
+    for (int q = 0; q < RG; ++q)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
+    if constexpr (STAGED) {
+      dp_consume_staged<RG>(r, nchunks, xs, acc, cw, lane);
+    } else {
+      static_assert(STAGED || RG == 1, "the L2 activation path handles single row groups");
+      dp_consume_l2(r, nchunks, xg, ldxg, M, acc, cw, lane);
+    }
+    // cross-warp reduction: C fragment (feature g | g+8, batch 2t | 2t+1) -> red[par][warp][q][feature*8 + batch]
+    float* rp = red + red_par * (DP_CONSUMERS * 2 * 128);
+#pragma unroll
+    for (int q = 0; q < RG; ++q) {
+      float* d = rp + (cw * 2 + q) * 128;
+      d[g * 8 + 2 * t] = acc[q][0];
+      d[g * 8 + 2 * t + 1] = acc[q][1];
+      d[(g + 8) * 8 + 2 * t] = acc[q][2];
+      d[(g + 8) * 8 + 2 * t + 1] = acc[q][3];
+    }
+    dp_cbar();
+    if (ct < 128) {
+      const int b = ct >> 4, f = ct & 15;  // consecutive threads -> consecutive features
+      float v[RG];
+#pragma unroll
+      for (int q = 0; q < RG; ++q) {
+        float s = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < DP_CONSUMERS; ++w8) s += rp[(w8 * 2 + q) * 128 + f * 8 + b];
+        v[q] = s;
+      }
+      if (b < M) {
+        if (EPI == DP_EPI_SWIGLU) {
+          const float gate = v[0], up = v[RG - 1];
+          const float o = (gate / (1.0f + __expf(-gate))) * up;
+          out_bf[static_cast<int64_t>(b) * ldo + u * 16 + f] = __float2bfloat16(o);
+        } else {
+          const int col = u * 16 + f;
+          float o = v[0];
+          if (EPI == DP_EPI_BIAS && bias != nullptr) o += __ldg(bias + col);
+          if (EPI == DP_EPI_RESIDUAL) {
+            const unsigned short rbits = __ldcg(reinterpret_cast<const unsigned short*>(out_bf + static_cast<int64_t>(b) * ldo + col));
+            o += __uint_as_float(static_cast<uint32_t>(rbits) << 16);
+          }
+          if (EPI == DP_EPI_F32) out_f32[static_cast<int64_t>(b) * ldo + col] = o;
+          else out_bf[static_cast<int64_t>(b) * ldo + col] = __float2bfloat16(o);
+        }
+      }
+    }
+    red_par ^= 1;  // the next unit writes the other buffer; its barrier orders this unit's reads before the reuse after it
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention phase
+// M-RoPE (mcore_adapter/.../modeling_qwen2_5_vl.py:21-41) on q and the new k, KV-cache append, split-KV attention of the
+// new token against the cache (the arithmetic of mrope_kv_kernel + decode_attn_kernel; see sr_tail.cu for the per-pass
+// formulation).  Unit = (sample, kv head, key split); the split that owns the newest key appends it to the cache first.
+SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, float* sm) {
+  const int ct = threadIdx.x - 32, lane = ct & 31, warp = ct >> 5;
+  const int G = p.nq / p.nkv, ns = p.ns;
+  float* sq = sm + DPA_SQ;
+  float* sp = sm + DPA_SP;
+  float* s_red = sm + DPA_RED;
+  float* s_m = sm + DPA_M;
+  float* s_l = sm + DPA_L;
+  float* s_alpha = sm + DPA_ALPHA;
+  float* m_ms = sm + DPA_MS;
+  float* m_ls = sm + DPA_LS;
+  float* m_f = sm + DPA_F;
+  float* m_L = sm + DPA_LL;
+  int* s_flag = reinterpret_cast<int*>(sm + DPA_FLAG);
+  __nv_bfloat16* Kc = p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride;
+  __nv_bfloat16* Vt = p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride;
+  const int ldq = (p.nq + 2 * p.nkv) * 128;
+  const int n_units = p.B * p.nkv * ns;
+  const int half = ct >> 7;   // heads [half*4, half*4+4)
+  const int kk = ct & 127;    // key within the pass / output dim
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int split = unit % ns, bk = unit / ns;
+    const int kvh = bk % p.nkv, b = bk / p.nkv;
+    dp_cbar();  // scratch reuse between units (and after the staged-activation use of this region)
+    const int start = __ldg(p.kv_start + b), len = __ldcg(p.kv_len + b), crow = __ldcg(p.cache_row + b);
+    int per = (len + ns - 1) / ns;
+    per = (per + 7) & ~7;  // V^T vectors are 8 keys wide
+    const int k_begin = split * per, k_end = min(len, k_begin + per);
+    const __nv_bfloat16* qrow = p.qkv + static_cast<int64_t>(b) * ldq;
+    // roped, scaled q of the G heads -> sq (rounded through bf16 like the cached path)
+    for (int i = ct; i < G * 64; i += DP_CTHREADS) {
+      const int h = i >> 6, d = i & 63;
+      const float c = __ldcg(p.cosb + b * 64 + d), s = __ldcg(p.sinb + b * 64 + d);
+      const __nv_bfloat16* qh = qrow + (kvh * G + h) * 128;
+      const float x1 = __bfloat162float(__ldcg(reinterpret_cast<const __nv_bfloat16*>(qh + d)));
+      const float x2 = __bfloat162float(__ldcg(reinterpret_cast<const __nv_bfloat16*>(qh + d + 64)));
+      sq[h * 128 + d] = __bfloat162float(__float2bfloat16(x1 * c - x2 * s)) * p.scale_log2;
+      sq[h * 128 + d + 64] = __bfloat162float(__float2bfloat16(x2 * c + x1 * s)) * p.scale_log2;
+    }
+    if (ct < DP_GMAX) { s_m[ct] = -INFINITY; s_l[ct] = 0.f; }
+    // the split that owns the newest key (index len-1 = cache row crow) appends roped k and v for this kv head
+    if (len > 0 && (len - 1) / per == split) {
+      if (ct < 64) {
+        const float c = __ldcg(p.cosb + b * 64 + ct), s = __ldcg(p.sinb + b * 64 + ct);
+        const __nv_bfloat16* kh = qrow + (p.nq + kvh) * 128;
+        const float x1 = __bfloat162float(__ldcg(kh + ct)), x2 = __bfloat162float(__ldcg(kh + ct + 64));
+        __nv_bfloat16* kd = Kc + (static_cast<int64_t>(crow) * p.nkv + kvh) * 128;
+        kd[ct] = __float2bfloat16(x1 * c - x2 * s);
+        kd[ct + 64] = __float2bfloat16(x2 * c + x1 * s);
+      } else if (ct < 64 + 128) {
+        const int d = ct - 64;
+        Vt[static_cast<int64_t>(kvh * 128 + d) * p.ldvt + crow] = __ldcg(qrow + (p.nq + p.nkv + kvh) * 128 + d);
+      }
+      __threadfence();
+    }
+    float o_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    dp_cbar();
+    for (int p0 = k_begin; p0 < k_end; p0 += DP_KEYS) {
+      const int nk = min(DP_KEYS, k_end - p0);
+      float sc4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (kk < nk) {
+        const __nv_bfloat16* kr = Kc + (static_cast<int64_t>(start + p0 + kk) * p.nkv + kvh) * 128;
+        uint4 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = dp_ldcg(kr + i * 8);
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          const int h = half * 4 + hh;
+          if (h < G) {
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 q0 = *reinterpret_cast<const float4*>(&sq[h * 128 + i * 8]);
+              const float4 q1 = *reinterpret_cast<const float4*>(&sq[h * 128 + i * 8 + 4]);
+              d += bf16_lo(v[i].x) * q0.x + bf16_hi(v[i].x) * q0.y + bf16_lo(v[i].y) * q0.z + bf16_hi(v[i].y) * q0.w +
+                   bf16_lo(v[i].z) * q1.x + bf16_hi(v[i].z) * q1.y + bf16_lo(v[i].w) * q1.z + bf16_hi(v[i].w) * q1.w;
+            }
+            sc4[hh] = d;
+          }
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const float m = warp_max(sc4[hh]);
+        if (lane == 0) s_red[warp * DP_GMAX + hh] = m;  // warps 0-3 hold half 0, warps 4-7 half 1
+      }
+      dp_cbar();
+      if (ct < G) {
+        const int hf = ct >> 2, hh = ct & 3;
+        float m = s_m[ct];
+        for (int w = 0; w < 4; ++w) m = fmaxf(m, s_red[(hf * 4 + w) * DP_GMAX + hh]);
+        const float m_use = (m == -INFINITY) ? 0.f : m;
+        s_alpha[ct] = exp2f(s_m[ct] - m_use);
+        s_m[ct] = m;
+      }
+      dp_cbar();
+      float ps[4];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const int h = half * 4 + hh;
+        float pv = 0.f;
+        if (h < G && kk < nk) {
+          const float m = s_m[h];
+          pv = exp2f(sc4[hh] - ((m == -INFINITY) ? 0.f : m));
+        }
+        if (h < G) sp[h * DP_KEYS + kk] = pv;
+        ps[hh] = warp_sum(pv);
+        if (lane == 0) s_red[warp * DP_GMAX + hh] = ps[hh];
+      }
+      dp_cbar();
+      if (ct < G) {
+        const int hf = ct >> 2, hh = ct & 3;
+        float l = 0.f;
+        for (int w = 0; w < 4; ++w) l += s_red[(hf * 4 + w) * DP_GMAX + hh];
+        s_l[ct] = s_l[ct] * s_alpha[ct] + l;
+      }
+      const __nv_bfloat16* vrow = Vt + static_cast<int64_t>(kvh * 128 + kk) * p.ldvt + start + p0;
+      const int nvec = (nk + 7) >> 3;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int i = 0; i < nvec; ++i) {
+        const uint4 u = dp_ldcg(vrow + i * 8);
+        const float vv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          const int h = half * 4 + hh;
+          if (h < G) {
+            const float4 p0v = *reinterpret_cast<const float4*>(&sp[h * DP_KEYS + i * 8]);
+            const float4 p1v = *reinterpret_cast<const float4*>(&sp[h * DP_KEYS + i * 8 + 4]);
+            acc[hh] += vv[0] * p0v.x + vv[1] * p0v.y + vv[2] * p0v.z + vv[3] * p0v.w + vv[4] * p1v.x + vv[5] * p1v.y +
+                       vv[6] * p1v.z + vv[7] * p1v.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const int h = half * 4 + hh;
+        if (h < G) o_acc[hh] = o_acc[hh] * s_alpha[h] + acc[hh];
+      }
+      dp_cbar();  // sp / s_red / s_alpha are reused by the next pass
+    }
+    // publish this split's un-normalised partial (o, m, l)
+    float* wo = p.attn_ws + (static_cast<int64_t>(bk) * ns + split) * DP_PART;
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = half * 4 + hh;
+      if (h < G) wo[h * 128 + kk] = o_acc[hh];
+    }
+    if (ct < G) {
+      wo[DP_GMAX * 128 + ct] = s_m[ct];
+      wo[DP_GMAX * 128 + DP_GMAX + ct] = s_l[ct];
+    }
+    __threadfence();
+    dp_cbar();
+    if (ct == 0) {
+      const int ticket = atomicAdd(p.attn_tickets + bk, 1);
+      *s_flag = (ticket == ns - 1) ? 1 : 0;
+    }
+    dp_cbar();
+    if (*s_flag == 0) continue;
+    __threadfence();
+    // merge (last CTA of this (sample, kv head)); all loads issued in parallel
+    const float* wb = p.attn_ws + static_cast<int64_t>(bk) * ns * DP_PART;
+    for (int i = ct; i < ns * G; i += DP_CTHREADS) {
+      const int s2 = i / G, h = i % G;
+      m_ms[s2 * DP_GMAX + h] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + h);
+      m_ls[s2 * DP_GMAX + h] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + DP_GMAX + h);
+    }
+    dp_cbar();
+    if (ct < G) {
+      float Mx = -INFINITY;
+      for (int s2 = 0; s2 < ns; ++s2) Mx = fmaxf(Mx, m_ms[s2 * DP_GMAX + ct]);
+      const float Mu = (Mx == -INFINITY) ? 0.f : Mx;
+      float L = 0.f;
+      for (int s2 = 0; s2 < ns; ++s2) {
+        const float f = exp2f(m_ms[s2 * DP_GMAX + ct] - Mu);
+        m_f[s2 * DP_GMAX + ct] = f;
+        L += m_ls[s2 * DP_GMAX + ct] * f;
+      }
+      m_L[ct] = L;
+    }
+    dp_cbar();
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = half * 4 + hh;
+      if (h >= G) continue;
+      float O = 0.f;
+      for (int s0 = 0; s0 < ns; s0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (s0 + j < ns) ? __ldcg(wb + (s0 + j) * DP_PART + h * 128 + kk) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) O += (s0 + j < ns) ? v[j] * m_f[(s0 + j) * DP_GMAX + h] : 0.f;
+      }
+      const float L = m_L[h];
+      p.ao[static_cast<int64_t>(b) * (p.nq * 128) + (kvh * G + h) * 128 + kk] = __float2bfloat16(L > 0.f ? O / L : 0.f);
+    }
+    if (ct == 0) p.attn_tickets[bk] = 0;  // re-arm for the next layer / launch
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const DpParams p) {
+  extern __shared__ uint8_t dp_smem_raw[];
+  uint8_t* smem = dp_smem_raw + ((1024u - (smem_u32(dp_smem_raw) & 1023u)) & 1023u);
+  DpRing ring;
+  ring.data = smem + DP_OFF_RING;
+  ring.full = reinterpret_cast<uint64_t*>(smem + DP_OFF_BAR);
+  ring.empty = ring.full + DP_STAGES;
+  ring.slot = 0;
+  ring.phase = 0;
+  uint8_t* xs = smem + DP_OFF_XS;
+  float* red = reinterpret_cast<float*>(smem + DP_OFF_RED);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < DP_STAGES; ++i) {
+      mbar_init(&ring.full[i], 1);
+      mbar_init(&ring.empty[i], DP_CONSUMERS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int kq = DP_H >> 5;                       // k-chunks of the hidden-size matrices
+  const int n_qkv = (p.nq + 2 * p.nkv) * 128 / 16;  // 16-row units
+  const int n_o = DP_H / 16;
+  const int n_gu = p.I / 16;                      // units of 32 packed rows (gate|up pairs) = I/16
+  const int kd = p.I >> 5;
+  const int n_head = p.vocab / 16;
+  const int limit = p.stop_after > 0 ? p.stop_after : 0x7fffffff;
+
+  if (warp == 0) {
+    // ---------------- producer: weights only; runs ahead of the consumers across phases ----------------
+    if (lane == 0) {
+      int ph = 0;
+      for (int l = 0; l < p.n_layers; ++l) {
+        const DpLayer L = p.layers[l];
+        if (ph++ >= limit) return;
+        dp_produce<1>(ring, L.qkv_wp, n_qkv, kq);
+        if (ph++ >= limit) return;  // attention phase: no weights
+        if (ph++ >= limit) return;
+        dp_produce<1>(ring, L.o_wp, n_o, kq);
+        if (ph++ >= limit) return;
+        dp_produce<2>(ring, L.gu_wp, n_gu, kq);
+        if (ph++ >= limit) return;
+        dp_produce<1>(ring, L.down_wp, n_o, kd);
+      }
+      if (ph++ >= limit) return;
+      dp_produce<1>(ring, p.lm_head_p, n_head, kq);
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int cw = warp - 1;
+  int red_par = 0;
+  unsigned int bar_gen = 0;
+  int ph = 0;
+  const unsigned int G = gridDim.x;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const DpLayer L = p.layers[l];
+    // A: qkv = rmsnorm(x; ln1) . Wqkv^T + b
+    if (ph++ >= limit) return;
+    dp_stage_rows<true>(xs, p.x, p.ldx, p.B, L.ln1, p.eps, cw, lane);
+    dp_cbar();
+    dp_gemv_phase<1, DP_EPI_BIAS, true>(ring, n_qkv, kq, xs, nullptr, 0, p.B, red, red_par, L.qkv_b, p.qkv, nullptr,
+                                        static_cast<int64_t>(n_qkv) * 16, cw, lane);
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    // B: rope + KV append + attention -> ao
+    if (ph++ >= limit) return;
+    dp_attention_phase(p, l, reinterpret_cast<float*>(xs));
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    // C: x += ao . Wo^T
+    if (ph++ >= limit) return;
+    dp_stage_rows<false>(xs, p.ao, DP_H, p.B, nullptr, 0.f, cw, lane);
+    dp_cbar();
+    dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, n_o, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    // D: act = silu(gate) * up, [gate|up] = rmsnorm(x; ln2) . Wgu^T
+    if (ph++ >= limit) return;
+    dp_stage_rows<true>(xs, p.x, p.ldx, p.B, L.ln2, p.eps, cw, lane);
+    dp_cbar();
+    dp_gemv_phase<2, DP_EPI_SWIGLU, true>(ring, n_gu, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.act, nullptr, p.I, cw, lane);
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    // E: x += act . Wdown^T
+    if (ph++ >= limit) return;
+    dp_gemv_phase<1, DP_EPI_RESIDUAL, false>(ring, n_o, kd, nullptr, p.act, p.I, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+  }
+  // final norm + LM head -> fp32 logits
+  if (ph++ >= limit) return;
+  dp_stage_rows<true>(xs, p.x, p.ldx, p.B, p.final_norm, p.eps, cw, lane);
+  dp_cbar();
+  dp_gemv_phase<1, DP_EPI_F32, true>(ring, n_head, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, nullptr, p.logits, p.ld_logits, cw, lane);
+}
+
+}  // namespace sr
+
+using namespace sr;
+
+extern "C" int64_t sr_decode_persistent_workspace_bytes(int batch, int n_kv_heads) {
+  // [16 B: grid barrier counter][tickets: batch*nkv int32, 16 B aligned][partials: batch*nkv*DP_NS_MAX*DP_PART fp32]
+  const int64_t bk = static_cast<int64_t>(batch) * n_kv_heads;
+  return 16 + ((bk * 4 + 15) / 16) * 16 + bk * DP_NS_MAX * DP_PART * 4;
+}
+
+static int g_dp_coop = -1;
+extern "C" int sr_set_decode_persistent_coop(int on) {
+  g_dp_coop = on ? 1 : 0;
+  return SR_OK;
+}
+
+extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, const void* lm_head_packed, const float* final_norm,
+                                         int vocab, void* x, int64_t ldx, void* qkv_scratch, void* ao_scratch, void* act_scratch,
+                                         float* logits, int64_t ld_logits, const float* cosb, const float* sinb,
+                                         const int32_t* cache_row, const int32_t* kv_start, const int32_t* kv_len, void* Kc,
+                                         int64_t k_layer_stride, void* Vt, int64_t vt_layer_stride, int64_t ldvt, int batch,
+                                         int n_q_heads, int n_kv_heads, int intermediate, float norm_eps, float scale,
+                                         void* workspace, int stop_after_phases, void* stream) {
+  SR_REQUIRE(layer_table && lm_head_packed && final_norm && x && qkv_scratch && ao_scratch && act_scratch && logits && cosb && sinb &&
+                 cache_row && kv_start && kv_len && Kc && Vt && workspace,
+             "sr_decode_step_persistent: null pointer");
+  SR_REQUIRE(batch > 0 && batch <= 8, "sr_decode_step_persistent: batch must be in [1, 8] (got %d)", batch);
+  SR_REQUIRE(n_q_heads * 128 == DP_H && n_kv_heads > 0 && n_q_heads % n_kv_heads == 0 && n_q_heads / n_kv_heads <= DP_GMAX,
+             "sr_decode_step_persistent: needs hidden 2048 = n_q_heads * 128 and <= 8 query heads per kv head");
+  SR_REQUIRE(intermediate % 32 == 0 && vocab % 16 == 0 && n_layers > 0, "sr_decode_step_persistent: intermediate %% 32, vocab %% 16");
+  SR_REQUIRE(ldx % 8 == 0 && ldvt % 8 == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(act_scratch) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(ao_scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(lm_head_packed) & 15) == 0,
+             "sr_decode_step_persistent: alignment");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  static int grid_cached = 0;
+  if (grid_cached == 0) {
+    SR_CHECK_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_BYTES));
+    int per_sm = 0;
+    SR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel, DP_THREADS, DP_SMEM_BYTES));
+    SR_REQUIRE(per_sm >= 1, "sr_decode_step_persistent: kernel does not fit on an SM (smem %d B)", DP_SMEM_BYTES);
+    grid_cached = sm_count();  // one CTA per SM: all co-resident (required by the grid barrier)
+  }
+  if (g_dp_coop < 0) {
+    const char* e = getenv("SR_DECODE_COOP");
+    g_dp_coop = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  DpParams p;
+  p.layers = reinterpret_cast<const DpLayer*>(layer_table);
+  p.n_layers = n_layers;
+  p.lm_head_p = reinterpret_cast<const __nv_bfloat16*>(lm_head_packed);
+  p.final_norm = final_norm;
+  p.vocab = vocab;
+  p.x = reinterpret_cast<__nv_bfloat16*>(x);
+  p.ldx = ldx;
+  p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv_scratch);
+  p.ao = reinterpret_cast<__nv_bfloat16*>(ao_scratch);
+  p.act = reinterpret_cast<__nv_bfloat16*>(act_scratch);
+  p.logits = logits;
+  p.ld_logits = ld_logits;
+  p.cosb = cosb;
+  p.sinb = sinb;
+  p.cache_row = cache_row;
+  p.kv_start = kv_start;
+  p.kv_len = kv_len;
+  p.Kc = reinterpret_cast<__nv_bfloat16*>(Kc);
+  p.k_layer_stride = k_layer_stride;
+  p.Vt = reinterpret_cast<__nv_bfloat16*>(Vt);
+  p.vt_layer_stride = vt_layer_stride;
+  p.ldvt = ldvt;
+  p.B = batch;
+  p.nq = n_q_heads;
+  p.nkv = n_kv_heads;
+  p.I = intermediate;
+  p.eps = norm_eps;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const int64_t bk = static_cast<int64_t>(batch) * n_kv_heads;
+  char* ws = reinterpret_cast<char*>(workspace);
+  p.grid_bar = reinterpret_cast<unsigned int*>(ws);
+  p.attn_tickets = reinterpret_cast<int*>(ws + 16);
+  p.attn_ws = reinterpret_cast<float*>(ws + 16 + ((bk * 4 + 15) / 16) * 16);
+  int ns = grid_cached / static_cast<int>(bk);
+  p.ns = ns < 1 ? 1 : (ns > DP_NS_MAX ? DP_NS_MAX : ns);
+  p.stop_after = stop_after_phases;
+  // the barrier counter (and, defensively, the tickets) start at zero for every launch
+  SR_CHECK_CUDA(cudaMemsetAsync(ws, 0, 16 + ((bk * 4 + 15) / 16) * 16, s));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid_cached);
+  cfg.blockDim = dim3(DP_THREADS);
+  cfg.dynamicSmemBytes = DP_SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_dp_coop ? 1 : 0;
+  SR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_persistent_kernel, p));
+  return SR_OK;
+}

@@ -93,6 +93,10 @@ class Engine:
         self._decode_launches = 0
         self.use_cuda_graph = True
         self.vit_narrow_block_n = int(os.environ.get("SR_VIT_N1280_BLOCK_N", "0"))  # 0 = auto (256)
+        # persistent decode step (sr_decode_persistent.cu): one launch per token for <= 8 live sequences; SR_DECODE_PERSISTENT=0
+        # selects the per-layer kernels (the only path for larger batches)
+        self.use_persistent_decode = os.environ.get("SR_DECODE_PERSISTENT", "1") != "0"
+        self._layer_table: Optional[torch.Tensor] = None
         self.stage_events = None  # optional list: generate_greedy appends (stage, cuda event) pairs (bench.py stage split)
 
     @staticmethod
@@ -349,8 +353,27 @@ class Engine:
                 u=torch.zeros((B, T), dtype=torch.float32, device=dev),
                 x=torch.zeros((B, self.cfg.text.hidden_size), dtype=torch.bfloat16, device=dev),
             )
+            if self._persistent_ok(B):
+                t = self.cfg.text
+                st.update(
+                    qkv=torch.zeros((B, (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim), dtype=torch.bfloat16, device=dev),
+                    ao=torch.zeros((B, t.num_attention_heads * t.head_dim), dtype=torch.bfloat16, device=dev),
+                    act=torch.zeros((B, t.intermediate_size), dtype=torch.bfloat16, device=dev),
+                    ws=lib.decode_persistent_workspace(B, t.num_key_value_heads, dev),
+                )
             self._dstate[key] = st
         return st
+
+    def set_persistent_decode(self, on: bool) -> None:
+        """Switch between the persistent decode-step kernel and the per-layer decode kernels (drops captured graphs)."""
+        self.use_persistent_decode = bool(on)
+        self._graphs.clear()
+        self._dstate.clear()
+
+    def _persistent_ok(self, B: int) -> bool:
+        t = self.cfg.text
+        return (self.use_persistent_decode and B <= 8 and self.w.lm_head_p is not None and len(self.w.layers) > 0
+                and self.w.layers[0].qkv_wp is not None and t.intermediate_size % 32 == 0 and t.vocab_size % 16 == 0)
 
     def _pick_token(self, st, sampling) -> None:
         if sampling is None:
@@ -367,6 +390,14 @@ class Engine:
                            st["kv_len"], st["pos3"])
         cos, sin = lib.mrope_table(st["pos3"], self.txt_inv_freq, t.mrope_section)
         lib.embed_scatter(self.w.embed, st["nxt"], None, None, out=st["x"])
+        if "ws" in st and self.use_persistent_decode:
+            if self._layer_table is None:
+                self._layer_table = lib.decode_layer_table(self.w.layers, self.device)
+            lib.decode_step_persistent(self._layer_table, self.w.lm_head_p, self.w.final_norm, t.vocab_size, st["x"], st["qkv"],
+                                       st["ao"], st["act"], st["logits"], cos, sin, st["cache_row"], st["kv_start"], st["kv_len"],
+                                       cache.k, cache.vt, t.num_attention_heads, t.num_key_value_heads, t.intermediate_size,
+                                       t.rms_norm_eps, t.head_dim ** -0.5, st["ws"])
+            return
         xo = self._decoder_layers(st["x"], cos, sin, cache, st["cache_row"], None, (st["kv_start"], st["kv_len"], cache.l_max))
         self.final_logits(xo, torch.float32, out=st["logits"])
 
@@ -408,7 +439,7 @@ class Engine:
         if use_graph is None:
             use_graph = self.use_cuda_graph and not return_logits and lib.timeline is None
         if use_graph and T > 1:
-            gkey = (B, T, l_max, sampling)
+            gkey = (B, T, l_max, sampling, self.use_persistent_decode)
             g = self._graphs.get(gkey)
             if g is None:
                 # warm-up outside capture (buffer allocation, function attributes), then restore the state it advanced

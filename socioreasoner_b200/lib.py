@@ -51,6 +51,10 @@ SYMBOLS = {
     "sr_sample_topk_topp": (c_int, [_P, c_int64, c_int, c_int, _P, c_int, _P, c_float, c_int, c_float, _P, _P]),
     "sr_logprob_entropy": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sr_decode_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    "sr_decode_persistent_workspace_bytes": (c_int64, [c_int, c_int]),
+    "sr_set_decode_persistent_coop": (c_int, [c_int]),
+    "sr_decode_step_persistent": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P,
+                                          c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
     "sr_mask_iou": (c_int, [_P, _P, c_int, c_int64, c_float, _P, _P, _P]),
 }
@@ -372,6 +376,46 @@ def decode_advance(nxt, tokens, step, row0, len0, pos0, cache_row, kv_len, pos3)
                                     len0.data_ptr(), pos0.data_ptr(), cache_row.data_ptr(), kv_len.data_ptr(), pos3.data_ptr(),
                                     tokens.shape[0], _stream()), "sr_decode_advance")
     launch_count += 1
+
+
+def decode_layer_table(layers, device) -> torch.Tensor:
+    """Device array of ``sr_decode_layer`` structs (7 pointers per layer) for ``decode_step_persistent``."""
+    rows = []
+    for L in layers:
+        assert L.qkv_wp is not None and L.o_wp is not None and L.gu_wp is not None and L.down_wp is not None
+        rows.append([L.qkv_wp.data_ptr(), L.qkv_b.data_ptr() if L.qkv_b is not None else 0, L.ln1.data_ptr(), L.o_wp.data_ptr(),
+                     L.ln2.data_ptr(), L.gu_wp.data_ptr(), L.down_wp.data_ptr()])
+    return torch.tensor(rows, dtype=torch.int64).to(device)
+
+
+def decode_persistent_workspace(batch: int, n_kv_heads: int, device) -> torch.Tensor:
+    return torch.zeros((load().sr_decode_persistent_workspace_bytes(batch, n_kv_heads),), dtype=torch.uint8, device=device)
+
+
+def decode_step_persistent(layer_table: torch.Tensor, lm_head_p: torch.Tensor, final_norm: torch.Tensor, vocab: int,
+                           x: torch.Tensor, qkv: torch.Tensor, ao: torch.Tensor, act: torch.Tensor, logits: torch.Tensor,
+                           cos: torch.Tensor, sin: torch.Tensor, cache_row: torch.Tensor, kv_start: torch.Tensor,
+                           kv_len: torch.Tensor, kc: torch.Tensor, vt: torch.Tensor, n_q_heads: int, n_kv_heads: int,
+                           intermediate: int, eps: float, scale: float, workspace: torch.Tensor, stop_after: int = 0) -> torch.Tensor:
+    """One whole decode step (all layers + LM head) in one persistent launch.  kc [L, rows, n_kv, 128], vt [L, n_kv*128, rows];
+    x [B, 2048] is updated in place; logits fp32 [B, vocab]."""
+    global launch_count
+    _req(x, torch.bfloat16, "decode_persistent.x"); _req(logits, torch.float32, "decode_persistent.logits")
+    _req(kc, torch.bfloat16, "decode_persistent.kc"); _req(vt, torch.bfloat16, "decode_persistent.vt")
+    _req(cache_row, torch.int32, "decode_persistent.cache_row"); _req(kv_start, torch.int32, "decode_persistent.kv_start")
+    _req(kv_len, torch.int32, "decode_persistent.kv_len"); _req(cos, torch.float32, "decode_persistent.cos")
+    B = x.shape[0]
+    assert kc.dim() == 4 and vt.dim() == 3 and kc.is_contiguous() and vt.is_contiguous() and layer_table.shape[1] == 7
+    assert qkv.is_contiguous() and ao.is_contiguous() and act.is_contiguous() and cos.is_contiguous() and sin.is_contiguous()
+    assert qkv.shape == (B, (n_q_heads + 2 * n_kv_heads) * 128) and ao.shape == (B, n_q_heads * 128) and act.shape == (B, intermediate)
+    rc = load().sr_decode_step_persistent(
+        layer_table.data_ptr(), layer_table.shape[0], lm_head_p.data_ptr(), final_norm.data_ptr(), vocab, x.data_ptr(), x.stride(0),
+        qkv.data_ptr(), ao.data_ptr(), act.data_ptr(), logits.data_ptr(), logits.stride(0), cos.data_ptr(), sin.data_ptr(),
+        cache_row.data_ptr(), kv_start.data_ptr(), kv_len.data_ptr(), kc.data_ptr(), kc.stride(0), vt.data_ptr(), vt.stride(0),
+        vt.stride(1), B, n_q_heads, n_kv_heads, intermediate, float(eps), float(scale), workspace.data_ptr(), int(stop_after), _stream())
+    _check(rc, "sr_decode_step_persistent")
+    launch_count += 1
+    return logits
 
 
 def sample_topk_topp(logits: torch.Tensor, uniforms: torch.Tensor, temperature: float, top_k: int, top_p: float,

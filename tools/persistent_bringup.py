@@ -1,0 +1,264 @@
+"""Bring-up / regression check of the persistent decode-step kernel (sr_decode_persistent.cu) against the per-layer decode
+kernels, phase by phase (stop_after), then a whole step, CUDA-graph replay and timing at the 3B geometry.
+Synthetic packed weights (both paths read the same packed tensors).  Usage: python tools/persistent_bringup.py [layers] [vocab]"""
+import os
+import sys
+import time
+from types import SimpleNamespace
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from socioreasoner_b200 import lib  # noqa: E402
+
+dev = "cuda"
+H, NQ, NKV, HD, I = 2048, 16, 2, 128, 11008
+QKV = (NQ + 2 * NKV) * HD
+
+
+def rnd_packed(n, k, std=0.02):
+    return (torch.randn(n // 16, k // 32, 16, 32, device=dev) * std).bfloat16()
+
+
+def make_layers(n_layers):
+    out = []
+    for _ in range(n_layers):
+        out.append(SimpleNamespace(
+            qkv_wp=rnd_packed(QKV, H), qkv_b=(torch.randn(QKV, device=dev) * 0.02), ln1=1 + 0.1 * torch.randn(H, device=dev),
+            o_wp=rnd_packed(H, H), ln2=1 + 0.1 * torch.randn(H, device=dev), gu_wp=rnd_packed(2 * I, H), down_wp=rnd_packed(H, I)))
+    return out
+
+
+def err(name, got, ref):
+    got, ref = got.float(), ref.float()
+    d = (got - ref).abs().max().item()
+    r = ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-20)).item()
+    ok = torch.isfinite(got).all().item() and r < 2e-2
+    print(f"  {name:34s} max|d|={d:.4e} rel_rms={r:.3e} {'OK' if ok else 'MISMATCH'}", flush=True)
+    return ok
+
+
+class State:
+    def __init__(self, B, n_layers, l_max, lens, vocab):
+        g = torch.Generator(device=dev).manual_seed(1)
+        self.B, self.l_max = B, l_max
+        self.x0 = torch.randn(B, H, device=dev, generator=g).bfloat16()
+        self.kc0 = (torch.randn(n_layers, B * l_max, NKV, HD, device=dev, generator=g)).bfloat16()
+        self.vt0 = (torch.randn(n_layers, NKV * HD, B * l_max, device=dev, generator=g)).bfloat16()
+        self.kv_start = (torch.arange(B, device=dev) * l_max).int()
+        self.kv_len = torch.tensor(lens, device=dev, dtype=torch.int32)            # includes the new token
+        self.cache_row = (self.kv_start + self.kv_len - 1).int()
+        pos = (self.kv_len.long() + 3)[None].repeat(3, 1).contiguous()
+        inv = (1.0 / (1e6 ** (torch.arange(0, HD, 2, dtype=torch.float32) / HD))).to(dev)
+        self.cos, self.sin = lib.mrope_table(pos, inv, (16, 24, 24))
+        self.final_norm = 1 + 0.1 * torch.randn(H, device=dev, generator=g)
+        self.lm_head_p = rnd_packed(vocab, H)
+        self.vocab = vocab
+
+
+def reference_step(S, layers, upto_layers=None):
+    """Per-layer kernels (the path generate_greedy used before): returns intermediates of layer 0 and the final logits."""
+    x = S.x0.clone()
+    kc, vt = S.kc0.clone(), S.vt0.clone()
+    B = S.B
+    qkv = torch.empty(B, QKV, device=dev, dtype=torch.bfloat16)
+    ao = torch.empty(B, H, device=dev, dtype=torch.bfloat16)
+    act = torch.empty(B, I, device=dev, dtype=torch.bfloat16)
+    inter = {}
+    for li, L in enumerate(layers):
+        lib.gemm_skinny_packed(x, L.qkv_wp, QKV, H, out=qkv, bias=L.qkv_b, norm_weight=L.ln1, norm_eps=1e-6)
+        if li == 0:
+            inter["qkv"] = qkv.clone()
+        lib.mrope_kv(qkv, S.cos, S.sin, S.cache_row, kc[li], vt[li], NQ, NKV)
+        lib.decode_attention(qkv, kc[li], vt[li], S.kv_start, S.kv_len, S.l_max, ao, NQ, NKV, HD ** -0.5)
+        if li == 0:
+            inter["ao"] = ao.clone()
+        lib.gemm_skinny_packed(ao, L.o_wp, H, H, out=x, residual=x)
+        if li == 0:
+            inter["x_o"] = x.clone()
+        lib.gemm_skinny_packed(x, L.gu_wp, 2 * I, H, out=act, epilogue=lib.EPI_SWIGLU, norm_weight=L.ln2, norm_eps=1e-6)
+        if li == 0:
+            inter["act"] = act.clone()
+        lib.gemm_skinny_packed(act, L.down_wp, H, I, out=x, residual=x)
+        if li == 0:
+            inter["x_down"] = x.clone()
+    y = lib.rmsnorm(x, S.final_norm, 1e-6)
+    logits = lib.gemm_skinny_packed(y, S.lm_head_p, S.vocab, H, out_dtype=torch.float32)
+    inter.update(x=x, logits=logits, kc=kc, vt=vt)
+    return inter
+
+
+class Persistent:
+    def __init__(self, S, layers):
+        self.S, self.layers = S, layers
+        self.table = lib.decode_layer_table(layers, dev)
+        B = S.B
+        self.qkv = torch.zeros(B, QKV, device=dev, dtype=torch.bfloat16)
+        self.ao = torch.zeros(B, H, device=dev, dtype=torch.bfloat16)
+        self.act = torch.zeros(B, I, device=dev, dtype=torch.bfloat16)
+        self.logits = torch.zeros(B, S.vocab, device=dev, dtype=torch.float32)
+        self.ws = lib.decode_persistent_workspace(B, NKV, dev)
+        self.x = S.x0.clone()
+        self.kc, self.vt = S.kc0.clone(), S.vt0.clone()
+
+    def reset(self):
+        self.x.copy_(self.S.x0); self.kc.copy_(self.S.kc0); self.vt.copy_(self.S.vt0)
+        for t in (self.qkv, self.ao, self.act, self.logits):
+            t.zero_()
+
+    def run(self, stop_after=0):
+        S = self.S
+        lib.decode_step_persistent(self.table, S.lm_head_p, S.final_norm, S.vocab, self.x, self.qkv, self.ao, self.act, self.logits,
+                                   S.cos, S.sin, S.cache_row, S.kv_start, S.kv_len, self.kc, self.vt, NQ, NKV, I, 1e-6, HD ** -0.5,
+                                   self.ws, stop_after)
+
+
+def check_case(B, n_layers, lens, vocab, l_max=1024, phases=True):
+    print(f"== case B={B} layers={n_layers} lens={lens} vocab={vocab}", flush=True)
+    torch.manual_seed(0)
+    layers = make_layers(n_layers)
+    S = State(B, n_layers, l_max, lens, vocab)
+    ref = reference_step(S, layers)
+    torch.cuda.synchronize()
+    P = Persistent(S, layers)
+    ok = True
+    if phases:
+        for k, (name, got_fn, refkey) in enumerate([
+                ("phase1 qkv", lambda: P.qkv, "qkv"), ("phase2 attention out", lambda: P.ao, "ao"),
+                ("phase3 x after o-proj", lambda: P.x, "x_o"), ("phase4 act (SwiGLU)", lambda: P.act, "act"),
+                ("phase5 x after down", lambda: P.x, "x_down")], start=1):
+            P.reset()
+            P.run(stop_after=k)
+            torch.cuda.synchronize()
+            ok &= err(name, got_fn(), ref[refkey])
+            if k == 2:
+                ok &= err("  K cache (layer 0)", P.kc[0], ref["kc"][0])
+                ok &= err("  V^T cache (layer 0)", P.vt[0], ref["vt"][0])
+    P.reset()
+    P.run(0)
+    torch.cuda.synchronize()
+    ok &= err("full step: hidden", P.x, ref["x"])
+    ok &= err("full step: logits", P.logits, ref["logits"])
+    ok &= err("full step: K cache (all)", P.kc, ref["kc"])
+    ok &= err("full step: V^T cache (all)", P.vt, ref["vt"])
+    am = (P.logits.argmax(-1) == ref["logits"].argmax(-1)).float().mean().item()
+    print(f"  argmax agreement {am:.2f}", flush=True)
+    # second run on the same object (barrier counter / tickets re-armed)
+    P.reset(); P.run(0); torch.cuda.synchronize()
+    ok &= err("full step again: logits", P.logits, ref["logits"])
+    return ok, S, layers, P, ref
+
+
+def graph_check(P, ref):
+    print("== CUDA graph capture + replay", flush=True)
+    P.reset(); P.run(0); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    P.reset()
+    torch.cuda.synchronize()
+    try:
+        with torch.cuda.graph(g):
+            P.run(0)
+    except Exception as e:  # noqa: BLE001
+        print("  capture with cooperative launch failed:", repr(e)[:300], flush=True)
+        lib.load().sr_set_decode_persistent_coop(0)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            P.run(0)
+        print("  captured with plain launch (SR_DECODE_COOP=0)", flush=True)
+    P.reset()
+    g.replay(); torch.cuda.synchronize()
+    ok = err("graph replay: logits", P.logits, ref["logits"])
+    P.reset(); g.replay(); torch.cuda.synchronize()
+    ok &= err("graph replay 2: logits", P.logits, ref["logits"])
+    return ok, g
+
+
+def timing(n_layers=36, vocab=151936, B=8, lens=None, iters=20):
+    print(f"== timing layers={n_layers} vocab={vocab} B={B}", flush=True)
+    torch.manual_seed(0)
+    lens = lens or [900 - 7 * i for i in range(B)]
+    layers = make_layers(n_layers)
+    S = State(B, n_layers, 1024, lens, vocab)
+    P = Persistent(S, layers)
+    wbytes = n_layers * (QKV * H + H * H + 2 * I * H + H * I) * 2 + vocab * H * 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        P.run(0)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        P.run(0)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"  persistent (stream launches): {ms:.3f} ms/step  {wbytes / ms / 1e9:.2f} TB/s of weights ({wbytes / 1e9:.2f} GB)", flush=True)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        P.run(0)
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    print(f"  persistent (graph replay):    {ms:.3f} ms/step  {wbytes / ms / 1e9:.2f} TB/s of weights", flush=True)
+    # per-phase cumulative timing: stop_after = k phases of layer 0..1, and the no-LM-head prefix
+    for k in (1, 2, 3, 4, 5, 10, 5 * n_layers):
+        for _ in range(2):
+            P.run(k)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            P.run(k)
+        e1.record(); torch.cuda.synchronize()
+        print(f"    first {k:4d} phases: {e0.elapsed_time(e1) / iters * 1e3:9.1f} us", flush=True)
+    # the per-layer kernels on the same data, captured in a graph (what generate_greedy replayed before)
+    x = S.x0.clone(); kc, vt = S.kc0.clone(), S.vt0.clone()
+    qkv = torch.empty(B, QKV, device=dev, dtype=torch.bfloat16); ao = torch.empty(B, H, device=dev, dtype=torch.bfloat16)
+    act = torch.empty(B, I, device=dev, dtype=torch.bfloat16); y = torch.empty(B, H, device=dev, dtype=torch.bfloat16)
+    logits = torch.empty(B, vocab, device=dev, dtype=torch.float32)
+
+    def old():
+        for li, L in enumerate(layers):
+            lib.gemm_skinny_packed(x, L.qkv_wp, QKV, H, out=qkv, bias=L.qkv_b, norm_weight=L.ln1, norm_eps=1e-6)
+            lib.mrope_kv(qkv, S.cos, S.sin, S.cache_row, kc[li], vt[li], NQ, NKV)
+            lib.decode_attention(qkv, kc[li], vt[li], S.kv_start, S.kv_len, S.l_max, ao, NQ, NKV, HD ** -0.5)
+            lib.gemm_skinny_packed(ao, L.o_wp, H, H, out=x, residual=x)
+            lib.gemm_skinny_packed(x, L.gu_wp, 2 * I, H, out=act, epilogue=lib.EPI_SWIGLU, norm_weight=L.ln2, norm_eps=1e-6)
+            lib.gemm_skinny_packed(act, L.down_wp, H, I, out=x, residual=x)
+        lib.rmsnorm(x, S.final_norm, 1e-6, out=y)
+        lib.gemm_skinny_packed(y, S.lm_head_p, vocab, H, out=logits, out_dtype=torch.float32)
+    old(); torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        old()
+    for _ in range(2):
+        g2.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        g2.replay()
+    e1.record(); torch.cuda.synchronize()
+    ms2 = e0.elapsed_time(e1) / iters
+    print(f"  per-layer kernels (graph replay): {ms2:.3f} ms/step  {wbytes / ms2 / 1e9:.2f} TB/s of weights", flush=True)
+
+
+if __name__ == "__main__":
+    n_layers = int(sys.argv[1]) if len(sys.argv) > 1 else 36
+    vocab = int(sys.argv[2]) if len(sys.argv) > 2 else 151936
+    lib.device_check()
+    t0 = time.time()
+    all_ok = True
+    ok, S, layers, P, ref = check_case(8, 2, [900, 897, 640, 512, 129, 128, 9, 1], 8192)
+    all_ok &= ok
+    ok, _g = graph_check(P, ref)
+    all_ok &= ok
+    del S, layers, P, ref, _g
+    ok, *_ = check_case(3, 3, [300, 17, 1000], 4096, phases=False)
+    all_ok &= ok
+    del _
+    torch.cuda.empty_cache()
+    print(f"correctness: {'ALL OK' if all_ok else 'FAILURES'} ({time.time() - t0:.1f}s)", flush=True)
+    timing(n_layers, vocab)

@@ -203,6 +203,12 @@ typedef struct sr_decode_layer {
 } sr_decode_layer;
 int64_t sr_decode_persistent_workspace_bytes(int batch, int n_kv_heads);
 int sr_set_decode_persistent_coop(int enabled);
+/* Tuning knobs of the producer: pf_stages = L2 prefetch lookahead beyond the shared-memory ring, in 16 KB stages per CTA
+ * (0 = off; env SR_DECODE_PF_STAGES); flags bit 0 = L2 evict_first hint on the ring copies (env SR_DECODE_FLAGS). */
+int sr_set_decode_persistent_tuning(int pf_stages, int flags);
+/* Tuning aid: when buffer != NULL every later sr_decode_step_persistent launch records (globaltimer ns, clock64) pairs at its
+ * phase boundaries into buffer[n_SMs][2 roles: producer, consumer][events_per_role][2] (uint64); NULL switches it off. */
+int sr_set_decode_persistent_trace(void* buffer, int events_per_role);
 int sr_decode_step_persistent(const void* layer_table, int n_layers, const void* lm_head_packed, const float* final_norm,
                               int vocab, void* x, int64_t ldx, void* qkv_scratch, void* ao_scratch, void* act_scratch,
                               float* logits, int64_t ld_logits, const float* cosb, const float* sinb, const int32_t* cache_row,

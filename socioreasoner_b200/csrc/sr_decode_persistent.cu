@@ -35,7 +35,8 @@ constexpr int DP_STAGE_BYTES = DP_STAGE_BLOCKS * 1024;
 constexpr int DP_STAGES = 10;
 constexpr int DP_H = 2048;                            // staged activation width (hidden size = n_q_heads * 128)
 constexpr int DP_XS_STRIDE = DP_H * 2 + 64;           // bytes per staged row (+64 B: conflict-free 16 B fragment reads)
-constexpr int DP_XPF = 3;                             // activation prefetch distance (stages) on the L2 path
+constexpr int DP_XPF = 4;                             // activation prefetch distance (stages) on the L2 path (loaded L2 latency ~1.5 us)
+constexpr int DP_MAX_LAYERS = 64;                     // layer table staged in shared memory
 constexpr int DP_GMAX = 8;                            // query heads per kv head (max)
 constexpr int DP_KEYS = 128;                          // keys per attention pass
 constexpr int DP_NS_MAX = 32;                         // max key splits
@@ -48,7 +49,11 @@ constexpr int DP_XS_BYTES = 8 * DP_XS_STRIDE;                         // 33280
 constexpr int DP_OFF_RED = DP_OFF_XS + DP_XS_BYTES;                   // [2][8 warps][2 rg][128] fp32
 constexpr int DP_RED_BYTES = 2 * DP_CONSUMERS * 2 * 128 * 4;          // 16384
 constexpr int DP_OFF_BAR = DP_OFF_RED + DP_RED_BYTES;
-constexpr int DP_SMEM_BYTES = DP_OFF_BAR + 2 * DP_STAGES * 8 + 64 + 1024;  // + alignment slack
+constexpr int DP_OFF_LAYERS = DP_OFF_BAR + 2 * DP_STAGES * 8 + 32;    // DpLayer[DP_MAX_LAYERS]
+constexpr int DP_OFF_ROPE = DP_OFF_LAYERS + DP_MAX_LAYERS * 56;       // cos[8][64], sin[8][64] fp32 of this step
+constexpr int DP_OFF_SCAL = DP_OFF_ROPE + 2 * 8 * 64 * 4;             // kv_start[8], kv_len[8], cache_row[8]
+constexpr int DP_SMEM_BYTES = DP_OFF_SCAL + 3 * 8 * 4 + 64 + 1024;    // + alignment slack
+static_assert(DP_SMEM_BYTES <= 232448, "shared-memory budget of one sm_100 CTA");
 
 // attention scratch inside the xs region (floats)
 constexpr int DPA_SQ = 0;                              // [8][128]
@@ -62,7 +67,11 @@ constexpr int DPA_LS = DPA_MS + DP_NS_MAX * DP_GMAX;
 constexpr int DPA_F = DPA_LS + DP_NS_MAX * DP_GMAX;
 constexpr int DPA_LL = DPA_F + DP_NS_MAX * DP_GMAX;    // [8]
 constexpr int DPA_FLAG = DPA_LL + DP_GMAX;             // 1 int
-constexpr int DPA_END = DPA_FLAG + 4;
+constexpr int DPA_NK = DPA_FLAG + 4;                   // [128] roped k of the new token (bf16-rounded values)
+constexpr int DPA_NV = DPA_NK + 128;                   // [128] v of the new token
+constexpr int DPA_PNEW = DPA_NV + 128;                 // [8] probability of the new key per head
+constexpr int DPA_EX = DPA_PNEW + DP_GMAX;             // [2 halves][8 heads][128]: partial scores, later partial outputs
+constexpr int DPA_END = DPA_EX + 2 * DP_GMAX * 128;
 static_assert(DPA_END * 4 <= DP_XS_BYTES, "attention scratch must fit in the staged-activation region");
 
 struct DpLayer {  // == sr_decode_layer (include/socioreasoner_b200.h)
@@ -105,7 +114,32 @@ struct DpParams {
   int ns;
   unsigned int* grid_bar;  // zero before launch
   int stop_after;          // debug: run only the first `stop_after` phases (<= 0: all)
+  int pf_stages;           // L2 prefetch lookahead of the producer beyond the ring, in 16 KB stages per CTA (0 = off)
+  int flags;               // bit 0: L2 evict_first hint on the ring copies (weights are consumed exactly once)
+  unsigned long long* trace;  // optional [gridDim.x][2 roles][trace_events][2] (globaltimer ns, clock64) -- sr_set_decode_persistent_trace
+  int trace_events;
 };
+
+// In-kernel timeline (bring-up / tuning aid): thread-level timestamps at phase boundaries, read back by tools/persistent_trace.py.
+SR_DEVINL void dp_trace_at(const DpParams& p, int role, int idx) {
+  if (p.trace != nullptr && idx < p.trace_events) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned long long* d = p.trace + ((static_cast<int64_t>(blockIdx.x) * 2 + role) * p.trace_events + idx) * 2;
+    d[0] = t;
+    d[1] = static_cast<unsigned long long>(clock64());
+  }
+}
+SR_DEVINL void dp_trace(const DpParams& p, int role, int& idx) {
+  if (p.trace != nullptr && idx < p.trace_events) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned long long* d = p.trace + ((static_cast<int64_t>(blockIdx.x) * 2 + role) * p.trace_events + idx) * 2;
+    d[0] = t;
+    d[1] = static_cast<unsigned long long>(clock64());
+    ++idx;
+  }
+}
 
 SR_DEVINL void dp_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
@@ -128,20 +162,19 @@ SR_DEVINL uint4 dp_ldcg(const void* p) { return __ldcg(reinterpret_cast<const ui
 // release-add and polls with acquire loads until all CTAs of this generation have arrived.  Bounded: a broken schedule
 // traps (CUDA error through the C ABI) instead of hanging the GPU.
 SR_DEVINL void dp_grid_barrier(unsigned int* ctr, unsigned int target) {
-  __threadfence();
-  dp_cbar();
+  dp_cbar();  // orders every consumer thread's global stores before the release below (cumulativity through the CTA barrier)
   if (threadIdx.x == 32) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
     unsigned int v = 0, spins = 0;
     while (true) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
       if (v >= target) break;
       if (++spins > SR_GRIDBAR_SPIN_LIMIT) {
         printf("sr: grid barrier timeout block=%d have=%u want=%u\n", blockIdx.x, v, target);
         __trap();
       }
     }
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   dp_cbar();
 }
@@ -160,21 +193,38 @@ struct DpRing {
 // ------------------------------------------------------------------------------------------------ producer
 // Streams this CTA's units of one packed matrix: unit u = RG consecutive 16-row groups; stage = 16 blocks of 1 KB
 // (RG = 1: 16 k-chunks of the group; RG = 2: 8 k-chunks of each of the two groups, second group at +8 KB).
-template <int RG>
-SR_DEVINL void dp_produce(DpRing& r, const __nv_bfloat16* Wp, int n_units, int nchunks) {
+// ONE thread issues every copy of the CTA, so this loop is kept minimal (a generic schedule walker with an L2-prefetch
+// cursor was measured 15% slower end to end: the producer thread became the bottleneck).
+// ROT: the stage order of unit u is rotated by (7u mod nst) -- used for the down projection, whose activations are read
+// from L2 by every CTA: without the rotation all CTAs request the same 8 KB of activations at the same time (hot L2 slices).
+SR_DEVINL int dp_rot(int u, int nst) { return (u * 7) % nst; }
+template <int RG, bool ROT>
+SR_DEVINL void dp_produce(DpRing& r, const __nv_bfloat16* Wp, int n_units, int nchunks, uint64_t policy, bool hint) {
   constexpr int CPS = DP_STAGE_BLOCKS / RG;
   const int nst = (nchunks + CPS - 1) / CPS;
   for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-    for (int st = 0; st < nst; ++st) {
+    int st = ROT ? dp_rot(u, nst) : 0;
+    for (int i = 0; i < nst; ++i) {
       mbar_wait(&r.empty[r.slot], r.phase ^ 1);
       const int nch = min(CPS, nchunks - st * CPS);
       mbar_arrive_expect_tx(&r.full[r.slot], static_cast<uint32_t>(RG * nch * 1024));
 #pragma unroll
       for (int g = 0; g < RG; ++g) {
         const __nv_bfloat16* src = Wp + (static_cast<int64_t>(u * RG + g) * nchunks + st * CPS) * 512;
-        dp_bulk_g2s(r.data + r.slot * DP_STAGE_BYTES + g * (CPS * 1024), src, static_cast<uint32_t>(nch * 1024), &r.full[r.slot]);
+        uint8_t* dst = r.data + r.slot * DP_STAGE_BYTES + g * (CPS * 1024);
+        if (hint) {
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                  smem_u32(dst)),
+              "l"(src), "r"(static_cast<uint32_t>(nch * 1024)), "r"(smem_u32(&r.full[r.slot])), "l"(policy)
+              : "memory");
+        } else {
+          dp_bulk_g2s(dst, src, static_cast<uint32_t>(nch * 1024), &r.full[r.slot]);
+        }
       }
       r.advance();
+      if (ROT && ++st == nst) st = 0;
+      if (!ROT) ++st;
     }
   }
 }
@@ -265,35 +315,40 @@ SR_DEVINL void dp_consume_staged(DpRing& r, int nchunks, const uint8_t* xs, floa
 }
 
 // K loop of one unit (RG = 1) with the activations read from global memory / L2 (long K: the down projection).
-SR_DEVINL void dp_consume_l2(DpRing& r, int nchunks, const __nv_bfloat16* xg, int64_t ldx, int M, float (&acc)[1][4], int cw,
+// Stage order rotated per unit (see dp_produce<.., ROT>); activation fragments are prefetched DP_XPF stages ahead.
+SR_DEVINL void dp_consume_l2(DpRing& r, int u, int nchunks, const __nv_bfloat16* xg, int64_t ldx, int M, float (&acc)[1][4], int cw,
                              int lane) {
   constexpr int CPS = DP_STAGE_BLOCKS;
   const int g = lane >> 2, t = lane & 3;
   const int nst = (nchunks + CPS - 1) / CPS;
+  const int rot = dp_rot(u, nst);
   const bool xok = g < M;
   const __nv_bfloat16* xrow = xg + static_cast<int64_t>(xok ? g : 0) * ldx + t * 8;
   uint4 xq[DP_XPF][2];
-  auto load_x = [&](int i, int st) {
+  auto stage_of = [&](int i) { const int s2 = i + rot; return s2 >= nst ? s2 - nst : s2; };
+  auto load_x = [&](int slot_i, int i) {
+    const int st = stage_of(i);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int c = st * CPS + cw + 8 * j;
-      xq[i][j] = (xok && c < nchunks) ? dp_ldcg(xrow + c * 32) : make_uint4(0, 0, 0, 0);
+      xq[slot_i][j] = (xok && i < nst && c < nchunks) ? dp_ldcg(xrow + c * 32) : make_uint4(0, 0, 0, 0);
     }
   };
 #pragma unroll
   for (int i = 0; i < DP_XPF; ++i) load_x(i, i);
-  for (int st0 = 0; st0 < nst; st0 += DP_XPF) {
+  for (int i0 = 0; i0 < nst; i0 += DP_XPF) {
 #pragma unroll
-    for (int i = 0; i < DP_XPF; ++i) {
-      const int st = st0 + i;
-      if (st < nst) {
+    for (int q = 0; q < DP_XPF; ++q) {
+      const int i = i0 + q;
+      if (i < nst) {
+        const int st = stage_of(i);
         mbar_wait(&r.full[r.slot], r.phase);
         const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int c = st * CPS + cw + 8 * j;
           if (c < nchunks) {
-            const uint4 xv = xq[i][j];
+            const uint4 xv = xq[q][j];
             const uint8_t* blk = stage + (cw + 8 * j) * 1024;
             const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
             const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
@@ -303,7 +358,7 @@ SR_DEVINL void dp_consume_l2(DpRing& r, int nchunks, const __nv_bfloat16* xg, in
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&r.empty[r.slot]);
-        load_x(i, st + DP_XPF);
+        load_x(q, i + DP_XPF);
         r.advance();
       }
     }
@@ -325,11 +380,21 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t*
     for (int q = 0; q < RG; ++q)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
+    // epilogue operands of this thread's output element: requested before the K loop so their latency is hidden
+    float epi_add = 0.f;
+    if (ct < 128 && (ct >> 4) < M) {
+      const int col = u * 16 + (ct & 15);
+      if (EPI == DP_EPI_BIAS && bias != nullptr) epi_add = __ldg(bias + col);
+      if (EPI == DP_EPI_RESIDUAL) {
+        const unsigned short rbits = __ldcg(reinterpret_cast<const unsigned short*>(out_bf + static_cast<int64_t>(ct >> 4) * ldo + col));
+        epi_add = __uint_as_float(static_cast<uint32_t>(rbits) << 16);
+      }
+    }
     if constexpr (STAGED) {
       dp_consume_staged<RG>(r, nchunks, xs, acc, cw, lane);
     } else {
       static_assert(STAGED || RG == 1, "the L2 activation path handles single row groups");
-      dp_consume_l2(r, nchunks, xg, ldxg, M, acc, cw, lane);
+      dp_consume_l2(r, u, nchunks, xg, ldxg, M, acc, cw, lane);
     }
     // cross-warp reduction: C fragment (feature g | g+8, batch 2t | 2t+1) -> red[par][warp][q][feature*8 + batch]
     float* rp = red + red_par * (DP_CONSUMERS * 2 * 128);
@@ -359,12 +424,7 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t*
           out_bf[static_cast<int64_t>(b) * ldo + u * 16 + f] = __float2bfloat16(o);
         } else {
           const int col = u * 16 + f;
-          float o = v[0];
-          if (EPI == DP_EPI_BIAS && bias != nullptr) o += __ldg(bias + col);
-          if (EPI == DP_EPI_RESIDUAL) {
-            const unsigned short rbits = __ldcg(reinterpret_cast<const unsigned short*>(out_bf + static_cast<int64_t>(b) * ldo + col));
-            o += __uint_as_float(static_cast<uint32_t>(rbits) << 16);
-          }
+          const float o = v[0] + epi_add;
           if (EPI == DP_EPI_F32) out_f32[static_cast<int64_t>(b) * ldo + col] = o;
           else out_bf[static_cast<int64_t>(b) * ldo + col] = __float2bfloat16(o);
         }
@@ -376,9 +436,77 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t*
 
 // ------------------------------------------------------------------------------------------------ attention phase
 // M-RoPE (mcore_adapter/.../modeling_qwen2_5_vl.py:21-41) on q and the new k, KV-cache append, split-KV attention of the
-// new token against the cache (the arithmetic of mrope_kv_kernel + decode_attn_kernel; see sr_tail.cu for the per-pass
-// formulation).  Unit = (sample, kv head, key split); the split that owns the newest key appends it to the cache first.
-SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, float* sm) {
+// new token against the cache (the arithmetic of mrope_kv_kernel + decode_attn_kernel in sr_elementwise.cu / sr_tail.cu).
+// Unit = (sample, kv head, key split), exactly one per CTA (n_units <= gridDim.x).  The phase is a chain of dependent global
+// round trips (~1-2 us each while the producer saturates HBM), so it is arranged to need as few as possible:
+//   * kv_start / kv_len / cache_row and the step's cos/sin table sit in shared memory (loaded once per launch);
+//   * the K rows and V^T vectors of the OLD keys do not depend on this layer's qkv: they are requested into registers
+//     BEFORE the grid barrier that ends the qkv phase (dp_attn_prefetch) and arrive while the CTA waits there;
+//   * after the barrier: one round trip for q (+ the new k, v of the owning split, which never re-reads them from the
+//     cache: they go to shared memory and, fire-and-forget, to the cache), then scores / softmax / P.V from registers;
+//   * partial (o, m, l) -> workspace, one acq_rel ticket; the last CTA of a (sample, kv head) merges with ALL its loads
+//     (statistics and partial outputs) in flight at once.
+struct DpAttnUnit {
+  int b, kvh, split, bk;
+  int start, len, crow;
+  int k_begin, k_end;
+  bool active, owner;  // owner: this split contains the newest key (index len - 1 = cache row crow)
+};
+struct DpAttnPre {
+  uint4 k[8];  // thread (key kk, half): dims [64*half, 64*half + 64) of the key row (first pass)
+  uint4 v[8];  // thread (dim kk, half): V^T vectors (8 keys each) i = 2*ii + half of output dim kk (first pass)
+};
+SR_DEVINL DpAttnUnit dp_attn_unit(const DpParams& p, const int* s_scal) {
+  DpAttnUnit U;
+  const int unit = blockIdx.x, ns = p.ns;
+  U.active = unit < p.B * p.nkv * ns;
+  U.split = unit % ns;
+  U.bk = unit / ns;
+  U.kvh = U.bk % p.nkv;
+  U.b = U.active ? U.bk / p.nkv : 0;
+  U.start = s_scal[U.b];
+  U.len = s_scal[8 + U.b];
+  U.crow = s_scal[16 + U.b];
+  int per = (U.len + ns - 1) / ns;
+  per = (per + 7) & ~7;  // V^T vectors are 8 keys wide
+  U.k_begin = U.split * per;
+  U.k_end = min(U.len, U.k_begin + per);
+  U.owner = U.active && U.len > 0 && (U.len - 1) / per == U.split;
+  return U;
+}
+// K / V^T loads of one pass (keys [p0, p0 + nk)); the newest key (jnew within the pass, or -1) is never read from the cache.
+// Every cache element is requested by exactly one thread.
+SR_DEVINL void dp_attn_load(const DpParams& p, const DpAttnUnit& U, const __nv_bfloat16* Kc, const __nv_bfloat16* Vt, int p0, int nk,
+                            int jnew, DpAttnPre& pre) {
+  const int ct = threadIdx.x - 32;
+  const int kk = ct & 127, half = ct >> 7;
+  if (kk < nk && kk != jnew) {
+    const __nv_bfloat16* kr = Kc + (static_cast<int64_t>(U.start + p0 + kk) * p.nkv + U.kvh) * 128 + half * 64;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pre.k[i] = dp_ldcg(kr + i * 8);
+  }
+  const __nv_bfloat16* vrow = Vt + static_cast<int64_t>(U.kvh * 128 + kk) * p.ldvt + U.start + p0;
+  const int nvec = (nk + 7) >> 3;
+#pragma unroll
+  for (int ii = 0; ii < 8; ++ii) {
+    const int i = 2 * ii + half;
+    if (i < nvec) pre.v[ii] = dp_ldcg(vrow + i * 8);
+  }
+}
+SR_DEVINL int dp_attn_jnew(const DpAttnUnit& U, int p0, int nk) {
+  const int j = U.len - 1 - p0;
+  return (U.owner && j >= 0 && j < nk) ? j : -1;
+}
+SR_DEVINL void dp_attn_prefetch(const DpParams& p, int layer, const DpAttnUnit& U, DpAttnPre& pre) {
+  if (!U.active || U.k_begin >= U.k_end) return;
+  const int nk = min(DP_KEYS, U.k_end - U.k_begin);
+  dp_attn_load(p, U, p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride, p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride,
+               U.k_begin, nk, dp_attn_jnew(U, U.k_begin, nk), pre);
+}
+
+SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, float* sm, const float* s_cos, const float* s_sin,
+                                  const DpAttnUnit& U, DpAttnPre& pre) {
+  if (!U.active) return;  // uniform per CTA
   const int ct = threadIdx.x - 32, lane = ct & 31, warp = ct >> 5;
   const int G = p.nq / p.nkv, ns = p.ns;
   float* sq = sm + DPA_SQ;
@@ -392,191 +520,227 @@ SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, float* sm) {
   float* m_f = sm + DPA_F;
   float* m_L = sm + DPA_LL;
   int* s_flag = reinterpret_cast<int*>(sm + DPA_FLAG);
+  float* snk = sm + DPA_NK;
+  float* snv = sm + DPA_NV;
+  float* s_pnew = sm + DPA_PNEW;
+  float* s_ex = sm + DPA_EX;
   __nv_bfloat16* Kc = p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride;
   __nv_bfloat16* Vt = p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride;
   const int ldq = (p.nq + 2 * p.nkv) * 128;
-  const int n_units = p.B * p.nkv * ns;
-  const int half = ct >> 7;   // heads [half*4, half*4+4)
+  const int half = ct >> 7;   // scores: dims [64*half, +64) of all heads, then heads [4*half, +4); P.V: vectors of parity `half`
   const int kk = ct & 127;    // key within the pass / output dim
-  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-    const int split = unit % ns, bk = unit / ns;
-    const int kvh = bk % p.nkv, b = bk / p.nkv;
-    dp_cbar();  // scratch reuse between units (and after the staged-activation use of this region)
-    const int start = __ldg(p.kv_start + b), len = __ldcg(p.kv_len + b), crow = __ldcg(p.cache_row + b);
-    int per = (len + ns - 1) / ns;
-    per = (per + 7) & ~7;  // V^T vectors are 8 keys wide
-    const int k_begin = split * per, k_end = min(len, k_begin + per);
-    const __nv_bfloat16* qrow = p.qkv + static_cast<int64_t>(b) * ldq;
-    // roped, scaled q of the G heads -> sq (rounded through bf16 like the cached path)
-    for (int i = ct; i < G * 64; i += DP_CTHREADS) {
-      const int h = i >> 6, d = i & 63;
-      const float c = __ldcg(p.cosb + b * 64 + d), s = __ldcg(p.sinb + b * 64 + d);
-      const __nv_bfloat16* qh = qrow + (kvh * G + h) * 128;
-      const float x1 = __bfloat162float(__ldcg(reinterpret_cast<const __nv_bfloat16*>(qh + d)));
-      const float x2 = __bfloat162float(__ldcg(reinterpret_cast<const __nv_bfloat16*>(qh + d + 64)));
-      sq[h * 128 + d] = __bfloat162float(__float2bfloat16(x1 * c - x2 * s)) * p.scale_log2;
-      sq[h * 128 + d + 64] = __bfloat162float(__float2bfloat16(x2 * c + x1 * s)) * p.scale_log2;
+  const int b = U.b, kvh = U.kvh;
+  const __nv_bfloat16* qrow = p.qkv + static_cast<int64_t>(b) * ldq;
+  const float* cs = s_cos + b * 64;
+  const float* sn = s_sin + b * 64;
+  // one round trip: q of the G heads (threads 0..8G-1, 8 + 8 elements each), new k (threads 64..127), new v (128..255)
+  if (ct < G * 8) {
+    const int h = ct >> 3, d0 = (ct & 7) * 8;
+    const __nv_bfloat16* qh = qrow + (kvh * G + h) * 128;
+    const uint4 lo = dp_ldcg(qh + d0), hi = dp_ldcg(qh + 64 + d0);
+    const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x1 = (j & 1) ? bf16_hi(lw[j >> 1]) : bf16_lo(lw[j >> 1]);
+      const float x2 = (j & 1) ? bf16_hi(hw[j >> 1]) : bf16_lo(hw[j >> 1]);
+      const float c = cs[d0 + j], s = sn[d0 + j];
+      // rounded through bf16 like the q the per-layer path writes back before its attention kernel reads it
+      sq[h * 128 + d0 + j] = __bfloat162float(__float2bfloat16(x1 * c - x2 * s)) * p.scale_log2;
+      sq[h * 128 + 64 + d0 + j] = __bfloat162float(__float2bfloat16(x2 * c + x1 * s)) * p.scale_log2;
     }
-    if (ct < DP_GMAX) { s_m[ct] = -INFINITY; s_l[ct] = 0.f; }
-    // the split that owns the newest key (index len-1 = cache row crow) appends roped k and v for this kv head
-    if (len > 0 && (len - 1) / per == split) {
-      if (ct < 64) {
-        const float c = __ldcg(p.cosb + b * 64 + ct), s = __ldcg(p.sinb + b * 64 + ct);
-        const __nv_bfloat16* kh = qrow + (p.nq + kvh) * 128;
-        const float x1 = __bfloat162float(__ldcg(kh + ct)), x2 = __bfloat162float(__ldcg(kh + ct + 64));
-        __nv_bfloat16* kd = Kc + (static_cast<int64_t>(crow) * p.nkv + kvh) * 128;
-        kd[ct] = __float2bfloat16(x1 * c - x2 * s);
-        kd[ct + 64] = __float2bfloat16(x2 * c + x1 * s);
-      } else if (ct < 64 + 128) {
-        const int d = ct - 64;
-        Vt[static_cast<int64_t>(kvh * 128 + d) * p.ldvt + crow] = __ldcg(qrow + (p.nq + p.nkv + kvh) * 128 + d);
-      }
-      __threadfence();
-    }
-    float o_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    dp_cbar();
-    for (int p0 = k_begin; p0 < k_end; p0 += DP_KEYS) {
-      const int nk = min(DP_KEYS, k_end - p0);
-      float sc4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      if (kk < nk) {
-        const __nv_bfloat16* kr = Kc + (static_cast<int64_t>(start + p0 + kk) * p.nkv + kvh) * 128;
-        uint4 v[16];
+  } else if (U.owner && ct >= 64 && ct < 128) {
+    const int d = ct - 64;
+    const __nv_bfloat16* kh = qrow + (p.nq + kvh) * 128;
+    const float x1 = __bfloat162float(__ldcg(kh + d)), x2 = __bfloat162float(__ldcg(kh + d + 64));
+    const __nv_bfloat16 k1 = __float2bfloat16(x1 * cs[d] - x2 * sn[d]), k2 = __float2bfloat16(x2 * cs[d] + x1 * sn[d]);
+    __nv_bfloat16* kd = Kc + (static_cast<int64_t>(U.crow) * p.nkv + kvh) * 128;
+    kd[d] = k1;
+    kd[d + 64] = k2;
+    snk[d] = __bfloat162float(k1);
+    snk[d + 64] = __bfloat162float(k2);
+  } else if (U.owner && ct >= 128) {
+    const int d = ct - 128;
+    const __nv_bfloat16 v = __ldcg(qrow + (p.nq + p.nkv + kvh) * 128 + d);
+    Vt[static_cast<int64_t>(kvh * 128 + d) * p.ldvt + U.crow] = v;
+    snv[d] = __bfloat162float(v);
+  }
+  if (ct < DP_GMAX) { s_m[ct] = -INFINITY; s_l[ct] = 0.f; }
+  float o_acc[DP_GMAX];  // un-normalised partial output of dim kk over this thread's key vectors, all heads
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = dp_ldcg(kr + i * 8);
+  for (int h = 0; h < DP_GMAX; ++h) o_acc[h] = 0.f;
+  dp_cbar();
+  for (int p0 = U.k_begin; p0 < U.k_end; p0 += DP_KEYS) {
+    const int nk = min(DP_KEYS, U.k_end - p0);
+    const int jnew = dp_attn_jnew(U, p0, nk);
+    if (p0 != U.k_begin) dp_attn_load(p, U, Kc, Vt, p0, nk, jnew, pre);  // first pass: prefetched before the barrier
+    // ---- partial scores over this thread's 64 dims, all heads -> s_ex[half][h][kk]
+    if (kk < nk) {
 #pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
-          const int h = half * 4 + hh;
-          if (h < G) {
-            float d = 0.f;
+      for (int h = 0; h < DP_GMAX; ++h) {
+        if (h < G) {
+          const float* qv = sq + h * 128 + half * 64;
+          float d = 0.f;
+          if (kk == jnew) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float4 q0 = *reinterpret_cast<const float4*>(&sq[h * 128 + i * 8]);
-              const float4 q1 = *reinterpret_cast<const float4*>(&sq[h * 128 + i * 8 + 4]);
-              d += bf16_lo(v[i].x) * q0.x + bf16_hi(v[i].x) * q0.y + bf16_lo(v[i].y) * q0.z + bf16_hi(v[i].y) * q0.w +
-                   bf16_lo(v[i].z) * q1.x + bf16_hi(v[i].z) * q1.y + bf16_lo(v[i].w) * q1.z + bf16_hi(v[i].w) * q1.w;
+            for (int i = 0; i < 8; ++i) {
+              const float4 q0 = *reinterpret_cast<const float4*>(qv + i * 8), q1 = *reinterpret_cast<const float4*>(qv + i * 8 + 4);
+              const float4 k0 = *reinterpret_cast<const float4*>(snk + half * 64 + i * 8);
+              const float4 k1 = *reinterpret_cast<const float4*>(snk + half * 64 + i * 8 + 4);
+              d += k0.x * q0.x + k0.y * q0.y + k0.z * q0.z + k0.w * q0.w + k1.x * q1.x + k1.y * q1.y + k1.z * q1.z + k1.w * q1.w;
             }
-            sc4[hh] = d;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q0 = *reinterpret_cast<const float4*>(qv + i * 8), q1 = *reinterpret_cast<const float4*>(qv + i * 8 + 4);
+              const uint4 v = pre.k[i];
+              d += bf16_lo(v.x) * q0.x + bf16_hi(v.x) * q0.y + bf16_lo(v.y) * q0.z + bf16_hi(v.y) * q0.w +
+                   bf16_lo(v.z) * q1.x + bf16_hi(v.z) * q1.y + bf16_lo(v.w) * q1.z + bf16_hi(v.w) * q1.w;
+            }
           }
+          s_ex[(half * DP_GMAX + h) * 128 + kk] = d;
         }
       }
+    }
+    dp_cbar();
+    // ---- full scores of heads [4*half, +4) for key kk; per-head max over the pass
+    float sc4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
-        const float m = warp_max(sc4[hh]);
-        if (lane == 0) s_red[warp * DP_GMAX + hh] = m;  // warps 0-3 hold half 0, warps 4-7 half 1
-      }
-      dp_cbar();
-      if (ct < G) {
-        const int hf = ct >> 2, hh = ct & 3;
-        float m = s_m[ct];
-        for (int w = 0; w < 4; ++w) m = fmaxf(m, s_red[(hf * 4 + w) * DP_GMAX + hh]);
-        const float m_use = (m == -INFINITY) ? 0.f : m;
-        s_alpha[ct] = exp2f(s_m[ct] - m_use);
-        s_m[ct] = m;
-      }
-      dp_cbar();
-      float ps[4];
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = half * 4 + hh;
+      if (h < G && kk < nk) sc4[hh] = s_ex[h * 128 + kk] + s_ex[(DP_GMAX + h) * 128 + kk];
+      const float m = warp_max(sc4[hh]);
+      if (lane == 0) s_red[warp * DP_GMAX + hh] = m;  // warps 0-3 hold half 0, warps 4-7 half 1
+    }
+    dp_cbar();
+    if (ct < G) {
+      const int hf = ct >> 2, hh = ct & 3;
+      float m = s_m[ct];
+      for (int w = 0; w < 4; ++w) m = fmaxf(m, s_red[(hf * 4 + w) * DP_GMAX + hh]);
+      const float m_use = (m == -INFINITY) ? 0.f : m;
+      s_alpha[ct] = exp2f(s_m[ct] - m_use);
+      s_m[ct] = m;
+    }
+    dp_cbar();
+    float ps[4];
 #pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
-        const int h = half * 4 + hh;
-        float pv = 0.f;
-        if (h < G && kk < nk) {
-          const float m = s_m[h];
-          pv = exp2f(sc4[hh] - ((m == -INFINITY) ? 0.f : m));
-        }
-        if (h < G) sp[h * DP_KEYS + kk] = pv;
-        ps[hh] = warp_sum(pv);
-        if (lane == 0) s_red[warp * DP_GMAX + hh] = ps[hh];
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = half * 4 + hh;
+      float pv = 0.f;
+      if (h < G && kk < nk) {
+        const float m = s_m[h];
+        pv = exp2f(sc4[hh] - ((m == -INFINITY) ? 0.f : m));
       }
-      dp_cbar();
-      if (ct < G) {
-        const int hf = ct >> 2, hh = ct & 3;
-        float l = 0.f;
-        for (int w = 0; w < 4; ++w) l += s_red[(hf * 4 + w) * DP_GMAX + hh];
-        s_l[ct] = s_l[ct] * s_alpha[ct] + l;
+      if (h < G) {
+        sp[h * DP_KEYS + kk] = (kk == jnew) ? 0.f : pv;  // the new key's value comes from snv, not from the V^T registers
+        if (kk == jnew) s_pnew[h] = pv;
       }
-      const __nv_bfloat16* vrow = Vt + static_cast<int64_t>(kvh * 128 + kk) * p.ldvt + start + p0;
-      const int nvec = (nk + 7) >> 3;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-      for (int i = 0; i < nvec; ++i) {
-        const uint4 u = dp_ldcg(vrow + i * 8);
+      ps[hh] = warp_sum(pv);
+      if (lane == 0) s_red[warp * DP_GMAX + hh] = ps[hh];
+    }
+    dp_cbar();
+    if (ct < G) {
+      const int hf = ct >> 2, hh = ct & 3;
+      float l = 0.f;
+      for (int w = 0; w < 4; ++w) l += s_red[(hf * 4 + w) * DP_GMAX + hh];
+      s_l[ct] = s_l[ct] * s_alpha[ct] + l;
+    }
+    // ---- P.V over this thread's vectors (i = 2*ii + half), all heads
+    const int nvec = (nk + 7) >> 3;
+    float acc[DP_GMAX];
+#pragma unroll
+    for (int h = 0; h < DP_GMAX; ++h) acc[h] = 0.f;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {
+      const int i = 2 * ii + half;
+      if (i < nvec) {
+        const uint4 u = pre.v[ii];
         const float vv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
-        for (int hh = 0; hh < 4; ++hh) {
-          const int h = half * 4 + hh;
+        for (int h = 0; h < DP_GMAX; ++h) {
           if (h < G) {
             const float4 p0v = *reinterpret_cast<const float4*>(&sp[h * DP_KEYS + i * 8]);
             const float4 p1v = *reinterpret_cast<const float4*>(&sp[h * DP_KEYS + i * 8 + 4]);
-            acc[hh] += vv[0] * p0v.x + vv[1] * p0v.y + vv[2] * p0v.z + vv[3] * p0v.w + vv[4] * p1v.x + vv[5] * p1v.y +
-                       vv[6] * p1v.z + vv[7] * p1v.w;
+            acc[h] += vv[0] * p0v.x + vv[1] * p0v.y + vv[2] * p0v.z + vv[3] * p0v.w + vv[4] * p1v.x + vv[5] * p1v.y +
+                      vv[6] * p1v.z + vv[7] * p1v.w;
           }
         }
       }
+    }
+    if (jnew >= 0 && half == 0) {
+      const float vn = snv[kk];
 #pragma unroll
-      for (int hh = 0; hh < 4; ++hh) {
-        const int h = half * 4 + hh;
-        if (h < G) o_acc[hh] = o_acc[hh] * s_alpha[h] + acc[hh];
-      }
-      dp_cbar();  // sp / s_red / s_alpha are reused by the next pass
+      for (int h = 0; h < DP_GMAX; ++h)
+        if (h < G) acc[h] += vn * s_pnew[h];
     }
-    // publish this split's un-normalised partial (o, m, l)
-    float* wo = p.attn_ws + (static_cast<int64_t>(bk) * ns + split) * DP_PART;
 #pragma unroll
-    for (int hh = 0; hh < 4; ++hh) {
-      const int h = half * 4 + hh;
-      if (h < G) wo[h * 128 + kk] = o_acc[hh];
-    }
-    if (ct < G) {
-      wo[DP_GMAX * 128 + ct] = s_m[ct];
-      wo[DP_GMAX * 128 + DP_GMAX + ct] = s_l[ct];
-    }
-    __threadfence();
-    dp_cbar();
-    if (ct == 0) {
-      const int ticket = atomicAdd(p.attn_tickets + bk, 1);
-      *s_flag = (ticket == ns - 1) ? 1 : 0;
-    }
-    dp_cbar();
-    if (*s_flag == 0) continue;
-    __threadfence();
-    // merge (last CTA of this (sample, kv head)); all loads issued in parallel
-    const float* wb = p.attn_ws + static_cast<int64_t>(bk) * ns * DP_PART;
-    for (int i = ct; i < ns * G; i += DP_CTHREADS) {
-      const int s2 = i / G, h = i % G;
-      m_ms[s2 * DP_GMAX + h] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + h);
-      m_ls[s2 * DP_GMAX + h] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + DP_GMAX + h);
-    }
-    dp_cbar();
-    if (ct < G) {
-      float Mx = -INFINITY;
-      for (int s2 = 0; s2 < ns; ++s2) Mx = fmaxf(Mx, m_ms[s2 * DP_GMAX + ct]);
-      const float Mu = (Mx == -INFINITY) ? 0.f : Mx;
-      float L = 0.f;
-      for (int s2 = 0; s2 < ns; ++s2) {
-        const float f = exp2f(m_ms[s2 * DP_GMAX + ct] - Mu);
-        m_f[s2 * DP_GMAX + ct] = f;
-        L += m_ls[s2 * DP_GMAX + ct] * f;
-      }
-      m_L[ct] = L;
-    }
-    dp_cbar();
-#pragma unroll
-    for (int hh = 0; hh < 4; ++hh) {
-      const int h = half * 4 + hh;
-      if (h >= G) continue;
-      float O = 0.f;
-      for (int s0 = 0; s0 < ns; s0 += 8) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (s0 + j < ns) ? __ldcg(wb + (s0 + j) * DP_PART + h * 128 + kk) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) O += (s0 + j < ns) ? v[j] * m_f[(s0 + j) * DP_GMAX + h] : 0.f;
-      }
-      const float L = m_L[h];
-      p.ao[static_cast<int64_t>(b) * (p.nq * 128) + (kvh * G + h) * 128 + kk] = __float2bfloat16(L > 0.f ? O / L : 0.f);
-    }
-    if (ct == 0) p.attn_tickets[bk] = 0;  // re-arm for the next layer / launch
+    for (int h = 0; h < DP_GMAX; ++h)
+      if (h < G) o_acc[h] = o_acc[h] * s_alpha[h] + acc[h];
+    dp_cbar();  // sp / s_red / s_alpha / s_pnew / s_ex are reused by the next pass
   }
+  // ---- combine the two key-parity halves: thread (kk, half) owns heads [4*half, +4)
+#pragma unroll
+  for (int h = 0; h < DP_GMAX; ++h)
+    if (h < G) s_ex[(half * DP_GMAX + h) * 128 + kk] = o_acc[h];
+  dp_cbar();
+  // publish this split's un-normalised partial (o, m, l)
+  float* wo = p.attn_ws + (static_cast<int64_t>(U.bk) * ns + U.split) * DP_PART;
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+    const int h = half * 4 + hh;
+    if (h < G) wo[h * 128 + kk] = s_ex[h * 128 + kk] + s_ex[(DP_GMAX + h) * 128 + kk];
+  }
+  if (ct < G) {
+    wo[DP_GMAX * 128 + ct] = s_m[ct];
+    wo[DP_GMAX * 128 + DP_GMAX + ct] = s_l[ct];
+  }
+  dp_cbar();
+  if (ct == 0) {  // release our partial (cumulative through the CTA barrier), acquire the others'
+    int ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(p.attn_tickets + U.bk) : "memory");
+    *s_flag = (ticket == ns - 1) ? 1 : 0;
+  }
+  dp_cbar();
+  if (*s_flag == 0) return;
+  // merge (last CTA of this (sample, kv head)): statistics and partial outputs requested together
+  const float* wb = p.attn_ws + static_cast<int64_t>(U.bk) * ns * DP_PART;
+  float ov[4][16];
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+    const int h = half * 4 + hh;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ov[hh][j] = (h < G && j < ns) ? __ldcg(wb + j * DP_PART + h * 128 + kk) : 0.f;
+  }
+  for (int i = ct; i < ns * G; i += DP_CTHREADS) {
+    const int s2 = i / G, h = i % G;
+    m_ms[s2 * DP_GMAX + h] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + h);
+    m_ls[s2 * DP_GMAX + h] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + DP_GMAX + h);
+  }
+  dp_cbar();
+  if (ct < G) {
+    float Mx = -INFINITY;
+    for (int s2 = 0; s2 < ns; ++s2) Mx = fmaxf(Mx, m_ms[s2 * DP_GMAX + ct]);
+    const float Mu = (Mx == -INFINITY) ? 0.f : Mx;
+    float L = 0.f;
+    for (int s2 = 0; s2 < ns; ++s2) {
+      const float f = exp2f(m_ms[s2 * DP_GMAX + ct] - Mu);
+      m_f[s2 * DP_GMAX + ct] = f;
+      L += m_ls[s2 * DP_GMAX + ct] * f;
+    }
+    m_L[ct] = L;
+  }
+  dp_cbar();
+#pragma unroll
+  for (int hh = 0; hh < 4; ++hh) {
+    const int h = half * 4 + hh;
+    if (h >= G) continue;
+    float O = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) O += (j < ns) ? ov[hh][j] * m_f[j * DP_GMAX + h] : 0.f;
+    for (int j = 16; j < ns; ++j) O += __ldcg(wb + j * DP_PART + h * 128 + kk) * m_f[j * DP_GMAX + h];
+    const float L = m_L[h];
+    p.ao[static_cast<int64_t>(b) * (p.nq * 128) + (kvh * G + h) * 128 + kk] = __float2bfloat16(L > 0.f ? O / L : 0.f);
+  }
+  if (ct == 0) p.attn_tickets[U.bk] = 0;  // re-arm for the next layer / launch
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -592,7 +756,27 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   uint8_t* xs = smem + DP_OFF_XS;
   float* red = reinterpret_cast<float*>(smem + DP_OFF_RED);
 
+  DpLayer* s_layers = reinterpret_cast<DpLayer*>(smem + DP_OFF_LAYERS);
+  float* s_cos = reinterpret_cast<float*>(smem + DP_OFF_ROPE);
+  float* s_sin = s_cos + 8 * 64;
+  int* s_scal = reinterpret_cast<int*>(smem + DP_OFF_SCAL);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {  // per-launch constants -> shared memory (pointer / scalar loads off the critical paths)
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.layers);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_layers);
+    for (int i = threadIdx.x; i < p.n_layers * 7; i += DP_THREADS) dst[i] = src[i];
+    for (int i = threadIdx.x; i < 8 * 64; i += DP_THREADS) {
+      const bool ok = i < p.B * 64;
+      s_cos[i] = ok ? p.cosb[i] : 0.f;
+      s_sin[i] = ok ? p.sinb[i] : 0.f;
+    }
+    if (threadIdx.x < 8) {
+      const bool ok = static_cast<int>(threadIdx.x) < p.B;
+      s_scal[threadIdx.x] = ok ? p.kv_start[threadIdx.x] : 0;
+      s_scal[8 + threadIdx.x] = ok ? p.kv_len[threadIdx.x] : 0;
+      s_scal[16 + threadIdx.x] = ok ? p.cache_row[threadIdx.x] : 0;
+    }
+  }
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < DP_STAGES; ++i) {
@@ -614,21 +798,30 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   if (warp == 0) {
     // ---------------- producer: weights only; runs ahead of the consumers across phases ----------------
     if (lane == 0) {
+      uint64_t policy = 0;
+      const bool hint = (p.flags & 1) != 0;
+      if (hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       int ph = 0;
+      dp_trace_at(p, 0, 0);
       for (int l = 0; l < p.n_layers; ++l) {
-        const DpLayer L = p.layers[l];
+        const DpLayer L = s_layers[l];
         if (ph++ >= limit) return;
-        dp_produce<1>(ring, L.qkv_wp, n_qkv, kq);
+        dp_produce<1, false>(ring, L.qkv_wp, n_qkv, kq, policy, hint);
+        dp_trace_at(p, 0, 1 + 4 * l);
         if (ph++ >= limit) return;  // attention phase: no weights
         if (ph++ >= limit) return;
-        dp_produce<1>(ring, L.o_wp, n_o, kq);
+        dp_produce<1, false>(ring, L.o_wp, n_o, kq, policy, hint);
+        dp_trace_at(p, 0, 2 + 4 * l);
         if (ph++ >= limit) return;
-        dp_produce<2>(ring, L.gu_wp, n_gu, kq);
+        dp_produce<2, false>(ring, L.gu_wp, n_gu, kq, policy, hint);
+        dp_trace_at(p, 0, 3 + 4 * l);
         if (ph++ >= limit) return;
-        dp_produce<1>(ring, L.down_wp, n_o, kd);
+        dp_produce<1, true>(ring, L.down_wp, n_o, kd, policy, hint);
+        dp_trace_at(p, 0, 4 + 4 * l);
       }
       if (ph++ >= limit) return;
-      dp_produce<1>(ring, p.lm_head_p, n_head, kq);
+      dp_produce<1, false>(ring, p.lm_head_p, n_head, kq, policy, hint);
+      dp_trace_at(p, 0, 1 + 4 * p.n_layers);
     }
     return;
   }
@@ -637,43 +830,62 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   const int cw = warp - 1;
   int red_par = 0;
   unsigned int bar_gen = 0;
-  int ph = 0;
+  int ph = 0, tr = 0;
   const unsigned int G = gridDim.x;
+  const bool tracer = threadIdx.x == 32;
+  const DpAttnUnit U = dp_attn_unit(p, s_scal);
+  DpAttnPre pre;
+#define DP_TRACE() do { if (tracer) dp_trace(p, 1, tr); } while (0)
+  DP_TRACE();
   for (int l = 0; l < p.n_layers; ++l) {
-    const DpLayer L = p.layers[l];
+    const DpLayer L = s_layers[l];
     // A: qkv = rmsnorm(x; ln1) . Wqkv^T + b
     if (ph++ >= limit) return;
     dp_stage_rows<true>(xs, p.x, p.ldx, p.B, L.ln1, p.eps, cw, lane);
     dp_cbar();
     dp_gemv_phase<1, DP_EPI_BIAS, true>(ring, n_qkv, kq, xs, nullptr, 0, p.B, red, red_par, L.qkv_b, p.qkv, nullptr,
                                         static_cast<int64_t>(n_qkv) * 16, cw, lane);
+    const bool do_attn = ph < limit;
+    if (do_attn) dp_attn_prefetch(p, l, U, pre);  // old K / V^T rows fly while the CTA waits at the barrier
+    DP_TRACE();
     dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    DP_TRACE();
     // B: rope + KV append + attention -> ao
     if (ph++ >= limit) return;
-    dp_attention_phase(p, l, reinterpret_cast<float*>(xs));
+    dp_attention_phase(p, l, reinterpret_cast<float*>(xs), s_cos, s_sin, U, pre);
+    DP_TRACE();
     dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    DP_TRACE();
     // C: x += ao . Wo^T
     if (ph++ >= limit) return;
     dp_stage_rows<false>(xs, p.ao, DP_H, p.B, nullptr, 0.f, cw, lane);
     dp_cbar();
     dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, n_o, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
+    DP_TRACE();
     dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    DP_TRACE();
     // D: act = silu(gate) * up, [gate|up] = rmsnorm(x; ln2) . Wgu^T
     if (ph++ >= limit) return;
     dp_stage_rows<true>(xs, p.x, p.ldx, p.B, L.ln2, p.eps, cw, lane);
     dp_cbar();
     dp_gemv_phase<2, DP_EPI_SWIGLU, true>(ring, n_gu, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.act, nullptr, p.I, cw, lane);
+    DP_TRACE();
     dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    DP_TRACE();
     // E: x += act . Wdown^T
     if (ph++ >= limit) return;
     dp_gemv_phase<1, DP_EPI_RESIDUAL, false>(ring, n_o, kd, nullptr, p.act, p.I, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
+    DP_TRACE();
     dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    DP_TRACE();
   }
   // final norm + LM head -> fp32 logits
   if (ph++ >= limit) return;
   dp_stage_rows<true>(xs, p.x, p.ldx, p.B, p.final_norm, p.eps, cw, lane);
   dp_cbar();
   dp_gemv_phase<1, DP_EPI_F32, true>(ring, n_head, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, nullptr, p.logits, p.ld_logits, cw, lane);
+  DP_TRACE();
+#undef DP_TRACE
 }
 
 }  // namespace sr
@@ -684,6 +896,23 @@ extern "C" int64_t sr_decode_persistent_workspace_bytes(int batch, int n_kv_head
   // [16 B: grid barrier counter][tickets: batch*nkv int32, 16 B aligned][partials: batch*nkv*DP_NS_MAX*DP_PART fp32]
   const int64_t bk = static_cast<int64_t>(batch) * n_kv_heads;
   return 16 + ((bk * 4 + 15) / 16) * 16 + bk * DP_NS_MAX * DP_PART * 4;
+}
+
+static unsigned long long* g_dp_trace = nullptr;
+static int g_dp_trace_events = 0;
+extern "C" int sr_set_decode_persistent_trace(void* buffer, int events_per_role) {
+  g_dp_trace = reinterpret_cast<unsigned long long*>(buffer);
+  g_dp_trace_events = buffer ? events_per_role : 0;
+  return SR_OK;
+}
+
+static int g_dp_pf_stages = -1;  // -1: env SR_DECODE_PF_STAGES (default below)
+static int g_dp_flags = -1;      // -1: env SR_DECODE_FLAGS
+extern "C" int sr_set_decode_persistent_tuning(int pf_stages, int flags) {
+  if (pf_stages < 0 || pf_stages > 4096) return SR_ERR_INVALID;
+  g_dp_pf_stages = pf_stages;
+  g_dp_flags = flags;
+  return SR_OK;
 }
 
 static int g_dp_coop = -1;
@@ -705,6 +934,7 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
   SR_REQUIRE(batch > 0 && batch <= 8, "sr_decode_step_persistent: batch must be in [1, 8] (got %d)", batch);
   SR_REQUIRE(n_q_heads * 128 == DP_H && n_kv_heads > 0 && n_q_heads % n_kv_heads == 0 && n_q_heads / n_kv_heads <= DP_GMAX,
              "sr_decode_step_persistent: needs hidden 2048 = n_q_heads * 128 and <= 8 query heads per kv head");
+  SR_REQUIRE(n_layers <= DP_MAX_LAYERS, "sr_decode_step_persistent: at most %d layers", DP_MAX_LAYERS);
   SR_REQUIRE(intermediate % 32 == 0 && vocab % 16 == 0 && n_layers > 0, "sr_decode_step_persistent: intermediate %% 32, vocab %% 16");
   SR_REQUIRE(ldx % 8 == 0 && ldvt % 8 == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(act_scratch) & 15) == 0 &&
@@ -757,9 +987,22 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
   p.grid_bar = reinterpret_cast<unsigned int*>(ws);
   p.attn_tickets = reinterpret_cast<int*>(ws + 16);
   p.attn_ws = reinterpret_cast<float*>(ws + 16 + ((bk * 4 + 15) / 16) * 16);
+  SR_REQUIRE(bk <= grid_cached, "sr_decode_step_persistent: batch * n_kv_heads must not exceed the SM count");
   int ns = grid_cached / static_cast<int>(bk);
   p.ns = ns < 1 ? 1 : (ns > DP_NS_MAX ? DP_NS_MAX : ns);
   p.stop_after = stop_after_phases;
+  if (g_dp_pf_stages < 0) {
+    const char* e = getenv("SR_DECODE_PF_STAGES");
+    g_dp_pf_stages = e ? atoi(e) : 0;
+  }
+  if (g_dp_flags < 0) {
+    const char* e = getenv("SR_DECODE_FLAGS");
+    g_dp_flags = e ? atoi(e) : 0;
+  }
+  p.pf_stages = g_dp_pf_stages;  // (reserved: the L2-prefetch cursor was removed, see dp_produce)
+  p.flags = g_dp_flags;
+  p.trace = g_dp_trace;
+  p.trace_events = g_dp_trace_events;
   // the barrier counter (and, defensively, the tickets) start at zero for every launch
   SR_CHECK_CUDA(cudaMemsetAsync(ws, 0, 16 + ((bk * 4 + 15) / 16) * 16, s));
   cudaLaunchConfig_t cfg = {};

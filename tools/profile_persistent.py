@@ -1,0 +1,13 @@
+"""One persistent decode step at the bench geometry (36 layers, vocab 151936, B=8, ~900 cached tokens) for ncu:
+ncu --set full --clock-control none --import-source on -k regex:decode_persistent -s 1 -c 1 python tools/profile_persistent.py"""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import persistent_bringup as PB
+torch.manual_seed(0)
+layers = PB.make_layers(36)
+S = PB.State(8, 36, 1024, [900 - 7 * i for i in range(8)], 151936)
+P = PB.Persistent(S, layers)
+for _ in range(3):
+    P.run(0)
+torch.cuda.synchronize()
+print("done")

@@ -25,11 +25,15 @@
 
 #include "sr_host.h"
 
+#ifndef SR_DP_ATTN
+#define SR_DP_ATTN 3  // attention phase formulation: 3 = mma (default); 1, 2 = earlier scalar formulations (A/B builds)
+#endif
+
 namespace sr {
 
 constexpr int DP_CONSUMERS = 8;
 constexpr int DP_CTHREADS = DP_CONSUMERS * 32;
-constexpr int DP_THREADS = DP_CTHREADS + 32;          // warp 0 = producer
+constexpr int DP_THREADS = DP_CTHREADS + 64;          // warp 0 = producer, warps 1-8 = consumers, warp 9 = L2 prefetcher
 constexpr int DP_STAGE_BLOCKS = 16;                   // 1 KB weight blocks per ring stage
 constexpr int DP_STAGE_BYTES = DP_STAGE_BLOCKS * 1024;
 constexpr int DP_STAGES = 10;
@@ -52,7 +56,8 @@ constexpr int DP_OFF_BAR = DP_OFF_RED + DP_RED_BYTES;
 constexpr int DP_OFF_LAYERS = DP_OFF_BAR + 2 * DP_STAGES * 8 + 32;    // DpLayer[DP_MAX_LAYERS]
 constexpr int DP_OFF_ROPE = DP_OFF_LAYERS + DP_MAX_LAYERS * 56;       // cos[8][64], sin[8][64] fp32 of this step
 constexpr int DP_OFF_SCAL = DP_OFF_ROPE + 2 * 8 * 64 * 4;             // kv_start[8], kv_len[8], cache_row[8]
-constexpr int DP_SMEM_BYTES = DP_OFF_SCAL + 3 * 8 * 4 + 64 + 1024;    // + alignment slack
+constexpr int DP_OFF_PCNT = DP_OFF_SCAL + 3 * 8 * 4;                  // stages issued by the producer so far (read by the prefetcher)
+constexpr int DP_SMEM_BYTES = DP_OFF_PCNT + 64 + 1024;                // + alignment slack
 static_assert(DP_SMEM_BYTES <= 232448, "shared-memory budget of one sm_100 CTA");
 
 // attention scratch inside the xs region (floats)
@@ -161,7 +166,22 @@ SR_DEVINL uint4 dp_ldcg(const void* p) { return __ldcg(reinterpret_cast<const ui
 // Grid barrier for the consumer threads of all CTAs: every thread's global stores are fenced, one thread per CTA does a
 // release-add and polls with acquire loads until all CTAs of this generation have arrived.  Bounded: a broken schedule
 // traps (CUDA error through the C ABI) instead of hanging the GPU.
-SR_DEVINL void dp_grid_barrier(unsigned int* ctr, unsigned int target) {
+SR_DEVINL void dp_grid_barrier(unsigned int* ctr, unsigned int target, bool old_style = false) {
+  if (old_style) {
+    __threadfence();
+    dp_cbar();
+    if (threadIdx.x == 32) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
+      unsigned int v = 0;
+      while (true) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        if (v >= target) break;
+      }
+      __threadfence();
+    }
+    dp_cbar();
+    return;
+  }
   dp_cbar();  // orders every consumer thread's global stores before the release below (cumulativity through the CTA barrier)
   if (threadIdx.x == 32) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
@@ -199,7 +219,8 @@ struct DpRing {
 // from L2 by every CTA: without the rotation all CTAs request the same 8 KB of activations at the same time (hot L2 slices).
 SR_DEVINL int dp_rot(int u, int nst) { return (u * 7) % nst; }
 template <int RG, bool ROT>
-SR_DEVINL void dp_produce(DpRing& r, const __nv_bfloat16* Wp, int n_units, int nchunks, uint64_t policy, bool hint) {
+SR_DEVINL void dp_produce(DpRing& r, const __nv_bfloat16* Wp, int n_units, int nchunks, uint64_t policy, bool hint, volatile int* pcnt,
+                          int& issued) {
   constexpr int CPS = DP_STAGE_BLOCKS / RG;
   const int nst = (nchunks + CPS - 1) / CPS;
   for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -223,6 +244,39 @@ SR_DEVINL void dp_produce(DpRing& r, const __nv_bfloat16* Wp, int n_units, int n
         }
       }
       r.advance();
+      *pcnt = ++issued;
+      if (ROT && ++st == nst) st = 0;
+      if (!ROT) ++st;
+    }
+  }
+}
+
+// L2 prefetcher (warp 9, one thread): walks the SAME stage sequence as the producer, at most `lead` stages ahead of it, and asks
+// the memory system to bring each stage into L2 (cp.async.bulk.prefetch.L2).  The shared-memory ring holds only 160 KB per CTA
+// (3.7 us of HBM time chip-wide), and the consumers spend most of a layer in latency chains (qkv -> attention -> o-proj: grid
+// barriers, L2 round trips) during which the ring is full and HBM would idle; with the prefetcher the HBM stream continues into
+// L2 (`lead` x 16 KB x 148 CTAs), and the ring later refills at L2 speed.
+template <int RG, bool ROT>
+SR_DEVINL void dp_prefetch_l2(int& sidx, const volatile int* pcnt, int lead, const __nv_bfloat16* Wp, int n_units, int nchunks) {
+  constexpr int CPS = DP_STAGE_BLOCKS / RG;
+  const int nst = (nchunks + CPS - 1) / CPS;
+  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    int st = ROT ? dp_rot(u, nst) : 0;
+    for (int i = 0; i < nst; ++i) {
+      int pc = *pcnt;
+      while (sidx >= pc + lead) {
+        __nanosleep(100);
+        pc = *pcnt;
+      }
+      if (sidx > pc) {  // (the producer is about to request stage `pc` itself)
+        const int nch = min(CPS, nchunks - st * CPS);
+#pragma unroll
+        for (int g = 0; g < RG; ++g) {
+          const __nv_bfloat16* src = Wp + (static_cast<int64_t>(u * RG + g) * nchunks + st * CPS) * 512;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(static_cast<uint32_t>(nch * 1024)) : "memory");
+        }
+      }
+      ++sidx;
       if (ROT && ++st == nst) st = 0;
       if (!ROT) ++st;
     }
@@ -237,7 +291,15 @@ SR_DEVINL void dp_stage_rows(uint8_t* xs, const __nv_bfloat16* src, int64_t ld, 
                              int lane) {
   constexpr int NV = DP_H / 256;  // 16 B vectors per lane
   uint4 v[NV];
+  float4 nw0[NORM ? NV : 1], nw1[NORM ? NV : 1];
   const bool ok = cw < M;
+  if (NORM) {  // the norm weights do not depend on x: requested together with it (one round trip instead of two)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      nw0[i] = __ldg(reinterpret_cast<const float4*>(nw + (lane + 32 * i) * 8));
+      nw1[i] = __ldg(reinterpret_cast<const float4*>(nw + (lane + 32 * i) * 8 + 4));
+    }
+  }
 #pragma unroll
   for (int i = 0; i < NV; ++i)
     v[i] = ok ? dp_ldcg(src + static_cast<int64_t>(cw) * ld + (lane + 32 * i) * 8) : make_uint4(0, 0, 0, 0);
@@ -256,9 +318,7 @@ SR_DEVINL void dp_stage_rows(uint8_t* xs, const __nv_bfloat16* src, int64_t ld, 
     const float inv = rsqrtf(ss / static_cast<float>(DP_H) + eps);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(nw + c));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(nw + c + 4));
+      const float4 w0 = nw0[i], w1 = nw1[i];
       uint4 o;
       o.x = pack_bf16x2(bf16_lo(v[i].x) * inv * w0.x, bf16_hi(v[i].x) * inv * w0.y);
       o.y = pack_bf16x2(bf16_lo(v[i].y) * inv * w0.z, bf16_hi(v[i].y) * inv * w0.w);
@@ -317,11 +377,11 @@ SR_DEVINL void dp_consume_staged(DpRing& r, int nchunks, const uint8_t* xs, floa
 // K loop of one unit (RG = 1) with the activations read from global memory / L2 (long K: the down projection).
 // Stage order rotated per unit (see dp_produce<.., ROT>); activation fragments are prefetched DP_XPF stages ahead.
 SR_DEVINL void dp_consume_l2(DpRing& r, int u, int nchunks, const __nv_bfloat16* xg, int64_t ldx, int M, float (&acc)[1][4], int cw,
-                             int lane) {
+                             int lane, bool rot_on) {
   constexpr int CPS = DP_STAGE_BLOCKS;
   const int g = lane >> 2, t = lane & 3;
   const int nst = (nchunks + CPS - 1) / CPS;
-  const int rot = dp_rot(u, nst);
+  const int rot = rot_on ? dp_rot(u, nst) : 0;
   const bool xok = g < M;
   const __nv_bfloat16* xrow = xg + static_cast<int64_t>(xok ? g : 0) * ldx + t * 8;
   uint4 xq[DP_XPF][2];
@@ -371,7 +431,7 @@ enum { DP_EPI_BIAS = 0, DP_EPI_RESIDUAL = 1, DP_EPI_SWIGLU = 2, DP_EPI_F32 = 3 }
 template <int RG, int EPI, bool STAGED>
 SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t* xs, const __nv_bfloat16* xg, int64_t ldxg,
                              int M, float* red, int& red_par, const float* bias, __nv_bfloat16* out_bf, float* out_f32,
-                             int64_t ldo, int cw, int lane) {
+                             int64_t ldo, int cw, int lane, bool rot_on = true, bool late_epi = false) {
   const int g = lane >> 2, t = lane & 3;
   const int ct = threadIdx.x - 32;
   for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -382,7 +442,7 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t*
       for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
     // epilogue operands of this thread's output element: requested before the K loop so their latency is hidden
     float epi_add = 0.f;
-    if (ct < 128 && (ct >> 4) < M) {
+    if (ct < 128 && (ct >> 4) < M && !late_epi) {
       const int col = u * 16 + (ct & 15);
       if (EPI == DP_EPI_BIAS && bias != nullptr) epi_add = __ldg(bias + col);
       if (EPI == DP_EPI_RESIDUAL) {
@@ -394,7 +454,7 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t*
       dp_consume_staged<RG>(r, nchunks, xs, acc, cw, lane);
     } else {
       static_assert(STAGED || RG == 1, "the L2 activation path handles single row groups");
-      dp_consume_l2(r, u, nchunks, xg, ldxg, M, acc, cw, lane);
+      dp_consume_l2(r, u, nchunks, xg, ldxg, M, acc, cw, lane, rot_on);
     }
     // cross-warp reduction: C fragment (feature g | g+8, batch 2t | 2t+1) -> red[par][warp][q][feature*8 + batch]
     float* rp = red + red_par * (DP_CONSUMERS * 2 * 128);
@@ -424,6 +484,13 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t*
           out_bf[static_cast<int64_t>(b) * ldo + u * 16 + f] = __float2bfloat16(o);
         } else {
           const int col = u * 16 + f;
+          if (late_epi) {
+            if (EPI == DP_EPI_BIAS && bias != nullptr) epi_add = __ldg(bias + col);
+            if (EPI == DP_EPI_RESIDUAL) {
+              const unsigned short rbits = __ldcg(reinterpret_cast<const unsigned short*>(out_bf + static_cast<int64_t>(b) * ldo + col));
+              epi_add = __uint_as_float(static_cast<uint32_t>(rbits) << 16);
+            }
+          }
           const float o = v[0] + epi_add;
           if (EPI == DP_EPI_F32) out_f32[static_cast<int64_t>(b) * ldo + col] = o;
           else out_bf[static_cast<int64_t>(b) * ldo + col] = __float2bfloat16(o);
@@ -452,10 +519,12 @@ struct DpAttnUnit {
   int k_begin, k_end;
   bool active, owner;  // owner: this split contains the newest key (index len - 1 = cache row crow)
 };
+#if SR_DP_ATTN == 2
 struct DpAttnPre {
   uint4 k[8];  // thread (key kk, half): dims [64*half, 64*half + 64) of the key row (first pass)
   uint4 v[8];  // thread (dim kk, half): V^T vectors (8 keys each) i = 2*ii + half of output dim kk (first pass)
 };
+#endif
 SR_DEVINL DpAttnUnit dp_attn_unit(const DpParams& p, const int* s_scal) {
   DpAttnUnit U;
   const int unit = blockIdx.x, ns = p.ns;
@@ -474,6 +543,7 @@ SR_DEVINL DpAttnUnit dp_attn_unit(const DpParams& p, const int* s_scal) {
   U.owner = U.active && U.len > 0 && (U.len - 1) / per == U.split;
   return U;
 }
+#if SR_DP_ATTN == 2
 // K / V^T loads of one pass (keys [p0, p0 + nk)); the newest key (jnew within the pass, or -1) is never read from the cache.
 // Every cache element is requested by exactly one thread.
 SR_DEVINL void dp_attn_load(const DpParams& p, const DpAttnUnit& U, const __nv_bfloat16* Kc, const __nv_bfloat16* Vt, int p0, int nk,
@@ -743,6 +813,498 @@ SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, float* sm, const
   if (ct == 0) p.attn_tickets[U.bk] = 0;  // re-arm for the next layer / launch
 }
 
+#endif  // SR_DP_ATTN == 2
+
+#if SR_DP_ATTN == 3
+// ------------------------------------------------------------------------------------------------ attention phase (mma)
+// Compact formulation on mma.sync (the instruction footprint of a persistent kernel matters: everything beyond the 32 KB
+// L1.5 instruction cache is re-fetched from L2 every layer, in competition with 6 TB/s of weight traffic).
+// Scores: A = K rows (16 keys per warp, 8 warps = one 128-key pass), B = q (8 heads); P.V: A = V^T rows (16 output dims per
+// warp), B = P (bf16, shared memory).  As in the GEMV phases a thread's 16-byte global load IS an A fragment (the k index is
+// permuted identically in both operands), so every cache element is requested exactly once, with 16 loads per thread and pass
+// that are issued BEFORE the grid barrier that ends the qkv phase (they do not depend on this layer's qkv).
+// Thread (warp w, g = lane / 4, t = lane % 4) owns heads 2t, 2t+1 in both accumulators:
+//   scores  c0..c3 = (key 16w+g | 16w+g+8) x (head 2t | 2t+1),   output c0..c3 = (dim 16w+g | 16w+g+8) x (head 2t | 2t+1).
+// The newest key is never read from the cache: its roped k / v go to shared memory (and, fire-and-forget, to the cache) and
+// enter the online softmax as one more key of the owning split.
+constexpr int DPB_ROW = 320;                           // bytes per bf16 [128] row (+64 B: conflict-free 16 B fragment reads)
+constexpr int DPB_Q = 0;                               // bf16 [8 heads][128]: roped q
+constexpr int DPB_P = DPB_Q + 8 * DPB_ROW;             // bf16 [8 heads][128 keys]: probabilities of the pass
+constexpr int DPB_RED = DPB_P + 8 * DPB_ROW;           // float [2][8 warps][8 heads]
+constexpr int DPB_KNEW = DPB_RED + 2 * 8 * 8 * 4;      // float [128] roped k of the new token (bf16-rounded values)
+constexpr int DPB_VNEW = DPB_KNEW + 128 * 4;           // float [128]
+constexpr int DPB_SNEW = DPB_VNEW + 128 * 4;           // float [8] score of the new key per head (log2 domain)
+constexpr int DPB_MS = DPB_SNEW + 8 * 4;               // merge: float m[32][8], l[32][8], f[32][8]
+constexpr int DPB_LL = DPB_MS + 3 * DP_NS_MAX * 8 * 4; // float [8]
+constexpr int DPB_FLAG = DPB_LL + 8 * 4;               // int
+constexpr int DPB_END = DPB_FLAG + 16;
+static_assert(DPB_END <= DP_XS_BYTES, "attention scratch must fit in the staged-activation region");
+
+struct DpAttnFrag {
+  uint4 k[8];  // k[c], k[4+c]: key rows 16w+g, 16w+g+8, dims 32c + 8t .. +8
+  uint4 v[8];  // v[c], v[4+c]: V^T rows (dims) 16w+g, 16w+g+8, keys 32c + 8t .. +8 of the pass
+};
+// keys [p0, p0 + nk) of the split, all of them OLD keys (the caller clips the range at the newest key)
+SR_DEVINL void dp_attn_load3(const DpParams& p, const DpAttnUnit& U, const __nv_bfloat16* Kc, const __nv_bfloat16* Vt, int p0, int nk,
+                             DpAttnFrag& f) {
+  const int ct = threadIdx.x - 32, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int key = 16 * w + g + 8 * r;
+    const __nv_bfloat16* kr = Kc + (static_cast<int64_t>(U.start + p0 + key) * p.nkv + U.kvh) * 128 + t * 8;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) f.k[4 * r + c] = key < nk ? dp_ldcg(kr + c * 32) : z;
+    const __nv_bfloat16* vr = Vt + static_cast<int64_t>(U.kvh * 128 + 16 * w + g + 8 * r) * p.ldvt + U.start + p0 + t * 8;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) f.v[4 * r + c] = (c * 32 + t * 8) < nk ? dp_ldcg(vr + c * 32) : z;
+  }
+}
+// zero the V^T elements of keys >= nk (stale cache columns must not meet a zero probability as NaN / Inf)
+SR_DEVINL uint4 dp_mask_keys(uint4 v, int nvalid) {
+  if (nvalid >= 8) return v;
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = w[j] & ((2 * j < nvalid ? 0xffffu : 0u) | (2 * j + 1 < nvalid ? 0xffff0000u : 0u));
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+SR_DEVINL int dp_attn_old_end(const DpAttnUnit& U) { return U.owner ? min(U.k_end, U.len - 1) : U.k_end; }
+SR_DEVINL void dp_attn_prefetch3(const DpParams& p, int layer, const DpAttnUnit& U, DpAttnFrag& f) {
+  const int ke = dp_attn_old_end(U);
+  if (!U.active || U.k_begin >= ke) return;
+  dp_attn_load3(p, U, p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride, p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride,
+                U.k_begin, min(DP_KEYS, ke - U.k_begin), f);
+}
+
+SR_DEVINL void dp_attention_phase3(const DpParams& p, int layer, uint8_t* sm, const float* s_cos, const float* s_sin,
+                                   const DpAttnUnit& U, DpAttnFrag& f) {
+  if (!U.active) return;  // uniform per CTA
+  const int ct = threadIdx.x - 32, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
+  const int G = p.nq / p.nkv, ns = p.ns;
+  float* s_red = reinterpret_cast<float*>(sm + DPB_RED);
+  float* s_knew = reinterpret_cast<float*>(sm + DPB_KNEW);
+  float* s_vnew = reinterpret_cast<float*>(sm + DPB_VNEW);
+  float* s_snew = reinterpret_cast<float*>(sm + DPB_SNEW);
+  float* m_ms = reinterpret_cast<float*>(sm + DPB_MS);
+  float* m_ls = m_ms + DP_NS_MAX * 8;
+  float* m_f = m_ls + DP_NS_MAX * 8;
+  float* m_L = reinterpret_cast<float*>(sm + DPB_LL);
+  int* s_flag = reinterpret_cast<int*>(sm + DPB_FLAG);
+  __nv_bfloat16* Kc = p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride;
+  __nv_bfloat16* Vt = p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride;
+  const int ldq = (p.nq + 2 * p.nkv) * 128;
+  const int b = U.b, kvh = U.kvh;
+  const __nv_bfloat16* qrow = p.qkv + static_cast<int64_t>(b) * ldq;
+  const float* cs = s_cos + b * 64;
+  const float* sn = s_sin + b * 64;
+  // one round trip: q of the heads (threads 0..63: head ct/8, dims 8(ct%8).. and +64), new k (64..127), new v (128..255)
+  if (ct < 64) {
+    const int h = ct >> 3, d0 = (ct & 7) * 8;
+    uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+    if (h < G) {
+      const __nv_bfloat16* qh = qrow + (kvh * G + h) * 128;
+      lo = dp_ldcg(qh + d0);
+      hi = dp_ldcg(qh + 64 + d0);
+    }
+    const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // rotate-half; one rounding to bf16, like the q the per-layer path writes back
+      const float a1 = bf16_lo(lw[j]), a2 = bf16_lo(hw[j]), b1 = bf16_hi(lw[j]), b2 = bf16_hi(hw[j]);
+      const float ca = cs[d0 + 2 * j], sa = sn[d0 + 2 * j], cb = cs[d0 + 2 * j + 1], sb = sn[d0 + 2 * j + 1];
+      o1[j] = pack_bf16x2(a1 * ca - a2 * sa, b1 * cb - b2 * sb);
+      o2[j] = pack_bf16x2(a2 * ca + a1 * sa, b2 * cb + b1 * sb);
+    }
+    *reinterpret_cast<uint4*>(sm + DPB_Q + h * DPB_ROW + d0 * 2) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+    *reinterpret_cast<uint4*>(sm + DPB_Q + h * DPB_ROW + (64 + d0) * 2) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+  } else if (U.owner && ct < 128) {
+    const int d = ct - 64;
+    const __nv_bfloat16* kh = qrow + (p.nq + kvh) * 128;
+    const float x1 = __bfloat162float(__ldcg(kh + d)), x2 = __bfloat162float(__ldcg(kh + d + 64));
+    const __nv_bfloat16 k1 = __float2bfloat16(x1 * cs[d] - x2 * sn[d]), k2 = __float2bfloat16(x2 * cs[d] + x1 * sn[d]);
+    __nv_bfloat16* kd = Kc + (static_cast<int64_t>(U.crow) * p.nkv + kvh) * 128;
+    kd[d] = k1;
+    kd[d + 64] = k2;
+    s_knew[d] = __bfloat162float(k1);
+    s_knew[d + 64] = __bfloat162float(k2);
+  } else if (U.owner && ct >= 128) {
+    const int d = ct - 128;
+    const __nv_bfloat16 v = __ldcg(qrow + (p.nq + p.nkv + kvh) * 128 + d);
+    Vt[static_cast<int64_t>(kvh * 128 + d) * p.ldvt + U.crow] = v;
+    s_vnew[d] = __bfloat162float(v);
+  }
+  dp_cbar();
+  if (U.owner) {  // score of the new key: warp w <-> head w
+    const uint2 qv = *reinterpret_cast<const uint2*>(sm + DPB_Q + w * DPB_ROW + lane * 8);
+    const float4 kv = *reinterpret_cast<const float4*>(s_knew + lane * 4);
+    float d = bf16_lo(qv.x) * kv.x + bf16_hi(qv.x) * kv.y + bf16_lo(qv.y) * kv.z + bf16_hi(qv.y) * kv.w;
+    d = warp_sum(d);
+    if (lane == 0) s_snew[w] = d * p.scale_log2;
+  }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // heads 2t, 2t+1: running max, this thread's share of the sum
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  const int k_old_end = dp_attn_old_end(U);
+  const uint8_t* qf = sm + DPB_Q + g * DPB_ROW + t * 16;
+  const uint8_t* pf = sm + DPB_P + g * DPB_ROW + t * 16;
+  int par = 0;
+  for (int p0 = U.k_begin; p0 < k_old_end; p0 += DP_KEYS) {
+    const int nk = min(DP_KEYS, k_old_end - p0);
+    if (p0 != U.k_begin) dp_attn_load3(p, U, Kc, Vt, p0, nk, f);  // first pass: requested before the grid barrier
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 xv = *reinterpret_cast<const uint4*>(qf + c * 64);
+      dp_mma(s, f.k[c].x, f.k[4 + c].x, f.k[c].y, f.k[4 + c].y, xv.x, xv.y);
+      dp_mma(s, f.k[c].z, f.k[4 + c].z, f.k[c].w, f.k[4 + c].w, xv.z, xv.w);
+    }
+    const bool ok0 = 16 * w + g < nk, ok1 = 16 * w + g + 8 < nk;
+    s[0] = ok0 ? s[0] * p.scale_log2 : -INFINITY;
+    s[1] = ok0 ? s[1] * p.scale_log2 : -INFINITY;
+    s[2] = ok1 ? s[2] * p.scale_log2 : -INFINITY;
+    s[3] = ok1 ? s[3] * p.scale_log2 : -INFINITY;
+    float x0 = fmaxf(s[0], s[2]), x1 = fmaxf(s[1], s[3]);
+#pragma unroll
+    for (int d = 4; d < 32; d <<= 1) {
+      x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, d));
+      x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, d));
+    }
+    float* rp = s_red + par * 64;
+    if (g == 0) *reinterpret_cast<float2*>(rp + w * 8 + 2 * t) = make_float2(x0, x1);
+    dp_cbar();
+#pragma unroll
+    for (int w8 = 0; w8 < DP_CONSUMERS; ++w8) {
+      const float2 v = *reinterpret_cast<const float2*>(rp + w8 * 8 + 2 * t);
+      x0 = fmaxf(x0, v.x);
+      x1 = fmaxf(x1, v.y);
+    }
+    const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);
+    const float u0 = n0 == -INFINITY ? 0.f : n0, u1 = n1 == -INFINITY ? 0.f : n1;
+    const float a0 = exp2f(m0 - u0), a1 = exp2f(m1 - u1);
+    m0 = n0;
+    m1 = n1;
+    const float e0 = exp2f(s[0] - u0), e1 = exp2f(s[1] - u1), e2 = exp2f(s[2] - u0), e3 = exp2f(s[3] - u1);
+    l0 = l0 * a0 + e0 + e2;
+    l1 = l1 * a1 + e1 + e3;
+    o[0] *= a0; o[1] *= a1; o[2] *= a0; o[3] *= a1;
+    __nv_bfloat16* pr = reinterpret_cast<__nv_bfloat16*>(sm + DPB_P);
+    const int kq = 16 * w + g;
+    pr[(2 * t) * (DPB_ROW / 2) + kq] = __float2bfloat16(e0);
+    pr[(2 * t + 1) * (DPB_ROW / 2) + kq] = __float2bfloat16(e1);
+    pr[(2 * t) * (DPB_ROW / 2) + kq + 8] = __float2bfloat16(e2);
+    pr[(2 * t + 1) * (DPB_ROW / 2) + kq + 8] = __float2bfloat16(e3);
+    dp_cbar();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 pv = *reinterpret_cast<const uint4*>(pf + c * 64);
+      const int nv = nk - (c * 32 + t * 8);
+      const uint4 va = dp_mask_keys(f.v[c], nv), vb = dp_mask_keys(f.v[4 + c], nv);
+      dp_mma(o, va.x, vb.x, va.y, vb.y, pv.x, pv.y);
+      dp_mma(o, va.z, vb.z, va.w, vb.w, pv.z, pv.w);
+    }
+    par ^= 1;
+  }
+  if (U.owner) {  // the new key: one more online-softmax update (s_snew was written before the loop's barriers or the one below)
+    if (U.k_begin >= k_old_end) dp_cbar();
+    const float sn0 = s_snew[2 * t], sn1 = s_snew[2 * t + 1];
+    const float n0 = fmaxf(m0, sn0), n1 = fmaxf(m1, sn1);
+    const float a0 = exp2f(m0 - n0), a1 = exp2f(m1 - n1), e0 = exp2f(sn0 - n0), e1 = exp2f(sn1 - n1);
+    m0 = n0;
+    m1 = n1;
+    const float v0 = s_vnew[16 * w + g], v1 = s_vnew[16 * w + g + 8];
+    o[0] = o[0] * a0 + e0 * v0;
+    o[1] = o[1] * a1 + e1 * v0;
+    o[2] = o[2] * a0 + e0 * v1;
+    o[3] = o[3] * a1 + e1 * v1;
+    l0 = l0 * a0 + ((w == 0 && g == 0) ? e0 : 0.f);
+    l1 = l1 * a1 + ((w == 0 && g == 0) ? e1 : 0.f);
+  }
+  // softmax denominators: sum this thread's shares over the keys (g, warps)
+#pragma unroll
+  for (int d = 4; d < 32; d <<= 1) {
+    l0 += __shfl_xor_sync(0xffffffffu, l0, d);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, d);
+  }
+  dp_cbar();  // (the last pass's reads of s_red are done)
+  if (g == 0) *reinterpret_cast<float2*>(s_red + w * 8 + 2 * t) = make_float2(l0, l1);
+  // publish this split's un-normalised partial (o, m, l)
+  float* wo = p.attn_ws + (static_cast<int64_t>(U.bk) * ns + U.split) * DP_PART;
+  const int d0 = 16 * w + g;
+  wo[(2 * t) * 128 + d0] = o[0];
+  wo[(2 * t + 1) * 128 + d0] = o[1];
+  wo[(2 * t) * 128 + d0 + 8] = o[2];
+  wo[(2 * t + 1) * 128 + d0 + 8] = o[3];
+  dp_cbar();
+  if (ct < 4) {  // lanes t = 0..3 of warp 0 hold the running maxima of heads 2t, 2t+1
+    float L0 = 0.f, L1 = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < DP_CONSUMERS; ++w8) {
+      L0 += s_red[w8 * 8 + 2 * ct];
+      L1 += s_red[w8 * 8 + 2 * ct + 1];
+    }
+    wo[DP_GMAX * 128 + 2 * ct] = m0;
+    wo[DP_GMAX * 128 + 2 * ct + 1] = m1;
+    wo[DP_GMAX * 128 + DP_GMAX + 2 * ct] = L0;
+    wo[DP_GMAX * 128 + DP_GMAX + 2 * ct + 1] = L1;
+  }
+  dp_cbar();
+  if (ct == 0) {  // release our partial (cumulative through the CTA barrier), acquire the others'
+    int ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(p.attn_tickets + U.bk) : "memory");
+    *s_flag = (ticket == ns - 1) ? 1 : 0;
+  }
+  dp_cbar();
+  if (*s_flag == 0) return;
+  // merge (last CTA of this (sample, kv head)): statistics and partial outputs requested together
+  const float* wb = p.attn_ws + static_cast<int64_t>(U.bk) * ns * DP_PART;
+  float ov[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float* src = wb + (2 * t + (i & 1)) * 128 + d0 + 8 * (i >> 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ov[i][j] = j < ns ? __ldcg(src + j * DP_PART) : 0.f;
+  }
+  for (int i = ct; i < ns * 8; i += DP_CTHREADS) {
+    const int s2 = i >> 3, h = i & 7;
+    m_ms[i] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + h);
+    m_ls[i] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + DP_GMAX + h);
+  }
+  dp_cbar();
+  if (ct < 8) {
+    float Mx = -INFINITY;
+    for (int s2 = 0; s2 < ns; ++s2) Mx = fmaxf(Mx, m_ms[s2 * 8 + ct]);
+    const float Mu = (Mx == -INFINITY) ? 0.f : Mx;
+    float L = 0.f;
+    for (int s2 = 0; s2 < ns; ++s2) {
+      const float fz = exp2f(m_ms[s2 * 8 + ct] - Mu);
+      m_f[s2 * 8 + ct] = fz;
+      L += m_ls[s2 * 8 + ct] * fz;
+    }
+    m_L[ct] = L;
+  }
+  dp_cbar();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int h = 2 * t + (i & 1);
+    float O = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) O += j < ns ? ov[i][j] * m_f[j * 8 + h] : 0.f;
+    for (int j = 16; j < ns; ++j) O += __ldcg(wb + j * DP_PART + h * 128 + d0 + 8 * (i >> 1)) * m_f[j * 8 + h];
+    const float L = m_L[h];
+    if (h < G) p.ao[static_cast<int64_t>(b) * (p.nq * 128) + (kvh * G + h) * 128 + d0 + 8 * (i >> 1)] = __float2bfloat16(L > 0.f ? O / L : 0.f);
+  }
+  if (ct == 0) p.attn_tickets[U.bk] = 0;  // re-arm for the next layer / launch
+}
+
+#endif  // SR_DP_ATTN == 3
+
+#if SR_DP_ATTN == 1
+// First formulation of the attention phase (K/V loaded after the barrier, every half-CTA reads whole key rows): kept selectable
+// (flags bit 4) for A/B measurements.
+SR_DEVINL void dp_attention_phase_v1(const DpParams& p, int layer, float* sm) {
+  const int ct = threadIdx.x - 32, lane = ct & 31, warp = ct >> 5;
+  const int G = p.nq / p.nkv, ns = p.ns;
+  float* sq = sm + DPA_SQ;
+  float* sp = sm + DPA_SP;
+  float* s_red = sm + DPA_RED;
+  float* s_m = sm + DPA_M;
+  float* s_l = sm + DPA_L;
+  float* s_alpha = sm + DPA_ALPHA;
+  float* m_ms = sm + DPA_MS;
+  float* m_ls = sm + DPA_LS;
+  float* m_f = sm + DPA_F;
+  float* m_L = sm + DPA_LL;
+  int* s_flag = reinterpret_cast<int*>(sm + DPA_FLAG);
+  __nv_bfloat16* Kc = p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride;
+  __nv_bfloat16* Vt = p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride;
+  const int ldq = (p.nq + 2 * p.nkv) * 128;
+  const int n_units = p.B * p.nkv * ns;
+  const int half = ct >> 7;   // heads [half*4, half*4+4)
+  const int kk = ct & 127;    // key within the pass / output dim
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    const int split = unit % ns, bk = unit / ns;
+    const int kvh = bk % p.nkv, b = bk / p.nkv;
+    dp_cbar();  // scratch reuse between units (and after the staged-activation use of this region)
+    const int start = __ldg(p.kv_start + b), len = __ldcg(p.kv_len + b), crow = __ldcg(p.cache_row + b);
+    int per = (len + ns - 1) / ns;
+    per = (per + 7) & ~7;  // V^T vectors are 8 keys wide
+    const int k_begin = split * per, k_end = min(len, k_begin + per);
+    const __nv_bfloat16* qrow = p.qkv + static_cast<int64_t>(b) * ldq;
+    // roped, scaled q of the G heads -> sq (rounded through bf16 like the cached path)
+    for (int i = ct; i < G * 64; i += DP_CTHREADS) {
+      const int h = i >> 6, d = i & 63;
+      const float c = __ldcg(p.cosb + b * 64 + d), s = __ldcg(p.sinb + b * 64 + d);
+      const __nv_bfloat16* qh = qrow + (kvh * G + h) * 128;
+      const float x1 = __bfloat162float(__ldcg(reinterpret_cast<const __nv_bfloat16*>(qh + d)));
+      const float x2 = __bfloat162float(__ldcg(reinterpret_cast<const __nv_bfloat16*>(qh + d + 64)));
+      sq[h * 128 + d] = __bfloat162float(__float2bfloat16(x1 * c - x2 * s)) * p.scale_log2;
+      sq[h * 128 + d + 64] = __bfloat162float(__float2bfloat16(x2 * c + x1 * s)) * p.scale_log2;
+    }
+    if (ct < DP_GMAX) { s_m[ct] = -INFINITY; s_l[ct] = 0.f; }
+    // the split that owns the newest key (index len-1 = cache row crow) appends roped k and v for this kv head
+    if (len > 0 && (len - 1) / per == split) {
+      if (ct < 64) {
+        const float c = __ldcg(p.cosb + b * 64 + ct), s = __ldcg(p.sinb + b * 64 + ct);
+        const __nv_bfloat16* kh = qrow + (p.nq + kvh) * 128;
+        const float x1 = __bfloat162float(__ldcg(kh + ct)), x2 = __bfloat162float(__ldcg(kh + ct + 64));
+        __nv_bfloat16* kd = Kc + (static_cast<int64_t>(crow) * p.nkv + kvh) * 128;
+        kd[ct] = __float2bfloat16(x1 * c - x2 * s);
+        kd[ct + 64] = __float2bfloat16(x2 * c + x1 * s);
+      } else if (ct < 64 + 128) {
+        const int d = ct - 64;
+        Vt[static_cast<int64_t>(kvh * 128 + d) * p.ldvt + crow] = __ldcg(qrow + (p.nq + p.nkv + kvh) * 128 + d);
+      }
+      __threadfence();
+    }
+    float o_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    dp_cbar();
+    for (int p0 = k_begin; p0 < k_end; p0 += DP_KEYS) {
+      const int nk = min(DP_KEYS, k_end - p0);
+      float sc4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (kk < nk) {
+        const __nv_bfloat16* kr = Kc + (static_cast<int64_t>(start + p0 + kk) * p.nkv + kvh) * 128;
+        uint4 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = dp_ldcg(kr + i * 8);
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          const int h = half * 4 + hh;
+          if (h < G) {
+            float d = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 q0 = *reinterpret_cast<const float4*>(&sq[h * 128 + i * 8]);
+              const float4 q1 = *reinterpret_cast<const float4*>(&sq[h * 128 + i * 8 + 4]);
+              d += bf16_lo(v[i].x) * q0.x + bf16_hi(v[i].x) * q0.y + bf16_lo(v[i].y) * q0.z + bf16_hi(v[i].y) * q0.w +
+                   bf16_lo(v[i].z) * q1.x + bf16_hi(v[i].z) * q1.y + bf16_lo(v[i].w) * q1.z + bf16_hi(v[i].w) * q1.w;
+            }
+            sc4[hh] = d;
+          }
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const float m = warp_max(sc4[hh]);
+        if (lane == 0) s_red[warp * DP_GMAX + hh] = m;  // warps 0-3 hold half 0, warps 4-7 half 1
+      }
+      dp_cbar();
+      if (ct < G) {
+        const int hf = ct >> 2, hh = ct & 3;
+        float m = s_m[ct];
+        for (int w = 0; w < 4; ++w) m = fmaxf(m, s_red[(hf * 4 + w) * DP_GMAX + hh]);
+        const float m_use = (m == -INFINITY) ? 0.f : m;
+        s_alpha[ct] = exp2f(s_m[ct] - m_use);
+        s_m[ct] = m;
+      }
+      dp_cbar();
+      float ps[4];
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const int h = half * 4 + hh;
+        float pv = 0.f;
+        if (h < G && kk < nk) {
+          const float m = s_m[h];
+          pv = exp2f(sc4[hh] - ((m == -INFINITY) ? 0.f : m));
+        }
+        if (h < G) sp[h * DP_KEYS + kk] = pv;
+        ps[hh] = warp_sum(pv);
+        if (lane == 0) s_red[warp * DP_GMAX + hh] = ps[hh];
+      }
+      dp_cbar();
+      if (ct < G) {
+        const int hf = ct >> 2, hh = ct & 3;
+        float l = 0.f;
+        for (int w = 0; w < 4; ++w) l += s_red[(hf * 4 + w) * DP_GMAX + hh];
+        s_l[ct] = s_l[ct] * s_alpha[ct] + l;
+      }
+      const __nv_bfloat16* vrow = Vt + static_cast<int64_t>(kvh * 128 + kk) * p.ldvt + start + p0;
+      const int nvec = (nk + 7) >> 3;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int i = 0; i < nvec; ++i) {
+        const uint4 u = dp_ldcg(vrow + i * 8);
+        const float vv[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+        for (int hh = 0; hh < 4; ++hh) {
+          const int h = half * 4 + hh;
+          if (h < G) {
+            const float4 p0v = *reinterpret_cast<const float4*>(&sp[h * DP_KEYS + i * 8]);
+            const float4 p1v = *reinterpret_cast<const float4*>(&sp[h * DP_KEYS + i * 8 + 4]);
+            acc[hh] += vv[0] * p0v.x + vv[1] * p0v.y + vv[2] * p0v.z + vv[3] * p0v.w + vv[4] * p1v.x + vv[5] * p1v.y +
+                       vv[6] * p1v.z + vv[7] * p1v.w;
+          }
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const int h = half * 4 + hh;
+        if (h < G) o_acc[hh] = o_acc[hh] * s_alpha[h] + acc[hh];
+      }
+      dp_cbar();  // sp / s_red / s_alpha are reused by the next pass
+    }
+    // publish this split's un-normalised partial (o, m, l)
+    float* wo = p.attn_ws + (static_cast<int64_t>(bk) * ns + split) * DP_PART;
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = half * 4 + hh;
+      if (h < G) wo[h * 128 + kk] = o_acc[hh];
+    }
+    if (ct < G) {
+      wo[DP_GMAX * 128 + ct] = s_m[ct];
+      wo[DP_GMAX * 128 + DP_GMAX + ct] = s_l[ct];
+    }
+    __threadfence();
+    dp_cbar();
+    if (ct == 0) {
+      const int ticket = atomicAdd(p.attn_tickets + bk, 1);
+      *s_flag = (ticket == ns - 1) ? 1 : 0;
+    }
+    dp_cbar();
+    if (*s_flag == 0) continue;
+    __threadfence();
+    // merge (last CTA of this (sample, kv head)); all loads issued in parallel
+    const float* wb = p.attn_ws + static_cast<int64_t>(bk) * ns * DP_PART;
+    for (int i = ct; i < ns * G; i += DP_CTHREADS) {
+      const int s2 = i / G, h = i % G;
+      m_ms[s2 * DP_GMAX + h] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + h);
+      m_ls[s2 * DP_GMAX + h] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + DP_GMAX + h);
+    }
+    dp_cbar();
+    if (ct < G) {
+      float Mx = -INFINITY;
+      for (int s2 = 0; s2 < ns; ++s2) Mx = fmaxf(Mx, m_ms[s2 * DP_GMAX + ct]);
+      const float Mu = (Mx == -INFINITY) ? 0.f : Mx;
+      float L = 0.f;
+      for (int s2 = 0; s2 < ns; ++s2) {
+        const float f = exp2f(m_ms[s2 * DP_GMAX + ct] - Mu);
+        m_f[s2 * DP_GMAX + ct] = f;
+        L += m_ls[s2 * DP_GMAX + ct] * f;
+      }
+      m_L[ct] = L;
+    }
+    dp_cbar();
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = half * 4 + hh;
+      if (h >= G) continue;
+      float O = 0.f;
+      for (int s0 = 0; s0 < ns; s0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (s0 + j < ns) ? __ldcg(wb + (s0 + j) * DP_PART + h * 128 + kk) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) O += (s0 + j < ns) ? v[j] * m_f[(s0 + j) * DP_GMAX + h] : 0.f;
+      }
+      const float L = m_L[h];
+      p.ao[static_cast<int64_t>(b) * (p.nq * 128) + (kvh * G + h) * 128 + kk] = __float2bfloat16(L > 0.f ? O / L : 0.f);
+    }
+    if (ct == 0) p.attn_tickets[bk] = 0;  // re-arm for the next layer / launch
+  }
+}
+
+
+#endif  // SR_DP_ATTN == 1
+
 // ------------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const DpParams p) {
   extern __shared__ uint8_t dp_smem_raw[];
@@ -760,6 +1322,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   float* s_cos = reinterpret_cast<float*>(smem + DP_OFF_ROPE);
   float* s_sin = s_cos + 8 * 64;
   int* s_scal = reinterpret_cast<int*>(smem + DP_OFF_SCAL);
+  volatile int* s_pcnt = reinterpret_cast<volatile int*>(smem + DP_OFF_PCNT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {  // per-launch constants -> shared memory (pointer / scalar loads off the critical paths)
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.layers);
@@ -778,6 +1341,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     }
   }
   if (threadIdx.x == 0) {
+    *s_pcnt = 0;
 #pragma unroll
     for (int i = 0; i < DP_STAGES; ++i) {
       mbar_init(&ring.full[i], 1);
@@ -801,27 +1365,51 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       uint64_t policy = 0;
       const bool hint = (p.flags & 1) != 0;
       if (hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      int ph = 0;
+      int ph = 0, issued = 0;
       dp_trace_at(p, 0, 0);
       for (int l = 0; l < p.n_layers; ++l) {
         const DpLayer L = s_layers[l];
         if (ph++ >= limit) return;
-        dp_produce<1, false>(ring, L.qkv_wp, n_qkv, kq, policy, hint);
+        dp_produce<1, false>(ring, L.qkv_wp, n_qkv, kq, policy, hint, s_pcnt, issued);
         dp_trace_at(p, 0, 1 + 4 * l);
         if (ph++ >= limit) return;  // attention phase: no weights
         if (ph++ >= limit) return;
-        dp_produce<1, false>(ring, L.o_wp, n_o, kq, policy, hint);
+        dp_produce<1, false>(ring, L.o_wp, n_o, kq, policy, hint, s_pcnt, issued);
         dp_trace_at(p, 0, 2 + 4 * l);
         if (ph++ >= limit) return;
-        dp_produce<2, false>(ring, L.gu_wp, n_gu, kq, policy, hint);
+        dp_produce<2, false>(ring, L.gu_wp, n_gu, kq, policy, hint, s_pcnt, issued);
         dp_trace_at(p, 0, 3 + 4 * l);
         if (ph++ >= limit) return;
-        dp_produce<1, true>(ring, L.down_wp, n_o, kd, policy, hint);
+        if (p.flags & 4) dp_produce<1, false>(ring, L.down_wp, n_o, kd, policy, hint, s_pcnt, issued);
+        else dp_produce<1, true>(ring, L.down_wp, n_o, kd, policy, hint, s_pcnt, issued);
         dp_trace_at(p, 0, 4 + 4 * l);
       }
       if (ph++ >= limit) return;
-      dp_produce<1, false>(ring, p.lm_head_p, n_head, kq, policy, hint);
+      dp_produce<1, false>(ring, p.lm_head_p, n_head, kq, policy, hint, s_pcnt, issued);
       dp_trace_at(p, 0, 1 + 4 * p.n_layers);
+    }
+    return;
+  }
+  if (warp == DP_CONSUMERS + 1) {
+    // ---------------- L2 prefetcher: same walk as the producer, `pf_stages` ahead of it ----------------
+    if (lane == 0 && p.pf_stages > 0) {
+      int ph = 0, sidx = 0;
+      const int lead = p.pf_stages;
+      for (int l = 0; l < p.n_layers; ++l) {
+        const DpLayer L = s_layers[l];
+        if (ph++ >= limit) return;
+        dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, L.qkv_wp, n_qkv, kq);
+        if (ph++ >= limit) return;
+        if (ph++ >= limit) return;
+        dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, L.o_wp, n_o, kq);
+        if (ph++ >= limit) return;
+        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, L.gu_wp, n_gu, kq);
+        if (ph++ >= limit) return;
+        if (p.flags & 4) dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, L.down_wp, n_o, kd);
+        else dp_prefetch_l2<1, true>(sidx, s_pcnt, lead, L.down_wp, n_o, kd);
+      }
+      if (ph++ >= limit) return;
+      dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, p.lm_head_p, n_head, kq);
     }
     return;
   }
@@ -833,8 +1421,18 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   int ph = 0, tr = 0;
   const unsigned int G = gridDim.x;
   const bool tracer = threadIdx.x == 32;
+  const bool late_kv = (p.flags & 2) != 0, old_bar = (p.flags & 8) != 0, late_epi = (p.flags & 32) != 0;  // bisect switches (tools/persistent_sweep.py)
   const DpAttnUnit U = dp_attn_unit(p, s_scal);
-  DpAttnPre pre;
+#if SR_DP_ATTN == 2
+  DpAttnPre fr;
+#define DP_ATTN_PREFETCH dp_attn_prefetch
+#elif SR_DP_ATTN == 3
+  DpAttnFrag fr;
+#define DP_ATTN_PREFETCH dp_attn_prefetch3
+#else
+  int fr = 0;
+#define DP_ATTN_PREFETCH(p, l, U, fr) (void)fr
+#endif
 #define DP_TRACE() do { if (tracer) dp_trace(p, 1, tr); } while (0)
   DP_TRACE();
   for (int l = 0; l < p.n_layers; ++l) {
@@ -844,25 +1442,32 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     dp_stage_rows<true>(xs, p.x, p.ldx, p.B, L.ln1, p.eps, cw, lane);
     dp_cbar();
     dp_gemv_phase<1, DP_EPI_BIAS, true>(ring, n_qkv, kq, xs, nullptr, 0, p.B, red, red_par, L.qkv_b, p.qkv, nullptr,
-                                        static_cast<int64_t>(n_qkv) * 16, cw, lane);
+                                        static_cast<int64_t>(n_qkv) * 16, cw, lane, true, late_epi);
     const bool do_attn = ph < limit;
-    if (do_attn) dp_attn_prefetch(p, l, U, pre);  // old K / V^T rows fly while the CTA waits at the barrier
+    if (do_attn && !late_kv) DP_ATTN_PREFETCH(p, l, U, fr);  // old K / V^T rows fly while the CTA waits at the barrier
     DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G, old_bar);
     DP_TRACE();
+    if (do_attn && late_kv) DP_ATTN_PREFETCH(p, l, U, fr);
     // B: rope + KV append + attention -> ao
     if (ph++ >= limit) return;
-    dp_attention_phase(p, l, reinterpret_cast<float*>(xs), s_cos, s_sin, U, pre);
+#if SR_DP_ATTN == 1
+    dp_attention_phase_v1(p, l, reinterpret_cast<float*>(xs));
+#elif SR_DP_ATTN == 2
+    dp_attention_phase(p, l, reinterpret_cast<float*>(xs), s_cos, s_sin, U, fr);
+#else
+    dp_attention_phase3(p, l, xs, s_cos, s_sin, U, fr);
+#endif
     DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G, old_bar);
     DP_TRACE();
     // C: x += ao . Wo^T
     if (ph++ >= limit) return;
     dp_stage_rows<false>(xs, p.ao, DP_H, p.B, nullptr, 0.f, cw, lane);
     dp_cbar();
-    dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, n_o, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
+    dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, n_o, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane, true, late_epi);
     DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G, old_bar);
     DP_TRACE();
     // D: act = silu(gate) * up, [gate|up] = rmsnorm(x; ln2) . Wgu^T
     if (ph++ >= limit) return;
@@ -870,13 +1475,13 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     dp_cbar();
     dp_gemv_phase<2, DP_EPI_SWIGLU, true>(ring, n_gu, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.act, nullptr, p.I, cw, lane);
     DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G, old_bar);
     DP_TRACE();
     // E: x += act . Wdown^T
     if (ph++ >= limit) return;
-    dp_gemv_phase<1, DP_EPI_RESIDUAL, false>(ring, n_o, kd, nullptr, p.act, p.I, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
+    dp_gemv_phase<1, DP_EPI_RESIDUAL, false>(ring, n_o, kd, nullptr, p.act, p.I, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane, (p.flags & 4) == 0, late_epi);
     DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
+    dp_grid_barrier(p.grid_bar, ++bar_gen * G, old_bar);
     DP_TRACE();
   }
   // final norm + LM head -> fp32 logits
@@ -886,6 +1491,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   dp_gemv_phase<1, DP_EPI_F32, true>(ring, n_head, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, nullptr, p.logits, p.ld_logits, cw, lane);
   DP_TRACE();
 #undef DP_TRACE
+#undef DP_ATTN_PREFETCH
 }
 
 }  // namespace sr
@@ -999,7 +1605,7 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
     const char* e = getenv("SR_DECODE_FLAGS");
     g_dp_flags = e ? atoi(e) : 0;
   }
-  p.pf_stages = g_dp_pf_stages;  // (reserved: the L2-prefetch cursor was removed, see dp_produce)
+  p.pf_stages = g_dp_pf_stages;
   p.flags = g_dp_flags;
   p.trace = g_dp_trace;
   p.trace_events = g_dp_trace_events;

@@ -14,7 +14,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsocioreasoner_b200.so")
+# SR_LIB_PATH: A/B builds of the same C ABI (tools/); the default is the in-tree library built by csrc/Makefile
+LIB_PATH = os.environ.get("SR_LIB_PATH") or os.path.join(_HERE, "libsocioreasoner_b200.so")
 
 EPI_NONE, EPI_RESIDUAL, EPI_SWIGLU, EPI_GELU = 0, 1, 2, 3
 DT_BF16, DT_F32 = 0, 1

@@ -1,5 +1,5 @@
 """A/B timing of the persistent decode step at the bench geometry: one (pf_stages, flags) configuration per argument
-`pf:flags`, all on the same weights.  SR_LIB_PATH selects an alternative build of the same C ABI.
+`pf:flags[:ring_stages]`, all on the same weights.  SR_LIB_PATH selects an alternative build of the same C ABI.
 Usage: python tools/persistent_ab.py 0:0 0:1 24:1 ..."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -7,7 +7,7 @@ import persistent_bringup as PB
 from socioreasoner_b200 import lib
 
 n_layers, vocab = 36, 151936
-cfgs = [tuple(int(v) for v in a.split(":")) for a in sys.argv[1:]] or [(0, 0)]
+cfgs = [tuple(int(v) for v in (a + ":0").split(":")[:3]) for a in sys.argv[1:]] or [(0, 1, 0)]
 torch.manual_seed(0)
 layers = PB.make_layers(n_layers)
 S = PB.State(8, n_layers, 1024, [900 - 7 * i for i in range(8)], vocab)
@@ -16,8 +16,9 @@ wbytes = n_layers * (PB.QKV * PB.H + PB.H * PB.H + 2 * PB.I * PB.H + PB.H * PB.I
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 ref = None
 print("lib:", lib.LIB_PATH)
-for pf, flags in cfgs:
-    lib.load().sr_set_decode_persistent_tuning(pf, flags)
+for pf, flags, ring in cfgs:
+    rc = lib.load().sr_set_decode_persistent_tuning(pf, flags | (ring << 8))
+    assert rc == 0
     P.reset()
     for _ in range(3):
         P.run(0)
@@ -36,5 +37,5 @@ for pf, flags in cfgs:
         P.run(5 * n_layers)
     e1.record(); torch.cuda.synchronize()
     ms_l = e0.elapsed_time(e1) / 20
-    print(f"pf={pf:3d} flags={flags:2d}: {ms:.3f} ms/step ({wbytes / ms / 1e9:.2f} TB/s), {ms_l / n_layers * 1e3:.1f} us/layer, "
+    print(f"pf={pf:3d} flags={flags:3d} ring={ring:2d}: {ms:.3f} ms/step ({wbytes / ms / 1e9:.2f} TB/s), {ms_l / n_layers * 1e3:.1f} us/layer, "
           f"LM head {1e3 * (ms - ms_l):.0f} us, same logits: {same}", flush=True)

@@ -381,7 +381,7 @@ class Engine:
         else:  # (temperature, top_k, top_p): uniforms[b, step] drive the inverse-CDF pick
             lib.sample_topk_topp(st["logits"], st["u"], sampling[0], sampling[1], sampling[2], step=st["step"], out=st["nxt"])
 
-    def _decode_step(self, st, cache: KVCache, sampling=None) -> None:
+    def _decode_step(self, st, cache: KVCache, sampling=None, kv_tokens: Optional[int] = None) -> None:
         """One decode step, entirely on the device (graph-capturable): pick token -> append/advance -> embed -> 36 layers ->
         final norm + LM head -> st['logits']."""
         t = self.cfg.text
@@ -396,7 +396,7 @@ class Engine:
             lib.decode_step_persistent(self._layer_table, self.w.lm_head_p, self.w.final_norm, t.vocab_size, st["x"], st["qkv"],
                                        st["ao"], st["act"], st["logits"], cos, sin, st["cache_row"], st["kv_start"], st["kv_len"],
                                        cache.k, cache.vt, t.num_attention_heads, t.num_key_value_heads, t.intermediate_size,
-                                       t.rms_norm_eps, t.head_dim ** -0.5, st["ws"])
+                                       t.rms_norm_eps, t.head_dim ** -0.5, st["ws"], kv_tokens=kv_tokens)
             return
         xo = self._decoder_layers(st["x"], cos, sin, cache, st["cache_row"], None, (st["kv_start"], st["kv_len"], cache.l_max))
         self.final_logits(xo, torch.float32, out=st["logits"])
@@ -467,7 +467,7 @@ class Engine:
                 if return_logits:
                     all_logits[:, step] = st["logits"]
                 l0 = lib.launch_count
-                self._decode_step(st, cache, sampling)
+                self._decode_step(st, cache, sampling, kv_tokens=int(sp.lengths.sum()) + B * (step + 1))
                 self._decode_launches = lib.launch_count - l0
         if return_logits:
             all_logits[:, T - 1] = st["logits"]

@@ -399,9 +399,11 @@ def decode_step_persistent(layer_table: torch.Tensor, lm_head_p: torch.Tensor, f
                            x: torch.Tensor, qkv: torch.Tensor, ao: torch.Tensor, act: torch.Tensor, logits: torch.Tensor,
                            cos: torch.Tensor, sin: torch.Tensor, cache_row: torch.Tensor, kv_start: torch.Tensor,
                            kv_len: torch.Tensor, kc: torch.Tensor, vt: torch.Tensor, n_q_heads: int, n_kv_heads: int,
-                           intermediate: int, eps: float, scale: float, workspace: torch.Tensor, stop_after: int = 0) -> torch.Tensor:
+                           intermediate: int, eps: float, scale: float, workspace: torch.Tensor, stop_after: int = 0,
+                           kv_tokens: Optional[int] = None) -> torch.Tensor:
     """One whole decode step (all layers + LM head) in one persistent launch.  kc [L, rows, n_kv, 128], vt [L, n_kv*128, rows];
-    x [B, 2048] is updated in place; logits fp32 [B, vocab]."""
+    x [B, 2048] is updated in place; logits fp32 [B, vocab].  ``kv_tokens`` (sum of the live sequences' cached tokens, host-side)
+    only feeds the bench timeline: algorithmic bytes = every weight once + the K and V rows of the live sequences."""
     global launch_count
     _req(x, torch.bfloat16, "decode_persistent.x"); _req(logits, torch.float32, "decode_persistent.logits")
     _req(kc, torch.bfloat16, "decode_persistent.kc"); _req(vt, torch.bfloat16, "decode_persistent.vt")
@@ -411,14 +413,24 @@ def decode_step_persistent(layer_table: torch.Tensor, lm_head_p: torch.Tensor, f
     assert kc.dim() == 4 and vt.dim() == 3 and kc.is_contiguous() and vt.is_contiguous() and layer_table.shape[1] == 7
     assert qkv.is_contiguous() and ao.is_contiguous() and act.is_contiguous() and cos.is_contiguous() and sin.is_contiguous()
     assert qkv.shape == (B, (n_q_heads + 2 * n_kv_heads) * 128) and ao.shape == (B, n_q_heads * 128) and act.shape == (B, intermediate)
-    rc = load().sr_decode_step_persistent(
+    n_layers, H = int(layer_table.shape[0]), n_q_heads * 128
+    work = 2.0 * (n_layers * ((n_q_heads + 2 * n_kv_heads) * 128 * H + H * H + 3 * intermediate * H) + vocab * H)
+    work += 2.0 * n_layers * (kv_tokens if kv_tokens is not None else 0) * 2 * n_kv_heads * 128
+    with _Timed("decode", (B, n_layers, vocab), work):
+        rc = _decode_persistent_call(layer_table, lm_head_p, final_norm, vocab, x, qkv, ao, act, logits, cos, sin, cache_row, kv_start,
+                                     kv_len, kc, vt, B, n_q_heads, n_kv_heads, intermediate, eps, scale, workspace, stop_after)
+    _check(rc, "sr_decode_step_persistent")
+    launch_count += 1
+    return logits
+
+
+def _decode_persistent_call(layer_table, lm_head_p, final_norm, vocab, x, qkv, ao, act, logits, cos, sin, cache_row, kv_start, kv_len,
+                            kc, vt, B, n_q_heads, n_kv_heads, intermediate, eps, scale, workspace, stop_after) -> int:
+    return load().sr_decode_step_persistent(
         layer_table.data_ptr(), layer_table.shape[0], lm_head_p.data_ptr(), final_norm.data_ptr(), vocab, x.data_ptr(), x.stride(0),
         qkv.data_ptr(), ao.data_ptr(), act.data_ptr(), logits.data_ptr(), logits.stride(0), cos.data_ptr(), sin.data_ptr(),
         cache_row.data_ptr(), kv_start.data_ptr(), kv_len.data_ptr(), kc.data_ptr(), kc.stride(0), vt.data_ptr(), vt.stride(0),
         vt.stride(1), B, n_q_heads, n_kv_heads, intermediate, float(eps), float(scale), workspace.data_ptr(), int(stop_after), _stream())
-    _check(rc, "sr_decode_step_persistent")
-    launch_count += 1
-    return logits
 
 
 def sample_topk_topp(logits: torch.Tensor, uniforms: torch.Tensor, temperature: float, top_k: int, top_p: float,

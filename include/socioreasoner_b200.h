@@ -167,6 +167,16 @@ int sr_sample_topk_topp(const float* logits, int64_t ld, int rows, int V, const 
 int sr_logprob_entropy(const void* logits, int64_t ld, int dtype, int rows, int V, const int64_t* labels, float* logprob,
                        float* entropy, void* stream);
 
+/* Fused LM head + log-prob / entropy for compute_log_probs (roll/pipeline/base_worker.py:206-246 -> forward_func_log_probs ->
+ * strategy.py:123-138 -> roll/utils/functionals.py:193-205; lm_head HF:1385): logits = A[M,K] . W[N,K]^T are reduced to
+ * per-row softmax statistics inside the tcgen05 GEMM epilogue and merged by a second kernel, so the [M, N] fp32 logits
+ * (0.6 MB per position for N = 151936) never reach HBM.  logprob[r] = log_softmax(logits[r])[labels[r]], entropy[r] =
+ * logsumexp(logits[r]) - sum softmax(logits[r]) * logits[r]; either output may be NULL.  labels: int64 [M] (a label outside
+ * [0, N) yields logprob = -logsumexp).  workspace: sr_lmhead_logprob_workspace_bytes(M, N) bytes, 16-byte aligned. */
+int64_t sr_lmhead_logprob_workspace_bytes(int M, int N);
+int sr_lmhead_logprob_entropy(const void* A, int64_t lda, const void* W, int64_t ldw, const int64_t* labels, int M, int N, int K,
+                              void* workspace, float* logprob, float* entropy, void* stream);
+
 /* Decode-loop bookkeeping on the device (makes one decode step a replayable CUDA graph): tokens[:, *step] = next_tokens;
  * cache_row = row0 + *step; kv_len = len0 + *step + 1; pos3[3,batch] = pos0 + 1 + *step; (*step)++.
  * Response positions follow roll/utils/functionals.py:838-852. */

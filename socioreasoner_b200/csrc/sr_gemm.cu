@@ -19,6 +19,7 @@
 
 namespace sr {
 
+constexpr int SR_EPI_LSE = 4;  // internal: no C; per (row, N tile) softmax statistics for sr_lmhead_logprob_entropy
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 192;
@@ -30,6 +31,8 @@ struct GemmParams {
   int64_t ldc, ldr;
   int M, N, K;
   int num_m_blocks, num_n_blocks;
+  const int64_t* labels;  // SR_EPI_LSE: [M] target column per row (out of range: no target)
+  float4* partial;        // SR_EPI_LSE: [num_n_blocks][M] (max, sum exp(x - max), sum exp(x - max) * x, x[label] or 0)
 };
 
 template <int BLOCK_N>
@@ -174,11 +177,41 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+      float lse_m = -INFINITY, lse_s = 0.f, lse_w = 0.f, lse_t = 0.f;
+      int lse_label = -1;
+      if (EPI == SR_EPI_LSE && row_ok) {
+        const int64_t lb = p.labels[row];
+        lse_label = (lb >= 0 && lb < p.N) ? static_cast<int>(lb) : -1;
+      }
 #pragma unroll 1
       for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(chunk * 32), v);
         const int col0 = n_blk * BLOCK_N + chunk * 32;
+        if (EPI == SR_EPI_LSE) {
+          // online softmax statistics over the tile's columns (the logits never leave the SM):
+          // log Z = m + log s,  sum p x = w / s,  x[label]  (roll/utils/functionals.py:193-205)
+          tmem_ld_wait();
+          if (col0 < p.N) {
+            float cm = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) cm = fmaxf(cm, (col0 + j < p.N) ? __uint_as_float(v[j]) : -INFINITY);
+            const float mn = fmaxf(lse_m, cm);
+            const float sc = __expf(lse_m - mn);  // exp(-inf) = 0 on the first chunk
+            lse_s *= sc;
+            lse_w *= sc;
+            lse_m = mn;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = __uint_as_float(v[j]);
+              const float e = (col0 + j < p.N) ? __expf(x - mn) : 0.f;
+              lse_s += e;
+              lse_w = fmaf(e, (col0 + j < p.N) ? x : 0.f, lse_w);
+              if (col0 + j == lse_label) lse_t = x;
+            }
+          }
+          continue;
+        }
         uint4 rcur[4];
         if (EPI == SR_EPI_RESIDUAL) {
 #pragma unroll
@@ -258,6 +291,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+      if (EPI == SR_EPI_LSE && row_ok)
+        p.partial[static_cast<int64_t>(n_blk) * p.M + row] = make_float4(lse_m, lse_s, lse_w, lse_t);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -311,6 +346,40 @@ static int dispatch_epi(int epi, int out_f32, const CUtensorMap& a, const CUtens
   return SR_ERR_INVALID;
 }
 
+// Merge of the per-tile statistics: one warp per row, lanes stride over the N tiles, online merge through shuffles.
+__global__ void lse_merge_kernel(const float4* __restrict__ partial, int M, int n_tiles, float* __restrict__ logprob,
+                                 float* __restrict__ entropy) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float m = -INFINITY, s = 0.f, w = 0.f, t = 0.f;
+  for (int nb = lane; nb < n_tiles; nb += 32) {
+    const float4 q = __ldg(partial + static_cast<int64_t>(nb) * M + row);
+    const float mn = fmaxf(m, q.x);
+    const float a = __expf(m - mn), b = __expf(q.x - mn);
+    s = s * a + q.y * b;
+    w = w * a + q.z * b;
+    t += q.w;
+    m = mn;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, d), s2 = __shfl_xor_sync(0xffffffffu, s, d);
+    const float w2 = __shfl_xor_sync(0xffffffffu, w, d), t2 = __shfl_xor_sync(0xffffffffu, t, d);
+    const float mn = fmaxf(m, m2);
+    const float a = (m == -INFINITY) ? 0.f : __expf(m - mn), b = (m2 == -INFINITY) ? 0.f : __expf(m2 - mn);
+    s = s * a + s2 * b;
+    w = w * a + w2 * b;
+    t += t2;
+    m = mn;
+  }
+  if (lane == 0) {
+    const float logz = m + logf(s);
+    if (logprob != nullptr) logprob[row] = t - logz;
+    if (entropy != nullptr) entropy[row] = logz - w / s;
+  }
+}
+
 }  // namespace sr
 
 extern "C" int sr_gemm_skinny_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc,
@@ -353,7 +422,7 @@ extern "C" int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
     int rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box, 128);
     if (rc != SR_OK) return rc;
   }
-  GemmParams p;
+  GemmParams p = {};
   p.C = C;
   p.bias = bias;
   p.residual = residual;
@@ -369,4 +438,54 @@ extern "C" int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   if (bn == 256) return dispatch_epi<256>(epilogue, f32, tmA, tmB, p, s);
   if (bn == 128) return dispatch_epi<128>(epilogue, f32, tmA, tmB, p, s);
   return dispatch_epi<32>(epilogue, f32, tmA, tmB, p, s);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused LM head + log_probs_from_logits / entropy_from_logits: logits = A . W^T are reduced tile by tile inside the GEMM
+// epilogue; the [M, V] fp32 logits (0.6 MB per position for V = 151936) are never written.
+extern "C" int64_t sr_lmhead_logprob_workspace_bytes(int M, int N) {
+  const int64_t nb = (N + 255) / 256;
+  return nb * static_cast<int64_t>(M) * 16;
+}
+
+extern "C" int sr_lmhead_logprob_entropy(const void* A, int64_t lda, const void* W, int64_t ldw, const int64_t* labels, int M, int N,
+                                         int K, void* workspace, float* logprob, float* entropy, void* stream) {
+  using namespace sr;
+  SR_REQUIRE(A && W && labels && workspace, "sr_lmhead_logprob_entropy: null operand");
+  SR_REQUIRE(logprob || entropy, "sr_lmhead_logprob_entropy: no output requested");
+  SR_REQUIRE(M > 0 && N > 0 && K > 0, "sr_lmhead_logprob_entropy: bad shape M=%d N=%d K=%d", M, N, K);
+  SR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "sr_lmhead_logprob_entropy: lda/ldw must be >=K and multiples of 8");
+  SR_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "sr_lmhead_logprob_entropy: workspace not 16B aligned");
+  constexpr int bn = 256;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {(uint32_t)GEMM_BLOCK_K, (uint32_t)GEMM_BLOCK_M};
+    int rc = encode_tmap_bf16(&tmA, A, 2, dims, strides, box, 128);
+    if (rc != SR_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)ldw * 2};
+    uint32_t box[2] = {(uint32_t)GEMM_BLOCK_K, (uint32_t)bn};
+    int rc = encode_tmap_bf16(&tmB, W, 2, dims, strides, box, 128);
+    if (rc != SR_OK) return rc;
+  }
+  GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m_blocks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  p.num_n_blocks = (N + bn - 1) / bn;
+  p.labels = labels;
+  p.partial = reinterpret_cast<float4*>(workspace);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int rc = launch_gemm<bn, SR_EPI_LSE, false>(tmA, tmB, p, s);
+  if (rc != SR_OK) return rc;
+  constexpr int warps = 8;
+  lse_merge_kernel<<<(M + warps - 1) / warps, warps * 32, 0, s>>>(p.partial, M, p.num_n_blocks, logprob, entropy);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
 }

@@ -321,6 +321,39 @@ class Engine:
         full[_dev(sp.flat_index, self.device)] = packed
         return full.view(sp.B, sp.S, V)
 
+    def forward_log_probs(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, response_mask,
+                          want_entropy: bool = True):
+        """``compute_log_probs`` without the logits (roll/pipeline/base_worker.py:206-246): returns (log_probs, entropy), both
+        fp32 [B, S-1] with the semantics of ``op_compute_log_probs`` / ``op_compute_entropy`` (strategy.py:123-138):
+        ``log_probs[b, s] = log_softmax(logits[b, s])[input_ids[b, s+1]] * response_mask[b, s+1]`` and the same mask on the
+        entropy.  Positions whose mask is 0 are multiplied by 0 in the reference, so only the rows with
+        ``response_mask[b, s+1] == 1`` go through the LM head -- fused with the softmax statistics in the GEMM epilogue
+        (``sr_lmhead_logprob_entropy``): neither the [B, S, V] logits nor the prompt rows' logits are ever computed."""
+        t = self.cfg.text
+        x, sp, _, _ = self.prefill(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw)
+        ids = input_ids.detach().cpu().numpy() if torch.is_tensor(input_ids) else np.asarray(input_ids)
+        rm = response_mask.detach().cpu().numpy() if torch.is_tensor(response_mask) else np.asarray(response_mask)
+        B, S = sp.B, sp.S
+        row_of = np.full(B * S, -1, dtype=np.int64)          # padded grid position -> packed row
+        row_of[sp.flat_index] = np.arange(sp.total, dtype=np.int64)
+        want = np.zeros((B, S), dtype=bool)
+        want[:, :-1] = rm[:, 1:] != 0                          # position s predicts token s + 1
+        want &= row_of.reshape(B, S) >= 0                      # (a masked-in position on padding has no hidden row)
+        bs, ss = np.nonzero(want)
+        lp = torch.zeros((B, S - 1), dtype=torch.float32, device=self.device)
+        ent = torch.zeros((B, S - 1), dtype=torch.float32, device=self.device) if want_entropy else None
+        if len(bs) == 0:
+            return lp, ent
+        rows = _dev(row_of.reshape(B, S)[bs, ss], self.device)
+        labels = _dev(ids[bs, ss + 1].astype(np.int64), self.device)
+        y = lib.rmsnorm(x.index_select(0, rows), self.w.final_norm, t.rms_norm_eps)
+        l_rows, e_rows = lib.lm_head_logprob_entropy(y, self.w.lm_head, labels, want_entropy=want_entropy)
+        flat = _dev(bs * (S - 1) + ss, self.device)
+        lp.view(-1).index_copy_(0, flat, l_rows)
+        if want_entropy:
+            ent.view(-1).index_copy_(0, flat, e_rows)
+        return lp, ent
+
     def last_token_rows(self, x: torch.Tensor, sp: SeqPlan) -> torch.Tensor:
         idx = _dev((sp.q_starts + sp.lengths - 1).astype(np.int32), self.device)
         return lib.gather_rows(x, idx)

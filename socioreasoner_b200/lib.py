@@ -51,6 +51,8 @@ SYMBOLS = {
     "sr_argmax_rows": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
     "sr_sample_topk_topp": (c_int, [_P, c_int64, c_int, c_int, _P, c_int, _P, c_float, c_int, c_float, _P, _P]),
     "sr_logprob_entropy": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "sr_lmhead_logprob_workspace_bytes": (c_int64, [c_int, c_int]),
+    "sr_lmhead_logprob_entropy": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sr_decode_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "sr_decode_persistent_workspace_bytes": (c_int64, [c_int, c_int]),
     "sr_set_decode_persistent_coop": (c_int, [c_int]),
@@ -456,6 +458,28 @@ def logprob_entropy(logits: torch.Tensor, labels: Optional[torch.Tensor], want_e
     _check(load().sr_logprob_entropy(logits.data_ptr(), logits.stride(0), DT_F32 if logits.dtype == torch.float32 else DT_BF16,
                                      rows, V, _ptr(labels), _ptr(lp), _ptr(ent), _stream()), "sr_logprob_entropy")
     launch_count += 1
+    return lp, ent
+
+
+def lm_head_logprob_entropy(h: torch.Tensor, w: torch.Tensor, labels: torch.Tensor, want_logprob: bool = True,
+                            want_entropy: bool = True):
+    """Fused LM head + log-prob / entropy (sr_lmhead_logprob_entropy): h bf16 [M, K] (final-normed hidden rows), w bf16 [V, K]
+    (lm_head.weight), labels int64 [M] -> (logprob fp32 [M] | None, entropy fp32 [M] | None).  The logits are never written."""
+    global launch_count
+    _req(h, torch.bfloat16, "lm_head_logprob.h"); _req(w, torch.bfloat16, "lm_head_logprob.w"); _req(labels, torch.int64, "lm_head_logprob.labels")
+    M, K = h.shape
+    V = w.shape[0]
+    assert w.shape[1] == K and labels.shape == (M,) and h.stride(1) == 1 and w.stride(1) == 1 and labels.is_contiguous()
+    lp = torch.empty((M,), dtype=torch.float32, device=h.device) if want_logprob else None
+    ent = torch.empty((M,), dtype=torch.float32, device=h.device) if want_entropy else None
+    if M == 0:
+        return lp, ent
+    ws = torch.empty((int(load().sr_lmhead_logprob_workspace_bytes(M, V)),), dtype=torch.uint8, device=h.device)
+    with _Timed("gemm", (M, V, K, 4), 2.0 * M * V * K):
+        rc = load().sr_lmhead_logprob_entropy(h.data_ptr(), h.stride(0), w.data_ptr(), w.stride(0), labels.data_ptr(), M, V, K,
+                                              ws.data_ptr(), _ptr(lp), _ptr(ent), _stream())
+    _check(rc, "sr_lmhead_logprob_entropy")
+    launch_count += 2
     return lp, ent
 
 

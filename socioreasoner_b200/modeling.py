@@ -118,6 +118,18 @@ class SocioReasonerB200ForConditionalGeneration:
         return CausalLMOutput(logits=logits, past_key_values=None, rope_deltas=None)
 
     @torch.no_grad()
+    def compute_log_probs(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, position_ids: torch.Tensor,
+                          response_mask: torch.Tensor, pixel_values: Optional[torch.Tensor] = None,
+                          image_grid_thw: Optional[torch.Tensor] = None, want_entropy: bool = True, **unused):
+        """Fused forward of ``ActorWorker.compute_log_probs`` (roll/pipeline/base_worker.py:206-246): (log_probs, entropy)
+        fp32 [b, S-1], identical in meaning to ``forward_func_log_probs`` applied to ``forward(...).logits`` -- without
+        materialising the logits (Engine.forward_log_probs)."""
+        if pixel_values is not None and image_grid_thw is None:
+            raise ValueError("pixel_values requires image_grid_thw")
+        return self.engine.forward_log_probs(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, response_mask,
+                                             want_entropy=want_entropy)
+
+    @torch.no_grad()
     def get_image_features(self, pixel_values: torch.Tensor, image_grid_thw: torch.Tensor) -> torch.Tensor:
         return self.engine.image_features(pixel_values.to(self.device), image_grid_thw)
 

@@ -89,6 +89,7 @@ def _concat_multi_modal(data: DataProto, forward_args: dict, device) -> dict:
 
 class B200InferStrategy(InferenceStrategy):
     strategy_name = "b200_infer"
+    fuse_log_probs = True  # forward_step(forward_func_log_probs) -> fused LM head + log-prob / entropy kernel
 
     def initialize(self, model_provider):
         """Sets ``self.model`` / ``self.tokenizer`` and the worker's rank_info (dispatch depends on it,
@@ -118,6 +119,15 @@ class B200InferStrategy(InferenceStrategy):
             if position_ids.dim() == 3:
                 position_ids = position_ids.transpose(0, 1)  # (bsz, 3, seqlen) -> (3, bsz, seqlen)
             forward_args = _concat_multi_modal(data, forward_args, input_ids.device)
+            if self.fuse_log_probs and getattr(forward_func, "__name__", "") == "forward_func_log_probs" \
+                    and hasattr(self.model, "compute_log_probs") and "response_mask" in data.batch.keys():
+                # the stock forward_func (base_worker.py:236-246) only reduces the logits to log-probs and entropy under the
+                # response mask: run it fused with the LM head, on the masked-in rows only (no [b, S, V] logits)
+                fa = {k: v for k, v in forward_args.items() if k != "force_vit_image"}
+                lp, ent = self.model.compute_log_probs(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                                                       response_mask=data.batch["response_mask"], **fa)
+                losses_reduced.append({"log_probs": lp, "entropy": ent})
+                continue
             output = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids, use_cache=False,
                                 **forward_args)
             loss, loss_reduced = forward_func(data, output.logits)

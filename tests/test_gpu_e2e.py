@@ -92,6 +92,33 @@ def test_log_probs_and_entropy_from_logits(model, oracle_tiny, tiny_batch, golde
     np.testing.assert_allclose(ent[m].numpy(), torch.from_numpy(golden_tiny["entropy"])[m].numpy(), atol=3e-2)
 
 
+def test_fused_compute_log_probs_matches_the_logits_path(model, tiny_batch, golden_tiny):
+    """compute_log_probs (fused LM head + log-prob/entropy, masked-in rows only) == forward_func_log_probs applied to the
+    [B,S,V] logits (base_worker.py:236-246, strategy.py:123-138), and both match the committed oracle vectors."""
+    from socioreasoner_b200.roll_shim import B200InferStrategy
+    b = tiny_batch
+    rm = b.attention_mask.clone()
+    rm[:, : rm.shape[1] // 2] = 0            # "response" = second half of every sequence (ragged through left padding)
+    lp, ent = model.compute_log_probs(input_ids=b.input_ids, attention_mask=b.attention_mask, position_ids=b.position_ids,
+                                      response_mask=rm, pixel_values=b.pixel_values, image_grid_thw=b.image_grid_thw)
+    logits = model(input_ids=b.input_ids, attention_mask=b.attention_mask, position_ids=b.position_ids,
+                   pixel_values=b.pixel_values, image_grid_thw=b.image_grid_thw).logits
+    st = B200InferStrategy(None)
+    lp_ref = st.op_compute_log_probs(logits, b.input_ids.cuda(), rm.cuda())
+    ent_ref = st.op_compute_entropy(logits, rm.cuda())
+    assert lp.shape == lp_ref.shape == (b.input_ids.shape[0], b.input_ids.shape[1] - 1)
+    np.testing.assert_allclose(lp.cpu().numpy(), lp_ref.cpu().numpy(), atol=2e-4)
+    np.testing.assert_allclose(ent.cpu().numpy(), ent_ref.cpu().numpy(), atol=2e-4)
+    assert (lp.cpu()[rm[:, 1:] == 0] == 0).all() and (ent.cpu()[rm[:, 1:] == 0] == 0).all()
+    m = (rm[:, 1:] * b.attention_mask[:, :-1]).bool()
+    np.testing.assert_allclose(lp.cpu()[m].numpy(), torch.from_numpy(golden_tiny["log_probs"])[m].numpy(), atol=6e-2)
+    np.testing.assert_allclose(ent.cpu()[m].numpy(), torch.from_numpy(golden_tiny["entropy"])[m].numpy(), atol=3e-2)
+    # all-zero response mask: nothing goes through the LM head
+    z, ze = model.compute_log_probs(input_ids=b.input_ids, attention_mask=b.attention_mask, position_ids=b.position_ids,
+                                    response_mask=torch.zeros_like(rm), pixel_values=b.pixel_values, image_grid_thw=b.image_grid_thw)
+    assert z.abs().sum().item() == 0 and ze.abs().sum().item() == 0
+
+
 def test_greedy_decode_tokens(model, oracle_tiny, tiny_batch, golden_tiny):
     b = tiny_batch
     T = golden_tiny["greedy_tokens"].shape[1]

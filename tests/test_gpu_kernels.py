@@ -329,6 +329,30 @@ def test_argmax_logprob_entropy():
     np.testing.assert_allclose(ent.cpu().numpy(), host_ref.entropy_from_logits(lg).numpy(), atol=2e-5)
 
 
+@pytest.mark.parametrize("M,V,K", [(300, 8192, 2048), (5, 8200, 2048), (129, 151936, 2048), (1, 256, 64)])
+def test_fused_lm_head_logprob_entropy(M, V, K):
+    """sr_lmhead_logprob_entropy (softmax statistics in the tcgen05 GEMM epilogue, no logits in HBM) against
+    log_probs_from_logits / entropy_from_logits (roll/utils/functionals.py:193-205) of the fp32 logits of the same bf16
+    operands; ragged last N tile (8200 = 32 * 256 + 8), ragged M tile, single row."""
+    h = rnd(M, K, scale=1.0, seed=1).bfloat16()
+    w = rnd(V, K, scale=0.05, seed=2).bfloat16()
+    labels = torch.randint(0, V, (M,), generator=torch.Generator().manual_seed(3))
+    labels[0] = V - 1
+    lp, ent = lib.lm_head_logprob_entropy(h.to(DEV), w.to(DEV), labels.to(DEV))
+    logits = h.double() @ w.double().t()
+    lp_ref = host_ref.log_probs_from_logits(logits.float(), labels)
+    ent_ref = host_ref.entropy_from_logits(logits.float())
+    np.testing.assert_allclose(lp.cpu().numpy(), lp_ref.numpy(), atol=2e-3)
+    np.testing.assert_allclose(ent.cpu().numpy(), ent_ref.numpy(), atol=2e-3)
+    # against the unfused device path (same accumulators): fp32 logits GEMM + sr_logprob_entropy
+    lg = lib.gemm(h.to(DEV), w.to(DEV), out_dtype=torch.float32, block_n=256)
+    lp2, ent2 = lib.logprob_entropy(lg, labels.to(DEV))
+    np.testing.assert_allclose(lp.cpu().numpy(), lp2.cpu().numpy(), atol=1e-4)
+    np.testing.assert_allclose(ent.cpu().numpy(), ent2.cpu().numpy(), atol=1e-4)
+    only_lp, none = lib.lm_head_logprob_entropy(h.to(DEV), w.to(DEV), labels.to(DEV), want_entropy=False)
+    assert none is None and torch.equal(only_lp, lp)
+
+
 def test_sampling_topk_topp_against_oracle():
     """temperature -> top-k -> top-p sampling (reference rollout config T=1, top-p 0.8, top-k 100) with given uniforms:
     the picked token must be the oracle's inverse-CDF token (or, at an fp32 boundary, a neighbour whose CDF interval

@@ -89,6 +89,47 @@ def test_forward_step_micro_batching_and_multimodal_concat():
     assert c0["extra"] == ["image_grid_thw", "pixel_values"]
 
 
+def test_forward_step_takes_the_fused_log_prob_path_for_the_stock_forward_func():
+    """forward_step(forward_func_log_probs) (base_worker.py:226-246) -> model.compute_log_probs (no logits); any other
+    forward_func keeps the generic logits path.  Same keys, shapes and micro-batch collation either way."""
+    class FusedModel(FakeModel):
+        def __init__(self):
+            super().__init__()
+            self.fused_calls = []
+
+        def compute_log_probs(self, input_ids, attention_mask, position_ids, response_mask, pixel_values=None,
+                              image_grid_thw=None, **kw):
+            assert "force_vit_image" not in kw
+            self.fused_calls.append(input_ids.shape[0])
+            logits = FakeModel()(input_ids, None, position_ids, False, pixel_values=pixel_values, image_grid_thw=image_grid_thw).logits
+            return (host_ref.op_compute_log_probs(logits, input_ids, response_mask),
+                    host_ref.op_compute_entropy(logits, response_mask))
+
+    st = create_strategy(worker("hf_infer"))
+    st.model = FusedModel()
+    d = make_proto(7)
+    d.batch["response_mask"][:, :2] = 0
+    d.meta_info["forward_args"] = {"force_vit_image": True}
+
+    def forward_func_log_probs(data, logits):  # the stock reduction, by name
+        lp = host_ref.op_compute_log_probs(logits, data.batch["input_ids"], data.batch["response_mask"])
+        ent = host_ref.op_compute_entropy(logits, data.batch["response_mask"])
+        return lp, {"log_probs": lp.clone(), "entropy": ent.clone()}
+
+    fused = st.forward_step(d, forward_func_log_probs)
+    assert st.model.fused_calls == [3, 2, 2] and st.model.calls == []
+    st.fuse_log_probs = False
+    plain = st.forward_step(d, forward_func_log_probs)
+    assert [c["ids"].shape[0] for c in st.model.calls] == [3, 2, 2]
+    for k in ("log_probs", "entropy"):
+        assert fused[k].shape == plain[k].shape == (7, 4)
+        assert torch.allclose(fused[k], plain[k])
+    st.fuse_log_probs = True
+    st.model.calls.clear()
+    st.forward_step(d, lambda data, logits: (logits.sum(), {"s": logits.sum(-1)}))  # custom forward_func: generic path
+    assert len(st.model.calls) == 3
+
+
 def test_generate_pads_ragged_micro_batches():
     st = create_strategy(worker("vllm"))
     st.model = FakeModel()

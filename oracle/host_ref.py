@@ -192,3 +192,62 @@ def sample_topk_topp_ref(logits: torch.Tensor, u: float, temperature: float, top
     j = int(np.searchsorted(cdf, u, side="right"))
     j = min(j, len(q) - 1)
     return int(order[keep][j]), (float(cdf[j] - q[j]), float(cdf[j])), order[keep]
+
+
+# ----------------------------------------------------------------------------------------------
+# Sender side of the bucketed weight transfer -- roll/utils/send_recv_utils.py:64-135 (TensorBucket,
+# SendBucketManager) as driven by roll/distributed/strategy/megatron_strategy.py:411-448.  Test infrastructure for
+# the receive side in socioreasoner_b200/roll_shim/send_recv.py: produces the exact wire format
+# (int8 bucket buffer + {name: {bucket_start, tensor_start, save_bytes, tensor_meta}}).
+# ----------------------------------------------------------------------------------------------
+class SendBucketManager:
+    def __init__(self, bucket_size: int, device="cpu"):
+        self.bucket_size = bucket_size
+        self.buffer = torch.empty(bucket_size, dtype=torch.int8, device=device)
+        self.write_index = 0
+        self.tensors_meta = {}
+
+    def _push_part(self, tensor, tensor_start, name):
+        required = tensor.numel() * tensor.element_size() - tensor_start
+        bucket_start = self.write_index
+        save_bytes = min(required, self.bucket_size - bucket_start)
+        self.buffer[bucket_start: bucket_start + save_bytes].copy_(tensor.view(-1).view(torch.int8)[tensor_start: tensor_start + save_bytes])
+        self.tensors_meta[name] = {"bucket_start": bucket_start, "tensor_start": tensor_start, "save_bytes": save_bytes,
+                                   "tensor_meta": torch.empty_like(tensor, device="meta")}
+        self.write_index += save_bytes
+        return save_bytes
+
+    def push_tensor(self, tensor: torch.Tensor, name: str):
+        """Generator: yields (tensors_meta, buffer) every time the bucket fills up (send_recv_utils.py:112-120)."""
+        tensor_start, required = 0, tensor.numel() * tensor.element_size()
+        while tensor_start < required:
+            tensor_start += self._push_part(tensor, tensor_start, name)
+            if self.write_index == self.bucket_size:
+                yield self.tensors_meta, self.buffer
+                self.tensors_meta, self.write_index = {}, 0
+
+    def pop_last_bucket(self):
+        if self.write_index > 0:
+            return self.tensors_meta, self.buffer
+        return None, None
+
+    @staticmethod
+    def meta_to_dict(meta_infos):
+        """send_recv_utils.py:127-141: meta tensors -> plain dicts (what crosses the RPC boundary)."""
+        for meta_info in meta_infos.values():
+            t = meta_info["tensor_meta"]
+            meta_info["tensor_meta"] = {"shape": list(t.shape), "dtype": t.dtype, "layout": t.layout, "device": t.device}
+        return meta_infos
+
+
+def send_buckets(named_tensors, bucket_size: int, as_dict: bool = True):
+    """All buckets of one model update, in order: list of (meta_infos, buffer copy)."""
+    mgr, out = SendBucketManager(bucket_size), []
+    emit = lambda meta, buf: out.append((SendBucketManager.meta_to_dict(dict(meta)) if as_dict else dict(meta), buf.clone()))
+    for name, t in named_tensors:
+        for meta, buf in mgr.push_tensor(t.contiguous(), name):
+            emit(meta, buf)
+    meta, buf = mgr.pop_last_bucket()
+    if meta is not None:
+        emit(meta, buf)
+    return out

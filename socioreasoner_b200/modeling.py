@@ -80,6 +80,12 @@ class SocioReasonerB200ForConditionalGeneration:
                     sd[k] = fh.get_tensor(k)
         return cls.from_state_dict(sd, cfg, device, **{k: v for k, v in kw.items() if k in ("logits_dtype",)})
 
+    def load_weights(self, named_tensors) -> List[str]:
+        """In-place update from ``(hf_name, tensor)`` pairs -- the call the reference's weight sync ends in
+        (``roll/third_party/vllm/worker_helper.py:104-116``).  Pointers stay stable: captured decode graphs remain valid."""
+        from .weights import update_weights
+        return update_weights(self.engine.w, named_tensors, self.config)
+
     # ---- nn.Module-ish surface ------------------------------------------------------------------------
     def eval(self):
         self.training = False

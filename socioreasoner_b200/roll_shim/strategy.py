@@ -50,11 +50,62 @@ class InferenceStrategy:
     def offload_states(self, include=None, non_blocking=False):
         return None
 
-    # weight-sync hooks (megatron_strategy.py:411-448 -> strategy.py broadcast_*/update_*): ranked "next" row
-    def broadcast_parameter(self, *a, **k):
-        raise NotImplementedError("weight sync over NVLink is a ranked next row (SURVEY.md 8f-4)")
+    # ---- weight sync, receive side (worker_helper.py:64-116 behind vllm_strategy.py:258-271) ----
+    # The train worker (rank 0 of a named group) broadcasts every parameter under its HF checkpoint name, whole
+    # (``broadcast_parameter``) or in int8 buckets (``broadcast_bucket``); co-located workers get the tensors directly
+    # (``update_parameter*``).  Received tensors overwrite the kernel-layout weights in place (``model.load_weights``).
+    def _worker_rank(self) -> int:
+        import torch.distributed as dist
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
-    broadcast_bucket = update_parameter = update_parameter_in_bucket = broadcast_parameter
+    def _sync_device(self):
+        dev = getattr(self.model, "device", None)
+        return torch.device(dev) if dev is not None else torch.device("cpu")
+
+    def setup_collective_group(self, comm_plan, backend="nccl"):
+        from . import collective
+        rank_in_cluster = getattr(self.worker, "rank", 0)
+        rank, args = get_dist_info_from_comm_plan(comm_plan, rank_in_cluster=rank_in_cluster, rank_in_worker=self._worker_rank())
+        if rank is None:
+            return
+        world_size = len(args["tgt_devices"]) + 1
+        collective.init_collective_group(world_size, rank, backend=backend, group_name=args["group_name"],
+                                         master_addr=args["master_addr"], master_port=args["master_port"])
+        warm = torch.zeros(1, device=self._sync_device())
+        collective.allreduce(warm, group_name=args["group_name"])  # a small all_reduce for warm-up, as the reference does
+        self.model_update_comm_plan[args["src_pp_rank"]] = dict(rank=rank, world_size=world_size, src_pp_rank=args["src_pp_rank"],
+                                                                group_name=args["group_name"], comm_plan=comm_plan,
+                                                                comm_plan_args=args)
+
+    def broadcast_parameter(self, src_pp_rank, dtype, shape, parameter_name):
+        from . import collective
+        if src_pp_rank not in self.model_update_comm_plan:
+            return
+        weight = torch.empty(shape, dtype=dtype, device=self._sync_device())
+        collective.broadcast(tensor=weight, src_rank=0, group_name=self.model_update_comm_plan[src_pp_rank]["group_name"])
+        self.update_parameter(parameter_name, weight, [self._worker_rank()])
+
+    def broadcast_bucket(self, src_pp_rank, meta_infos, bucket_size):
+        from . import collective
+        if src_pp_rank not in self.model_update_comm_plan:
+            return
+        buffer = torch.empty(bucket_size, dtype=torch.int8, device=self._sync_device())
+        collective.broadcast(tensor=buffer, src_rank=0, group_name=self.model_update_comm_plan[src_pp_rank]["group_name"])
+        self.update_parameter_in_bucket(meta_infos, buffer, [self._worker_rank()])
+
+    def update_parameter(self, parameter_name, weight, ranks_in_worker):
+        if self._worker_rank() not in ranks_in_worker:
+            return
+        self.model.load_weights([(parameter_name, weight)])
+
+    def update_parameter_in_bucket(self, meta_infos, buffer, ranks_in_worker):
+        from .send_recv import RecvBucketManager
+        if self._worker_rank() not in ranks_in_worker:
+            return
+        if getattr(self, "recv_manager", None) is None:
+            self.recv_manager = RecvBucketManager()
+        named = self.recv_manager.process_bucket(meta_infos, buffer)
+        self.model.load_weights(list(named.items()))
 
     # ---- distributed ops (strategy.py:123-138) on the fused device kernel ----
     def op_compute_log_probs(self, logits: torch.Tensor, input_ids: torch.Tensor, attention_mask: torch.Tensor):
@@ -72,6 +123,17 @@ class InferenceStrategy:
         b, S, V = logits.shape
         _, ent = lib.logprob_entropy(logits.reshape(-1, V), None, want_entropy=True)
         return ent.view(b, S)[:, :-1] * attention_mask[:, 1:].to(ent.device)
+
+
+def get_dist_info_from_comm_plan(comm_plan, rank_in_cluster, rank_in_worker):
+    """``roll/utils/functionals.py:875-882``: this worker's rank inside the broadcast group (sender = 0) and the plan entry."""
+    for src_rank, comm_plan_args in comm_plan.items():
+        start_rank = 0
+        for tgt_device in comm_plan_args["tgt_devices"]:
+            start_rank += 1
+            if tgt_device["rank"] == rank_in_cluster and tgt_device["device"]["rank"] == rank_in_worker:
+                return start_rank, comm_plan_args
+    return None, None
 
 
 def _concat_multi_modal(data: DataProto, forward_args: dict, device) -> dict:

@@ -208,3 +208,103 @@ def random_state_dict(cfg: SocioReasonerConfig, seed: int = 42, device="cuda", s
         sd[p + "mlp.down_proj.weight"] = rn(t.hidden_size, t.intermediate_size)
     sd["model.norm.weight"] = nw(t.hidden_size)
     return sd
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# In-place weight update (train -> infer weight sync).  The reference pushes the trained parameters into the rollout engine
+# tensor by tensor under their HF checkpoint names (``worker_helper.py:104-116`` -> ``load_weights([(name, weight)])``) every
+# pipeline step (``rlvr_socioseg_vlm_pipeline_infer.py:608-612,634``).  Here each name maps to a slice of a kernel-layout
+# tensor; every destination is overwritten IN PLACE, so device pointers held by the decode layer table and by captured CUDA
+# graphs stay valid.
+def _put_interleaved(dst: torch.Tensor, src: torch.Tensor, which: int) -> None:
+    """rows of ``src`` [I, ...] -> the gate (which=0) or up (which=1) rows of ``dst`` [2*Ipad, ...] ([16 gate | 16 up] groups)."""
+    I = src.shape[0]
+    rest = tuple(dst.shape[1:])
+    view = dst.view(dst.shape[0] // (2 * GROUP), 2, GROUP, *rest)
+    full = I // GROUP
+    src = src.to(device=dst.device, dtype=dst.dtype)
+    if full:
+        view[:full, which].copy_(src[: full * GROUP].reshape(full, GROUP, *rest))
+    if I % GROUP:
+        view[full, which, : I % GROUP].copy_(src[full * GROUP:])
+
+
+def update_weights(W: PackedWeights, named_tensors, cfg: SocioReasonerConfig) -> List[str]:
+    """Overwrite the kernel-layout weights from ``(hf_name, tensor)`` pairs (any subset, any order).  Returns the names
+    consumed; an unknown name raises ``KeyError`` (the reference's ``load_weights`` fails the same way on a foreign key)."""
+    v, t = cfg.vision, cfg.text
+    H, kvd = t.hidden_size, t.num_key_value_heads * t.head_dim
+    done: List[str] = []
+    dirty = set()  # (layer index, matrix) whose decode-streaming copy must be re-packed
+    with torch.no_grad():
+        for raw_name, w in named_tensors:
+            name = next(iter(normalize_keys({raw_name: None})))
+            put = lambda dst, src: dst.copy_(src.to(device=dst.device, dtype=dst.dtype).reshape(dst.shape))
+            parts = name.split(".")
+            if name == "visual.patch_embed.proj.weight":
+                put(W.patch_w, w)
+            elif name.startswith("visual.blocks."):
+                B, leaf = W.vit_blocks[int(parts[2])], ".".join(parts[3:])
+                simple = {"norm1.weight": B.norm1, "norm2.weight": B.norm2, "attn.qkv.weight": B.qkv_w, "attn.qkv.bias": B.qkv_b,
+                          "attn.proj.weight": B.proj_w, "attn.proj.bias": B.proj_b, "mlp.down_proj.bias": B.down_b}
+                if leaf in simple:
+                    put(simple[leaf], w)
+                elif leaf in ("mlp.gate_proj.weight", "mlp.up_proj.weight"):
+                    _put_interleaved(B.gu_w, w, 0 if "gate" in leaf else 1)
+                elif leaf in ("mlp.gate_proj.bias", "mlp.up_proj.bias"):
+                    _put_interleaved(B.gu_b, w, 0 if "gate" in leaf else 1)
+                elif leaf == "mlp.down_proj.weight":
+                    B.down_w[:, : v.intermediate_size].copy_(w.to(device=B.down_w.device, dtype=B.down_w.dtype))
+                else:
+                    raise KeyError(raw_name)
+            elif name.startswith("visual.merger."):
+                leaf = ".".join(parts[2:])
+                put({"ln_q.weight": W.merger_ln, "mlp.0.weight": W.merger_w0, "mlp.0.bias": W.merger_b0, "mlp.2.weight": W.merger_w2,
+                     "mlp.2.bias": W.merger_b2}[leaf], w)
+            elif name == "model.embed_tokens.weight":
+                put(W.embed, w)
+                if W.lm_head is W.embed:
+                    dirty.add((-1, "lm_head"))
+            elif name == "lm_head.weight":
+                if W.lm_head is not W.embed:  # tied head: the embedding update already covers it
+                    put(W.lm_head, w)
+                    dirty.add((-1, "lm_head"))
+            elif name == "model.norm.weight":
+                put(W.final_norm, w)
+            elif name.startswith("model.layers."):
+                li = int(parts[2])
+                L, leaf = W.layers[li], ".".join(parts[3:])
+                rows = {"q_proj": (0, H), "k_proj": (H, H + kvd), "v_proj": (H + kvd, H + 2 * kvd)}
+                if leaf in ("input_layernorm.weight", "post_attention_layernorm.weight"):
+                    put(L.ln1 if leaf.startswith("input") else L.ln2, w)
+                elif parts[3] == "self_attn" and parts[4] in rows:
+                    a, b = rows[parts[4]]
+                    if parts[5] == "weight":
+                        put(L.qkv_w[a:b], w)
+                        dirty.add((li, "qkv"))
+                    else:
+                        put(L.qkv_b[a:b], w)
+                elif leaf == "self_attn.o_proj.weight":
+                    put(L.o_w, w)
+                    dirty.add((li, "o"))
+                elif leaf in ("mlp.gate_proj.weight", "mlp.up_proj.weight"):
+                    _put_interleaved(L.gu_w, w, 0 if "gate" in leaf else 1)
+                    dirty.add((li, "gu"))
+                elif leaf == "mlp.down_proj.weight":
+                    put(L.down_w, w)
+                    dirty.add((li, "down"))
+                else:
+                    raise KeyError(raw_name)
+            else:
+                raise KeyError(raw_name)
+            done.append(raw_name)
+        for li, which in sorted(dirty):
+            if li < 0:
+                if W.lm_head_p is not None:
+                    W.lm_head_p.copy_(_stream_pack(W.lm_head))
+                continue
+            L = W.layers[li]
+            src, dst = {"qkv": (L.qkv_w, L.qkv_wp), "o": (L.o_w, L.o_wp), "gu": (L.gu_w, L.gu_wp), "down": (L.down_w, L.down_wp)}[which]
+            if dst is not None:
+                dst.copy_(_stream_pack(src))
+    return done

@@ -249,3 +249,26 @@ def test_rollout_step_matches_oracle_epilogue(model, tiny_batch):
         assert int((res.masks[i].cpu().numpy() != ref).sum()) == 0
         assert abs(res.iou[i].item() - host_ref.compute_giou(ref, gt[i])) < 1e-6
     assert res.tokens.shape == (n, 4)
+
+
+def test_load_weights_in_place_equals_a_fresh_model_and_keeps_decode_graphs(oracle_tiny, tiny_batch):
+    """Weight sync (worker_helper.py:104-116 -> load_weights): after an in-place update from HF-named tensors the model is
+    bit-identical to one built from the new state dict -- logits, and tokens through the decode graph captured BEFORE the
+    update (its device pointers must still be the live weights)."""
+    from socioreasoner_b200.config import SocioReasonerConfig
+    from socioreasoner_b200.weights import random_state_dict
+    cfg = SocioReasonerConfig.from_hf(oracle_tiny.config)
+    b = tiny_batch
+    args = dict(input_ids=b.input_ids, attention_mask=b.attention_mask, position_ids=b.position_ids, pixel_values=b.pixel_values,
+                image_grid_thw=b.image_grid_thw)
+    sd_a, sd_b = random_state_dict(cfg, seed=7, device="cuda"), random_state_dict(cfg, seed=8, device="cuda")
+    m = Model.from_state_dict(sd_a, cfg, device="cuda")
+    fresh = Model.from_state_dict(sd_b, cfg, device="cuda")
+    gen = lambda mm: mm.engine.generate_greedy(b.input_ids, b.attention_mask, b.position_ids, b.pixel_values, b.image_grid_thw, 5)
+    t_a = gen(m)                                  # captures the decode graph on the seed-7 weights
+    names = m.load_weights(list(sd_b.items()))    # (on the GPU box these arrive through broadcast_bucket / broadcast_parameter)
+    assert len(names) == len(sd_b)
+    assert torch.equal(m(**args).logits, fresh(**args).logits)
+    t_b, t_f = gen(m), gen(fresh)
+    assert torch.equal(t_b, t_f)
+    assert not torch.equal(t_a, t_b)              # the update really changed the model

@@ -151,11 +151,9 @@ def test_factory_names_and_seg_empty_prompt():
     assert out["mask"].shape == (2,) and out["mask"][0].shape == (768, 768) and out["mask"][0].sum() == 0
 
 
-def test_offload_hooks_are_noops_and_weight_sync_is_declared_next():
+def test_offload_hooks_are_noops():
     st = B200InferStrategy(worker("b200_infer"))
     assert st.load_states(include=None, non_blocking=True) is None and st.offload_states() is None
-    with pytest.raises(NotImplementedError):
-        st.update_parameter_in_bucket({}, None, [0])
 
 
 # ---------------------------------------------------------------------------------------------- world_size 2, gloo

@@ -101,6 +101,10 @@ int sr_set_gemv_warps(int warps);
 /* Tuning knob: weight-load instruction flavour of the skinny GEMM at M <= 8 (0 nc/no-allocate, 1 + L2::256B, 2 plain). */
 int sr_set_gemv_load(int flavour);
 
+/* Attention kernel variant: 1 (default; env SR_ATTN_LEAN) = two CTAs per SM, single K/V stage, P aliases K, 256 TMEM columns;
+ * 0 = one CTA per SM with a 2-stage K/V ring and double-buffered S.  Results are bit-identical. */
+int sr_set_attention_lean(int enabled);
+
 /* ---- attention (tcgen05 + TMA) --------------------------------------------------------------
  * Variable-length softmax(Q K^T * scale) V; query row r attends key rows k with row_lo[r] <= k < row_hi[r].
  * Replaces flash_attn_varlen_func / eager per-window attention at HF:244-283 (ViT windowed + full attention,

@@ -18,6 +18,15 @@
 // S = Q K^T (M128 N128 K128) into a double-buffered TMEM S and PV = P V (M128 N=HDV K128) into TMEM.
 // warps 2-5: one query row per thread: tcgen05.ld S, mask, online softmax in fp32 (exp2), P -> bf16 into
 // 128B-swizzled smem (A operand of the PV MMA), O accumulated in registers with the usual rescale.
+//
+// Two instantiations per head size.  STAGES = 2: one CTA per SM, K/V 2-stage ring, S double-buffered in TMEM (512 columns),
+// the next block's S = Q K^T overlaps this block's softmax.  STAGES = 1 ("lean"): TWO CTAs per SM -- one K/V stage, one S
+// buffer (256 TMEM columns), and the P tile ALIASES the K tile (K is dead once S has been committed), 84-96 KB of shared
+// memory -- so that the second CTA's loads / MMAs / softmax fill the bubbles of the first one's dependency chain
+// (load -> S -> softmax -> P V -> rescale).  The per-block chain is latency-bound (ncu: tensor pipe 6-14 % busy at one CTA
+// per SM), which is why the second resident CTA pays off, most of all for the single-block windowed tiles.
+#include <stdlib.h>
+
 #include "sr_host.h"
 
 namespace sr {
@@ -26,6 +35,12 @@ constexpr int ATT_THREADS = 192;
 constexpr int ATT_BM = 128;   // query rows per tile
 constexpr int ATT_BN = 128;   // keys per block
 constexpr int ATT_D = 128;    // (padded) qk head dim
+
+SR_DEVINL float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct AttnParams {
   __nv_bfloat16* O;
@@ -37,30 +52,37 @@ struct AttnParams {
   int group;  // q heads per kv head
 };
 
-template <int HDV>
+template <int HDV, int STAGES>
 struct AttnCfg {
+  static constexpr bool kLean = STAGES == 1;
   static constexpr int kQBytes = ATT_BM * ATT_D * 2;      // 32 KB (2 boxes)
   static constexpr int kKBytes = ATT_BN * ATT_D * 2;      // 32 KB (2 boxes)
   static constexpr int kVBoxBytes = HDV * 128;            // [HDV rows x 64 keys]
   static constexpr int kVBytes = 2 * kVBoxBytes;
   static constexpr int kKVStage = kKBytes + ((kVBytes + 1023) / 1024) * 1024;
-  static constexpr int kPBytes = ATT_BM * ATT_BN * 2;     // 32 KB
-  static constexpr int kSmemBytes = kQBytes + 2 * kKVStage + kPBytes + 1024 + 256;
+  static constexpr int kPBytes = ATT_BM * ATT_BN * 2;     // 32 KB (lean: aliases the K tile of the single stage)
+  static constexpr int kSmemBytes = kQBytes + STAGES * kKVStage + (kLean ? 0 : kPBytes) + 1024 + 256;
+  static constexpr int kTmemCols = kLean ? 256 : 512;     // S (x STAGES) + PV
+  static constexpr uint32_t kTmemPV = kLean ? 128 : 256;
 };
 
-template <int HDV>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int HDV, int STAGES>
+__global__ void __launch_bounds__(ATT_THREADS, STAGES == 1 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using Cfg = AttnCfg<HDV>;
-  static_assert(HDV % 16 == 0 && HDV <= 128, "HDV");
+  using Cfg = AttnCfg<HDV, STAGES>;
+  constexpr bool LEAN = Cfg::kLean;
+  static_assert(HDV % 16 == 0 && HDV <= 128 && (STAGES == 1 || STAGES == 2), "HDV / STAGES");
+  // stage and mbarrier parity of KV block j
+  auto st_of = [](int j) { return LEAN ? 0 : (j & 1); };
+  auto ph_of = [](int j) { return static_cast<uint32_t>(LEAN ? (j & 1) : ((j >> 1) & 1)); };
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + Cfg::kQBytes;
-  uint8_t* sP = sKV + 2 * Cfg::kKVStage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPBytes);
+  uint8_t* sP = LEAN ? sKV : sKV + 2 * Cfg::kKVStage;  // lean: P overwrites K after S = Q K^T has been committed
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * Cfg::kKVStage + (LEAN ? 0 : Cfg::kPBytes));
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -94,12 +116,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(pv_full, 1);
     fence_mbar_init();
   }
-  if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+  if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t kTmemPV = 256;
+  constexpr uint32_t kTmemPV = Cfg::kTmemPV;
 
   if (nblk > 0) {
     if (warp_idx == 0) {
@@ -109,8 +131,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_3d(sQ, &tmQ, q_full, 0, head, q_row0);
         tma_load_3d(sQ + 16384, &tmQ, q_full, 64, head, q_row0);
         for (int j = 0; j < nblk; ++j) {
-          const int s = j & 1;
-          const uint32_t ph = (j >> 1) & 1;
+          const int s = st_of(j);
+          const uint32_t ph = ph_of(j);
           mbar_wait(&kv_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&kv_full[s], Cfg::kKBytes + Cfg::kVBytes);
           uint8_t* sK = sKV + s * Cfg::kKVStage;
@@ -130,8 +152,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t aQ = smem_u32(sQ);
         const uint32_t aP = smem_u32(sP);
         auto issue_s = [&](int j) {
-          const int s = j & 1;
-          mbar_wait(&kv_full[s], (j >> 1) & 1);
+          const int s = st_of(j);
+          mbar_wait(&kv_full[s], ph_of(j));
           tc_fence_after();
           const uint32_t aK = smem_u32(sKV + s * Cfg::kKVStage);
           const uint32_t tS = tmem_base + static_cast<uint32_t>(s * ATT_BN);
@@ -144,12 +166,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_commit(&s_full[s]);
         };
         mbar_wait(q_full, 0);
-        issue_s(0);
+        if (!LEAN) issue_s(0);
         for (int j = 0; j < nblk; ++j) {
-          if (j + 1 < nblk) issue_s(j + 1);
+          // lean: one S buffer and one K/V stage -- S_j is issued here, after P V of block j-1 (program order on the tensor
+          // pipe; the softmax warps finished reading S_{j-1} before they signalled p_ready for block j-1)
+          if (LEAN) issue_s(j);
+          else if (j + 1 < nblk) issue_s(j + 1);
           mbar_wait(p_ready, j & 1);
           tc_fence_after();
-          const int s = j & 1;
+          const int s = st_of(j);
           const uint32_t aV = smem_u32(sKV + s * Cfg::kKVStage + Cfg::kKBytes);
 #pragma unroll
           for (int k = 0; k < ATT_BN / 16; ++k) {
@@ -180,28 +205,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int sw = r & 7;
 
       for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
+        const int s = st_of(j);
         const int kbase = kv_lo + j * ATT_BN;
-        mbar_wait(&s_full[s], (j >> 1) & 1);
+        mbar_wait(&s_full[s], ph_of(j));
         tc_fence_after();
         const uint32_t tS = tmem_base + lane_off + static_cast<uint32_t>(s * ATT_BN);
-        // pass 1: row max
-        float mx = m;
+        // The softmax warps are the critical path (one warp per SM sub-partition): keep the per-element instruction count
+        // low and the dependency chains short -- 4 independent max / sum accumulators, scale folded into one FFMA in front of
+        // MUFU.EX2, and no per-key range tests when the whole block is visible to this row (the common case away from
+        // window / sample / causal boundaries).
+        const bool all_visible = kbase >= lo && kbase + ATT_BN <= hi;
+        // pass 1: row max (of the raw scores: scale_log2 > 0, so max commutes with the scaling)
+        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
         for (int c = 0; c < ATT_BN / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tS + c * 32, v);
           tmem_ld_wait();
+          if (all_visible) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int key = kbase + c * 32 + i;
-            const float sv = (key >= lo && key < hi) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
-            mx = fmaxf(mx, sv);
+            for (int i = 0; i < 32; ++i) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int key = kbase + c * 32 + i;
+              mxa[i & 3] = fmaxf(mxa[i & 3], (key >= lo && key < hi) ? __uint_as_float(v[i]) : -INFINITY);
+            }
           }
         }
+        const float mx = fmaxf(m, fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * p.scale_log2);
         const float m_use = (mx == -INFINITY) ? 0.f : mx;
         const float alpha = exp2f(m - m_use);
-        float rowsum = 0.f;
+        const float neg_m = -m_use;
+        float rsa[4] = {0.f, 0.f, 0.f, 0.f};
         // pass 2: probabilities -> bf16 P tile (K-major, 128B swizzle: 16B chunk index XOR (row & 7))
 #pragma unroll 1
         for (int c = 0; c < ATT_BN / 32; ++c) {
@@ -209,12 +245,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_ld_32x32b_x32(tS + c * 32, v);
           tmem_ld_wait();
           float pr[32];
+          if (all_visible) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int key = kbase + c * 32 + i;
-            const float sv = (key >= lo && key < hi) ? __uint_as_float(v[i]) * p.scale_log2 : -INFINITY;
-            pr[i] = exp2f(sv - m_use);
-            rowsum += pr[i];
+            for (int i = 0; i < 32; ++i) {
+              pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+              rsa[i & 3] += pr[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int key = kbase + c * 32 + i;
+              const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+              pr[i] = (key >= lo && key < hi) ? e : 0.f;
+              rsa[i & 3] += pr[i];
+            }
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -228,6 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             *reinterpret_cast<uint4*>(dst) = pk;
           }
         }
+        const float rowsum = (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
         l = l * alpha + rowsum;
         m = mx;
         tc_fence_before();         // our TMEM reads of S / PV are ordered before the MMAs released below
@@ -266,15 +311,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int HDV>
+template <int HDV, int STAGES>
 static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p, int n_tiles,
                        int n_heads, cudaStream_t stream) {
-  using Cfg = AttnCfg<HDV>;
-  auto kern = attn_fwd_kernel<HDV>;
+  using Cfg = AttnCfg<HDV, STAGES>;
+  auto kern = attn_fwd_kernel<HDV, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
     SR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -286,7 +331,14 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
   return SR_OK;
 }
 
+static int g_attn_lean = -1;  // -1: env SR_ATTN_LEAN (default 1)
+
 }  // namespace sr
+
+extern "C" int sr_set_attention_lean(int enabled) {
+  sr::g_attn_lean = enabled ? 1 : 0;
+  return SR_OK;
+}
 
 extern "C" int sr_attention_fwd(const void* Q, int64_t q_row_stride, int64_t q_head_stride, int n_q_rows, int n_q_heads,
                                 const void* K, int64_t k_row_stride, int64_t k_head_stride, int n_k_rows, int n_kv_heads,
@@ -334,6 +386,14 @@ extern "C" int sr_attention_fwd(const void* Q, int64_t q_row_stride, int64_t q_h
   p.scale_log2 = scale * 1.4426950408889634f;
   p.group = n_q_heads / n_kv_heads;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (head_dim_v == 80) return launch_attn<80>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
-  return launch_attn<128>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
+  if (g_attn_lean < 0) {
+    const char* e = getenv("SR_ATTN_LEAN");
+    g_attn_lean = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  if (g_attn_lean) {
+    if (head_dim_v == 80) return launch_attn<80, 1>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
+    return launch_attn<128, 1>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
+  }
+  if (head_dim_v == 80) return launch_attn<80, 2>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
+  return launch_attn<128, 2>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
 }

@@ -428,14 +428,20 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t*
     for (int q = 0; q < RG; ++q)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
-    // epilogue operands of this thread's output element: requested before the K loop so their latency is hidden
-    float epi_add = 0.f;
-    if (ct < 128 && (ct >> 4) < M) {
-      const int col = u * 16 + (ct & 15);
-      if (EPI == DP_EPI_BIAS && bias != nullptr) epi_add = __ldg(bias + col);
-      if (EPI == DP_EPI_RESIDUAL) {
-        const unsigned short rbits = __ldcg(reinterpret_cast<const unsigned short*>(out_bf + static_cast<int64_t>(ct >> 4) * ldo + col));
-        epi_add = __uint_as_float(static_cast<uint32_t>(rbits) << 16);
+    // epilogue operands of this thread's output element(s): requested before the K loop so their latency is hidden.
+    // Units of the non-SwiGLU epilogues with RG = 2 are two independent 16-column groups (columns (u*RG + q)*16 ..).
+    constexpr int NG = (EPI == DP_EPI_SWIGLU) ? 1 : RG;
+    float epi_add[NG];
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+      epi_add[q] = 0.f;
+      if (ct < 128 && (ct >> 4) < M) {
+        const int col = (u * NG + q) * 16 + (ct & 15);
+        if (EPI == DP_EPI_BIAS && bias != nullptr) epi_add[q] = __ldg(bias + col);
+        if (EPI == DP_EPI_RESIDUAL) {
+          const unsigned short rbits = __ldcg(reinterpret_cast<const unsigned short*>(out_bf + static_cast<int64_t>(ct >> 4) * ldo + col));
+          epi_add[q] = __uint_as_float(static_cast<uint32_t>(rbits) << 16);
+        }
       }
     }
     if constexpr (STAGED) {
@@ -471,10 +477,13 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t*
           const float o = (gate / (1.0f + __expf(-gate))) * up;
           out_bf[static_cast<int64_t>(b) * ldo + u * 16 + f] = __float2bfloat16(o);
         } else {
-          const int col = u * 16 + f;
-          const float o = v[0] + epi_add;
-          if (EPI == DP_EPI_F32) out_f32[static_cast<int64_t>(b) * ldo + col] = o;
-          else out_bf[static_cast<int64_t>(b) * ldo + col] = __float2bfloat16(o);
+#pragma unroll
+          for (int q = 0; q < NG; ++q) {
+            const int col = (u * NG + q) * 16 + f;
+            const float o = v[q] + epi_add[q];
+            if (EPI == DP_EPI_F32) out_f32[static_cast<int64_t>(b) * ldo + col] = o;
+            else out_bf[static_cast<int64_t>(b) * ldo + col] = __float2bfloat16(o);
+          }
         }
       }
     }
@@ -864,7 +873,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       for (int l = 0; l < p.n_layers; ++l) {
         const DpLayer L = s_layers[l];
         if (ph++ >= limit) return;
-        dp_produce<1, false>(ring, L.qkv_wp, n_qkv, kq, policy, hint, s_pcnt, issued);
+        dp_produce<2, false>(ring, L.qkv_wp, n_qkv / 2, kq, policy, hint, s_pcnt, issued);
         dp_trace_at(p, 0, 1 + 4 * l);
         if (ph++ >= limit) return;  // attention phase: no weights
         if (ph++ >= limit) return;
@@ -894,7 +903,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       for (int l = 0; l < p.n_layers; ++l) {
         const DpLayer L = s_layers[l];
         if (ph++ >= limit) return;
-        dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, L.qkv_wp, n_qkv, kq, pf_policy, pf_hint);
+        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, L.qkv_wp, n_qkv / 2, kq, pf_policy, pf_hint);
         if (ph++ >= limit) return;
         if (ph++ >= limit) return;
         dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, L.o_wp, n_o, kq, pf_policy, pf_hint);
@@ -926,7 +935,9 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     if (ph++ >= limit) return;
     dp_stage_rows<true>(xs, p.x, p.ldx, p.B, L.ln1, p.eps, cw, lane);
     dp_cbar();
-    dp_gemv_phase<1, DP_EPI_BIAS, true>(ring, n_qkv, kq, xs, nullptr, 0, p.B, red, red_par, L.qkv_b, p.qkv, nullptr,
+    // units of 32 rows: (nq + 2 nkv) * 8 = 160 16-row groups would leave 12 of 148 CTAs with two serial units; 80 double
+    // units fit the ring (128 KB) and take one pass (the 68 CTAs without a unit let their producers run ahead)
+    dp_gemv_phase<2, DP_EPI_BIAS, true>(ring, n_qkv / 2, kq, xs, nullptr, 0, p.B, red, red_par, L.qkv_b, p.qkv, nullptr,
                                         static_cast<int64_t>(n_qkv) * 16, cw, lane);
     const bool do_attn = ph < limit;
     if (do_attn) dp_attn_prefetch(p, l, U, fr);  // old K / V^T rows fly while the CTA waits at the barrier

@@ -111,7 +111,7 @@ def _named(seed=3):
             ("visual.blocks.0.attn.qkv.weight", torch.randn(384, 128, generator=g).bfloat16())]
 
 
-def _sync_worker(rank, port, q):
+def _sync_worker(rank, port, q, done):
     from socioreasoner_b200.roll_shim import collective
     torch.manual_seed(0)
     named = _named()
@@ -125,6 +125,8 @@ def _sync_worker(rank, port, q):
             collective.broadcast(buf, src_rank=0, group_name="model_update_test")
         collective.broadcast(named[2][1], src_rank=0, group_name="model_update_test")
         q.put(("sender", "ok"))
+        done.wait(60)   # the store master leaves last: the receiver tears its side of the group down first
+        collective.destroy_collective_group("model_update_test")
         return
     st = B200InferStrategy(SimpleNamespace(worker_config=None, rank=5))
     st.model = RecordingModel()
@@ -137,13 +139,16 @@ def _sync_worker(rank, port, q):
     st.recv_manager.clear()
     ok = all(torch.equal(st.model.got[n], t) for n, t in named) and list(st.model.got) == [n for n, _ in named]
     q.put(("receiver", "ok" if ok else "mismatch"))
+    collective.destroy_collective_group("model_update_test")
+    done.set()
 
 
 def test_broadcast_bucket_and_parameter_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29800 + (os.getpid() % 150)
-    procs = [ctx.Process(target=_sync_worker, args=(r, port, q)) for r in range(2)]
+    done = ctx.Event()
+    procs = [ctx.Process(target=_sync_worker, args=(r, port, q, done)) for r in range(2)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=180) for _ in range(2))

@@ -191,6 +191,33 @@ def test_ragged_left_padded_and_mixed_resolution_batch(model, oracle_tiny):
         assert rel_rms(batched, single) < 4e-3   # not bit-exact: KV block boundaries of the varlen attention shift with packing
 
 
+def test_cfg4_mixed_resolution_at_full_size_is_batch_invariant(model):
+    """BASELINE configs[3] at its real sizes: {448, 896, 1344}^2 tiles in ONE batch (N = 1024 / 4096 / 9216 patches, the
+    1344^2 cap of the yaml instead of the reference-effective 768^2) -- the variable-tile TMA path of the attention kernel
+    (windows of 4..64 tokens, 72 key blocks in the full-attention layer, ragged causal samples).  Size-independent property
+    (the CPU oracle does not finish an eager 9216-token attention in seconds): every sample in the batch equals its own
+    single-sample run, and the merged vision features have exactly M = N / 4 rows per tile."""
+    sides = [448, 896, 1344]
+    b = O.make_batch([30, 31, 32], sides, "tiny", max_pixels=1344 * 1344, n_text=16)
+    assert b.image_grid_thw.tolist() == [[1, 32, 32], [1, 64, 64], [1, 96, 96]]
+    feat = model.get_image_features(b.pixel_values, b.image_grid_thw)
+    assert feat.shape[0] == (1024 + 4096 + 9216) // 4 and torch.isfinite(feat.float()).all()
+    out = model(input_ids=b.input_ids, attention_mask=b.attention_mask, position_ids=b.position_ids,
+                pixel_values=b.pixel_values, image_grid_thw=b.image_grid_thw).logits
+    assert out[~b.attention_mask.bool()].abs().max().item() == 0
+    off = 0
+    for i, side in enumerate(sides):
+        bi = O.make_batch([30 + i], [side], "tiny", max_pixels=1344 * 1344, n_text=16)
+        single = model(input_ids=bi.input_ids, attention_mask=bi.attention_mask, position_ids=bi.position_ids,
+                       pixel_values=bi.pixel_values, image_grid_thw=bi.image_grid_thw).logits[0]
+        n = bi.input_ids.shape[1]
+        assert rel_rms(out[i, -n:], single) < 4e-3
+        m = int(bi.image_grid_thw.prod()) // 4
+        f1 = model.get_image_features(bi.pixel_values, bi.image_grid_thw)
+        assert rel_rms(feat[off:off + m], f1) < 4e-3
+        off += m
+
+
 def test_two_images_per_prompt_and_long_left_padding(model, oracle_tiny):
     """The reference sends TWO images per prompt (map + satellite, rlvr_socioseg_vlm_pipeline_infer.py:74-81) and left-pads
     prompts to prompt_length (collator.py:421-565); both must go through the packed / varlen internals unchanged."""

@@ -220,6 +220,9 @@ int sr_set_decode_persistent_coop(int enabled);
 /* Tuning knobs of the producer: pf_stages = L2 prefetch lookahead beyond the shared-memory ring, in 16 KB stages per CTA
  * (0 = off; env SR_DECODE_PF_STAGES); flags bit 0 = L2 evict_first hint on the ring copies (env SR_DECODE_FLAGS). */
 int sr_set_decode_persistent_tuning(int pf_stages, int flags);
+/* Unit -> CTA rotation per matrix (unit u of the matrix runs on CTA (u + offset) mod #SMs); default 96, 40, 0, 20 (env
+ * SR_DECODE_UNIT_OFFSETS="q,o,g,d"): balances the bytes streamed per SM.  Results do not depend on it. */
+int sr_set_decode_persistent_offsets(int qkv, int o, int gate_up, int down);
 /* Tuning aid: when buffer != NULL every later sr_decode_step_persistent launch records (globaltimer ns, clock64) pairs at its
  * phase boundaries into buffer[n_SMs][2 roles: producer, consumer][events_per_role][2] (uint64); NULL switches it off. */
 int sr_set_decode_persistent_trace(void* buffer, int events_per_role);

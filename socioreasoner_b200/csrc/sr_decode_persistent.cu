@@ -21,6 +21,7 @@
 //     attention (flash-decoding, merge by the last CTA of a (sample, kv head)) | o-proj + residual | gate/up + SwiGLU |
 //     down + residual; then final norm + LM head (fp32 logits).
 // HBM-bound: algorithmic bytes per launch = all decoder weights + LM head (N*K*2 each) + KV cache of the live sequences.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "sr_host.h"
@@ -116,6 +117,7 @@ struct DpParams {
   int stop_after;          // debug: run only the first `stop_after` phases (<= 0: all)
   int pf_stages;           // L2 prefetch lookahead of the producer beyond the ring, in 16 KB stages per CTA (0 = off)
   int ring_stages;         // shared-memory ring stages in use (2 .. DP_STAGES)
+  int unit_off[4];         // unit -> CTA rotation of the qkv / o / gate-up / down matrices
   int flags;               // bit 0: L2 evict_first hint on the ring copies (weights are consumed exactly once)
   unsigned long long* trace;  // optional [gridDim.x][2 roles][trace_events][2] (globaltimer ns, clock64) -- sr_set_decode_persistent_trace
   int trace_events;
@@ -201,11 +203,11 @@ struct DpRing {
 // from L2 by every CTA: without the rotation all CTAs request the same 8 KB of activations at the same time (hot L2 slices).
 SR_DEVINL int dp_rot(int u, int nst) { return (u * 7) % nst; }
 template <int RG, bool ROT>
-SR_DEVINL void dp_produce(DpRing& r, const __nv_bfloat16* Wp, int n_units, int nchunks, uint64_t policy, bool hint, volatile int* pcnt,
-                          int& issued) {
+SR_DEVINL void dp_produce(DpRing& r, int v0, const __nv_bfloat16* Wp, int n_units, int nchunks, uint64_t policy, bool hint,
+                          volatile int* pcnt, int& issued) {
   constexpr int CPS = DP_STAGE_BLOCKS / RG;
   const int nst = (nchunks + CPS - 1) / CPS;
-  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+  for (int u = v0; u < n_units; u += gridDim.x) {
     int st = ROT ? dp_rot(u, nst) : 0;
     for (int i = 0; i < nst; ++i) {
       mbar_wait(&r.empty[r.slot], r.phase ^ 1);
@@ -239,11 +241,11 @@ SR_DEVINL void dp_produce(DpRing& r, const __nv_bfloat16* Wp, int n_units, int n
 // barriers, L2 round trips) during which the ring is full and HBM would idle; with the prefetcher the HBM stream continues into
 // L2 (`lead` x 16 KB x 148 CTAs), and the ring later refills at L2 speed.
 template <int RG, bool ROT>
-SR_DEVINL void dp_prefetch_l2(int& sidx, const volatile int* pcnt, int lead, const __nv_bfloat16* Wp, int n_units, int nchunks,
+SR_DEVINL void dp_prefetch_l2(int& sidx, const volatile int* pcnt, int lead, int v0, const __nv_bfloat16* Wp, int n_units, int nchunks,
                                uint64_t policy, bool hint) {
   constexpr int CPS = DP_STAGE_BLOCKS / RG;
   const int nst = (nchunks + CPS - 1) / CPS;
-  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+  for (int u = v0; u < n_units; u += gridDim.x) {
     int st = ROT ? dp_rot(u, nst) : 0;
     for (int i = 0; i < nst; ++i) {
       int pc = *pcnt;
@@ -417,12 +419,12 @@ enum { DP_EPI_BIAS = 0, DP_EPI_RESIDUAL = 1, DP_EPI_SWIGLU = 2, DP_EPI_F32 = 3 }
 
 // One GEMV phase: all units of this CTA.  `staged`: activations come from xs (K = DP_H), else from xg (L2).
 template <int RG, int EPI, bool STAGED>
-SR_DEVINL void dp_gemv_phase(DpRing& r, int n_units, int nchunks, const uint8_t* xs, const __nv_bfloat16* xg, int64_t ldxg,
+SR_DEVINL void dp_gemv_phase(DpRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, const __nv_bfloat16* xg, int64_t ldxg,
                              int M, float* red, int& red_par, const float* bias, __nv_bfloat16* out_bf, float* out_f32,
                              int64_t ldo, int cw, int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int ct = threadIdx.x - 32;
-  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+  for (int u = v0; u < n_units; u += gridDim.x) {
     float acc[RG][4];
 #pragma unroll
     for (int q = 0; q < RG; ++q)
@@ -861,6 +863,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   const int kd = p.I >> 5;
   const int n_head = p.vocab / 16;
   const int limit = p.stop_after > 0 ? p.stop_after : 0x7fffffff;
+  // Unit -> CTA mapping, rotated per matrix: unit u of a matrix goes to CTA (u + offset) mod gridDim.  The unit counts (80 / 128
+  // / 688 / 128 on 148 CTAs) leave some CTAs without a unit, or with one unit more; the offsets make those sets complement each
+  // other (e.g. the 20 CTAs idle in the down projection take a fifth gate/up unit), which lowers the bytes of the busiest CTA.
+  auto vidx = [&](int off) { const int g = static_cast<int>(gridDim.x); return (static_cast<int>(blockIdx.x) + g - (off % g)) % g; };
+  const int vq = vidx(p.unit_off[0]), vo = vidx(p.unit_off[1]), vg = vidx(p.unit_off[2]), vd = vidx(p.unit_off[3]);
 
   if (warp == 0) {
     // ---------------- producer: weights only; runs ahead of the consumers across phases ----------------
@@ -873,21 +880,21 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       for (int l = 0; l < p.n_layers; ++l) {
         const DpLayer L = s_layers[l];
         if (ph++ >= limit) return;
-        dp_produce<2, false>(ring, L.qkv_wp, n_qkv / 2, kq, policy, hint, s_pcnt, issued);
+        dp_produce<2, false>(ring, vq, L.qkv_wp, n_qkv / 2, kq, policy, hint, s_pcnt, issued);
         dp_trace_at(p, 0, 1 + 4 * l);
         if (ph++ >= limit) return;  // attention phase: no weights
         if (ph++ >= limit) return;
-        dp_produce<1, false>(ring, L.o_wp, n_o, kq, policy, hint, s_pcnt, issued);
+        dp_produce<1, false>(ring, vo, L.o_wp, n_o, kq, policy, hint, s_pcnt, issued);
         dp_trace_at(p, 0, 2 + 4 * l);
         if (ph++ >= limit) return;
-        dp_produce<2, false>(ring, L.gu_wp, n_gu, kq, policy, hint, s_pcnt, issued);
+        dp_produce<2, false>(ring, vg, L.gu_wp, n_gu, kq, policy, hint, s_pcnt, issued);
         dp_trace_at(p, 0, 3 + 4 * l);
         if (ph++ >= limit) return;
-        dp_produce<1, true>(ring, L.down_wp, n_o, kd, policy, hint, s_pcnt, issued);
+        dp_produce<1, true>(ring, vd, L.down_wp, n_o, kd, policy, hint, s_pcnt, issued);
         dp_trace_at(p, 0, 4 + 4 * l);
       }
       if (ph++ >= limit) return;
-      dp_produce<1, false>(ring, p.lm_head_p, n_head, kq, policy, hint, s_pcnt, issued);
+      dp_produce<1, false>(ring, static_cast<int>(blockIdx.x), p.lm_head_p, n_head, kq, policy, hint, s_pcnt, issued);
       dp_trace_at(p, 0, 1 + 4 * p.n_layers);
     }
     return;
@@ -903,17 +910,17 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       for (int l = 0; l < p.n_layers; ++l) {
         const DpLayer L = s_layers[l];
         if (ph++ >= limit) return;
-        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, L.qkv_wp, n_qkv / 2, kq, pf_policy, pf_hint);
+        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, vq, L.qkv_wp, n_qkv / 2, kq, pf_policy, pf_hint);
         if (ph++ >= limit) return;
         if (ph++ >= limit) return;
-        dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, L.o_wp, n_o, kq, pf_policy, pf_hint);
+        dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, vo, L.o_wp, n_o, kq, pf_policy, pf_hint);
         if (ph++ >= limit) return;
-        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, L.gu_wp, n_gu, kq, pf_policy, pf_hint);
+        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, vg, L.gu_wp, n_gu, kq, pf_policy, pf_hint);
         if (ph++ >= limit) return;
-        dp_prefetch_l2<1, true>(sidx, s_pcnt, lead, L.down_wp, n_o, kd, pf_policy, pf_hint);
+        dp_prefetch_l2<1, true>(sidx, s_pcnt, lead, vd, L.down_wp, n_o, kd, pf_policy, pf_hint);
       }
       if (ph++ >= limit) return;
-      dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, p.lm_head_p, n_head, kq, pf_policy, pf_hint);
+      dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, static_cast<int>(blockIdx.x), p.lm_head_p, n_head, kq, pf_policy, pf_hint);
     }
     return;
   }
@@ -937,7 +944,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     dp_cbar();
     // units of 32 rows: (nq + 2 nkv) * 8 = 160 16-row groups would leave 12 of 148 CTAs with two serial units; 80 double
     // units fit the ring (128 KB) and take one pass (the 68 CTAs without a unit let their producers run ahead)
-    dp_gemv_phase<2, DP_EPI_BIAS, true>(ring, n_qkv / 2, kq, xs, nullptr, 0, p.B, red, red_par, L.qkv_b, p.qkv, nullptr,
+    dp_gemv_phase<2, DP_EPI_BIAS, true>(ring, vq, n_qkv / 2, kq, xs, nullptr, 0, p.B, red, red_par, L.qkv_b, p.qkv, nullptr,
                                         static_cast<int64_t>(n_qkv) * 16, cw, lane);
     const bool do_attn = ph < limit;
     if (do_attn) dp_attn_prefetch(p, l, U, fr);  // old K / V^T rows fly while the CTA waits at the barrier
@@ -954,7 +961,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     if (ph++ >= limit) return;
     dp_stage_rows<false>(xs, p.ao, DP_H, p.B, nullptr, 0.f, cw, lane);
     dp_cbar();
-    dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, n_o, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
+    dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, vo, n_o, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
     DP_TRACE();
     dp_grid_barrier(p.grid_bar, ++bar_gen * G);
     DP_TRACE();
@@ -962,13 +969,13 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     if (ph++ >= limit) return;
     dp_stage_rows<true>(xs, p.x, p.ldx, p.B, L.ln2, p.eps, cw, lane);
     dp_cbar();
-    dp_gemv_phase<2, DP_EPI_SWIGLU, true>(ring, n_gu, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.act, nullptr, p.I, cw, lane);
+    dp_gemv_phase<2, DP_EPI_SWIGLU, true>(ring, vg, n_gu, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.act, nullptr, p.I, cw, lane);
     DP_TRACE();
     dp_grid_barrier(p.grid_bar, ++bar_gen * G);
     DP_TRACE();
     // E: x += act . Wdown^T
     if (ph++ >= limit) return;
-    dp_gemv_phase<1, DP_EPI_RESIDUAL, false>(ring, n_o, kd, nullptr, p.act, p.I, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
+    dp_gemv_phase<1, DP_EPI_RESIDUAL, false>(ring, vd, n_o, kd, nullptr, p.act, p.I, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
     DP_TRACE();
     dp_grid_barrier(p.grid_bar, ++bar_gen * G);
     DP_TRACE();
@@ -977,7 +984,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   if (ph++ >= limit) return;
   dp_stage_rows<true>(xs, p.x, p.ldx, p.B, p.final_norm, p.eps, cw, lane);
   dp_cbar();
-  dp_gemv_phase<1, DP_EPI_F32, true>(ring, n_head, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, nullptr, p.logits, p.ld_logits, cw, lane);
+  dp_gemv_phase<1, DP_EPI_F32, true>(ring, static_cast<int>(blockIdx.x), n_head, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, nullptr, p.logits, p.ld_logits, cw, lane);
   DP_TRACE();
 #undef DP_TRACE
 }
@@ -1009,6 +1016,16 @@ extern "C" int sr_set_decode_persistent_tuning(int pf_stages, int flags) {
   g_dp_flags = flags & 0xff;
   g_dp_ring = (flags >> 8) & 0xff;  // tuning aid: ring stages in bits 8..15 (0 = default)
   if (g_dp_ring == 1 || g_dp_ring > DP_STAGES) return SR_ERR_INVALID;
+  return SR_OK;
+}
+
+static int g_dp_unit_off[4] = {-1, 0, 0, 0};  // -1: env SR_DECODE_UNIT_OFFSETS="q,o,g,d" (default below)
+extern "C" int sr_set_decode_persistent_offsets(int qkv, int o, int gate_up, int down) {
+  if (qkv < 0 || o < 0 || gate_up < 0 || down < 0) return SR_ERR_INVALID;
+  g_dp_unit_off[0] = qkv;
+  g_dp_unit_off[1] = o;
+  g_dp_unit_off[2] = gate_up;
+  g_dp_unit_off[3] = down;
   return SR_OK;
 }
 
@@ -1103,6 +1120,13 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
     if (ring_stages < 2 || ring_stages > DP_STAGES) ring_stages = DP_STAGES;
   }
   p.ring_stages = g_dp_ring > 0 ? g_dp_ring : ring_stages;
+  if (g_dp_unit_off[0] < 0) {
+    const int dflt[4] = {96, 40, 0, 20};
+    for (int i = 0; i < 4; ++i) g_dp_unit_off[i] = dflt[i];
+    const char* e = getenv("SR_DECODE_UNIT_OFFSETS");
+    if (e) sscanf(e, "%d,%d,%d,%d", &g_dp_unit_off[0], &g_dp_unit_off[1], &g_dp_unit_off[2], &g_dp_unit_off[3]);
+  }
+  for (int i = 0; i < 4; ++i) p.unit_off[i] = g_dp_unit_off[i] < 0 ? 0 : g_dp_unit_off[i];
   p.pf_stages = g_dp_pf_stages;
   p.flags = g_dp_flags;
   p.trace = g_dp_trace;

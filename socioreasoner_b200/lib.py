@@ -59,6 +59,7 @@ SYMBOLS = {
     "sr_set_decode_persistent_coop": (c_int, [c_int]),
     "sr_set_decode_persistent_trace": (c_int, [_P, c_int]),
     "sr_set_decode_persistent_tuning": (c_int, [c_int, c_int]),
+    "sr_set_decode_persistent_offsets": (c_int, [c_int, c_int, c_int, c_int]),
     "sr_decode_step_persistent": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P,
                                           c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),

@@ -334,21 +334,14 @@ class Engine:
         ids = input_ids.detach().cpu().numpy() if torch.is_tensor(input_ids) else np.asarray(input_ids)
         rm = response_mask.detach().cpu().numpy() if torch.is_tensor(response_mask) else np.asarray(response_mask)
         B, S = sp.B, sp.S
-        row_of = np.full(B * S, -1, dtype=np.int64)          # padded grid position -> packed row
-        row_of[sp.flat_index] = np.arange(sp.total, dtype=np.int64)
-        want = np.zeros((B, S), dtype=bool)
-        want[:, :-1] = rm[:, 1:] != 0                          # position s predicts token s + 1
-        want &= row_of.reshape(B, S) >= 0                      # (a masked-in position on padding has no hidden row)
-        bs, ss = np.nonzero(want)
+        rows_np, labels_np, out_np = plan.logprob_rows(ids, rm, sp.flat_index)
         lp = torch.zeros((B, S - 1), dtype=torch.float32, device=self.device)
         ent = torch.zeros((B, S - 1), dtype=torch.float32, device=self.device) if want_entropy else None
-        if len(bs) == 0:
+        if len(rows_np) == 0:
             return lp, ent
-        rows = _dev(row_of.reshape(B, S)[bs, ss], self.device)
-        labels = _dev(ids[bs, ss + 1].astype(np.int64), self.device)
+        rows, labels, flat = _dev(rows_np, self.device), _dev(labels_np, self.device), _dev(out_np, self.device)
         y = lib.rmsnorm(x.index_select(0, rows), self.w.final_norm, t.rms_norm_eps)
         l_rows, e_rows = lib.lm_head_logprob_entropy(y, self.w.lm_head, labels, want_entropy=want_entropy)
-        flat = _dev(bs * (S - 1) + ss, self.device)
         lp.view(-1).index_copy_(0, flat, l_rows)
         if want_entropy:
             ent.view(-1).index_copy_(0, flat, e_rows)

@@ -181,3 +181,20 @@ def rope_index(input_ids: np.ndarray, image_grid_thw: Optional[np.ndarray], atte
         pos3[:, b, keep] = p
         deltas[b, 0] = (int(p.max()) + 1 if p.size else 0) - S
     return pos3, deltas
+
+
+def logprob_rows(input_ids: np.ndarray, response_mask: np.ndarray, flat_index: np.ndarray):
+    """Row selection of the fused ``compute_log_probs`` path (Engine.forward_log_probs).  The reference computes
+    ``log_softmax(logits[:, :-1])`` everywhere and multiplies by ``response_mask[:, 1:]`` (strategy.py:123-138); here only the
+    positions s with ``response_mask[b, s + 1] != 0`` that own a packed hidden row go through the LM head.
+    ``flat_index`` [T]: index into the flattened [B * S] grid of each packed (non-padding) token.
+    Returns (rows [R] packed hidden-row indices, labels [R] = input_ids[b, s + 1], out_index [R] = b * (S - 1) + s)."""
+    B, S = input_ids.shape
+    row_of = np.full(B * S, -1, dtype=np.int64)          # padded grid position -> packed row
+    row_of[flat_index] = np.arange(len(flat_index), dtype=np.int64)
+    row_of = row_of.reshape(B, S)
+    want = np.zeros((B, S), dtype=bool)
+    want[:, :-1] = np.asarray(response_mask)[:, 1:] != 0   # position s predicts token s + 1
+    want &= row_of >= 0                                    # (a masked-in position on padding has no hidden row)
+    bs, ss = np.nonzero(want)
+    return row_of[bs, ss], np.asarray(input_ids)[bs, ss + 1].astype(np.int64), (bs * (S - 1) + ss).astype(np.int64)

@@ -130,6 +130,36 @@ def test_seq_plan_and_shards():
         assert [c.tolist() for c in shard_indices(batch, world)] == [c.tolist() for c in host_ref.dp_chunk_indices(batch, world)]
 
 
+def test_logprob_rows_reproduce_the_masked_reference_outputs():
+    """Engine.forward_log_probs pushes only the rows selected by plan.logprob_rows through the LM head; scattering their
+    per-row results must equal op_compute_log_probs / op_compute_entropy (strategy.py:123-138) on the full logits -- for left
+    padding, masks that reach into the padding, an all-zero mask and the last position (which predicts nothing)."""
+    g = torch.Generator().manual_seed(0)
+    B, S, V = 4, 9, 23
+    attn = torch.ones(B, S, dtype=torch.long)
+    attn[0, :3] = 0; attn[2, :7] = 0                      # left padding, as the reference collator produces
+    ids = torch.randint(0, V, (B, S), generator=g)
+    logits_full = torch.randn(B, S, V, generator=g)
+    flat = np.nonzero(attn.numpy().reshape(-1))[0]        # packed tokens (SeqPlan.flat_index)
+    hidden_logits = logits_full.reshape(-1, V)[flat]      # what the LM head would produce for each packed row
+    for rm in (attn.clone(), torch.zeros_like(attn), torch.ones_like(attn),
+               torch.tensor([[0, 0, 0, 0, 1, 1, 1, 0, 0]] * B)):
+        rows, labels, out = plan.logprob_rows(ids.numpy(), rm.numpy(), flat)
+        lp = torch.zeros(B * (S - 1)); ent = torch.zeros(B * (S - 1))
+        sel = hidden_logits[rows]
+        lp[out] = host_ref.log_probs_from_logits(sel, torch.from_numpy(labels)) if len(rows) else torch.zeros(0)
+        ent[out] = host_ref.entropy_from_logits(sel) if len(rows) else torch.zeros(0)
+        ref_lp = host_ref.op_compute_log_probs(logits_full, ids, rm)
+        ref_ent = host_ref.op_compute_entropy(logits_full, rm)
+        # positions that are masked in but sit on padding have no hidden row here; the reference would score its zero-padded
+        # logits there -- such masks do not occur (response_mask is a subset of attention_mask), so compare on real tokens
+        real = (attn[:, :-1] != 0)
+        assert torch.allclose(lp.view(B, S - 1)[real], ref_lp[real], atol=1e-6)
+        assert torch.allclose(ent.view(B, S - 1)[real], ref_ent[real], atol=1e-6)
+        assert (lp.view(B, S - 1)[~real] == 0).all()
+        assert len(set(out.tolist())) == len(out) and (rows >= 0).all() and len(rows) == int(((rm[:, 1:] != 0) & real).sum())
+
+
 def test_library_exports_every_declared_symbol():
     """The C-ABI shared library loads (no GPU needed) and exports every function include/*.h declares."""
     from socioreasoner_b200 import lib

@@ -2,6 +2,12 @@
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 Pure numpy / torch on CPU; no CUDA, no imports from the product package.
+
+Pinned: tests/test_reference_fixtures.py checks these restatements bit-exactly against tests/golden/reference_intree.pt --
+outputs of the reference's OWN function sources, extracted with `ast` and executed by tools/make_reference_fixtures.py
+(get_rope_index, log-prob / entropy + masking wrappers, postprocess_generate, compute_giou, the segment() epilogue around a
+stub predictor, collate, the bucket wire format).  Not pinnable here: SAM2's bilinear-upsample + threshold tail (external
+`sam2`, no source in the tree) -- mask_epilogue() restates it with the same torch call on synthetic low-res logits.
 """
 from __future__ import annotations
 
@@ -168,6 +174,41 @@ def pad_generate_output(output: torch.Tensor, sequence_length: int, pad_token_id
     if output.shape[1] >= sequence_length:
         return output[:, :sequence_length]
     return F.pad(output, (0, sequence_length - output.shape[1]), value=pad_token_id)
+
+
+def postprocess_generate_ref(input_ids: torch.Tensor, attention_mask: torch.Tensor, position_ids: torch.Tensor,
+                             output: torch.Tensor, num_return_sequences: int, sequence_length: int, pad_token_id: int):
+    """What ``ActorWorker.generate`` hands to ``compute_log_probs`` (roll/utils/functionals.py:768-872, M-RoPE branch):
+    the generated ``[b*n, S_prompt + S_new]`` ids are padded to ``sequence_length``; every row is shifted left by its prompt's
+    left padding (-> right padding), ``response_mask`` marks the non-pad response tokens, ``attention_mask`` the valid prefix,
+    and the 3-axis position ids continue with last prompt position + 1, + 2, ... on all axes and are shifted the same way.
+    Returns a dict with the reference's keys (restated row by row: this is the oracle for the layout the fused log-prob path
+    has to accept, not product code)."""
+    out = pad_generate_output(output.clone(), sequence_length, pad_token_id)
+    n, S_p = num_return_sequences, input_ids.shape[1]
+    R = out.shape[0]
+    assert R == input_ids.shape[0] * n and position_ids.dim() == 3
+    prompts, responses = out[:, :S_p].clone(), out[:, S_p:].clone()
+    am = attention_mask.repeat_interleave(n, dim=0)
+    resp_mask = (responses != pad_token_id).to(am.dtype)
+    pos = position_ids.repeat_interleave(n, dim=0)                                            # [R, 3, S_p]
+    delta = torch.arange(1, sequence_length - S_p + 1).view(1, 1, -1)
+    pos = torch.cat([pos, pos[..., -1:] + delta], dim=-1)                                     # [R, 3, sequence_length]
+    new_am = torch.zeros(R, sequence_length, dtype=am.dtype)
+    new_rm = torch.zeros_like(new_am)
+    for i in range(R):
+        shift = int(am[i].float().argmax())                       # left padding of the prompt
+        valid = int(am[i].sum() + resp_mask[i].sum())
+        n_resp = int(resp_mask[i].sum())
+        if shift > 0:
+            out[i, :-shift] = out[i, shift:].clone()
+            pos[i, :, :-shift] = pos[i, :, shift:].clone()
+            if S_p > n_resp:
+                out[i, -shift:] = pad_token_id
+        new_am[i, :valid] = 1
+        new_rm[i, valid - n_resp: valid] = 1
+    return {"prompts": prompts, "responses": responses, "input_ids": out, "attention_mask": new_am, "position_ids": pos,
+            "prompt_mask": (new_am == 1) & (new_rm == 0), "response_mask": new_rm}
 
 
 # ----------------------------------------------------------------------------------------------

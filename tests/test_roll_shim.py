@@ -130,6 +130,37 @@ def test_forward_step_takes_the_fused_log_prob_path_for_the_stock_forward_func()
     assert len(st.model.calls) == 3
 
 
+def test_postprocessed_generate_layout_feeds_the_fused_log_prob_path():
+    """generate -> postprocess_generate (functionals.py:768-872: right padding, response_mask, continued M-RoPE ids) ->
+    compute_log_probs: the rows the fused path scores are exactly the response tokens of every sequence, labelled with them."""
+    from socioreasoner_b200 import plan
+    pad, eos, S_p, T, seq_len, n = 0, 9, 7, 5, 14, 2
+    ids = torch.tensor([[0, 0, 0, 3, 4, 5, 6], [0, 1, 2, 3, 4, 5, 6], [7, 1, 2, 3, 4, 5, 6]])
+    am = (ids != 0).long()
+    pos = torch.cumsum(am, -1).sub(1).clamp(min=0)[:, None, :].repeat(1, 3, 1)               # text-only M-RoPE ids
+    gen = torch.tensor([[11, 12, eos, pad, pad], [13, eos, pad, pad, pad], [14, 15, 16, 17, 18], [19, 20, 21, eos, pad],
+                        [22, 23, 24, 25, eos], [26, eos, pad, pad, pad]])
+    output = torch.cat([ids.repeat_interleave(n, 0), gen], 1)                                  # what strategy.generate returns
+    d = host_ref.postprocess_generate_ref(ids, am, pos, output, n, seq_len, pad)
+    assert d["input_ids"].shape == (6, seq_len) and d["position_ids"].shape == (6, 3, seq_len)
+    for i in range(6):
+        p_tok = ids[i // n][am[i // n].bool()].tolist()
+        r_tok = [t for t in gen[i].tolist() if t != pad]
+        valid = len(p_tok) + len(r_tok)
+        assert d["input_ids"][i, :valid].tolist() == p_tok + r_tok                              # right padded, nothing lost
+        assert d["attention_mask"][i].tolist() == [1] * valid + [0] * (seq_len - valid)
+        assert d["response_mask"][i].nonzero().flatten().tolist() == list(range(len(p_tok), valid))
+        assert d["position_ids"][i, 0, :valid].tolist() == list(range(valid))                   # positions continue after the prompt
+    flat = np.nonzero(d["attention_mask"].numpy().reshape(-1))[0]
+    rows, labels, out = plan.logprob_rows(d["input_ids"].numpy(), d["response_mask"].numpy(), flat)
+    want_labels = [t for i in range(6) for t in gen[i].tolist() if t != pad]
+    assert labels.tolist() == want_labels                                                       # every response token, once, in order
+    packed_ids = d["input_ids"].numpy().reshape(-1)[flat]
+    assert (packed_ids[rows + 1] == labels).all()                                               # row s predicts token s + 1
+    b, s_ = out // (seq_len - 1), out % (seq_len - 1)
+    assert (d["response_mask"].numpy()[b, s_ + 1] == 1).all()
+
+
 def test_generate_pads_ragged_micro_batches():
     st = create_strategy(worker("vllm"))
     st.model = FakeModel()

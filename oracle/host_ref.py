@@ -83,6 +83,32 @@ def get_rope_index(
 
 
 # ----------------------------------------------------------------------------------------------
+# M-RoPE table and application -- mcore_adapter/src/mcore_adapter/models/qwen2_5_vl/modeling_qwen2_5_vl.py:14-75
+# (= HF:595-608, 627-669).  freqs[axis] = position_ids[axis] * inv_freq; the 64 frequency slots are taken from the
+# temporal / height / width axis by mrope_section (16 | 24 | 24); x' = x * cos + rotate_half(x) * sin with the
+# 64-slot table repeated over both halves of the 128-wide head.
+# ----------------------------------------------------------------------------------------------
+def mrope_cos_sin(position_ids: torch.Tensor, inv_freq: torch.Tensor, mrope_section: Sequence[int] = (16, 24, 24)):
+    """position_ids [3, B, S] -> (cos, sin) fp32 [B, S, 64]: the section-selected half table sr_mrope_table produces."""
+    fr = position_ids.float()[..., None] * inv_freq.float()[None, None, None, :]          # [3, B, S, 64]
+    parts, lo = [], 0
+    for axis, n in enumerate(mrope_section):
+        parts.append(fr[axis % 3, :, :, lo: lo + n])
+        lo += n
+    sel = torch.cat(parts, -1)
+    return sel.cos(), sel.sin()
+
+
+def apply_mrope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """x [B, S, H, 128], cos / sin [B, S, 64] -> rotated x (rotate-half convention)."""
+    c = torch.cat([cos, cos], -1)[:, :, None, :]
+    s = torch.cat([sin, sin], -1)[:, :, None, :]
+    half = x.shape[-1] // 2
+    rot = torch.cat([-x[..., half:], x[..., :half]], -1)
+    return x * c + rot * s
+
+
+# ----------------------------------------------------------------------------------------------
 # log-prob / entropy from logits -- roll/utils/functionals.py:193-205 and the masking wrappers
 # roll/distributed/strategy/strategy.py:123-138.
 # ----------------------------------------------------------------------------------------------

@@ -33,6 +33,20 @@ def test_rope_index_restatement_and_product_planner_match_the_in_tree_reference(
         assert np.array_equal(p2, c["position_ids"].numpy()) and np.array_equal(d2.reshape(-1), c["rope_deltas"].numpy().reshape(-1))
 
 
+def test_mrope_table_and_apply_restatements_match_the_in_tree_reference(fx):
+    """mcore_adapter/.../modeling_qwen2_5_vl.py:14-75: Qwen2_5_VLRotaryEmbedding.forward + apply_multimodal_rotary_pos_emb
+    (reference layout [s, b, heads, dim]; the restatement works on [b, s, heads, dim] with the 64-slot half table)."""
+    c = fx["mrope"]
+    cos, sin = host_ref.mrope_cos_sin(c["position_ids"], c["inv_freq"], c["mrope_section"])
+    emb = c["emb"]                                                                  # [3, B, S, 128] = cat(freqs, freqs)
+    ref_sel = torch.cat([emb[0, :, :, :16], emb[1, :, :, 16:40], emb[2, :, :, 40:64]], -1)
+    assert torch.allclose(cos, ref_sel.cos(), atol=1e-6) and torch.allclose(sin, ref_sel.sin(), atol=1e-6)
+    q = c["q"].permute(1, 0, 2, 3)                                                   # [s, b, h, d] -> [b, s, h, d]
+    k = c["k"].permute(1, 0, 2, 3)
+    assert torch.allclose(host_ref.apply_mrope(q, cos, sin), c["q_embed"].permute(1, 0, 2, 3), atol=1e-5)
+    assert torch.allclose(host_ref.apply_mrope(k, cos, sin), c["k_embed"].permute(1, 0, 2, 3), atol=1e-5)
+
+
 def test_log_prob_and_entropy_restatements_match_the_reference(fx):
     """roll/utils/functionals.py:193-205 and the masking wrappers roll/distributed/strategy/strategy.py:123-138."""
     c = fx["logprob"]

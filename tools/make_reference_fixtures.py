@@ -9,6 +9,7 @@ logic against that file -- on any machine, without /root/reference.
 
 Functions executed (file:line in the reference):
   mcore_adapter/src/mcore_adapter/models/qwen2_5_vl/modeling_qwen2_5_vl.py  Qwen2_5_VLModel.get_rope_index      :319-441
+  (same file)  rotate_half :14, apply_multimodal_rotary_pos_emb :21-41, Qwen2_5_VLRotaryEmbedding.forward :62-75
   roll/utils/functionals.py   log_probs_from_logits :193, entropy_from_logits :200, get_pad_mask :301, pad_to_length :351,
                               postprocess_generate :768-872, get_dist_info_from_comm_plan :875
   roll/distributed/strategy/strategy.py      InferenceStrategy.op_compute_log_probs / op_compute_entropy   :123-138
@@ -114,6 +115,19 @@ def main():
         pos, deltas = ns["get_rope_index"](self_stub, ids, image_grid_thw=grid, attention_mask=am)
         cases.append(dict(input_ids=ids, attention_mask=am, image_grid_thw=grid, position_ids=pos, rope_deltas=deltas))
     fx["rope_index"] = cases
+
+    # ---- M-RoPE table + apply (in-tree copies, mcore ...:14-75) ----
+    d = extract("mcore_adapter/src/mcore_adapter/models/qwen2_5_vl/modeling_qwen2_5_vl.py",
+                ["rotate_half", "apply_multimodal_rotary_pos_emb", "Qwen2_5_VLRotaryEmbedding.forward"])
+    rns = run_defs(d, base_ns())
+    inv_freq = 1.0 / (1000000.0 ** (torch.arange(0, 128, 2, dtype=torch.float32) / 128))
+    Bm, Sm = 2, 11
+    pos3 = torch.randint(0, 4000, (3, Bm, Sm), generator=g)
+    emb = rns["forward"](SimpleNamespace(inv_freq=inv_freq), torch.zeros(1), pos3)               # [3, B, S, 128]
+    q = torch.randn(Sm, Bm, 4, 128, generator=g)
+    k = torch.randn(Sm, Bm, 2, 128, generator=g)
+    qe, ke = rns["apply_multimodal_rotary_pos_emb"](q, k, emb.cos(), emb.sin(), mrope_section=[16, 24, 24])
+    fx["mrope"] = dict(position_ids=pos3, inv_freq=inv_freq, mrope_section=[16, 24, 24], emb=emb, q=q, k=k, q_embed=qe, k_embed=ke)
 
     # ---- functionals + strategy ops ----
     d = extract("roll/utils/functionals.py", ["log_probs_from_logits", "entropy_from_logits", "get_pad_mask", "pad_to_length",

@@ -97,6 +97,7 @@ class Engine:
         # selects the per-layer kernels (the only path for larger batches)
         self.use_persistent_decode = os.environ.get("SR_DECODE_PERSISTENT", "1") != "0"
         self._layer_table: Optional[torch.Tensor] = None
+        self._sm_count = None
         self.stage_events = None  # optional list: generate_greedy appends (stage, cuda event) pairs (bench.py stage split)
 
     @staticmethod
@@ -401,6 +402,15 @@ class Engine:
         return (self.use_persistent_decode and B <= 8 and self.w.lm_head_p is not None and len(self.w.layers) > 0
                 and self.w.layers[0].qkv_wp is not None and t.intermediate_size % 32 == 0 and t.vocab_size % 16 == 0)
 
+    def _persistent_single_pass(self, B: int, l_max: int) -> bool:
+        """The persistent kernel splits every (sample, kv head) over ns = #SMs // (B * n_kv) CTAs (at most 32) and handles 128 keys
+        per pass.  Its single-pass path (contexts up to 128 * ns keys: 1152 at B = 8, 4096 at B <= 2) is the one covered by the GPU
+        parity tests; longer contexts take the per-layer decode kernels until the multi-pass loop has its own parity test."""
+        if self._sm_count is None:
+            self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
+        ns = max(1, min(32, self._sm_count // max(1, B * self.cfg.text.num_key_value_heads)))
+        return l_max <= 128 * ns
+
     def _pick_token(self, st, sampling) -> None:
         if sampling is None:
             lib.argmax_rows(st["logits"], out=st["nxt"])
@@ -416,7 +426,7 @@ class Engine:
                            st["kv_len"], st["pos3"])
         cos, sin = lib.mrope_table(st["pos3"], self.txt_inv_freq, t.mrope_section)
         lib.embed_scatter(self.w.embed, st["nxt"], None, None, out=st["x"])
-        if "ws" in st and self.use_persistent_decode:
+        if "ws" in st and self.use_persistent_decode and self._persistent_single_pass(st["x"].shape[0], cache.l_max):
             if self._layer_table is None:
                 self._layer_table = lib.decode_layer_table(self.w.layers, self.device)
             lib.decode_step_persistent(self._layer_table, self.w.lm_head_p, self.w.final_norm, t.vocab_size, st["x"], st["qkv"],

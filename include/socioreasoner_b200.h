@@ -217,8 +217,10 @@ typedef struct sr_decode_layer {
 } sr_decode_layer;
 int64_t sr_decode_persistent_workspace_bytes(int batch, int n_kv_heads);
 int sr_set_decode_persistent_coop(int enabled);
-/* Tuning knobs of the producer: pf_stages = L2 prefetch lookahead beyond the shared-memory ring, in 16 KB stages per CTA
- * (0 = off; env SR_DECODE_PF_STAGES); flags bit 0 = L2 evict_first hint on the ring copies (env SR_DECODE_FLAGS). */
+/* Tuning knobs of the weight stream.  pf_stages = look-ahead of the optional L2 prefetcher warp beyond the shared-memory ring, in
+ * 16 KB stages per CTA (default 0 = off; env SR_DECODE_PF_STAGES).  flags (env SR_DECODE_FLAGS, default 1): bit 0 = L2 evict_first
+ * hint on the ring copies, bit 7 = the same hint on the prefetches; bits 8..15 = ring stages in use, 2..10 (0 = default 8; env
+ * SR_DECODE_RING).  None of them changes results. */
 int sr_set_decode_persistent_tuning(int pf_stages, int flags);
 /* Unit -> CTA rotation per matrix (unit u of the matrix runs on CTA (u + offset) mod #SMs); default 96, 40, 0, 20 (env
  * SR_DECODE_UNIT_OFFSETS="q,o,g,d"): balances the bytes streamed per SM.  Results do not depend on it. */

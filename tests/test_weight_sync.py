@@ -169,3 +169,20 @@ def test_update_parameter_respects_ranks_in_worker():
     meta, buf = host_ref.send_buckets([("x", torch.arange(10.0))], bucket_size=64)[0]
     st.update_parameter_in_bucket(meta, buf, ranks_in_worker=[0])
     assert torch.equal(st.model.got["x"], torch.arange(10.0))
+
+
+def test_update_weights_accepts_every_key_of_an_hf_state_dict(oracle_tiny):
+    """The names a real sender walks are the HF module's own state-dict keys (transformers 5.x spelling here: model.visual.*,
+    model.language_model.*, tied lm_head): every key must be consumed, and the result must equal a fresh pack."""
+    from oracle import hf_oracle as O
+    cfg = SocioReasonerConfig.from_hf(oracle_tiny.config)
+    sd_a = {k: v.detach().clone() for k, v in oracle_tiny.state_dict().items()}
+    other = O.build_model("tiny", seed=43)
+    sd_b = {k: v.detach().clone() for k, v in other.state_dict().items()}
+    assert sd_a.keys() == sd_b.keys() and any(k.startswith("model.visual.") for k in sd_a)
+    W = pack(sd_a, cfg, device="cpu")
+    done = update_weights(W, list(sd_b.items()), cfg)
+    assert sorted(done) == sorted(sd_b)
+    want, got = all_tensors(pack(sd_b, cfg, device="cpu")), all_tensors(W)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k

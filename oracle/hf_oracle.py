@@ -160,8 +160,10 @@ def preprocess_tiles(tiles_chw_uint8: Sequence[np.ndarray], max_pixels: int = 76
     return pvs, thws
 
 
-def synth_prompt(i: int, merged_tokens: int, cfg_name: str = "3b", n_text: int = 128) -> torch.Tensor:
-    """[im_start, user, \\n] + [vision_start] + [image_pad]*M + [vision_end] + n_text random ids + chat tail."""
+def synth_prompt(i: int, merged_tokens, cfg_name: str = "3b", n_text: int = 128) -> torch.Tensor:
+    """[im_start, user, \\n] + per image ([vision_start] + [image_pad]*M + [vision_end]) + n_text random ids + chat tail.
+    ``merged_tokens``: int (one image) or a list (the reference's prompts carry two images, map + sat:
+    roll/pipeline/rlvr/rlvr_socioseg_vlm_pipeline_infer.py:74-81)."""
     tok = CONFIGS[cfg_name]["tokens"]
     vocab = CONFIGS[cfg_name]["text"]["vocab_size"]
     g = torch.Generator().manual_seed(2000 + i)
@@ -170,7 +172,11 @@ def synth_prompt(i: int, merged_tokens: int, cfg_name: str = "3b", n_text: int =
     else:
         head, tail, hi = [7001, 872, 198], [7002, 198, 7001, 6091, 198], 7000
     text = torch.randint(0, hi, (n_text,), generator=g).tolist()
-    ids = head + [tok["vision_start_token_id"]] + [tok["image_token_id"]] * merged_tokens + [tok["vision_end_token_id"]] + text + tail
+    ms = [merged_tokens] if isinstance(merged_tokens, int) else list(merged_tokens)
+    vis = []
+    for m in ms:
+        vis += [tok["vision_start_token_id"]] + [tok["image_token_id"]] * m + [tok["vision_end_token_id"]]
+    ids = head + vis + text + tail
     assert max(ids) < vocab
     return torch.tensor(ids, dtype=torch.long)
 
@@ -185,14 +191,19 @@ class Batch:
 
 
 def make_batch(tile_ids: Sequence[int], sides: Sequence[int], cfg_name: str, max_pixels: int = 768 * 768,
-               n_text: int = 128, pad_to: Optional[int] = None, pad_token_id: int = 0) -> Batch:
+               n_text=128, pad_to: Optional[int] = None, pad_token_id: int = 0, images_per_prompt: int = 1) -> Batch:
+    """``images_per_prompt`` = k: prompt j carries tiles [j*k, (j+1)*k) (its text ids are seeded by its first tile id).
+    ``n_text``: int, or one value per prompt (ragged batches)."""
     tiles = [synth_tile_uint8(i, s) for i, s in zip(tile_ids, sides)]
     pvs, thws = preprocess_tiles(tiles, max_pixels=max_pixels)
     tok = CONFIGS[cfg_name]["tokens"]
     prompts = []
-    for i, thw in zip(tile_ids, thws):
-        m = int(thw[0, 0] * thw[0, 1] * thw[0, 2]) // 4
-        prompts.append(synth_prompt(i, m, cfg_name, n_text))
+    k = images_per_prompt
+    assert len(tile_ids) % k == 0
+    for j in range(len(tile_ids) // k):
+        ms = [int(thw[0, 0] * thw[0, 1] * thw[0, 2]) // 4 for thw in thws[j * k:(j + 1) * k]]
+        nt = n_text if isinstance(n_text, int) else n_text[j]
+        prompts.append(synth_prompt(tile_ids[j * k], ms if k > 1 else ms[0], cfg_name, nt))
     S = max(len(p) for p in prompts) if pad_to is None else pad_to
     B = len(prompts)
     ids = torch.full((B, S), pad_token_id, dtype=torch.long)

@@ -193,18 +193,22 @@ int sr_decode_advance(const int64_t* next_tokens, int64_t* tokens, int T, int32_
  * append + attention over the cache, o-proj + residual, RMSNorm + gate/up + SwiGLU, down + residual; HF:762-827, 672-759,
  * 611-624 with use_cache) + final norm + lm_head (HF:1385) -> fp32 logits.  Replaces the body of the reference's rollout
  * decode loop (vLLM engine step, roll/distributed/strategy/vllm_strategy.py:114-141).  Persistent kernel, one CTA per SM
- * (cooperative launch; env SR_DECODE_COOP=0 or sr_set_decode_persistent_coop(0) = plain launch): a producer warp streams
- * the packed weights through a shared-memory ring with cp.async.bulk without ever draining between layers, consumer warps
- * feed mma.sync and synchronise phases with a grid barrier.  HBM-bound (all decoder weights + LM head per launch).
+ * (cooperative launch: the CTAs wait for each other's data): a producer warp streams the packed weights through a
+ * shared-memory ring with cp.async.bulk without ever draining between layers, consumer warps feed mma.sync.  There is no grid
+ * barrier: activations cross CTAs in flag-carrying 16-byte lines {data, gen, data, gen} that the reader polls (one L2 round
+ * trip per exchange).  HBM-bound (all decoder weights + LM head per launch).
  *   layer_table: DEVICE array of n_layers sr_decode_layer (weights in the sr_gemm_skinny_packed_bf16 streaming layout).
- *   x [batch, 2048] bf16 (ldx): residual stream, in = embedded tokens, out = last hidden state (pre final norm).
- *   qkv/ao/act scratch: bf16 [batch, (n_q+2 n_kv)*128], [batch, n_q*128], [batch, intermediate] (dense rows).
+ *   x [batch, 2048] bf16 (ldx): in = embedded tokens (read only, unless the dump flag is set).
+ *   qkv/ao/act scratch: bf16 [batch, (n_q+2 n_kv)*128], [batch, n_q*128], [batch, intermediate] (dense rows); written ONLY
+ *   when tuning flag bit 1 (dump) is set -- then they and x receive plain copies of the last layer's intermediates (bring-up /
+ *   tests); may be NULL otherwise.
  *   cosb/sinb fp32 [batch, 64] (sr_mrope_table of this step's positions); cache_row/kv_start/kv_len as sr_decode_advance
  *   writes them (kv_len INCLUDES the new token, cache_row = kv_start + kv_len - 1).
  *   Kc [n_layers][rows, n_kv, 128], Vt [n_layers][n_kv*128, ldvt]: layer strides in ELEMENTS.
- *   workspace: sr_decode_persistent_workspace_bytes() bytes, 16-byte aligned (barrier counter + tickets are reset by a
- *   memset node enqueued by this call).  stop_after_phases: 0 = everything; k > 0 runs only the first k phases
- *   (5 per layer: qkv, attention, o-proj, gate/up, down; then the LM head) -- bring-up / test aid.
+ *   workspace: sr_decode_persistent_workspace_bytes() bytes, 256-byte aligned, ZEROED once by the caller (it holds the
+ *   generation counter and the flag-carrying exchange buffers; launches on one workspace must be stream-ordered).
+ *   stop_after_phases: 0 = everything; k > 0 runs only the first k phases (5 per layer: qkv, attention, o-proj, gate/up,
+ *   down; then the LM head) -- bring-up / test aid.
  * Hidden size is fixed at 2048 (= n_q_heads * 128); intermediate % 32 == 0; vocab % 16 == 0. */
 typedef struct sr_decode_layer {
   const void* qkv_wp;   /* packed [ (n_q+2 n_kv)*128, 2048 ] */
@@ -215,16 +219,14 @@ typedef struct sr_decode_layer {
   const void* gu_wp;    /* packed [2*intermediate, 2048], rows interleaved 16 gate | 16 up */
   const void* down_wp;  /* packed [2048, intermediate] */
 } sr_decode_layer;
-int64_t sr_decode_persistent_workspace_bytes(int batch, int n_kv_heads);
-int sr_set_decode_persistent_coop(int enabled);
-/* Tuning knobs of the weight stream.  pf_stages = look-ahead of the optional L2 prefetcher warp beyond the shared-memory ring, in
- * 16 KB stages per CTA (default 0 = off; env SR_DECODE_PF_STAGES).  flags (env SR_DECODE_FLAGS, default 1): bit 0 = L2 evict_first
- * hint on the ring copies, bit 7 = the same hint on the prefetches; bits 8..15 = ring stages in use, 2..10 (0 = default 8; env
- * SR_DECODE_RING).  None of them changes results. */
-int sr_set_decode_persistent_tuning(int pf_stages, int flags);
-/* Unit -> CTA rotation per matrix (unit u of the matrix runs on CTA (u + offset) mod #SMs); default 96, 40, 0, 20 (env
- * SR_DECODE_UNIT_OFFSETS="q,o,g,d"): balances the bytes streamed per SM.  Results do not depend on it. */
-int sr_set_decode_persistent_offsets(int qkv, int o, int gate_up, int down);
+int64_t sr_decode_persistent_workspace_bytes(int n_q_heads, int n_kv_heads, int intermediate);
+/* Tuning knobs (none changes results; negative = keep).  flags (env SR_DECODE_FLAGS, default 1): bit 0 = L2 evict_first hint on
+ * the weight copies, bit 1 = dump plain intermediates into x / the scratch buffers, bit 4 = L2 prefetch of each layer's K/V slice at
+ * the start of the layer; bits 2, 3 are measurement aids (weight stream gated off during the exchange chain; K/V requested only
+ * after q arrived).  ring_stages: 16 KB shared-memory ring stages in use, 2..10 (0 = default 8; env SR_DECODE_RING).  pf_stages:
+ * look-ahead of the L2 prefetcher warp beyond the ring, 16 KB stages per CTA (env SR_DECODE_PF_STAGES).  off_*: unit -> CTA rotation
+ * per matrix (unit u runs on CTA (u + offset) mod #SMs; default 96, 40, 0, 20; env SR_DECODE_UNIT_OFFSETS="q,o,g,d"). */
+int sr_set_decode_persistent_tuning(int flags, int ring_stages, int pf_stages, int off_qkv, int off_o, int off_gate_up, int off_down);
 /* Tuning aid: when buffer != NULL every later sr_decode_step_persistent launch records (globaltimer ns, clock64) pairs at its
  * phase boundaries into buffer[n_SMs][2 roles: producer, consumer][events_per_role][2] (uint64); NULL switches it off. */
 int sr_set_decode_persistent_trace(void* buffer, int events_per_role);

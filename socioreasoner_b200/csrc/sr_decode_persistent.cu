@@ -5,43 +5,34 @@
 // HF:762-827, 672-759, 611-624, final norm + lm_head HF:1385) -- here for M <= 8 live sequences.
 //
 // Why: at M = 8 the step is pure weight streaming (6.2 GB for the 3B model).  Launched as ~6 kernels per layer, every kernel
-// pays a ramp (first bytes arrive after one HBM latency) and a tail (cross-warp reduction + epilogue with no loads in flight)
-// -- measured 2.84 ms/token against ~1.0 ms of streaming at the measured HBM rate.  Here the HBM stream
-// never stops:
-//   * grid = one CTA per SM, resident for the whole step (cooperative launch);
+// pays a ramp and a tail -- measured 2.84 ms/token against ~1.0 ms of streaming at the measured HBM rate.
+// Here the HBM stream never stops:
+//   * grid = one CTA per SM, resident for the whole step;
 //   * warp 0 of every CTA is a PRODUCER: one thread walks the static schedule (layer -> {qkv, o, gate/up, down} -> this CTA's
 //     row groups -> 16 KB stages) and issues cp.async.bulk copies of the pre-packed weights ([N/16][K/32][16][32], 1 KB
-//     blocks) into a 10-stage / 160 KB shared-memory ring guarded by full/empty mbarriers.  Weights never depend on
-//     activations, so the producer runs AHEAD of the consumers across phase boundaries and grid barriers: while the CTAs
-//     synchronise, do attention or run an epilogue, ~24 MB of the next matrices are already in flight chip-wide;
+//     blocks) into a shared-memory ring guarded by full/empty mbarriers.  Weights never depend on activations, so the producer
+//     runs AHEAD of the consumers across phase boundaries;
 //   * warps 1-8 are CONSUMERS: per phase they stage the 8 activation rows in shared memory (RMSNorm fused in the staging,
 //     HF:57-71), read 16-byte weight fragments from the ring straight into mma.sync.m16n8k16 A operands (same k permutation
 //     as sr_gemv.cu: a 16 B load IS a fragment), reduce across warps, run the fused epilogue (bias / residual / SwiGLU);
-//   * phases are separated by a grid barrier (release-add + acquire-poll on one counter): qkv | rope + KV append + split-KV
-//     attention (flash-decoding, merge by the last CTA of a (sample, kv head)) | o-proj + residual | gate/up + SwiGLU |
-//     down + residual; then final norm + LM head (fp32 logits).
+//   * phases per layer: A qkv | B rope + KV append + split-KV attention (flash-decoding) + merge | C o-proj + residual |
+//     D gate/up + SwiGLU | E down + residual; then final norm + LM head (fp32 logits).
+//
+// Round 2: NO grid barriers.  Round 1 separated the phases by 5 grid barriers per layer (release-add + acquire-poll + the
+// dependent activation load after it = 3-4 serialized L2 round trips each, 21 us of the 58 us a layer took, against 24 us of
+// weight streaming).  Now every activation that crosses CTAs (x after o-proj / after down, qkv, attention partials, attention
+// output, SwiGLU output) travels in FLAG-CARRYING lines, the "LL" protocol NCCL uses for latency-bound collectives: a 16-byte
+// line = {data0, gen, data1, gen}; the writer's store is fire-and-forget, the reader polls THE DATA ITSELF until both
+// generation words match (each 8-byte half is written atomically and carries its own flag, so no fence, no counter, no acquire
+// is needed) -- one L2 round trip per exchange instead of three or four, and a CTA only ever waits for the lines it actually
+// reads.  gen = epoch + 1 + layer; the epoch lives in the workspace and is advanced by the last CTA to leave the kernel, so
+// stale lines (previous layer / launch / CUDA-graph replay) never match.  Buffers are rewritten once per layer; a writer of
+// layer l+1 has (transitively, through the data it polled) observed results of every reader of the layer-l version.
 // HBM-bound: algorithmic bytes per launch = all decoder weights + LM head (N*K*2 each) + KV cache of the live sequences.
 #include <stdio.h>
 #include <stdlib.h>
 
 #include "sr_host.h"
-
-#ifndef SR_DP_NOINLINE_BAR
-#define SR_DP_NOINLINE_BAR 0  // measured: 2.07 ms/step inlined vs 2.16 as a call
-#endif
-#ifndef SR_DP_NOINLINE_STAGE
-#define SR_DP_NOINLINE_STAGE 0
-#endif
-#if SR_DP_NOINLINE_BAR
-#define DP_BAR_ATTR __device__ __noinline__
-#else
-#define DP_BAR_ATTR SR_DEVINL
-#endif
-#if SR_DP_NOINLINE_STAGE
-#define DP_STAGE_ATTR __device__ __noinline__
-#else
-#define DP_STAGE_ATTR SR_DEVINL
-#endif
 
 namespace sr {
 
@@ -52,28 +43,29 @@ constexpr int DP_STAGE_BLOCKS = 16;                   // 1 KB weight blocks per 
 constexpr int DP_STAGE_BYTES = DP_STAGE_BLOCKS * 1024;
 constexpr int DP_STAGES = 10;
 constexpr int DP_H = 2048;                            // staged activation width (hidden size = n_q_heads * 128)
+constexpr int DP_HL = DP_H / 4;                       // LL lines per hidden row (4 bf16 per line)
 constexpr int DP_XS_STRIDE = DP_H * 2 + 64;           // bytes per staged row (+64 B: conflict-free 16 B fragment reads)
-constexpr int DP_XPF = 4;                             // activation prefetch distance (stages) on the L2 path (loaded L2 latency ~1.5 us)
+constexpr int DP_XPF = 4;                             // activation prefetch distance (stages) of the down projection
 constexpr int DP_MAX_LAYERS = 64;                     // layer table staged in shared memory
 constexpr int DP_GMAX = 8;                            // query heads per kv head (max)
 constexpr int DP_KEYS = 128;                          // keys per attention pass
 constexpr int DP_NS_MAX = 32;                         // max key splits
-constexpr int DP_PART = DP_GMAX * 128 + 2 * DP_GMAX;  // floats per attention partial (o, m, l)
+constexpr int DP_PART_LINES = 128 * 4 + DP_GMAX;      // LL lines per attention partial: o[dim][head pair], then {m, l}[head]
+constexpr int DP_MERGE_CHUNK = 10;                    // splits merged per round trip
 
 // shared-memory carve-up (bytes, from a 1024-aligned base)
 constexpr int DP_OFF_RING = 0;
 constexpr int DP_OFF_XS = DP_STAGES * DP_STAGE_BYTES;                 // staged activations; aliased by attention scratch
 constexpr int DP_XS_BYTES = 8 * DP_XS_STRIDE;                         // 33280
-constexpr int DP_OFF_RED = DP_OFF_XS + DP_XS_BYTES;                   // [2][8 warps][2 rg][128] fp32
-constexpr int DP_RED_BYTES = 2 * DP_CONSUMERS * 2 * 128 * 4;          // 16384
+constexpr int DP_OFF_RED = DP_OFF_XS + DP_XS_BYTES;                   // [2][8 warps][2 rg][8 batch][20] fp32
+constexpr int DP_RED_WQ = 8 * 20;                                     // floats per (warp, row group): [batch][16 features + 4 pad]
+constexpr int DP_RED_BYTES = 2 * DP_CONSUMERS * 2 * DP_RED_WQ * 4;    // 20480
 constexpr int DP_OFF_BAR = DP_OFF_RED + DP_RED_BYTES;
 constexpr int DP_OFF_LAYERS = DP_OFF_BAR + 2 * DP_STAGES * 8 + 32;    // DpLayer[DP_MAX_LAYERS]
 constexpr int DP_OFF_ROPE = DP_OFF_LAYERS + DP_MAX_LAYERS * 56;       // cos[8][64], sin[8][64] fp32 of this step
-constexpr int DP_OFF_SCAL = DP_OFF_ROPE + 2 * 8 * 64 * 4;             // kv_start[8], kv_len[8], cache_row[8]
-constexpr int DP_OFF_PCNT = DP_OFF_SCAL + 3 * 8 * 4;                  // stages issued by the producer so far (read by the prefetcher)
-constexpr int DP_SMEM_BYTES = DP_OFF_PCNT + 64 + 1024;                // + alignment slack
+constexpr int DP_OFF_SCAL = DP_OFF_ROPE + 2 * 8 * 64 * 4;             // kv_start[8], kv_len[8], cache_row[8], epoch, gate, pcnt
+constexpr int DP_SMEM_BYTES = DP_OFF_SCAL + 4 * 8 * 4 + 1024;         // + alignment slack
 static_assert(DP_SMEM_BYTES <= 232448, "shared-memory budget of one sm_100 CTA");
-
 
 struct DpLayer {  // == sr_decode_layer (include/socioreasoner_b200.h)
   const __nv_bfloat16* qkv_wp;
@@ -91,11 +83,11 @@ struct DpParams {
   const __nv_bfloat16* lm_head_p;
   const float* final_norm;
   int vocab;
-  __nv_bfloat16* x;
+  __nv_bfloat16* x;        // in: embedded tokens [B, 2048] (ldx); debug: hidden state dumps
   int64_t ldx;
-  __nv_bfloat16* qkv;      // [B, (nq + 2 nkv) * 128]
-  __nv_bfloat16* ao;       // [B, nq * 128]
-  __nv_bfloat16* act;      // [B, I]
+  __nv_bfloat16* qkv;      // debug dumps (flags bit 1): [B, (nq + 2 nkv) * 128], [B, nq * 128]
+  __nv_bfloat16* ao;
+  __nv_bfloat16* act;      // [B, I] SwiGLU output, plain bf16 (workspace; the caller's act_scratch when dumping)
   float* logits;
   int64_t ld_logits;
   const float* cosb;       // [B, 64]
@@ -110,16 +102,20 @@ struct DpParams {
   int64_t ldvt;
   int B, nq, nkv, I;
   float eps, scale_log2;
-  float* attn_ws;
-  int* attn_tickets;
+  unsigned int* epoch;     // workspace header: [0] epoch, [1] CTAs that left the kernel
+  uint4* xa_ll;            // LL buffers (16-byte lines {d0, gen, d1, gen}; 4 bf16 or 2 fp32 per line)
+  uint4* xb_ll;
+  uint4* qkv_ll;
+  uint4* ao_ll;
+  unsigned int* act_flags; // [gridDim.x] generation of each CTA's last complete SwiGLU output (plain bf16 in `act`)
+  uint4* part_ll;          // [B*nkv][ns][DP_PART_LINES]
   int ns;
-  unsigned int* grid_bar;  // zero before launch
   int stop_after;          // debug: run only the first `stop_after` phases (<= 0: all)
-  int pf_stages;           // L2 prefetch lookahead of the producer beyond the ring, in 16 KB stages per CTA (0 = off)
   int ring_stages;         // shared-memory ring stages in use (2 .. DP_STAGES)
+  int pf_stages;           // L2 prefetch look-ahead beyond the ring, in 16 KB stages per CTA (0 = off)
   int unit_off[4];         // unit -> CTA rotation of the qkv / o / gate-up / down matrices
-  int flags;               // bit 0: L2 evict_first hint on the ring copies (weights are consumed exactly once)
-  unsigned long long* trace;  // optional [gridDim.x][2 roles][trace_events][2] (globaltimer ns, clock64) -- sr_set_decode_persistent_trace
+  int flags;               // bit 0: L2 evict_first hint on the ring copies; bit 1: dump plain intermediates (bring-up)
+  unsigned long long* trace;  // optional [gridDim.x][2 roles][trace_events][2] (globaltimer ns, clock64)
   int trace_events;
 };
 
@@ -131,16 +127,6 @@ SR_DEVINL void dp_trace_at(const DpParams& p, int role, int idx) {
     unsigned long long* d = p.trace + ((static_cast<int64_t>(blockIdx.x) * 2 + role) * p.trace_events + idx) * 2;
     d[0] = t;
     d[1] = static_cast<unsigned long long>(clock64());
-  }
-}
-SR_DEVINL void dp_trace(const DpParams& p, int role, int& idx) {
-  if (p.trace != nullptr && idx < p.trace_events) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    unsigned long long* d = p.trace + ((static_cast<int64_t>(blockIdx.x) * 2 + role) * p.trace_events + idx) * 2;
-    d[0] = t;
-    d[1] = static_cast<unsigned long long>(clock64());
-    ++idx;
   }
 }
 
@@ -158,31 +144,57 @@ SR_DEVINL void dp_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint
 SR_DEVINL void dp_cbar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // consumer warps only
 SR_DEVINL uint4 dp_ldcg(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 
-#ifndef SR_GRIDBAR_SPIN_LIMIT
-#define SR_GRIDBAR_SPIN_LIMIT (1u << 23)
+// ------------------------------------------------------------------------------------------------ LL lines
+#ifndef SR_LL_SPIN_LIMIT
+#define SR_LL_SPIN_LIMIT (1u << 22)
 #endif
-// Grid barrier for the consumer threads of all CTAs.  Arrive: the CTA barrier orders every consumer thread's global stores
-// before thread 32's red.release (cumulativity).  Wait: relaxed polls, then ONE ld.acquire of the counter -- it reads a value of
-// the RMW chain that contains every CTA's release-increment of this generation, so it synchronises with all of them; the second
-// CTA barrier extends that to the other threads.  (Measured: an acq_rel fence after the poll costs 0.3 us per barrier more than
-// the acquire load, 2.02 vs 1.96 ms per step; dropping the release too would save another 0.4 us but is not memory-model safe.)
+SR_DEVINL void ll_store(uint4* p, uint32_t d0, uint32_t d1, uint32_t gen) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(d0), "r"(gen), "r"(d1), "r"(gen) : "memory");
+}
+SR_DEVINL uint4 ll_load(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+SR_DEVINL bool ll_ok(const uint4& v, uint32_t gen) { return v.y == gen && v.w == gen; }
+// Re-poll one line until both halves carry `gen`.  The fast path (line already there) is two compares; the polling loop is a
+// real function call so that the ~150 inlined wait sites do not bloat the instruction footprint of the persistent kernel.
 // Bounded: a broken schedule traps (CUDA error through the C ABI) instead of hanging the GPU.
-DP_BAR_ATTR void dp_grid_barrier(unsigned int* ctr, unsigned int target) {
-  dp_cbar();
-  if (threadIdx.x == 32) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
-    unsigned int v = 0, spins = 0;
-    while (true) {
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-      if (v >= target) break;
-      if (++spins > SR_GRIDBAR_SPIN_LIMIT) {
-        printf("sr: grid barrier timeout block=%d have=%u want=%u\n", blockIdx.x, v, target);
-        __trap();
-      }
+__device__ __noinline__ uint4 ll_spin_slow(const uint4* p, uint32_t gen) {
+  unsigned int spins = 0;
+  uint4 v = ll_load(p);
+  while (!ll_ok(v, gen)) {
+    v = ll_load(p);
+    if (++spins > SR_LL_SPIN_LIMIT) {
+      printf("sr: LL wait timeout block=%d thread=%d want=%u have=%u/%u\n", blockIdx.x, threadIdx.x, gen, v.y, v.w);
+      __trap();
     }
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
   }
-  dp_cbar();
+  return v;
+}
+SR_DEVINL void ll_spin(uint4& v, const uint4* p, uint32_t gen) {
+  if (!ll_ok(v, gen)) v = ll_spin_slow(p, gen);
+}
+__device__ __noinline__ void ll_timeout(uint32_t gen) {
+  printf("sr: LL wait timeout block=%d thread=%d want=%u\n", blockIdx.x, threadIdx.x, gen);
+  __trap();
+}
+// Wait for N lines that were all requested already (v[i] = ll_load(addr(i))).  Lines that had not been written yet are NOT
+// polled one after the other (that would serialise up to N L2 round trips): every round re-requests ALL missing lines at once,
+// so the thread has its data one round trip after the last line was written.
+template <int N, typename F>
+SR_DEVINL void ll_wait(uint4 (&v)[N], F addr, uint32_t gen) {
+  unsigned int spins = 0;
+  while (true) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) ok = ok && ll_ok(v[i], gen);
+    if (ok) break;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (!ll_ok(v[i], gen)) v[i] = ll_load(addr(i));
+    if (++spins > SR_LL_SPIN_LIMIT) ll_timeout(gen);
+  }
 }
 
 struct DpRing {
@@ -191,7 +203,7 @@ struct DpRing {
   uint64_t* empty;
   int slot;
   uint32_t phase;
-  int n;  // stages in use (<= DP_STAGES): fewer stages = less lookahead but also a shorter queue in front of the latency chains
+  int n;  // stages in use (<= DP_STAGES)
   SR_DEVINL void advance() {
     if (++slot == n) { slot = 0; phase ^= 1; }
   }
@@ -200,17 +212,16 @@ struct DpRing {
 // ------------------------------------------------------------------------------------------------ producer
 // Streams this CTA's units of one packed matrix: unit u = RG consecutive 16-row groups; stage = 16 blocks of 1 KB
 // (RG = 1: 16 k-chunks of the group; RG = 2: 8 k-chunks of each of the two groups, second group at +8 KB).
-// ONE thread issues every copy of the CTA, so this loop is kept minimal (a generic schedule walker with an L2-prefetch
-// cursor was measured 15% slower end to end: the producer thread became the bottleneck).
+// ONE thread issues every copy of the CTA, so this loop is kept minimal.
 // ROT: the stage order of unit u is rotated by (7u mod nst) -- used for the down projection, whose activations are read
-// from L2 by every CTA: without the rotation all CTAs request the same 8 KB of activations at the same time (hot L2 slices).
+// from L2 by every CTA: without the rotation all CTAs request the same lines at the same time (hot L2 slices).
 SR_DEVINL int dp_rot(int u, int nst) { return (u * 7) % nst; }
 template <int RG, bool ROT>
 SR_DEVINL void dp_produce(DpRing& r, int v0, const __nv_bfloat16* Wp, int n_units, int nchunks, uint64_t policy, bool hint,
-                          volatile int* pcnt, int& issued) {
+                          volatile int* pcnt, int& issued, int stride) {
   constexpr int CPS = DP_STAGE_BLOCKS / RG;
   const int nst = (nchunks + CPS - 1) / CPS;
-  for (int u = v0; u < n_units; u += gridDim.x) {
+  for (int u = v0; u < n_units; u += stride) {
     int st = ROT ? dp_rot(u, nst) : 0;
     for (int i = 0; i < nst; ++i) {
       mbar_wait(&r.empty[r.slot], r.phase ^ 1);
@@ -239,16 +250,18 @@ SR_DEVINL void dp_produce(DpRing& r, int v0, const __nv_bfloat16* Wp, int n_unit
 }
 
 // L2 prefetcher (warp 9, one thread): walks the SAME stage sequence as the producer, at most `lead` stages ahead of it, and asks
-// the memory system to bring each stage into L2 (cp.async.bulk.prefetch.L2).  The shared-memory ring holds only 160 KB per CTA
-// (3.7 us of HBM time chip-wide), and the consumers spend most of a layer in latency chains (qkv -> attention -> o-proj: grid
-// barriers, L2 round trips) during which the ring is full and HBM would idle; with the prefetcher the HBM stream continues into
-// L2 (`lead` x 16 KB x 148 CTAs), and the ring later refills at L2 speed.
+// the memory system to bring each stage into L2 (cp.async.bulk.prefetch.L2).  The shared-memory ring holds 128-160 KB per CTA
+// (3 us of HBM time chip-wide), but a layer spends ~18 us in the qkv -> attention -> o-proj chain of cross-CTA exchanges during
+// which the ring is full and HBM would idle; with the prefetcher the HBM stream continues into L2 (`lead` x 16 KB x 148 CTAs),
+// and the ring later refills at L2 speed.  (Round 1 measured no gain from this -- its chain was made of grid barriers whose
+// many round trips slowed down under the extra traffic; the flag-carrying exchanges are insensitive to it: gating the weight
+// stream off during the chain does not shorten it.)
 template <int RG, bool ROT>
 SR_DEVINL void dp_prefetch_l2(int& sidx, const volatile int* pcnt, int lead, int v0, const __nv_bfloat16* Wp, int n_units, int nchunks,
-                               uint64_t policy, bool hint) {
+                               int stride) {
   constexpr int CPS = DP_STAGE_BLOCKS / RG;
   const int nst = (nchunks + CPS - 1) / CPS;
-  for (int u = v0; u < n_units; u += gridDim.x) {
+  for (int u = v0; u < n_units; u += stride) {
     int st = ROT ? dp_rot(u, nst) : 0;
     for (int i = 0; i < nst; ++i) {
       int pc = *pcnt;
@@ -261,12 +274,7 @@ SR_DEVINL void dp_prefetch_l2(int& sidx, const volatile int* pcnt, int lead, int
 #pragma unroll
         for (int g = 0; g < RG; ++g) {
           const __nv_bfloat16* src = Wp + (static_cast<int64_t>(u * RG + g) * nchunks + st * CPS) * 512;
-          if (hint)
-            asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(static_cast<uint32_t>(nch * 1024)),
-                         "l"(policy)
-                         : "memory");
-          else
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(static_cast<uint32_t>(nch * 1024)) : "memory");
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(static_cast<uint32_t>(nch * 1024)) : "memory");
         }
       }
       ++sidx;
@@ -277,51 +285,47 @@ SR_DEVINL void dp_prefetch_l2(int& sidx, const volatile int* pcnt, int lead, int
 }
 
 // ------------------------------------------------------------------------------------------------ consumers
-// Stage M (<= 8) rows of width DP_H into shared memory, warp cw <-> row cw, optional RMSNorm (y = w * x * rsqrt(mean x^2 + eps),
-// one rounding to bf16 -- the arithmetic of rmsnorm_kernel in sr_elementwise.cu).  Rows >= M are zero.
+// Stage M (<= 8) rows of width DP_H from an LL buffer into shared memory, warp cw <-> row cw, optional RMSNorm
+// (y = w * x * rsqrt(mean x^2 + eps), one rounding to bf16 -- the arithmetic of rmsnorm_kernel in sr_elementwise.cu).
+// All 16 lines of a lane are requested at once; only lines that are not there yet are polled again.  Rows >= M are zero.
 template <bool NORM>
-DP_STAGE_ATTR void dp_stage_rows(uint8_t* xs, const __nv_bfloat16* src, int64_t ld, int M, const float* nw, float eps, int cw,
-                             int lane) {
-  constexpr int NV = DP_H / 256;  // 16 B vectors per lane
-  uint4 v[NV];
-  float4 nw0[NORM ? NV : 1], nw1[NORM ? NV : 1];
+SR_DEVINL void dp_stage_rows(uint8_t* xs, const uint4* src, uint32_t gen, int M, const float* nw, float eps, int cw, int lane) {
+  constexpr int NL = DP_HL / 32;  // lines per lane
+  uint4 v[NL];
+  float4 w4[NORM ? NL : 1];
   const bool ok = cw < M;
-  if (NORM) {  // the norm weights do not depend on x: requested together with it (one round trip instead of two)
+  const uint4* row = src + cw * DP_HL + lane;
+  if (NORM) {  // the norm weights do not depend on x: requested together with it
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      nw0[i] = __ldg(reinterpret_cast<const float4*>(nw + (lane + 32 * i) * 8));
-      nw1[i] = __ldg(reinterpret_cast<const float4*>(nw + (lane + 32 * i) * 8 + 4));
-    }
+    for (int i = 0; i < NL; ++i) w4[i] = __ldg(reinterpret_cast<const float4*>(nw + (lane + 32 * i) * 4));
   }
+  if (ok) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-    v[i] = ok ? dp_ldcg(src + static_cast<int64_t>(cw) * ld + (lane + 32 * i) * 8) : make_uint4(0, 0, 0, 0);
+    for (int i = 0; i < NL; ++i) v[i] = ll_load(row + 32 * i);
+    ll_wait(v, [&](int i) { return row + 32 * i; }, gen);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NL; ++i) v[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
   if (NORM) {
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
-        ss += a * a + b * b;
-      }
+    for (int i = 0; i < NL; ++i) {
+      const float a = bf16_lo(v[i].x), b = bf16_hi(v[i].x), c = bf16_lo(v[i].z), d = bf16_hi(v[i].z);
+      ss += a * a + b * b + c * c + d * d;
     }
     ss = warp_sum(ss);
     const float inv = rsqrtf(ss / static_cast<float>(DP_H) + eps);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 w0 = nw0[i], w1 = nw1[i];
-      uint4 o;
-      o.x = pack_bf16x2(bf16_lo(v[i].x) * inv * w0.x, bf16_hi(v[i].x) * inv * w0.y);
-      o.y = pack_bf16x2(bf16_lo(v[i].y) * inv * w0.z, bf16_hi(v[i].y) * inv * w0.w);
-      o.z = pack_bf16x2(bf16_lo(v[i].z) * inv * w1.x, bf16_hi(v[i].z) * inv * w1.y);
-      o.w = pack_bf16x2(bf16_lo(v[i].w) * inv * w1.z, bf16_hi(v[i].w) * inv * w1.w);
-      v[i] = o;
+    for (int i = 0; i < NL; ++i) {
+      const float4 w = w4[i];
+      v[i].x = pack_bf16x2(bf16_lo(v[i].x) * inv * w.x, bf16_hi(v[i].x) * inv * w.y);
+      v[i].z = pack_bf16x2(bf16_lo(v[i].z) * inv * w.z, bf16_hi(v[i].z) * inv * w.w);
     }
   }
 #pragma unroll
-  for (int i = 0; i < NV; ++i) *reinterpret_cast<uint4*>(xs + cw * DP_XS_STRIDE + (lane + 32 * i) * 16) = v[i];
+  for (int i = 0; i < NL; ++i) *reinterpret_cast<uint2*>(xs + cw * DP_XS_STRIDE + (lane + 32 * i) * 8) = make_uint2(v[i].x, v[i].z);
 }
 
 // K loop of one unit with the activations staged in shared memory (K = DP_H).
@@ -367,8 +371,10 @@ SR_DEVINL void dp_consume_staged(DpRing& r, int nchunks, const uint8_t* xs, floa
   }
 }
 
-// K loop of one unit (RG = 1) with the activations read from global memory / L2 (long K: the down projection).
-// Stage order rotated per unit (see dp_produce<.., ROT>); activation fragments are prefetched DP_XPF stages ahead.
+// K loop of one unit (RG = 1) with the activations read as plain bf16 from L2 (long K: the down projection reads the SwiGLU
+// output of ALL CTAs, 176 KB per CTA -- as flag-carrying lines that would be 352 KB per CTA, as much as the weights, and the
+// phase becomes L2-throughput bound; the caller has already waited for every producer's release flag, see dp_wait_act).
+// Stage order rotated per unit (see dp_produce<.., ROT>); activation fragments are requested DP_XPF stages ahead.
 SR_DEVINL void dp_consume_l2(DpRing& r, int u, int nchunks, const __nv_bfloat16* xg, int64_t ldx, int M, float (&acc)[1][4], int cw,
                              int lane) {
   constexpr int CPS = DP_STAGE_BLOCKS;
@@ -418,36 +424,68 @@ SR_DEVINL void dp_consume_l2(DpRing& r, int u, int nchunks, const __nv_bfloat16*
   }
 }
 
+// The SwiGLU output is the one exchange that does NOT use flag-carrying lines (see dp_consume_l2): every CTA writes its columns
+// as plain bf16 and, after its last gate/up unit, publishes ONE release flag (its writer threads fence, then one of them stores
+// the generation); a down-projection CTA polls the flags of all CTAs, fences, and then reads the activations with plain loads.
+SR_DEVINL void dp_publish_act(unsigned int* flags, uint32_t gen, int ct) {
+  if (ct < 32) {  // the epilogue threads of the gate/up phase are the first consumer warp
+    __threadfence();
+    __syncwarp();
+    if (ct == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(gen) : "memory");
+  }
+}
+SR_DEVINL void dp_wait_act(const unsigned int* flags, uint32_t gen, int ct) {
+  if (ct < static_cast<int>(gridDim.x)) {
+    unsigned int v, spins = 0;
+    while (true) {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + ct) : "memory");
+      if (v == gen) break;
+      if (++spins > SR_LL_SPIN_LIMIT) ll_timeout(gen);
+    }
+    __threadfence();
+  }
+  dp_cbar();
+}
+
 enum { DP_EPI_BIAS = 0, DP_EPI_RESIDUAL = 1, DP_EPI_SWIGLU = 2, DP_EPI_F32 = 3 };
 
-// One GEMV phase: all units of this CTA.  `staged`: activations come from xs (K = DP_H), else from xg (L2).
+struct DpOut {
+  uint4* ll;             // LL destination (row-major, `row_lines` lines per batch row); nullptr for the fp32 epilogue
+  int row_lines;
+  uint32_t gen;
+  const uint4* res_ll;   // residual source (DP_HL lines per row), DP_EPI_RESIDUAL only
+  uint32_t res_gen;
+  const float* bias;
+  float* f32;            // fp32 destination (LM head)
+  int64_t ld_f32;
+  __nv_bfloat16* dbg;    // optional plain bf16 dump
+  int64_t ld_dbg;
+};
+
+// One GEMV phase: all units of this CTA.  STAGED: activations come from xs (K = DP_H), else plain bf16 from xg (L2).
+// Epilogue: thread (row group q, batch b, feature quad fg) sums the 8 warps' partials of 4 consecutive output columns and writes
+// one LL line (4 bf16) -- or 4 fp32 logits.
 template <int RG, int EPI, bool STAGED>
 SR_DEVINL void dp_gemv_phase(DpRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, const __nv_bfloat16* xg, int64_t ldxg,
-                             int M, float* red, int& red_par, const float* bias, __nv_bfloat16* out_bf, float* out_f32,
-                             int64_t ldo, int cw, int lane) {
+                             int M, float* red, int& red_par, const DpOut& o, int cw, int lane, int stride) {
   const int g = lane >> 2, t = lane & 3;
   const int ct = threadIdx.x - 32;
-  for (int u = v0; u < n_units; u += gridDim.x) {
+  constexpr int NG = (EPI == DP_EPI_SWIGLU) ? 1 : RG;   // independent 16-column groups per unit
+  const int eq = ct >> 5, eb = ct & 7, efg = (ct >> 3) & 3;
+  const bool epi_thread = ct < 32 * NG && eb < M;
+  for (int u = v0; u < n_units; u += stride) {
     float acc[RG][4];
 #pragma unroll
     for (int q = 0; q < RG; ++q)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[q][i] = 0.f;
-    // epilogue operands of this thread's output element(s): requested before the K loop so their latency is hidden.
-    // Units of the non-SwiGLU epilogues with RG = 2 are two independent 16-column groups (columns (u*RG + q)*16 ..).
-    constexpr int NG = (EPI == DP_EPI_SWIGLU) ? 1 : RG;
-    float epi_add[NG];
-#pragma unroll
-    for (int q = 0; q < NG; ++q) {
-      epi_add[q] = 0.f;
-      if (ct < 128 && (ct >> 4) < M) {
-        const int col = (u * NG + q) * 16 + (ct & 15);
-        if (EPI == DP_EPI_BIAS && bias != nullptr) epi_add[q] = __ldg(bias + col);
-        if (EPI == DP_EPI_RESIDUAL) {
-          const unsigned short rbits = __ldcg(reinterpret_cast<const unsigned short*>(out_bf + static_cast<int64_t>(ct >> 4) * ldo + col));
-          epi_add[q] = __uint_as_float(static_cast<uint32_t>(rbits) << 16);
-        }
-      }
+    // epilogue operands of this thread's output columns: requested before the K loop so their latency is hidden
+    const int col = (u * NG + eq) * 16 + efg * 4;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 resl = make_uint4(0, 0, 0, 0);
+    if (epi_thread) {
+      if (EPI == DP_EPI_BIAS && o.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(o.bias + col));
+      if (EPI == DP_EPI_RESIDUAL) resl = ll_load(o.res_ll + eb * DP_HL + (col >> 2));
     }
     if constexpr (STAGED) {
       dp_consume_staged<RG>(r, nchunks, xs, acc, cw, lane);
@@ -455,41 +493,45 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int v0, int n_units, int nchunks, const 
       static_assert(STAGED || RG == 1, "the L2 activation path handles single row groups");
       dp_consume_l2(r, u, nchunks, xg, ldxg, M, acc, cw, lane);
     }
-    // cross-warp reduction: C fragment (feature g | g+8, batch 2t | 2t+1) -> red[par][warp][q][feature*8 + batch]
-    float* rp = red + red_par * (DP_CONSUMERS * 2 * 128);
+    // cross-warp reduction: C fragment (feature g | g+8, batch 2t | 2t+1) -> red[par][warp][q][batch * 20 + feature]
+    float* rp = red + red_par * (DP_CONSUMERS * 2 * DP_RED_WQ);
 #pragma unroll
     for (int q = 0; q < RG; ++q) {
-      float* d = rp + (cw * 2 + q) * 128;
-      d[g * 8 + 2 * t] = acc[q][0];
-      d[g * 8 + 2 * t + 1] = acc[q][1];
-      d[(g + 8) * 8 + 2 * t] = acc[q][2];
-      d[(g + 8) * 8 + 2 * t + 1] = acc[q][3];
+      float* d = rp + (cw * 2 + q) * DP_RED_WQ;
+      d[(2 * t) * 20 + g] = acc[q][0];
+      d[(2 * t + 1) * 20 + g] = acc[q][1];
+      d[(2 * t) * 20 + g + 8] = acc[q][2];
+      d[(2 * t + 1) * 20 + g + 8] = acc[q][3];
     }
     dp_cbar();
-    if (ct < 128) {
-      const int b = ct >> 4, f = ct & 15;  // consecutive threads -> consecutive features
-      float v[RG];
+    if (epi_thread) {
+      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
 #pragma unroll
-      for (int q = 0; q < RG; ++q) {
-        float s = 0.f;
-#pragma unroll
-        for (int w8 = 0; w8 < DP_CONSUMERS; ++w8) s += rp[(w8 * 2 + q) * 128 + f * 8 + b];
-        v[q] = s;
-      }
-      if (b < M) {
+      for (int w8 = 0; w8 < DP_CONSUMERS; ++w8) {
+        const float4 a = *reinterpret_cast<const float4*>(rp + (w8 * 2 + (EPI == DP_EPI_SWIGLU ? 0 : eq)) * DP_RED_WQ + eb * 20 + efg * 4);
+        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
         if (EPI == DP_EPI_SWIGLU) {
-          const float gate = v[0], up = v[RG - 1];
-          const float o = (gate / (1.0f + __expf(-gate))) * up;
-          out_bf[static_cast<int64_t>(b) * ldo + u * 16 + f] = __float2bfloat16(o);
-        } else {
-#pragma unroll
-          for (int q = 0; q < NG; ++q) {
-            const int col = (u * NG + q) * 16 + f;
-            const float o = v[q] + epi_add[q];
-            if (EPI == DP_EPI_F32) out_f32[static_cast<int64_t>(b) * ldo + col] = o;
-            else out_bf[static_cast<int64_t>(b) * ldo + col] = __float2bfloat16(o);
-          }
+          const float4 b = *reinterpret_cast<const float4*>(rp + (w8 * 2 + 1) * DP_RED_WQ + eb * 20 + efg * 4);
+          s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
         }
+      }
+      float v[4] = {s0.x, s0.y, s0.z, s0.w};
+      if (EPI == DP_EPI_SWIGLU) {
+        const float up[4] = {s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (v[j] / (1.0f + __expf(-v[j]))) * up[j];
+      } else if (EPI == DP_EPI_BIAS) {
+        v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
+      } else if (EPI == DP_EPI_RESIDUAL) {
+        ll_spin(resl, o.res_ll + eb * DP_HL + (col >> 2), o.res_gen);
+        v[0] += bf16_lo(resl.x); v[1] += bf16_hi(resl.x); v[2] += bf16_lo(resl.z); v[3] += bf16_hi(resl.z);
+      }
+      if (EPI == DP_EPI_F32) {
+        *reinterpret_cast<float4*>(o.f32 + static_cast<int64_t>(eb) * o.ld_f32 + col) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+        const uint32_t d0 = pack_bf16x2(v[0], v[1]), d1 = pack_bf16x2(v[2], v[3]);
+        if (o.ll != nullptr) ll_store(o.ll + static_cast<int64_t>(eb) * o.row_lines + (col >> 2), d0, d1, o.gen);
+        if (o.dbg != nullptr) *reinterpret_cast<uint2*>(o.dbg + static_cast<int64_t>(eb) * o.ld_dbg + col) = make_uint2(d0, d1);
       }
     }
     red_par ^= 1;  // the next unit writes the other buffer; its barrier orders this unit's reads before the reuse after it
@@ -499,15 +541,14 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int v0, int n_units, int nchunks, const 
 // ------------------------------------------------------------------------------------------------ attention phase
 // M-RoPE (mcore_adapter/.../modeling_qwen2_5_vl.py:21-41) on q and the new k, KV-cache append, split-KV attention of the
 // new token against the cache (the arithmetic of mrope_kv_kernel + decode_attn_kernel in sr_elementwise.cu / sr_tail.cu).
-// Unit = (sample, kv head, key split), exactly one per CTA (n_units <= gridDim.x).  The phase is a chain of dependent global
-// round trips (~1-2 us each while the producer saturates HBM), so it is arranged to need as few as possible:
+// Unit = (sample, kv head, key split), exactly one per CTA (n_units <= gridDim.x).
 //   * kv_start / kv_len / cache_row and the step's cos/sin table sit in shared memory (loaded once per launch);
 //   * the K rows and V^T vectors of the OLD keys do not depend on this layer's qkv: they are requested into registers
-//     BEFORE the grid barrier that ends the qkv phase (dp_attn_prefetch) and arrive while the CTA waits there;
-//   * after the barrier: one round trip for q (+ the new k, v of the owning split, which never re-reads them from the
-//     cache: they go to shared memory and, fire-and-forget, to the cache), then scores / softmax / P.V from registers;
-//   * partial (o, m, l) -> workspace, one acq_rel ticket; the last CTA of a (sample, kv head) merges with ALL its loads
-//     (statistics and partial outputs) in flight at once.
+//     BEFORE q is polled (dp_attn_prefetch) and arrive while the qkv phase of the other CTAs finishes;
+//   * q (+ the new k, v of the owning split, which never re-reads them from the cache: they go to shared memory and,
+//     fire-and-forget, to the cache) are polled from the qkv LL buffer, then scores / softmax / P.V from registers;
+//   * the un-normalised partial (o, m, l) is published as LL lines; split 0 of every (sample, kv head) polls the other splits'
+//     partials (all loads in flight at once), merges, and publishes the attention output as LL lines.
 struct DpAttnUnit {
   int b, kvh, split, bk;
   int start, len, crow;
@@ -532,28 +573,23 @@ SR_DEVINL DpAttnUnit dp_attn_unit(const DpParams& p, const int* s_scal) {
   U.owner = U.active && U.len > 0 && (U.len - 1) / per == U.split;
   return U;
 }
-// ------------------------------------------------------------------------------------------------ attention phase (mma)
 // Compact formulation on mma.sync (the instruction footprint of a persistent kernel matters: everything beyond the 32 KB
 // L1.5 instruction cache is re-fetched from L2 every layer, in competition with 6 TB/s of weight traffic).
 // Scores: A = K rows (16 keys per warp, 8 warps = one 128-key pass), B = q (8 heads); P.V: A = V^T rows (16 output dims per
 // warp), B = P (bf16, shared memory).  As in the GEMV phases a thread's 16-byte global load IS an A fragment (the k index is
-// permuted identically in both operands), so every cache element is requested exactly once, with 16 loads per thread and pass
-// that are issued BEFORE the grid barrier that ends the qkv phase (they do not depend on this layer's qkv).
+// permuted identically in both operands), so every cache element is requested exactly once, 16 loads per thread and pass.
 // Thread (warp w, g = lane / 4, t = lane % 4) owns heads 2t, 2t+1 in both accumulators:
 //   scores  c0..c3 = (key 16w+g | 16w+g+8) x (head 2t | 2t+1),   output c0..c3 = (dim 16w+g | 16w+g+8) x (head 2t | 2t+1).
-// The newest key is never read from the cache: its roped k / v go to shared memory (and, fire-and-forget, to the cache) and
-// enter the online softmax as one more key of the owning split.
 constexpr int DPB_ROW = 320;                           // bytes per bf16 [128] row (+64 B: conflict-free 16 B fragment reads)
 constexpr int DPB_Q = 0;                               // bf16 [8 heads][128]: roped q
-constexpr int DPB_P = DPB_Q + 8 * DPB_ROW;             // bf16 [8 heads][128 keys]: probabilities of the pass
+constexpr int DPB_P = DPB_Q + 8 * DPB_ROW;             // bf16 [8 heads][128 keys]: probabilities of the pass / merged output
 constexpr int DPB_RED = DPB_P + 8 * DPB_ROW;           // float [2][8 warps][8 heads]
 constexpr int DPB_KNEW = DPB_RED + 2 * 8 * 8 * 4;      // float [128] roped k of the new token (bf16-rounded values)
 constexpr int DPB_VNEW = DPB_KNEW + 128 * 4;           // float [128]
 constexpr int DPB_SNEW = DPB_VNEW + 128 * 4;           // float [8] score of the new key per head (log2 domain)
 constexpr int DPB_MS = DPB_SNEW + 8 * 4;               // merge: float m[32][8], l[32][8], f[32][8]
 constexpr int DPB_LL = DPB_MS + 3 * DP_NS_MAX * 8 * 4; // float [8]
-constexpr int DPB_FLAG = DPB_LL + 8 * 4;               // int
-constexpr int DPB_END = DPB_FLAG + 16;
+constexpr int DPB_END = DPB_LL + 8 * 4;
 static_assert(DPB_END <= DP_XS_BYTES, "attention scratch must fit in the staged-activation region");
 
 struct DpAttnFrag {
@@ -593,9 +629,29 @@ SR_DEVINL void dp_attn_prefetch(const DpParams& p, int layer, const DpAttnUnit& 
                 U.k_begin, min(DP_KEYS, ke - U.k_begin), f);
 }
 
-SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, uint8_t* sm, const float* s_cos, const float* s_sin,
-                                   const DpAttnUnit& U, DpAttnFrag& f) {
-  if (!U.active) return;  // uniform per CTA
+// L2 prefetch of the split's old K rows (256 B each, one line pair per key) and V^T rows (one per dim, keys contiguous): issued at
+// the start of the layer, so that the register loads of dp_attn_prefetch (issued right before q is polled, and returning in
+// order with the poll loads behind them) come back at L2 instead of HBM latency.
+SR_DEVINL void dp_attn_prefetch_l2(const DpParams& p, int layer, const DpAttnUnit& U) {
+  const int ke = dp_attn_old_end(U);
+  const int n = ke - U.k_begin;
+  if (n <= 0) return;
+  const int ct = threadIdx.x - 32;
+  const __nv_bfloat16* Kc = p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride;
+  const __nv_bfloat16* Vt = p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride;
+  for (int k = ct; k < n; k += DP_CTHREADS) {
+    const __nv_bfloat16* kr = Kc + (static_cast<int64_t>(U.start + U.k_begin + k) * p.nkv + U.kvh) * 128;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(kr));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(kr + 64));
+  }
+  if (ct < 128) {
+    const __nv_bfloat16* vr = Vt + static_cast<int64_t>(U.kvh * 128 + ct) * p.ldvt + U.start + U.k_begin;
+    for (int k = 0; k < n; k += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(vr + k));
+  }
+}
+
+SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, uint32_t gen, uint8_t* sm, const float* s_cos, const float* s_sin,
+                                   const DpAttnUnit& U, DpAttnFrag& f, int tr_base) {
   const int ct = threadIdx.x - 32, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
   const int G = p.nq / p.nkv, ns = p.ns;
   float* s_red = reinterpret_cast<float*>(sm + DPB_RED);
@@ -606,24 +662,24 @@ SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, uint8_t* sm, con
   float* m_ls = m_ms + DP_NS_MAX * 8;
   float* m_f = m_ls + DP_NS_MAX * 8;
   float* m_L = reinterpret_cast<float*>(sm + DPB_LL);
-  int* s_flag = reinterpret_cast<int*>(sm + DPB_FLAG);
   __nv_bfloat16* Kc = p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride;
   __nv_bfloat16* Vt = p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride;
-  const int ldq = (p.nq + 2 * p.nkv) * 128;
+  const int qrow_lines = (p.nq + 2 * p.nkv) * 32;
   const int b = U.b, kvh = U.kvh;
-  const __nv_bfloat16* qrow = p.qkv + static_cast<int64_t>(b) * ldq;
+  const uint4* qrow = p.qkv_ll + static_cast<int64_t>(b) * qrow_lines;
   const float* cs = s_cos + b * 64;
   const float* sn = s_sin + b * 64;
-  // one round trip: q of the heads (threads 0..63: head ct/8, dims 8(ct%8).. and +64), new k (64..127), new v (128..255)
+  // one round trip: q of the heads (threads 0..63: head ct/8, dims 8(ct%8).. and +64), new k (64..79), new v (128..159)
   if (ct < 64) {
     const int h = ct >> 3, d0 = (ct & 7) * 8;
-    uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+    uint32_t lw[4] = {0, 0, 0, 0}, hw[4] = {0, 0, 0, 0};
     if (h < G) {
-      const __nv_bfloat16* qh = qrow + (kvh * G + h) * 128;
-      lo = dp_ldcg(qh + d0);
-      hi = dp_ldcg(qh + 64 + d0);
+      const uint4* ql = qrow + (kvh * G + h) * 32 + (d0 >> 2);
+      uint4 qv[4] = {ll_load(ql), ll_load(ql + 1), ll_load(ql + 16), ll_load(ql + 17)};
+      ll_wait(qv, [&](int i) { return ql + (i & 1) + 16 * (i >> 1); }, gen);
+      lw[0] = qv[0].x; lw[1] = qv[0].z; lw[2] = qv[1].x; lw[3] = qv[1].z;
+      hw[0] = qv[2].x; hw[1] = qv[2].z; hw[2] = qv[3].x; hw[3] = qv[3].z;
     }
-    const uint32_t lw[4] = {lo.x, lo.y, lo.z, lo.w}, hw[4] = {hi.x, hi.y, hi.z, hi.w};
     uint32_t o1[4], o2[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {  // rotate-half; one rounding to bf16, like the q the per-layer path writes back
@@ -634,23 +690,41 @@ SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, uint8_t* sm, con
     }
     *reinterpret_cast<uint4*>(sm + DPB_Q + h * DPB_ROW + d0 * 2) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
     *reinterpret_cast<uint4*>(sm + DPB_Q + h * DPB_ROW + (64 + d0) * 2) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-  } else if (U.owner && ct < 128) {
-    const int d = ct - 64;
-    const __nv_bfloat16* kh = qrow + (p.nq + kvh) * 128;
-    const float x1 = __bfloat162float(__ldcg(kh + d)), x2 = __bfloat162float(__ldcg(kh + d + 64));
-    const __nv_bfloat16 k1 = __float2bfloat16(x1 * cs[d] - x2 * sn[d]), k2 = __float2bfloat16(x2 * cs[d] + x1 * sn[d]);
+  } else if (U.owner && ct < 80) {
+    const int d = (ct - 64) * 4;  // dims d..d+3 and 64+d..
+    const uint4* kl = qrow + (p.nq + kvh) * 32 + (d >> 2);
+    uint4 kv2[2] = {ll_load(kl), ll_load(kl + 16)};
+    ll_wait(kv2, [&](int i) { return kl + 16 * i; }, gen);
+    const uint4 a = kv2[0], c = kv2[1];
+    const float x1[4] = {bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.z), bf16_hi(a.z)};
+    const float x2[4] = {bf16_lo(c.x), bf16_hi(c.x), bf16_lo(c.z), bf16_hi(c.z)};
+    __nv_bfloat16 k1[4], k2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      k1[j] = __float2bfloat16(x1[j] * cs[d + j] - x2[j] * sn[d + j]);
+      k2[j] = __float2bfloat16(x2[j] * cs[d + j] + x1[j] * sn[d + j]);
+      s_knew[d + j] = __bfloat162float(k1[j]);
+      s_knew[d + j + 64] = __bfloat162float(k2[j]);
+    }
     __nv_bfloat16* kd = Kc + (static_cast<int64_t>(U.crow) * p.nkv + kvh) * 128;
-    kd[d] = k1;
-    kd[d + 64] = k2;
-    s_knew[d] = __bfloat162float(k1);
-    s_knew[d + 64] = __bfloat162float(k2);
-  } else if (U.owner && ct >= 128) {
-    const int d = ct - 128;
-    const __nv_bfloat16 v = __ldcg(qrow + (p.nq + p.nkv + kvh) * 128 + d);
-    Vt[static_cast<int64_t>(kvh * 128 + d) * p.ldvt + U.crow] = v;
-    s_vnew[d] = __bfloat162float(v);
+    *reinterpret_cast<uint2*>(kd + d) = *reinterpret_cast<const uint2*>(k1);
+    *reinterpret_cast<uint2*>(kd + d + 64) = *reinterpret_cast<const uint2*>(k2);
+  } else if (U.owner && ct >= 128 && ct < 160) {
+    const int d = (ct - 128) * 4;
+    const uint4* vl = qrow + (p.nq + p.nkv + kvh) * 32 + (d >> 2);
+    uint4 a = ll_load(vl);
+    ll_spin(a, vl, gen);
+    const uint32_t u2[2] = {a.x, a.z};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned short bits = static_cast<unsigned short>(j & 1 ? u2[j >> 1] >> 16 : u2[j >> 1] & 0xffffu);
+      *reinterpret_cast<unsigned short*>(Vt + static_cast<int64_t>(kvh * 128 + d + j) * p.ldvt + U.crow) = bits;
+      s_vnew[d + j] = __uint_as_float(static_cast<uint32_t>(bits) << 16);
+    }
   }
   dp_cbar();
+  if (ct == 0) dp_trace_at(p, 1, tr_base);
+  if (p.flags & 8) dp_attn_prefetch(p, layer, U, f);  // diagnostic: K / V^T requested only after q has arrived
   if (U.owner) {  // score of the new key: warp w <-> head w
     const uint2 qv = *reinterpret_cast<const uint2*>(sm + DPB_Q + w * DPB_ROW + lane * 8);
     const float4 kv = *reinterpret_cast<const float4*>(s_knew + lane * 4);
@@ -666,7 +740,7 @@ SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, uint8_t* sm, con
   int par = 0;
   for (int p0 = U.k_begin; p0 < k_old_end; p0 += DP_KEYS) {
     const int nk = min(DP_KEYS, k_old_end - p0);
-    if (p0 != U.k_begin) dp_attn_load(p, U, Kc, Vt, p0, nk, f);  // first pass: requested before the grid barrier
+    if (p0 != U.k_begin) dp_attn_load(p, U, Kc, Vt, p0, nk, f);  // first pass: requested before q was polled
     float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -743,13 +817,11 @@ SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, uint8_t* sm, con
   }
   dp_cbar();  // (the last pass's reads of s_red are done)
   if (g == 0) *reinterpret_cast<float2*>(s_red + w * 8 + 2 * t) = make_float2(l0, l1);
-  // publish this split's un-normalised partial (o, m, l)
-  float* wo = p.attn_ws + (static_cast<int64_t>(U.bk) * ns + U.split) * DP_PART;
+  // publish this split's un-normalised partial (o, m, l): line (dim * 4 + t) = o[dim][heads 2t, 2t+1]
+  uint4* wo = p.part_ll + (static_cast<int64_t>(U.bk) * ns + U.split) * DP_PART_LINES;
   const int d0 = 16 * w + g;
-  wo[(2 * t) * 128 + d0] = o[0];
-  wo[(2 * t + 1) * 128 + d0] = o[1];
-  wo[(2 * t) * 128 + d0 + 8] = o[2];
-  wo[(2 * t + 1) * 128 + d0 + 8] = o[3];
+  ll_store(wo + d0 * 4 + t, __float_as_uint(o[0]), __float_as_uint(o[1]), gen);
+  ll_store(wo + (d0 + 8) * 4 + t, __float_as_uint(o[2]), __float_as_uint(o[3]), gen);
   dp_cbar();
   if (ct < 4) {  // lanes t = 0..3 of warp 0 hold the running maxima of heads 2t, 2t+1
     float L0 = 0.f, L1 = 0.f;
@@ -758,58 +830,82 @@ SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, uint8_t* sm, con
       L0 += s_red[w8 * 8 + 2 * ct];
       L1 += s_red[w8 * 8 + 2 * ct + 1];
     }
-    wo[DP_GMAX * 128 + 2 * ct] = m0;
-    wo[DP_GMAX * 128 + 2 * ct + 1] = m1;
-    wo[DP_GMAX * 128 + DP_GMAX + 2 * ct] = L0;
-    wo[DP_GMAX * 128 + DP_GMAX + 2 * ct + 1] = L1;
+    ll_store(wo + 512 + 2 * ct, __float_as_uint(m0), __float_as_uint(L0), gen);
+    ll_store(wo + 512 + 2 * ct + 1, __float_as_uint(m1), __float_as_uint(L1), gen);
   }
-  dp_cbar();
-  if (ct == 0) {  // release our partial (cumulative through the CTA barrier), acquire the others'
-    int ticket;
-    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(p.attn_tickets + U.bk) : "memory");
-    *s_flag = (ticket == ns - 1) ? 1 : 0;
-  }
-  dp_cbar();
-  if (*s_flag == 0) return;
-  // merge (last CTA of this (sample, kv head)): statistics and partial outputs requested together
-  const float* wb = p.attn_ws + static_cast<int64_t>(U.bk) * ns * DP_PART;
-  float ov[4][16];
+  if (ct == 0) dp_trace_at(p, 1, tr_base + 1);
+  dp_cbar();  // scratch reads done before the region is reused (merge below / next phase's staging)
+  if (U.split != 0) return;
+  // ---- merge (split 0 of this (sample, kv head)): statistics and partial outputs polled together
+  const uint4* wb = p.part_ll + static_cast<int64_t>(U.bk) * ns * DP_PART_LINES;
+  float O[4] = {0.f, 0.f, 0.f, 0.f};
+  uint4 st_line = make_uint4(0, 0, 0, 0);
+  const bool st_thread = ct < ns * 8;
+  const uint4* st_ptr = wb + (ct >> 3) * DP_PART_LINES + 512 + (ct & 7);
+  if (st_thread) st_line = ll_load(st_ptr);
+  for (int c0 = 0; c0 < ns; c0 += DP_MERGE_CHUNK) {
+    uint4 ov[2 * DP_MERGE_CHUNK];  // [split j][dim d0 | d0 + 8]
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float* src = wb + (2 * t + (i & 1)) * 128 + d0 + 8 * (i >> 1);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) ov[i][j] = j < ns ? __ldcg(src + j * DP_PART) : 0.f;
-  }
-  for (int i = ct; i < ns * 8; i += DP_CTHREADS) {
-    const int s2 = i >> 3, h = i & 7;
-    m_ms[i] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + h);
-    m_ls[i] = __ldcg(wb + s2 * DP_PART + DP_GMAX * 128 + DP_GMAX + h);
-  }
-  dp_cbar();
-  if (ct < 8) {
-    float Mx = -INFINITY;
-    for (int s2 = 0; s2 < ns; ++s2) Mx = fmaxf(Mx, m_ms[s2 * 8 + ct]);
-    const float Mu = (Mx == -INFINITY) ? 0.f : Mx;
-    float L = 0.f;
-    for (int s2 = 0; s2 < ns; ++s2) {
-      const float fz = exp2f(m_ms[s2 * 8 + ct] - Mu);
-      m_f[s2 * 8 + ct] = fz;
-      L += m_ls[s2 * 8 + ct] * fz;
+    for (int j = 0; j < DP_MERGE_CHUNK; ++j) {
+      if (c0 + j < ns) {
+        ov[2 * j] = ll_load(wb + (c0 + j) * DP_PART_LINES + d0 * 4 + t);
+        ov[2 * j + 1] = ll_load(wb + (c0 + j) * DP_PART_LINES + (d0 + 8) * 4 + t);
+      } else {
+        ov[2 * j] = ov[2 * j + 1] = make_uint4(0, gen, 0, gen);
+      }
     }
-    m_L[ct] = L;
+    if (c0 == 0) {
+      if (st_thread) {
+        ll_spin(st_line, st_ptr, gen);
+        m_ms[ct] = __uint_as_float(st_line.x);
+        m_ls[ct] = __uint_as_float(st_line.z);
+      }
+      dp_cbar();
+      if (ct < 8) {
+        float Mx = -INFINITY;
+        for (int s2 = 0; s2 < ns; ++s2) Mx = fmaxf(Mx, m_ms[s2 * 8 + ct]);
+        const float Mu = (Mx == -INFINITY) ? 0.f : Mx;
+        float L = 0.f;
+        for (int s2 = 0; s2 < ns; ++s2) {
+          const float fz = exp2f(m_ms[s2 * 8 + ct] - Mu);
+          m_f[s2 * 8 + ct] = fz;
+          L += m_ls[s2 * 8 + ct] * fz;
+        }
+        m_L[ct] = L;
+      }
+      dp_cbar();
+    }
+    ll_wait(ov, [&](int i) { return wb + (c0 + (i >> 1)) * DP_PART_LINES + (d0 + 8 * (i & 1)) * 4 + t; }, gen);
+#pragma unroll
+    for (int j = 0; j < DP_MERGE_CHUNK; ++j) {
+      if (c0 + j < ns) {
+        const float f0 = m_f[(c0 + j) * 8 + 2 * t], f1 = m_f[(c0 + j) * 8 + 2 * t + 1];
+        O[0] += __uint_as_float(ov[2 * j].x) * f0;
+        O[1] += __uint_as_float(ov[2 * j].z) * f1;
+        O[2] += __uint_as_float(ov[2 * j + 1].x) * f0;
+        O[3] += __uint_as_float(ov[2 * j + 1].z) * f1;
+      }
+    }
+    __syncwarp();
+  }
+  {  // normalise -> bf16 [8 heads][128] in shared memory (the P region is free now) -> LL lines
+    const float L0 = m_L[2 * t], L1 = m_L[2 * t + 1];
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(sm + DPB_P);
+    ob[(2 * t) * (DPB_ROW / 2) + d0] = __float2bfloat16(L0 > 0.f ? O[0] / L0 : 0.f);
+    ob[(2 * t + 1) * (DPB_ROW / 2) + d0] = __float2bfloat16(L1 > 0.f ? O[1] / L1 : 0.f);
+    ob[(2 * t) * (DPB_ROW / 2) + d0 + 8] = __float2bfloat16(L0 > 0.f ? O[2] / L0 : 0.f);
+    ob[(2 * t + 1) * (DPB_ROW / 2) + d0 + 8] = __float2bfloat16(L1 > 0.f ? O[3] / L1 : 0.f);
   }
   dp_cbar();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int h = 2 * t + (i & 1);
-    float O = 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) O += j < ns ? ov[i][j] * m_f[j * 8 + h] : 0.f;
-    for (int j = 16; j < ns; ++j) O += __ldcg(wb + j * DP_PART + h * 128 + d0 + 8 * (i >> 1)) * m_f[j * 8 + h];
-    const float L = m_L[h];
-    if (h < G) p.ao[static_cast<int64_t>(b) * (p.nq * 128) + (kvh * G + h) * 128 + d0 + 8 * (i >> 1)] = __float2bfloat16(L > 0.f ? O / L : 0.f);
+  {
+    const int h = ct >> 5, j = ct & 31;  // head h, dims 4j..4j+3
+    if (h < G) {
+      const uint2 v = *reinterpret_cast<const uint2*>(sm + DPB_P + h * DPB_ROW + j * 8);
+      ll_store(p.ao_ll + static_cast<int64_t>(b) * DP_HL + (kvh * G + h) * 32 + j, v.x, v.y, gen);
+      if (p.ao != nullptr) *reinterpret_cast<uint2*>(p.ao + static_cast<int64_t>(b) * DP_H + (kvh * G + h) * 128 + j * 4) = v;
+    }
   }
-  if (ct == 0) p.attn_tickets[U.bk] = 0;  // re-arm for the next layer / launch
+  dp_cbar();
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
@@ -830,7 +926,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   float* s_cos = reinterpret_cast<float*>(smem + DP_OFF_ROPE);
   float* s_sin = s_cos + 8 * 64;
   int* s_scal = reinterpret_cast<int*>(smem + DP_OFF_SCAL);
-  volatile int* s_pcnt = reinterpret_cast<volatile int*>(smem + DP_OFF_PCNT);
+  volatile int* s_pcnt = reinterpret_cast<volatile int*>(s_scal + 26);  // stages issued by the producer (read by the prefetcher)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {  // per-launch constants -> shared memory (pointer / scalar loads off the critical paths)
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.layers);
@@ -847,9 +943,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       s_scal[8 + threadIdx.x] = ok ? p.kv_len[threadIdx.x] : 0;
       s_scal[16 + threadIdx.x] = ok ? p.cache_row[threadIdx.x] : 0;
     }
+    if (threadIdx.x == 8) s_scal[24] = static_cast<int>(*reinterpret_cast<volatile unsigned int*>(p.epoch));
+    if (threadIdx.x == 9) s_scal[25] = 0;
+    if (threadIdx.x == 10) s_scal[26] = 0;
   }
   if (threadIdx.x == 0) {
-    *s_pcnt = 0;
 #pragma unroll
     for (int i = 0; i < DP_STAGES; ++i) {
       mbar_init(&ring.full[i], 1);
@@ -871,6 +969,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   // other (e.g. the 20 CTAs idle in the down projection take a fifth gate/up unit), which lowers the bytes of the busiest CTA.
   auto vidx = [&](int off) { const int g = static_cast<int>(gridDim.x); return (static_cast<int>(blockIdx.x) + g - (off % g)) % g; };
   const int vq = vidx(p.unit_off[0]), vo = vidx(p.unit_off[1]), vg = vidx(p.unit_off[2]), vd = vidx(p.unit_off[3]);
+  const int G = static_cast<int>(gridDim.x);
+  // measurement aid (flags bit 5): the LM head is streamed by every second CTA only -- does one SM ingest faster when fewer stream?
+  const bool half_head = (p.flags & 32) != 0;
+  const int hs = half_head ? (G + 1) / 2 : G;
+  const int hv = half_head ? ((blockIdx.x & 1) ? 0x7fffffff : static_cast<int>(blockIdx.x >> 1)) : static_cast<int>(blockIdx.x);
 
   if (warp == 0) {
     // ---------------- producer: weights only; runs ahead of the consumers across phases ----------------
@@ -883,21 +986,25 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       for (int l = 0; l < p.n_layers; ++l) {
         const DpLayer L = s_layers[l];
         if (ph++ >= limit) return;
-        dp_produce<2, false>(ring, vq, L.qkv_wp, n_qkv / 2, kq, policy, hint, s_pcnt, issued);
+        dp_produce<2, false>(ring, vq, L.qkv_wp, n_qkv / 2, kq, policy, hint, s_pcnt, issued, G);
         dp_trace_at(p, 0, 1 + 4 * l);
         if (ph++ >= limit) return;  // attention phase: no weights
         if (ph++ >= limit) return;
-        dp_produce<1, false>(ring, vo, L.o_wp, n_o, kq, policy, hint, s_pcnt, issued);
+        dp_produce<1, false>(ring, vo, L.o_wp, n_o, kq, policy, hint, s_pcnt, issued, G);
         dp_trace_at(p, 0, 2 + 4 * l);
         if (ph++ >= limit) return;
-        dp_produce<2, false>(ring, vg, L.gu_wp, n_gu, kq, policy, hint, s_pcnt, issued);
+        if (p.flags & 4) {  // diagnostic: no gate/up streaming before this CTA's consumers reach phase D (idle HBM during the chain)
+          volatile int* gate = s_scal + 25;
+          while (*gate < l + 1) __nanosleep(20);
+        }
+        dp_produce<2, false>(ring, vg, L.gu_wp, n_gu, kq, policy, hint, s_pcnt, issued, G);
         dp_trace_at(p, 0, 3 + 4 * l);
         if (ph++ >= limit) return;
-        dp_produce<1, true>(ring, vd, L.down_wp, n_o, kd, policy, hint, s_pcnt, issued);
+        dp_produce<1, true>(ring, vd, L.down_wp, n_o, kd, policy, hint, s_pcnt, issued, G);
         dp_trace_at(p, 0, 4 + 4 * l);
       }
       if (ph++ >= limit) return;
-      dp_produce<1, false>(ring, static_cast<int>(blockIdx.x), p.lm_head_p, n_head, kq, policy, hint, s_pcnt, issued);
+      if (hv < n_head) dp_produce<1, false>(ring, hv, p.lm_head_p, n_head, kq, policy, hint, s_pcnt, issued, hs);
       dp_trace_at(p, 0, 1 + 4 * p.n_layers);
     }
     return;
@@ -907,99 +1014,151 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     if (lane == 0 && p.pf_stages > 0) {
       int ph = 0, sidx = 0;
       const int lead = p.pf_stages;
-      uint64_t pf_policy = 0;
-      const bool pf_hint = (p.flags & 128) != 0;
-      if (pf_hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf_policy));
       for (int l = 0; l < p.n_layers; ++l) {
         const DpLayer L = s_layers[l];
         if (ph++ >= limit) return;
-        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, vq, L.qkv_wp, n_qkv / 2, kq, pf_policy, pf_hint);
+        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, vq, L.qkv_wp, n_qkv / 2, kq, G);
         if (ph++ >= limit) return;
         if (ph++ >= limit) return;
-        dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, vo, L.o_wp, n_o, kq, pf_policy, pf_hint);
+        dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, vo, L.o_wp, n_o, kq, G);
         if (ph++ >= limit) return;
-        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, vg, L.gu_wp, n_gu, kq, pf_policy, pf_hint);
+        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, vg, L.gu_wp, n_gu, kq, G);
         if (ph++ >= limit) return;
-        dp_prefetch_l2<1, true>(sidx, s_pcnt, lead, vd, L.down_wp, n_o, kd, pf_policy, pf_hint);
+        dp_prefetch_l2<1, true>(sidx, s_pcnt, lead, vd, L.down_wp, n_o, kd, G);
       }
       if (ph++ >= limit) return;
-      dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, static_cast<int>(blockIdx.x), p.lm_head_p, n_head, kq, pf_policy, pf_hint);
+      if (hv < n_head) dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, hv, p.lm_head_p, n_head, kq, hs);
     }
     return;
   }
 
   // ---------------- consumers ----------------
   const int cw = warp - 1;
+  const int ct = threadIdx.x - 32;
+  const uint32_t epoch_raw = static_cast<uint32_t>(s_scal[24]);
+  const uint32_t epoch = epoch_raw + 1u;  // generations epoch .. epoch + n_layers: never 0 on a zero-initialised workspace
+  const bool dump = (p.flags & 2) != 0;
+  {  // the step's input rows (embedded tokens, plain bf16) -> LL lines of generation `epoch + 0`, spread over all CTAs
+    const int line = static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) * ct;
+    if (line < p.B * DP_HL) {
+      const int b = line / DP_HL, j = line % DP_HL;
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p.x + static_cast<int64_t>(b) * p.ldx + j * 4));
+      ll_store(p.xb_ll + line, v.x, v.y, epoch);
+    }
+  }
   int red_par = 0;
-  unsigned int bar_gen = 0;
-  int ph = 0, tr = 0;
-  const unsigned int G = gridDim.x;
-  const bool tracer = threadIdx.x == 32;
+  int ph = 0;
+  const bool tracer = ct == 0;
   const DpAttnUnit U = dp_attn_unit(p, s_scal);
   DpAttnFrag fr;
-#define DP_TRACE() do { if (tracer) dp_trace(p, 1, tr); } while (0)
-  DP_TRACE();
-  for (int l = 0; l < p.n_layers; ++l) {
+  constexpr int EV = 9;  // trace events per layer (after event 0)
+#define DP_TRACE(k) do { if (tracer) dp_trace_at(p, 1, 1 + EV * l + (k)); } while (0)
+  if (tracer) dp_trace_at(p, 1, 0);
+  int l = 0;
+  for (; l < p.n_layers; ++l) {
     const DpLayer L = s_layers[l];
-    // A: qkv = rmsnorm(x; ln1) . Wqkv^T + b
-    if (ph++ >= limit) return;
-    dp_stage_rows<true>(xs, p.x, p.ldx, p.B, L.ln1, p.eps, cw, lane);
-    dp_cbar();
-    // units of 32 rows: (nq + 2 nkv) * 8 = 160 16-row groups would leave 12 of 148 CTAs with two serial units; 80 double
-    // units fit the ring (128 KB) and take one pass (the 68 CTAs without a unit let their producers run ahead)
-    dp_gemv_phase<2, DP_EPI_BIAS, true>(ring, vq, n_qkv / 2, kq, xs, nullptr, 0, p.B, red, red_par, L.qkv_b, p.qkv, nullptr,
-                                        static_cast<int64_t>(n_qkv) * 16, cw, lane);
-    const bool do_attn = ph < limit;
-    if (do_attn) dp_attn_prefetch(p, l, U, fr);  // old K / V^T rows fly while the CTA waits at the barrier
-    DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
-    DP_TRACE();
+    const uint32_t gin = epoch + static_cast<uint32_t>(l);      // generation of this layer's input x (written by layer l-1)
+    const uint32_t gen = gin + 1;                               // generation of everything this layer writes
+    DpOut o;
+    if ((p.flags & 16) && U.active) dp_attn_prefetch_l2(p, l, U);  // this layer's K / V^T slice -> L2 while the qkv phase runs
+    // A: qkv = rmsnorm(x; ln1) . Wqkv^T + b   (units of 32 rows: 80 double units, one pass)
+    if (ph++ >= limit) break;
+    if (vq < n_qkv / 2) {
+      dp_stage_rows<true>(xs, p.xb_ll, gin, p.B, L.ln1, p.eps, cw, lane);
+      dp_cbar();
+      DP_TRACE(0);
+      o = DpOut{p.qkv_ll, n_qkv * 4, gen, nullptr, 0, L.qkv_b, nullptr, 0, p.qkv, static_cast<int64_t>(n_qkv) * 16};
+      dp_gemv_phase<2, DP_EPI_BIAS, true>(ring, vq, n_qkv / 2, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
+    } else {
+      DP_TRACE(0);
+    }
+    DP_TRACE(1);
     // B: rope + KV append + attention -> ao
-    if (ph++ >= limit) return;
-    dp_attention_phase(p, l, xs, s_cos, s_sin, U, fr);
-    DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
-    DP_TRACE();
+    if (ph++ >= limit) break;
+    if (U.active) {
+      if (!(p.flags & 8)) dp_attn_prefetch(p, l, U, fr);  // old K / V^T rows fly while q is being produced
+      dp_cbar();                      // (phase A's shared-memory reads are done before the scratch region is written)
+      dp_attention_phase(p, l, gen, xs, s_cos, s_sin, U, fr, 1 + EV * l + 2);
+    } else {
+      DP_TRACE(2);
+      DP_TRACE(3);
+    }
     // C: x += ao . Wo^T
-    if (ph++ >= limit) return;
-    dp_stage_rows<false>(xs, p.ao, DP_H, p.B, nullptr, 0.f, cw, lane);
-    dp_cbar();
-    dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, vo, n_o, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
-    DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
-    DP_TRACE();
+    if (ph++ >= limit) break;
+    if (vo < n_o) {
+      dp_stage_rows<false>(xs, p.ao_ll, gen, p.B, nullptr, 0.f, cw, lane);
+      dp_cbar();
+      DP_TRACE(4);
+      o = DpOut{p.xa_ll, DP_HL, gen, p.xb_ll, gin, nullptr, nullptr, 0, dump ? p.x : nullptr, p.ldx};
+      dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, vo, n_o, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
+    } else {
+      DP_TRACE(4);
+    }
+    DP_TRACE(5);
     // D: act = silu(gate) * up, [gate|up] = rmsnorm(x; ln2) . Wgu^T
-    if (ph++ >= limit) return;
-    dp_stage_rows<true>(xs, p.x, p.ldx, p.B, L.ln2, p.eps, cw, lane);
+    if (ph++ >= limit) break;
     dp_cbar();
-    dp_gemv_phase<2, DP_EPI_SWIGLU, true>(ring, vg, n_gu, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, p.act, nullptr, p.I, cw, lane);
-    DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
-    DP_TRACE();
+    dp_stage_rows<true>(xs, p.xa_ll, gen, p.B, L.ln2, p.eps, cw, lane);
+    dp_cbar();
+    DP_TRACE(6);
+    if (tracer) *reinterpret_cast<volatile int*>(s_scal + 25) = l + 1;
+    o = DpOut{nullptr, 0, gen, nullptr, 0, nullptr, nullptr, 0, p.act, p.I};  // plain bf16 + one release flag per CTA
+    dp_gemv_phase<2, DP_EPI_SWIGLU, true>(ring, vg, n_gu, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
+    dp_publish_act(p.act_flags, gen, ct);
+    DP_TRACE(7);
     // E: x += act . Wdown^T
-    if (ph++ >= limit) return;
-    dp_gemv_phase<1, DP_EPI_RESIDUAL, false>(ring, vd, n_o, kd, nullptr, p.act, p.I, p.B, red, red_par, nullptr, p.x, nullptr, p.ldx, cw, lane);
-    DP_TRACE();
-    dp_grid_barrier(p.grid_bar, ++bar_gen * G);
-    DP_TRACE();
+    if (ph++ >= limit) break;
+    o = DpOut{p.xb_ll, DP_HL, gen, p.xa_ll, gen, nullptr, nullptr, 0, dump ? p.x : nullptr, p.ldx};
+    if (vd < n_o) {
+      dp_wait_act(p.act_flags, gen, ct);
+      dp_gemv_phase<1, DP_EPI_RESIDUAL, false>(ring, vd, n_o, kd, nullptr, p.act, p.I, p.B, red, red_par, o, cw, lane, G);
+    }
+    DP_TRACE(8);
+    dp_cbar();  // phase E's epilogue reads of `red` / phase D's of xs are done before the next layer restages
   }
   // final norm + LM head -> fp32 logits
-  if (ph++ >= limit) return;
-  dp_stage_rows<true>(xs, p.x, p.ldx, p.B, p.final_norm, p.eps, cw, lane);
-  dp_cbar();
-  dp_gemv_phase<1, DP_EPI_F32, true>(ring, static_cast<int>(blockIdx.x), n_head, kq, xs, nullptr, 0, p.B, red, red_par, nullptr, nullptr, p.logits, p.ld_logits, cw, lane);
-  DP_TRACE();
+  if (l == p.n_layers && ph++ < limit) {
+    dp_stage_rows<true>(xs, p.xb_ll, epoch + static_cast<uint32_t>(p.n_layers), p.B, p.final_norm, p.eps, cw, lane);
+    dp_cbar();
+    DpOut o = DpOut{nullptr, 0, 0, nullptr, 0, nullptr, p.logits, p.ld_logits, nullptr, 0};
+    if (hv < n_head) dp_gemv_phase<1, DP_EPI_F32, true>(ring, hv, n_head, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, hs);
+    DP_TRACE(0);
+  }
 #undef DP_TRACE
+  // the last CTA to leave advances the epoch (stream order makes it visible to the next launch / graph replay)
+  if (ct == 0) {
+    const unsigned int old = atomicAdd(p.epoch + 1, 1u);
+    if (old == gridDim.x - 1) {
+      p.epoch[1] = 0;
+      p.epoch[0] = epoch_raw + static_cast<uint32_t>(p.n_layers) + 2u;
+    }
+  }
 }
 
 }  // namespace sr
 
 using namespace sr;
 
-extern "C" int64_t sr_decode_persistent_workspace_bytes(int batch, int n_kv_heads) {
-  // [16 B: grid barrier counter][tickets: batch*nkv int32, 16 B aligned][partials: batch*nkv*DP_NS_MAX*DP_PART fp32]
-  const int64_t bk = static_cast<int64_t>(batch) * n_kv_heads;
-  return 16 + ((bk * 4 + 15) / 16) * 16 + bk * DP_NS_MAX * DP_PART * 4;
+static inline int64_t dp_align(int64_t v) { return (v + 255) / 256 * 256; }
+struct DpWsLayout {
+  int64_t xa, xb, qkv, ao, act, flags, part, total;
+};
+static DpWsLayout dp_ws_layout(int n_q_heads, int n_kv_heads, int intermediate) {
+  DpWsLayout w;
+  int64_t off = 256;  // header: epoch, exit counter
+  w.xa = off; off += dp_align(8LL * DP_HL * 16);
+  w.xb = off; off += dp_align(8LL * DP_HL * 16);
+  w.qkv = off; off += dp_align(8LL * (n_q_heads + 2 * n_kv_heads) * 32 * 16);
+  w.ao = off; off += dp_align(8LL * DP_HL * 16);
+  w.act = off; off += dp_align(8LL * intermediate * 2);
+  w.flags = off; off += dp_align(4096);
+  w.part = off; off += dp_align(8LL * n_kv_heads * DP_NS_MAX * DP_PART_LINES * 16);
+  w.total = off;
+  return w;
+}
+
+extern "C" int64_t sr_decode_persistent_workspace_bytes(int n_q_heads, int n_kv_heads, int intermediate) {
+  return dp_ws_layout(n_q_heads, n_kv_heads, intermediate).total;
 }
 
 static unsigned long long* g_dp_trace = nullptr;
@@ -1010,31 +1169,22 @@ extern "C" int sr_set_decode_persistent_trace(void* buffer, int events_per_role)
   return SR_OK;
 }
 
-static int g_dp_pf_stages = -1;  // -1: env SR_DECODE_PF_STAGES (default below)
 static int g_dp_flags = -1;      // -1: env SR_DECODE_FLAGS
-static int g_dp_ring = 0;        // 0: env SR_DECODE_RING (default DP_STAGES); set through bits 8.. of the tuning flags
-extern "C" int sr_set_decode_persistent_tuning(int pf_stages, int flags) {
-  if (pf_stages < 0 || pf_stages > 4096) return SR_ERR_INVALID;
-  g_dp_pf_stages = pf_stages;
-  g_dp_flags = flags & 0xff;
-  g_dp_ring = (flags >> 8) & 0xff;  // tuning aid: ring stages in bits 8..15 (0 = default)
-  if (g_dp_ring == 1 || g_dp_ring > DP_STAGES) return SR_ERR_INVALID;
-  return SR_OK;
-}
-
+static int g_dp_ring = 0;        // 0: env SR_DECODE_RING (default below)
+static int g_dp_pf = -1;         // -1: env SR_DECODE_PF_STAGES (default below)
 static int g_dp_unit_off[4] = {-1, 0, 0, 0};  // -1: env SR_DECODE_UNIT_OFFSETS="q,o,g,d" (default below)
-extern "C" int sr_set_decode_persistent_offsets(int qkv, int o, int gate_up, int down) {
-  if (qkv < 0 || o < 0 || gate_up < 0 || down < 0) return SR_ERR_INVALID;
-  g_dp_unit_off[0] = qkv;
-  g_dp_unit_off[1] = o;
-  g_dp_unit_off[2] = gate_up;
-  g_dp_unit_off[3] = down;
-  return SR_OK;
-}
-
-static int g_dp_coop = -1;
-extern "C" int sr_set_decode_persistent_coop(int on) {
-  g_dp_coop = on ? 1 : 0;
+extern "C" int sr_set_decode_persistent_tuning(int flags, int ring_stages, int pf_stages, int off_qkv, int off_o, int off_gate_up,
+                                               int off_down) {
+  if (ring_stages == 1 || ring_stages > DP_STAGES || ring_stages < 0 || pf_stages > 4096) return SR_ERR_INVALID;
+  if (flags >= 0) g_dp_flags = flags & 0xff;
+  g_dp_ring = ring_stages;
+  if (pf_stages >= 0) g_dp_pf = pf_stages;
+  if (off_qkv >= 0 && off_o >= 0 && off_gate_up >= 0 && off_down >= 0) {
+    g_dp_unit_off[0] = off_qkv;
+    g_dp_unit_off[1] = off_o;
+    g_dp_unit_off[2] = off_gate_up;
+    g_dp_unit_off[3] = off_down;
+  }
   return SR_OK;
 }
 
@@ -1045,17 +1195,17 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
                                          int64_t k_layer_stride, void* Vt, int64_t vt_layer_stride, int64_t ldvt, int batch,
                                          int n_q_heads, int n_kv_heads, int intermediate, float norm_eps, float scale,
                                          void* workspace, int stop_after_phases, void* stream) {
-  SR_REQUIRE(layer_table && lm_head_packed && final_norm && x && qkv_scratch && ao_scratch && act_scratch && logits && cosb && sinb &&
-                 cache_row && kv_start && kv_len && Kc && Vt && workspace,
+  SR_REQUIRE(layer_table && lm_head_packed && final_norm && x && logits && cosb && sinb && cache_row && kv_start && kv_len && Kc && Vt &&
+                 workspace,
              "sr_decode_step_persistent: null pointer");
   SR_REQUIRE(batch > 0 && batch <= 8, "sr_decode_step_persistent: batch must be in [1, 8] (got %d)", batch);
   SR_REQUIRE(n_q_heads * 128 == DP_H && n_kv_heads > 0 && n_q_heads % n_kv_heads == 0 && n_q_heads / n_kv_heads <= DP_GMAX,
              "sr_decode_step_persistent: needs hidden 2048 = n_q_heads * 128 and <= 8 query heads per kv head");
   SR_REQUIRE(n_layers <= DP_MAX_LAYERS, "sr_decode_step_persistent: at most %d layers", DP_MAX_LAYERS);
   SR_REQUIRE(intermediate % 32 == 0 && vocab % 16 == 0 && n_layers > 0, "sr_decode_step_persistent: intermediate %% 32, vocab %% 16");
-  SR_REQUIRE(ldx % 8 == 0 && ldvt % 8 == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(act_scratch) & 15) == 0 &&
-                 (reinterpret_cast<uintptr_t>(ao_scratch) & 15) == 0 && (reinterpret_cast<uintptr_t>(lm_head_packed) & 15) == 0,
+  SR_REQUIRE(ldx % 8 == 0 && ldvt % 8 == 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0 &&
+                 (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(lm_head_packed) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && ld_logits % 4 == 0,
              "sr_decode_step_persistent: alignment");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   static int grid_cached = 0;
@@ -1064,11 +1214,8 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
     int per_sm = 0;
     SR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel, DP_THREADS, DP_SMEM_BYTES));
     SR_REQUIRE(per_sm >= 1, "sr_decode_step_persistent: kernel does not fit on an SM (smem %d B)", DP_SMEM_BYTES);
-    grid_cached = sm_count();  // one CTA per SM: all co-resident (required by the grid barrier)
-  }
-  if (g_dp_coop < 0) {
-    const char* e = getenv("SR_DECODE_COOP");
-    g_dp_coop = (e != nullptr && e[0] == '0') ? 0 : 1;
+    grid_cached = sm_count();  // one CTA per SM: all co-resident (the CTAs wait for each other's data)
+    SR_REQUIRE(grid_cached <= 1024 && grid_cached <= DP_CTHREADS, "sr_decode_step_persistent: at most %d SMs", DP_CTHREADS);
   }
   DpParams p;
   p.layers = reinterpret_cast<const DpLayer*>(layer_table);
@@ -1078,9 +1225,6 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
   p.vocab = vocab;
   p.x = reinterpret_cast<__nv_bfloat16*>(x);
   p.ldx = ldx;
-  p.qkv = reinterpret_cast<__nv_bfloat16*>(qkv_scratch);
-  p.ao = reinterpret_cast<__nv_bfloat16*>(ao_scratch);
-  p.act = reinterpret_cast<__nv_bfloat16*>(act_scratch);
   p.logits = logits;
   p.ld_logits = ld_logits;
   p.cosb = cosb;
@@ -1100,29 +1244,35 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
   p.eps = norm_eps;
   p.scale_log2 = scale * 1.4426950408889634f;
   const int64_t bk = static_cast<int64_t>(batch) * n_kv_heads;
+  const DpWsLayout w = dp_ws_layout(n_q_heads, n_kv_heads, intermediate);
   char* ws = reinterpret_cast<char*>(workspace);
-  p.grid_bar = reinterpret_cast<unsigned int*>(ws);
-  p.attn_tickets = reinterpret_cast<int*>(ws + 16);
-  p.attn_ws = reinterpret_cast<float*>(ws + 16 + ((bk * 4 + 15) / 16) * 16);
+  p.epoch = reinterpret_cast<unsigned int*>(ws);
+  p.xa_ll = reinterpret_cast<uint4*>(ws + w.xa);
+  p.xb_ll = reinterpret_cast<uint4*>(ws + w.xb);
+  p.qkv_ll = reinterpret_cast<uint4*>(ws + w.qkv);
+  p.ao_ll = reinterpret_cast<uint4*>(ws + w.ao);
+  p.act_flags = reinterpret_cast<unsigned int*>(ws + w.flags);
+  p.part_ll = reinterpret_cast<uint4*>(ws + w.part);
   SR_REQUIRE(bk <= grid_cached, "sr_decode_step_persistent: batch * n_kv_heads must not exceed the SM count");
   int ns = grid_cached / static_cast<int>(bk);
   p.ns = ns < 1 ? 1 : (ns > DP_NS_MAX ? DP_NS_MAX : ns);
   p.stop_after = stop_after_phases;
-  if (g_dp_pf_stages < 0) {
-    const char* e = getenv("SR_DECODE_PF_STAGES");
-    g_dp_pf_stages = e ? atoi(e) : 0;
-  }
   if (g_dp_flags < 0) {
     const char* e = getenv("SR_DECODE_FLAGS");
-    g_dp_flags = e ? atoi(e) : 1;  // evict_first on the weight stream: keeps activations AND the kernel's instructions in L2
+    g_dp_flags = e ? atoi(e) : 17;  // evict_first on the weight stream (keeps activations and instructions in L2) + K/V L2 prefetch
   }
   static int ring_stages = -1;
   if (ring_stages < 0) {
     const char* e = getenv("SR_DECODE_RING");
-    ring_stages = e ? atoi(e) : 8;  // 8 of the 10 stages measured best (2.13 vs 2.16 ms/step; LM head 92 vs 103 us)
+    ring_stages = e ? atoi(e) : 8;
     if (ring_stages < 2 || ring_stages > DP_STAGES) ring_stages = DP_STAGES;
   }
   p.ring_stages = g_dp_ring > 0 ? g_dp_ring : ring_stages;
+  if (g_dp_pf < 0) {
+    const char* e = getenv("SR_DECODE_PF_STAGES");
+    g_dp_pf = e ? atoi(e) : 0;
+  }
+  p.pf_stages = g_dp_pf;
   if (g_dp_unit_off[0] < 0) {
     const int dflt[4] = {96, 40, 0, 20};
     for (int i = 0; i < 4; ++i) g_dp_unit_off[i] = dflt[i];
@@ -1130,22 +1280,24 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
     if (e) sscanf(e, "%d,%d,%d,%d", &g_dp_unit_off[0], &g_dp_unit_off[1], &g_dp_unit_off[2], &g_dp_unit_off[3]);
   }
   for (int i = 0; i < 4; ++i) p.unit_off[i] = g_dp_unit_off[i] < 0 ? 0 : g_dp_unit_off[i];
-  p.pf_stages = g_dp_pf_stages;
   p.flags = g_dp_flags;
+  const bool dump = (p.flags & 2) != 0;
+  SR_REQUIRE(!dump || (qkv_scratch && ao_scratch && act_scratch), "sr_decode_step_persistent: dump flag needs the three scratch buffers");
+  p.qkv = dump ? reinterpret_cast<__nv_bfloat16*>(qkv_scratch) : nullptr;
+  p.ao = dump ? reinterpret_cast<__nv_bfloat16*>(ao_scratch) : nullptr;
+  p.act = dump ? reinterpret_cast<__nv_bfloat16*>(act_scratch) : reinterpret_cast<__nv_bfloat16*>(ws + w.act);
   p.trace = g_dp_trace;
   p.trace_events = g_dp_trace_events;
-  // the barrier counter (and, defensively, the tickets) start at zero for every launch
-  SR_CHECK_CUDA(cudaMemsetAsync(ws, 0, 16 + ((bk * 4 + 15) / 16) * 16, s));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid_cached);
   cfg.blockDim = dim3(DP_THREADS);
   cfg.dynamicSmemBytes = DP_SMEM_BYTES;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].id = cudaLaunchAttributeCooperative;  // guarantees co-residency of the 148 CTAs (they poll each other's lines)
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_dp_coop ? 1 : 0;
+  cfg.numAttrs = 1;
   SR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, decode_persistent_kernel, p));
   return SR_OK;
 }

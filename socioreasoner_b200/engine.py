@@ -377,7 +377,7 @@ class Engine:
                 cache_row=torch.zeros((B,), dtype=torch.int32, device=dev), kv_len=torch.zeros((B,), dtype=torch.int32, device=dev),
                 pos3=torch.zeros((3, B), dtype=torch.int64, device=dev), kv_start=torch.zeros((B,), dtype=torch.int32, device=dev),
                 logits=torch.zeros((B, self.cfg.text.vocab_size), dtype=torch.float32, device=dev),
-                u=torch.zeros((B, T), dtype=torch.float32, device=dev),
+                u=torch.zeros((B, T), dtype=torch.float32, device=dev), forced=torch.zeros((B, T), dtype=torch.int64, device=dev),
                 x=torch.zeros((B, self.cfg.text.hidden_size), dtype=torch.bfloat16, device=dev),
             )
             if self._persistent_ok(B):
@@ -386,7 +386,7 @@ class Engine:
                     qkv=torch.zeros((B, (t.num_attention_heads + 2 * t.num_key_value_heads) * t.head_dim), dtype=torch.bfloat16, device=dev),
                     ao=torch.zeros((B, t.num_attention_heads * t.head_dim), dtype=torch.bfloat16, device=dev),
                     act=torch.zeros((B, t.intermediate_size), dtype=torch.bfloat16, device=dev),
-                    ws=lib.decode_persistent_workspace(B, t.num_key_value_heads, dev),
+                    ws=lib.decode_persistent_workspace(t.num_attention_heads, t.num_key_value_heads, t.intermediate_size, dev),
                 )
             self._dstate[key] = st
         return st
@@ -402,17 +402,11 @@ class Engine:
         return (self.use_persistent_decode and B <= 8 and self.w.lm_head_p is not None and len(self.w.layers) > 0
                 and self.w.layers[0].qkv_wp is not None and t.intermediate_size % 32 == 0 and t.vocab_size % 16 == 0)
 
-    def _persistent_single_pass(self, B: int, l_max: int) -> bool:
-        """The persistent kernel splits every (sample, kv head) over ns = #SMs // (B * n_kv) CTAs (at most 32) and handles 128 keys
-        per pass.  Its single-pass path (contexts up to 128 * ns keys: 1152 at B = 8, 4096 at B <= 2) is the one covered by the GPU
-        parity tests; longer contexts take the per-layer decode kernels until the multi-pass loop has its own parity test."""
-        if self._sm_count is None:
-            self._sm_count = torch.cuda.get_device_properties(self.device).multi_processor_count
-        ns = max(1, min(32, self._sm_count // max(1, B * self.cfg.text.num_key_value_heads)))
-        return l_max <= 128 * ns
-
     def _pick_token(self, st, sampling) -> None:
-        if sampling is None:
+        if st.get("use_forced"):  # teacher forcing (parity tests): token of this step from a given [B, T] table
+            B = st["nxt"].shape[0]
+            st["nxt"].copy_(st["forced"].gather(1, st["step"].long().view(1, 1).expand(B, 1)).view(B))
+        elif sampling is None:
             lib.argmax_rows(st["logits"], out=st["nxt"])
         else:  # (temperature, top_k, top_p): uniforms[b, step] drive the inverse-CDF pick
             lib.sample_topk_topp(st["logits"], st["u"], sampling[0], sampling[1], sampling[2], step=st["step"], out=st["nxt"])
@@ -426,7 +420,7 @@ class Engine:
                            st["kv_len"], st["pos3"])
         cos, sin = lib.mrope_table(st["pos3"], self.txt_inv_freq, t.mrope_section)
         lib.embed_scatter(self.w.embed, st["nxt"], None, None, out=st["x"])
-        if "ws" in st and self.use_persistent_decode and self._persistent_single_pass(st["x"].shape[0], cache.l_max):
+        if "ws" in st and self.use_persistent_decode:
             if self._layer_table is None:
                 self._layer_table = lib.decode_layer_table(self.w.layers, self.device)
             lib.decode_step_persistent(self._layer_table, self.w.lm_head_p, self.w.final_norm, t.vocab_size, st["x"], st["qkv"],
@@ -438,12 +432,15 @@ class Engine:
         self.final_logits(xo, torch.float32, out=st["logits"])
 
     def generate_greedy(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens: int,
-                        return_logits: bool = False, use_graph: Optional[bool] = None, sampling=None, uniforms=None):
+                        return_logits: bool = False, use_graph: Optional[bool] = None, sampling=None, uniforms=None,
+                        forced_tokens: Optional[torch.Tensor] = None):
         """Greedy decode, EOS ignored, fixed ``max_new_tokens``.  Response positions continue from the
         last prompt position + 1 on all three axes (roll/utils/functionals.py:838-852).  The decode step is captured
         once per (batch, cache) into a CUDA graph and replayed (launch-bound loop, ~300 kernels per token).
         ``sampling`` = (temperature, top_k, top_p) switches the per-step pick from argmax to the reference's sampling
         config; ``uniforms`` [B, T] in [0,1) are the random numbers consumed (one per sample and step).
+        ``forced_tokens`` [B, T] (teacher forcing, parity tests): step t appends forced_tokens[:, t] instead of its own pick, so
+        the logits of every step are comparable with an oracle that was fed the same tokens.
         Returns new tokens [B, T] (int64, device) and optionally fp32 logits [B, T, V]."""
         t = self.cfg.text
         T = max_new_tokens
@@ -462,6 +459,10 @@ class Engine:
         V = t.vocab_size
         st = self._decode_state(B, T)
         st["step"].zero_()
+        st["use_forced"] = forced_tokens is not None
+        if forced_tokens is not None:
+            assert tuple(forced_tokens.shape) == (B, T)
+            st["forced"].copy_(forced_tokens.to(self.device, torch.int64), non_blocking=True)
         if sampling is not None:
             sampling = (float(sampling[0]), int(sampling[1]), float(sampling[2]))
             assert uniforms is not None and tuple(uniforms.shape) == (B, T)
@@ -475,7 +476,7 @@ class Engine:
         if use_graph is None:
             use_graph = self.use_cuda_graph and not return_logits and lib.timeline is None
         if use_graph and T > 1:
-            gkey = (B, T, l_max, sampling, self.use_persistent_decode)
+            gkey = (B, T, l_max, sampling, self.use_persistent_decode, forced_tokens is not None)
             g = self._graphs.get(gkey)
             if g is None:
                 # warm-up outside capture (buffer allocation, function attributes), then restore the state it advanced

@@ -55,11 +55,9 @@ SYMBOLS = {
     "sr_lmhead_logprob_workspace_bytes": (c_int64, [c_int, c_int]),
     "sr_lmhead_logprob_entropy": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sr_decode_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
-    "sr_decode_persistent_workspace_bytes": (c_int64, [c_int, c_int]),
-    "sr_set_decode_persistent_coop": (c_int, [c_int]),
+    "sr_decode_persistent_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "sr_set_decode_persistent_trace": (c_int, [_P, c_int]),
-    "sr_set_decode_persistent_tuning": (c_int, [c_int, c_int]),
-    "sr_set_decode_persistent_offsets": (c_int, [c_int, c_int, c_int, c_int]),
+    "sr_set_decode_persistent_tuning": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "sr_decode_step_persistent": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P,
                                           c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
@@ -395,8 +393,18 @@ def decode_layer_table(layers, device) -> torch.Tensor:
     return torch.tensor(rows, dtype=torch.int64).to(device)
 
 
-def decode_persistent_workspace(batch: int, n_kv_heads: int, device) -> torch.Tensor:
-    return torch.zeros((load().sr_decode_persistent_workspace_bytes(batch, n_kv_heads),), dtype=torch.uint8, device=device)
+def decode_persistent_workspace(n_q_heads: int, n_kv_heads: int, intermediate: int, device) -> torch.Tensor:
+    """Zeroed workspace of ``decode_step_persistent`` (generation counter + flag-carrying exchange buffers, ~5 MB)."""
+    return torch.zeros((load().sr_decode_persistent_workspace_bytes(n_q_heads, n_kv_heads, intermediate),), dtype=torch.uint8,
+                       device=device)
+
+
+def decode_persistent_tuning(flags: int = -1, ring_stages: int = 0, pf_stages: int = -1, offsets=None) -> None:
+    """flags bit 0 = evict_first hint on the weight stream, bit 1 = dump plain intermediates (x / qkv / ao / act) for tests,
+    bit 4 = K/V L2 prefetch; pf_stages = look-ahead of the L2 prefetcher warp (16 KB stages per CTA)."""
+    o = offsets if offsets is not None else (-1, -1, -1, -1)
+    _check(load().sr_set_decode_persistent_tuning(int(flags), int(ring_stages), int(pf_stages), *[int(v) for v in o]),
+           "sr_set_decode_persistent_tuning")
 
 
 def decode_step_persistent(layer_table: torch.Tensor, lm_head_p: torch.Tensor, final_norm: torch.Tensor, vocab: int,
@@ -406,8 +414,10 @@ def decode_step_persistent(layer_table: torch.Tensor, lm_head_p: torch.Tensor, f
                            intermediate: int, eps: float, scale: float, workspace: torch.Tensor, stop_after: int = 0,
                            kv_tokens: Optional[int] = None) -> torch.Tensor:
     """One whole decode step (all layers + LM head) in one persistent launch.  kc [L, rows, n_kv, 128], vt [L, n_kv*128, rows];
-    x [B, 2048] is updated in place; logits fp32 [B, vocab].  ``kv_tokens`` (sum of the live sequences' cached tokens, host-side)
-    only feeds the bench timeline: algorithmic bytes = every weight once + the K and V rows of the live sequences."""
+    x [B, 2048] = the embedded input tokens (read only); logits fp32 [B, vocab].  qkv / ao / act may be None: they (and x) only
+    receive plain dumps of the intermediates after ``decode_persistent_tuning(flags=3)`` (tests / bring-up).  ``kv_tokens`` (sum of
+    the live sequences' cached tokens, host-side) only feeds the bench timeline: algorithmic bytes = every weight once + the K and
+    V rows of the live sequences."""
     global launch_count
     _req(x, torch.bfloat16, "decode_persistent.x"); _req(logits, torch.float32, "decode_persistent.logits")
     _req(kc, torch.bfloat16, "decode_persistent.kc"); _req(vt, torch.bfloat16, "decode_persistent.vt")
@@ -415,8 +425,10 @@ def decode_step_persistent(layer_table: torch.Tensor, lm_head_p: torch.Tensor, f
     _req(kv_len, torch.int32, "decode_persistent.kv_len"); _req(cos, torch.float32, "decode_persistent.cos")
     B = x.shape[0]
     assert kc.dim() == 4 and vt.dim() == 3 and kc.is_contiguous() and vt.is_contiguous() and layer_table.shape[1] == 7
-    assert qkv.is_contiguous() and ao.is_contiguous() and act.is_contiguous() and cos.is_contiguous() and sin.is_contiguous()
-    assert qkv.shape == (B, (n_q_heads + 2 * n_kv_heads) * 128) and ao.shape == (B, n_q_heads * 128) and act.shape == (B, intermediate)
+    assert cos.is_contiguous() and sin.is_contiguous()
+    if qkv is not None:
+        assert qkv.is_contiguous() and ao.is_contiguous() and act.is_contiguous()
+        assert qkv.shape == (B, (n_q_heads + 2 * n_kv_heads) * 128) and ao.shape == (B, n_q_heads * 128) and act.shape == (B, intermediate)
     n_layers, H = int(layer_table.shape[0]), n_q_heads * 128
     work = 2.0 * (n_layers * ((n_q_heads + 2 * n_kv_heads) * 128 * H + H * H + 3 * intermediate * H) + vocab * H)
     work += 2.0 * n_layers * (kv_tokens if kv_tokens is not None else 0) * 2 * n_kv_heads * 128
@@ -432,7 +444,7 @@ def _decode_persistent_call(layer_table, lm_head_p, final_norm, vocab, x, qkv, a
                             kc, vt, B, n_q_heads, n_kv_heads, intermediate, eps, scale, workspace, stop_after) -> int:
     return load().sr_decode_step_persistent(
         layer_table.data_ptr(), layer_table.shape[0], lm_head_p.data_ptr(), final_norm.data_ptr(), vocab, x.data_ptr(), x.stride(0),
-        qkv.data_ptr(), ao.data_ptr(), act.data_ptr(), logits.data_ptr(), logits.stride(0), cos.data_ptr(), sin.data_ptr(),
+        _ptr(qkv), _ptr(ao), _ptr(act), logits.data_ptr(), logits.stride(0), cos.data_ptr(), sin.data_ptr(),
         cache_row.data_ptr(), kv_start.data_ptr(), kv_len.data_ptr(), kc.data_ptr(), kc.stride(0), vt.data_ptr(), vt.stride(0),
         vt.stride(1), B, n_q_heads, n_kv_heads, intermediate, float(eps), float(scale), workspace.data_ptr(), int(stop_after), _stream())
 

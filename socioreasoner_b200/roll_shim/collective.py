@@ -1,7 +1,13 @@
 """Named collective groups for the train -> infer weight broadcast (the reference's ``roll/utils/collective/collective.py``
 as used by ``worker_helper.py:64-102``): a group is created from (world_size, rank, master_addr, master_port) independently
 of the default ``torch.distributed`` world -- the sender (rank 0 = the train worker holding the weights) and the rollout
-workers do not share a default process group.  NCCL over NVLink on the GPUs; gloo on CPU (tests)."""
+workers do not share a default process group.  NCCL over NVLink on the GPUs; gloo on CPU (tests).
+
+Wire compatibility: the UNMODIFIED reference sender builds its side with ``init_custom_process_group``
+(``roll/utils/collective/pg_utils.py:10-77``): a ``tcp://`` rendezvous, then ``PrefixStore(group_name, store)``, then torch's
+``_new_process_group_helper(..., group_name=group_name)``.  The keys under which the ncclUniqueId / gloo addresses are exchanged
+are derived from that prefix and that group name, so this side goes through the very same torch entry points with the same
+arguments (``tests/test_weight_sync.py::test_group_rendezvous_with_reference_sender`` pairs the two)."""
 from __future__ import annotations
 
 from datetime import timedelta
@@ -15,20 +21,21 @@ _groups: Dict[str, object] = {}
 
 def init_collective_group(world_size: int, rank: int, backend: str = "nccl", group_name: str = "default",
                           master_addr: str = "127.0.0.1", master_port: int = 29600, timeout_s: float = 600.0):
-    """Rendezvous through a TCP store at master_addr:master_port (rank 0 hosts it) and build a stand-alone backend."""
+    from torch.distributed import distributed_c10d as c10d
+
+    if not group_name:
+        raise ValueError(f"group_name {group_name!r} needs to be a non-empty string")
     if group_name in _groups:
         raise RuntimeError(f"collective group {group_name!r} already exists")
+    assert 0 <= rank < world_size
     timeout = timedelta(seconds=timeout_s)
-    store = dist.TCPStore(master_addr, int(master_port), world_size, is_master=(rank == 0), timeout=timeout, wait_for_workers=True)
-    store = dist.PrefixStore(f"sr_group/{group_name}", store)
-    if backend == "gloo":
-        pg = dist.ProcessGroupGloo(store, rank, world_size, timeout=timeout)
-    elif backend == "nccl":
-        opts = dist.ProcessGroupNCCL.Options()
-        opts._timeout = timeout
-        pg = dist.ProcessGroupNCCL(store, rank, world_size, opts)
-    else:
-        raise ValueError(f"unsupported backend {backend!r}")
+    store, rank, world_size = next(c10d.rendezvous(f"tcp://{master_addr}:{int(master_port)}", rank, world_size, timeout=timeout))
+    store.set_timeout(timeout)
+    store = c10d.PrefixStore(group_name, store)
+    opt_name = "backend_options" if tuple(int(v) for v in torch.__version__.split("+")[0].split(".")[:2]) >= (2, 6) else "pg_options"
+    pg, _ = c10d._new_process_group_helper(world_size, rank, [], c10d.Backend(backend), store, group_name=group_name,
+                                           timeout=timeout, **{opt_name: None})
+    c10d._world.pg_group_ranks[pg] = {i: i for i in range(world_size)}  # group rank == "global" rank inside this stand-alone group
     _groups[group_name] = pg
     return pg
 
@@ -42,11 +49,8 @@ def destroy_collective_group(group_name: str) -> None:
 
 
 def broadcast(tensor: torch.Tensor, src_rank: int = 0, group_name: str = "default") -> None:
-    opts = dist.BroadcastOptions()
-    opts.rootRank = src_rank
-    opts.rootTensor = 0
-    _groups[group_name].broadcast([tensor], opts).wait()
+    dist.broadcast(tensor, src=src_rank, group=_groups[group_name])
 
 
 def allreduce(tensor: torch.Tensor, group_name: str = "default") -> None:
-    _groups[group_name].allreduce([tensor], dist.AllreduceOptions()).wait()
+    dist.all_reduce(tensor, group=_groups[group_name])

@@ -47,3 +47,17 @@ def tiny_batch():
     from oracle import hf_oracle as O
 
     return O.make_batch([0, 1], [224, 336], "tiny", n_text=8)
+
+
+@pytest.fixture(scope="session")
+def model_3b():
+    """Full-depth 3B geometry on the GPU, weights from the seeded HF init (CPU build, ~2 min) -- shared by the 3B golden tests."""
+    import torch
+    from oracle import hf_oracle as O
+    from socioreasoner_b200.modeling import SocioReasonerB200ForConditionalGeneration as Model
+
+    torch.set_num_threads(os.cpu_count())
+    hf = O.build_model("3b")
+    model = Model.from_hf_model(hf, device="cuda")
+    del hf
+    return model

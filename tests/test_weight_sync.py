@@ -158,6 +158,55 @@ def test_broadcast_bucket_and_parameter_world2_gloo():
     assert res == {"sender": "ok", "receiver": "ok"}
 
 
+REF_PG_UTILS = "/root/reference/roll/utils/collective/pg_utils.py"
+
+
+def _ref_pair_worker(rank, port, q, done):
+    """rank 0 = the UNMODIFIED reference sender side (pg_utils.init_custom_process_group, a torch-only file loaded from the
+    reference checkout), rank 1 = this repo's receiver strategy.  They must meet in the same named group."""
+    import importlib.util
+    import torch.distributed as dist
+    named = _named(seed=9)
+    plan = {0: dict(group_name="model_update_ref_pair", master_addr="127.0.0.1", master_port=port, src_pp_rank=0,
+                    tgt_devices=[dict(rank=3, device=dict(rank=0))])}
+    if rank == 0:
+        spec = importlib.util.spec_from_file_location("ref_pg_utils", REF_PG_UTILS)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        pg = mod.init_custom_process_group(backend="gloo", init_method=f"tcp://127.0.0.1:{port}", world_size=2, rank=0,
+                                           group_name="model_update_ref_pair")      # collective.py:24-32 of the reference
+        dist.all_reduce(torch.zeros(1), group=pg)                                  # megatron_strategy.py warm-up
+        for _, t in named:
+            dist.broadcast(t, src=0, group=pg)                                     # collective.broadcast of the reference
+        q.put(("sender", "ok"))
+        done.wait(60)
+        return
+    st = B200InferStrategy(SimpleNamespace(worker_config=None, rank=3))
+    st.model = RecordingModel()
+    st.setup_collective_group(plan, backend="gloo")
+    for n, t in named:
+        st.broadcast_parameter(0, t.dtype, tuple(t.shape), n)
+    ok = all(torch.equal(st.model.got[n], t) for n, t in named)
+    q.put(("receiver", "ok" if ok else "mismatch"))
+    done.set()
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PG_UTILS), reason="reference checkout not present (GPU box)")
+def test_group_rendezvous_with_reference_sender():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29400 + (os.getpid() % 150)
+    done = ctx.Event()
+    procs = [ctx.Process(target=_ref_pair_worker, args=(r, port, q, done)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {"sender": "ok", "receiver": "ok"}
+
+
 def test_update_parameter_respects_ranks_in_worker():
     st = B200InferStrategy(SimpleNamespace(worker_config=None, rank=0))
     st.model = RecordingModel()

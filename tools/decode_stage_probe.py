@@ -33,13 +33,10 @@ def stage(tag):
     print(f"{tag:44s} vit+prefill {min(r['vit+prefill'] for r in res):7.2f} ms  decode {d:7.2f} ms = {d / (bench.NEW_TOKENS - 1):.3f} ms/token", flush=True)
 
 
-stage("graph replay, cooperative launch")
+stage("graph replay")
 eng.use_cuda_graph = False
-stage("eager launches, cooperative launch")
-lib.load().sr_set_decode_persistent_coop(0)
-stage("eager launches, plain launch")
+stage("eager launches")
 eng.use_cuda_graph = True
 eng._graphs.clear()
-stage("graph replay, plain launch")
 eng.set_persistent_decode(False)
 stage("per-layer kernels, graph replay")

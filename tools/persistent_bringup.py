@@ -1,6 +1,8 @@
-"""Bring-up / regression check of the persistent decode-step kernel (sr_decode_persistent.cu) against the per-layer decode
-kernels, phase by phase (stop_after), then a whole step, CUDA-graph replay and timing at the 3B geometry.
-Synthetic packed weights (both paths read the same packed tensors).  Usage: python tools/persistent_bringup.py [layers] [vocab]"""
+"""Bring-up / regression check of the persistent decode-step kernel (sr_decode_persistent.cu) against a plain fp32 torch
+restatement of one decode step (HF:762-827 with use_cache, M-RoPE per mcore_adapter/.../modeling_qwen2_5_vl.py:21-41; bf16
+rounding at the points where the kernel stores bf16) AND against the per-layer decode kernels, phase by phase (stop_after),
+then a whole step, CUDA-graph replay and timing at the 3B geometry.  Synthetic packed weights (all paths read the same packed
+tensors).  Usage: python tools/persistent_bringup.py [layers] [vocab]"""
 import os
 import sys
 import time
@@ -56,6 +58,67 @@ class State:
         self.vocab = vocab
 
 
+def unpack(wp, n, k):
+    """[N/16][K/32][16][32] streaming layout -> [N, K] fp32."""
+    return wp.permute(0, 2, 1, 3).reshape(n, k).float()
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def reference_step_torch(S, layers):
+    """fp32 torch restatement of the step (the parity reference of the GPU tests)."""
+    B = S.B
+    x = S.x0.float()
+    kc, vt = S.kc0.clone(), S.vt0.clone()
+    cos, sin = S.cos.float(), S.sin.float()            # [B, 64]
+    inter = {}
+
+    def norm(v, w):
+        return _bf(v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + 1e-6) * w)
+
+    def rope(t):                                       # [B, heads, 128]
+        x1, x2 = t[..., :64], t[..., 64:]
+        c, s_ = cos[:, None, :], sin[:, None, :]
+        return _bf(torch.cat([x1 * c - x2 * s_, x2 * c + x1 * s_], -1))
+
+    for li, L in enumerate(layers):
+        qkv = _bf(norm(x, L.ln1) @ unpack(L.qkv_wp, QKV, H).T + L.qkv_b)
+        if li == 0:
+            inter["qkv"] = qkv.clone()
+        q = rope(qkv[:, :NQ * HD].view(B, NQ, HD))
+        k = rope(qkv[:, NQ * HD:(NQ + NKV) * HD].view(B, NKV, HD))
+        v = qkv[:, (NQ + NKV) * HD:].view(B, NKV, HD)
+        ao = torch.zeros(B, NQ, HD, device=dev)
+        for b in range(B):
+            row, st, ln = int(S.cache_row[b]), int(S.kv_start[b]), int(S.kv_len[b])
+            kc[li][row] = k[b].to(torch.bfloat16)
+            vt[li][:, row] = v[b].reshape(-1).to(torch.bfloat16)
+            for kvh in range(NKV):
+                keys = kc[li][st:st + ln, kvh].float()                            # [len, 128]
+                vals = vt[li][kvh * HD:(kvh + 1) * HD, st:st + ln].float()       # [128, len]
+                qh = q[b, kvh * (NQ // NKV):(kvh + 1) * (NQ // NKV)]              # [8, 128]
+                pr = torch.softmax(qh @ keys.T * HD ** -0.5, -1)
+                ao[b, kvh * (NQ // NKV):(kvh + 1) * (NQ // NKV)] = pr @ vals.T
+        ao = _bf(ao.view(B, H))
+        if li == 0:
+            inter["ao"] = ao.clone()
+        x = _bf(x + ao @ unpack(L.o_wp, H, H).T)
+        if li == 0:
+            inter["x_o"] = x.clone()
+        gu = (norm(x, L.ln2) @ unpack(L.gu_wp, 2 * I, H).T).view(B, I // 16, 2, 16)
+        act = _bf((torch.nn.functional.silu(gu[:, :, 0]) * gu[:, :, 1]).reshape(B, I))
+        if li == 0:
+            inter["act"] = act.clone()
+        x = _bf(x + act @ unpack(L.down_wp, H, I).T)
+        if li == 0:
+            inter["x_down"] = x.clone()
+    logits = norm(x, S.final_norm) @ unpack(S.lm_head_p, S.vocab, H).T
+    inter.update(x=x, logits=logits, kc=kc, vt=vt)
+    return inter
+
+
 def reference_step(S, layers, upto_layers=None):
     """Per-layer kernels (the path generate_greedy used before): returns intermediates of layer 0 and the final logits."""
     x = S.x0.clone()
@@ -97,7 +160,7 @@ class Persistent:
         self.ao = torch.zeros(B, H, device=dev, dtype=torch.bfloat16)
         self.act = torch.zeros(B, I, device=dev, dtype=torch.bfloat16)
         self.logits = torch.zeros(B, S.vocab, device=dev, dtype=torch.float32)
-        self.ws = lib.decode_persistent_workspace(B, NKV, dev)
+        self.ws = lib.decode_persistent_workspace(NQ, NKV, I, dev)
         self.x = S.x0.clone()
         self.kc, self.vt = S.kc0.clone(), S.vt0.clone()
 
@@ -118,10 +181,12 @@ def check_case(B, n_layers, lens, vocab, l_max=1024, phases=True):
     torch.manual_seed(0)
     layers = make_layers(n_layers)
     S = State(B, n_layers, l_max, lens, vocab)
-    ref = reference_step(S, layers)
+    lib.decode_persistent_tuning(flags=3)  # dump plain intermediates (x / qkv / ao / act) next to the LL buffers
+    ref = reference_step_torch(S, layers)
+    ref_k = reference_step(S, layers)
     torch.cuda.synchronize()
+    ok = err("per-layer kernels vs torch fp32: logits", ref_k["logits"], ref["logits"])
     P = Persistent(S, layers)
-    ok = True
     if phases:
         for k, (name, got_fn, refkey) in enumerate([
                 ("phase1 qkv", lambda: P.qkv, "qkv"), ("phase2 attention out", lambda: P.ao, "ao"),
@@ -146,6 +211,9 @@ def check_case(B, n_layers, lens, vocab, l_max=1024, phases=True):
     # second run on the same object (barrier counter / tickets re-armed)
     P.reset(); P.run(0); torch.cuda.synchronize()
     ok &= err("full step again: logits", P.logits, ref["logits"])
+    lib.decode_persistent_tuning(flags=1)
+    P.reset(); P.run(0); torch.cuda.synchronize()
+    ok &= err("full step without dumps: logits", P.logits, ref["logits"])
     return ok, S, layers, P, ref
 
 
@@ -155,17 +223,8 @@ def graph_check(P, ref):
     g = torch.cuda.CUDAGraph()
     P.reset()
     torch.cuda.synchronize()
-    try:
-        with torch.cuda.graph(g):
-            P.run(0)
-    except Exception as e:  # noqa: BLE001
-        print("  capture with cooperative launch failed:", repr(e)[:300], flush=True)
-        lib.load().sr_set_decode_persistent_coop(0)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            P.run(0)
-        print("  captured with plain launch (SR_DECODE_COOP=0)", flush=True)
+    with torch.cuda.graph(g):
+        P.run(0)
     P.reset()
     g.replay(); torch.cuda.synchronize()
     ok = err("graph replay: logits", P.logits, ref["logits"])
@@ -259,9 +318,9 @@ if __name__ == "__main__":
     ok, *_ = check_case(3, 3, [300, 17, 1000], 4096, phases=False)
     all_ok &= ok
     del _
-    # contexts beyond 128 keys per split (multi-pass attention loop): not yet part of the pytest suite -- the engine keeps such
-    # contexts on the per-layer kernels (Engine._persistent_single_pass) until this case has been seen green on a B200
+    # contexts beyond 128 keys per split (multi-pass attention loop)
     ok, *_ = check_case(8, 2, [1500, 1400, 1300, 1200, 1153, 1152, 300, 1], 8192, l_max=1536, phases=False)
+    all_ok &= ok
     print(f"long-context (multi-pass) case: {'OK' if ok else 'MISMATCH'}", flush=True)
     torch.cuda.empty_cache()
     print(f"correctness: {'ALL OK' if all_ok else 'FAILURES'} ({time.time() - t0:.1f}s)", flush=True)

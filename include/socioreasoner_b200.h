@@ -237,6 +237,20 @@ int sr_decode_step_persistent(const void* layer_table, int n_layers, const void*
                               int64_t vt_layer_stride, int64_t ldvt, int batch, int n_q_heads, int n_kv_heads, int intermediate,
                               float norm_eps, float scale, void* workspace, int stop_after_phases, void* stream);
 
+/* ---- image preprocessing --------------------------------------------------------------------
+ * uint8 RGB tile [height, width, 3] (HWC, the PIL layout) -> pixel_values rows [N, 6 * patch^2] (N = out_height/patch * out_width/patch):
+ * PIL's 8-bit bicubic resize (process_image, roll/pipeline/rlvr/rlvr_socioseg_vlm_pipeline_infer.py:126-144) + the HF processor the
+ * collator calls (roll/datasets/collator.py:444-565 -> Qwen2VLImageProcessor: rescale, normalise, T = 2 duplicate, merge-block
+ * patchify), bit-exact with that CPU path.  h_/v_bounds int32 [out, 2] = (first input index, taps), h_/v_coeffs int32 [out, ksize]:
+ * PIL's 22-bit fixed-point tables for (width -> out_width) / (height -> out_height) (socioreasoner_b200.preprocess.pil_bicubic_coeffs);
+ * NULL when that axis keeps its size.  scratch: uint8 [height, out_width, 3] (only when the width changes).  mean3 / std3: HOST
+ * float[3], the processor's fused constants (mean * 255, std * 255 in fp32).  out_dtype SR_DTYPE_F32 | SR_DTYPE_BF16; row_map
+ * (optional, device int32 [N]): destination row of processor-order row r (lets the ViT's window permutation be applied here). */
+int sr_preprocess_tile(const uint8_t* image, int height, int width, int out_height, int out_width, const int32_t* h_bounds,
+                       const int32_t* h_coeffs, int h_ksize, const int32_t* v_bounds, const int32_t* v_coeffs, int v_ksize,
+                       uint8_t* scratch, const float* mean3, const float* std3, void* pixel_values, int out_dtype, int64_t ld_out,
+                       const int32_t* row_map, int patch_size, void* stream);
+
 /* ---- mask epilogue + IoU -------------------------------------------------------------------- */
 /* seg_strategy.py:47-65: per object pick argmax(scores) of 3 candidates, bilinear up-sample h x w -> image_size^2
  * (align_corners=False), > 0, OR over objects, cv2.INTER_NEAREST resize to out_size^2, uint8 {0,1}. */

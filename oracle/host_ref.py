@@ -318,3 +318,26 @@ def send_buckets(named_tensors, bucket_size: int, as_dict: bool = True):
     if meta is not None:
         emit(meta, buf)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# Image path in front of the ViT, exactly as the reference runs it on the CPU:
+#   process_image (roll/pipeline/rlvr/rlvr_socioseg_vlm_pipeline_infer.py:126-144): PIL resize to smart_resize(h, w) with the
+#   processor's resample (bicubic), THEN the HF processor (roll/datasets/collator.py:456-462), whose own resize is the identity
+#   on the pre-resized image.  Returns (pixel_values fp32 [sum N, 1176], image_grid_thw [n, 3], the resized uint8 images).
+# ----------------------------------------------------------------------------------------------
+def reference_image_path(images_hwc_uint8, min_pixels: int = 56 * 56, max_pixels: int = 768 * 768):
+    from PIL import Image
+    from transformers.models.qwen2_vl.image_processing_qwen2_vl import Qwen2VLImageProcessor, smart_resize
+
+    ip = Qwen2VLImageProcessor(min_pixels=min_pixels, max_pixels=max_pixels)
+    pvs, thws, resized = [], [], []
+    for a in images_hwc_uint8:
+        img = Image.fromarray(np.ascontiguousarray(a))
+        rh, rw = smart_resize(img.height, img.width, factor=28, min_pixels=min_pixels, max_pixels=max_pixels)
+        img = img.resize((rw, rh), resample=Image.BICUBIC)
+        resized.append(np.asarray(img))
+        out = ip(images=[img], return_tensors="pt")
+        pvs.append(out["pixel_values"])
+        thws.append(out["image_grid_thw"])
+    return torch.cat(pvs, 0), torch.cat(thws, 0), resized

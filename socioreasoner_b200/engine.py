@@ -378,6 +378,7 @@ class Engine:
                 pos3=torch.zeros((3, B), dtype=torch.int64, device=dev), kv_start=torch.zeros((B,), dtype=torch.int32, device=dev),
                 logits=torch.zeros((B, self.cfg.text.vocab_size), dtype=torch.float32, device=dev),
                 u=torch.zeros((B, T), dtype=torch.float32, device=dev), forced=torch.zeros((B, T), dtype=torch.int64, device=dev),
+                done=torch.zeros((B,), dtype=torch.bool, device=dev), eos=torch.full((16,), -1, dtype=torch.int64, device=dev),
                 x=torch.zeros((B, self.cfg.text.hidden_size), dtype=torch.bfloat16, device=dev),
             )
             if self._persistent_ok(B):
@@ -416,6 +417,8 @@ class Engine:
         final norm + LM head -> st['logits']."""
         t = self.cfg.text
         self._pick_token(st, sampling)
+        if st.get("track_eos"):  # a sequence is finished once it has emitted one of the stop ids (that token is still appended)
+            st["done"].logical_or_((st["nxt"].view(-1, 1) == st["eos"].view(1, -1)).any(1))
         lib.decode_advance(st["nxt"], st["tokens"], st["step"], st["row0"], st["len0"], st["pos0"], st["cache_row"],
                            st["kv_len"], st["pos3"])
         cos, sin = lib.mrope_table(st["pos3"], self.txt_inv_freq, t.mrope_section)
@@ -433,7 +436,8 @@ class Engine:
 
     def generate_greedy(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens: int,
                         return_logits: bool = False, use_graph: Optional[bool] = None, sampling=None, uniforms=None,
-                        forced_tokens: Optional[torch.Tensor] = None):
+                        forced_tokens: Optional[torch.Tensor] = None, eos_ids: Optional[Sequence[int]] = None, pad_id: int = 0,
+                        check_every: int = 16):
         """Greedy decode, EOS ignored, fixed ``max_new_tokens``.  Response positions continue from the
         last prompt position + 1 on all three axes (roll/utils/functionals.py:838-852).  The decode step is captured
         once per (batch, cache) into a CUDA graph and replayed (launch-bound loop, ~300 kernels per token).
@@ -441,6 +445,10 @@ class Engine:
         config; ``uniforms`` [B, T] in [0,1) are the random numbers consumed (one per sample and step).
         ``forced_tokens`` [B, T] (teacher forcing, parity tests): step t appends forced_tokens[:, t] instead of its own pick, so
         the logits of every step are comparable with an oracle that was fed the same tokens.
+        ``eos_ids`` (the reference's stop ids, vllm_strategy.py:289-309): a sequence is finished after emitting one of them; a
+        device-side flag is read back every ``check_every`` steps and the loop ends as soon as every sequence has finished (at the
+        reference's 2048-token cap a fixed-length loop would decode for seconds after the last stop).  Positions after a sequence's
+        stop token, and steps that never ran, hold ``pad_id``.
         Returns new tokens [B, T] (int64, device) and optionally fp32 logits [B, T, V]."""
         t = self.cfg.text
         T = max_new_tokens
@@ -460,6 +468,13 @@ class Engine:
         st = self._decode_state(B, T)
         st["step"].zero_()
         st["use_forced"] = forced_tokens is not None
+        st["track_eos"] = eos_ids is not None and len(eos_ids) > 0
+        if st["track_eos"]:
+            assert len(eos_ids) <= 16, "at most 16 stop ids"
+            st["eos"].fill_(-1)
+            st["eos"][:len(eos_ids)].copy_(torch.tensor(list(eos_ids), dtype=torch.int64), non_blocking=True)
+            st["done"].zero_()
+            st["tokens"].fill_(int(pad_id))
         if forced_tokens is not None:
             assert tuple(forced_tokens.shape) == (B, T)
             st["forced"].copy_(forced_tokens.to(self.device, torch.int64), non_blocking=True)
@@ -473,10 +488,11 @@ class Engine:
         st["pos0"].copy_(torch.from_numpy(sp.last_pos.astype(np.int64)), non_blocking=True)
         self.final_logits(self.last_token_rows(x, sp), torch.float32, out=st["logits"])
         all_logits = torch.empty((B, T, V), dtype=torch.float32, device=self.device) if return_logits else None
+        stopped = False
         if use_graph is None:
             use_graph = self.use_cuda_graph and not return_logits and lib.timeline is None
         if use_graph and T > 1:
-            gkey = (B, T, l_max, sampling, self.use_persistent_decode, forced_tokens is not None)
+            gkey = (B, T, l_max, sampling, self.use_persistent_decode, forced_tokens is not None, st["track_eos"])
             g = self._graphs.get(gkey)
             if g is None:
                 # warm-up outside capture (buffer allocation, function attributes), then restore the state it advanced
@@ -496,9 +512,14 @@ class Engine:
                 lib.launch_count = l0  # capture launches nothing
                 st["logits"].copy_(keep["logits"]); st["step"].copy_(keep["step"])
                 self._graphs[gkey] = g
-            for _ in range(T - 1):
+            n_run = 0
+            for i in range(T - 1):
                 g.replay()
-            lib.launch_count += (T - 1) * self._decode_launches
+                n_run += 1
+                if st["track_eos"] and (i + 1) % check_every == 0 and bool(st["done"].all().item()):
+                    stopped = True
+                    break
+            lib.launch_count += n_run * self._decode_launches
         else:
             for step in range(T - 1):
                 if return_logits:
@@ -506,16 +527,23 @@ class Engine:
                 l0 = lib.launch_count
                 self._decode_step(st, cache, sampling, kv_tokens=int(sp.lengths.sum()) + B * (step + 1))
                 self._decode_launches = lib.launch_count - l0
-        if return_logits:
+                if st["track_eos"] and (step + 1) % check_every == 0 and bool(st["done"].all().item()):
+                    stopped = True
+                    break
+        if return_logits and not stopped:
             all_logits[:, T - 1] = st["logits"]
-        # the last token: pick + append (no further forward needed)
-        self._pick_token(st, sampling)
-        lib.decode_advance(st["nxt"], st["tokens"], st["step"], st["row0"], st["len0"], st["pos0"], st["cache_row"],
-                           st["kv_len"], st["pos3"])
+        if not stopped:  # the last token: pick + append (no further forward needed)
+            self._pick_token(st, sampling)
+            lib.decode_advance(st["nxt"], st["tokens"], st["step"], st["row0"], st["len0"], st["pos0"], st["cache_row"],
+                               st["kv_len"], st["pos3"])
         cache.lengths = sp.lengths + T - 1
         if ev is not None:
             ev.append(("decode", self._event()))
         tokens = st["tokens"].clone()
+        if st["track_eos"]:  # everything after a sequence's first stop id is padding
+            is_eos = (tokens.unsqueeze(-1) == st["eos"].view(1, 1, -1)).any(-1)
+            after = (is_eos.cumsum(1) - is_eos.long()) > 0
+            tokens = torch.where(after, torch.full_like(tokens, int(pad_id)), tokens)
         return (tokens, all_logits) if return_logits else tokens
 
     # ------------------------------------------------------------------ mask epilogue

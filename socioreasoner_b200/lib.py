@@ -61,6 +61,8 @@ SYMBOLS = {
     "sr_decode_step_persistent": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P,
                                           c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "sr_preprocess_tile": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, _P, c_int, c_int64, _P,
+                                   c_int, _P]),
     "sr_mask_iou": (c_int, [_P, _P, c_int, c_int64, c_float, _P, _P, _P]),
 }
 
@@ -495,6 +497,26 @@ def lm_head_logprob_entropy(h: torch.Tensor, w: torch.Tensor, labels: torch.Tens
     _check(rc, "sr_lmhead_logprob_entropy")
     launch_count += 2
     return lp, ent
+
+
+def preprocess_tile(image_hwc_u8: torch.Tensor, out_h: int, out_w: int, h_tab, v_tab, scratch: Optional[torch.Tensor], mean3, std3,
+                    out: torch.Tensor, row_map: Optional[torch.Tensor] = None, patch_size: int = 14) -> torch.Tensor:
+    """uint8 [H, W, 3] device tile -> rows of ``out`` ([N, 6 * patch^2], fp32 or bf16).  h_tab / v_tab = (bounds, coeffs) device int32
+    tensors (None when that axis keeps its size); mean3 / std3 = host float32[3] (``preprocess.normalize_constants``)."""
+    global launch_count
+    _req(image_hwc_u8, torch.uint8, "preprocess.image")
+    H, W, C = image_hwc_u8.shape
+    assert C == 3 and image_hwc_u8.is_contiguous() and out.stride(1) == 1 and out.dtype in (torch.float32, torch.bfloat16)
+    hb, hk = h_tab if h_tab is not None else (None, None)
+    vb, vk = v_tab if v_tab is not None else (None, None)
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean3])
+    d = (ctypes.c_float * 3)(*[float(v) for v in std3])
+    _check(load().sr_preprocess_tile(image_hwc_u8.data_ptr(), H, W, out_h, out_w, _ptr(hb), _ptr(hk), hk.shape[1] if hk is not None else 0,
+                                     _ptr(vb), _ptr(vk), vk.shape[1] if vk is not None else 0, _ptr(scratch), ctypes.addressof(m),
+                                     ctypes.addressof(d), out.data_ptr(), 1 if out.dtype == torch.float32 else 0,
+                                     out.stride(0), _ptr(row_map), patch_size, _stream()), "sr_preprocess_tile")
+    launch_count += 1 + (1 if hk is not None else 0)
+    return out
 
 
 def mask_epilogue(low_res_logits: torch.Tensor, scores: torch.Tensor, image_size: int = 756, out_size: int = 768,

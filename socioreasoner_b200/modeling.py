@@ -151,10 +151,16 @@ class SocioReasonerB200ForConditionalGeneration:
         """Returns [b * num_return_sequences, S_in + max_new_tokens] like HF generate (prompt included).
         ``do_sample=False`` (or temperature 0 / top_k 1): greedy.  ``do_sample=True``: temperature -> top-k -> top-p sampling
         on the device (the reference's rollout config is T=1, top-p 0.8, top-k 100, examples/infer/rlvr_megatron.yaml:89-95);
-        1 <= top_k <= 1024 (top_k 0 = "disabled" is mapped to 1024).  ``num_return_sequences`` > 1 with sampling draws
-        independent continuations (the prompt batch is repeated, as HF does)."""
+        the device sampler keeps at most 1024 candidates: ``top_k`` 0 / None ("disabled" in HF) or > 1024 raises a warning and runs
+        with 1024 (with top-p < 1 the tail beyond 1024 candidates carries negligible mass, but it is not the same distribution).
+        ``num_return_sequences`` > 1 with sampling draws independent continuations (the prompt batch is repeated, as HF does).
+        Decoding stops as soon as every sequence has emitted a stop id (checked on the device, read back every 16 steps)."""
         if num_beams != 1 or repetition_penalty != 1.0:
             raise NotImplementedError("beam search / repetition penalty are not on the SocioSeg path")
+        eos = None
+        if not ignore_eos and eos_token_id is not None:
+            eos = [int(eos_token_id)] if isinstance(eos_token_id, int) else [int(e) for e in eos_token_id]
+        pad = int(pad_token_id) if pad_token_id is not None else (eos[0] if eos else 0)
         sample = do_sample and not (temperature == 0 or top_k == 1)
         if sample:
             n = num_return_sequences
@@ -171,21 +177,17 @@ class SocioReasonerB200ForConditionalGeneration:
             g = torch.Generator(device=self.device)
             g.manual_seed(int(seed) if seed is not None else int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
             u = torch.rand((ids_r.shape[0], max_new_tokens), generator=g, device=self.device, dtype=torch.float32)
+            if top_k in (0, None) or int(top_k) > 1024:
+                import warnings
+                warnings.warn(f"top_k={top_k} is outside the device sampler's range: sampling from the 1024 most likely tokens", stacklevel=2)
             k = 1024 if top_k in (0, None) else min(int(top_k), 1024)
             new = self.engine.generate_greedy(ids_r, mask_r, pos_r, pixel_values, image_grid_thw, max_new_tokens,
-                                              sampling=(float(temperature), k, float(top_p)), uniforms=u)
+                                              sampling=(float(temperature), k, float(top_p)), uniforms=u, eos_ids=eos, pad_id=pad)
             input_ids, num_return_sequences = ids_r, 1
         else:
-            new = self.engine.generate_greedy(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens)
+            new = self.engine.generate_greedy(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens,
+                                              eos_ids=eos, pad_id=pad)
         new = new.to(input_ids.device)
-        if not ignore_eos and eos_token_id is not None:
-            eos = [eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id)
-            pad = pad_token_id if pad_token_id is not None else eos[0]
-            is_eos = torch.zeros_like(new, dtype=torch.bool)
-            for e in eos:
-                is_eos |= new == e
-            after = (is_eos.cumsum(1) - is_eos.long()) > 0  # strictly after the first EOS
-            new = torch.where(after, torch.full_like(new, pad), new)
         out = torch.cat([input_ids, new], dim=1)
         if num_return_sequences > 1:
             out = out.repeat_interleave(num_return_sequences, dim=0)

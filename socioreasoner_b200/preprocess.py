@@ -92,3 +92,121 @@ def left_pad(prompts: List[torch.Tensor], pad_token_id: int = 151643, pad_to: in
         ids[b, S - len(p):] = p
         mask[b, S - len(p):] = 1
     return ids, mask
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# GPU preprocessing: uint8 tile -> pixel_values rows, bit-exact with what the reference's workers receive.
+# The reference resizes on the driver with PIL (``process_image``, rlvr_socioseg_vlm_pipeline_infer.py:126-144:
+# ``image.resize((w, h), resample=BICUBIC)``) and then calls the HF processor, whose own resize is then the identity.  PIL's
+# 8-bit resampler (libImaging/Resample.c, Pillow >= 7) is integer arithmetic on double-precision coefficient tables: the tables
+# are restated here on the host (one small table per (in, out) size pair, cached); the two integer passes, the 1/255 rescale,
+# the normalisation, the T = 2 frame duplication and the merge-block patch layout run in ``sr_preprocess_tile`` on the device.
+# ----------------------------------------------------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2
+IMAGE_MEAN = (0.48145466, 0.4578275, 0.40821073)
+IMAGE_STD = (0.26862954, 0.26130258, 0.27577711)
+_coeff_cache = {}
+
+
+def _bicubic(x: np.ndarray) -> np.ndarray:
+    """Pillow's bicubic kernel (a = -0.5), evaluated in float64 in the same operation order as Resample.c."""
+    a = -0.5
+    x = np.abs(x)
+    near = ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    far = (((x - 5) * x + 8) * x - 4) * a
+    return np.where(x < 1.0, near, np.where(x < 2.0, far, 0.0))
+
+
+def pil_bicubic_coeffs(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Pillow's ``precompute_coeffs`` + ``normalize_coeffs_8bpc`` for the bicubic filter (support 2) over the whole axis:
+    returns (bounds int32 [out, 2] = (first input index, tap count), coeffs int32 [out, ksize] in 22-bit fixed point)."""
+    key = (in_size, out_size)
+    if key in _coeff_cache:
+        return _coeff_cache[key]
+    scale = np.float64(np.float32(in_size) - np.float32(0.0)) / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    kk = np.zeros((out_size, ksize), dtype=np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = _bicubic((np.arange(xmax, dtype=np.float64) + xmin - center + 0.5) * ss)
+        ww = 0.0
+        for v in w:             # sequential sum, as the C loop
+            ww += v
+        if ww != 0.0:
+            w = w / ww
+        fx = w * float(1 << PIL_PRECISION_BITS)
+        kk[xx, :xmax] = np.where(w < 0, np.trunc(-0.5 + fx), np.trunc(0.5 + fx)).astype(np.int32)
+        bounds[xx] = (xmin, xmax)
+    _coeff_cache[key] = (bounds, kk)
+    return bounds, kk
+
+
+def normalize_constants() -> Tuple[np.ndarray, np.ndarray]:
+    """The fused rescale + normalise of the HF processor backend (``_fuse_mean_std_and_rescale_factor`` + torchvision
+    ``normalize``): pixel = (float(u8) - mean_s) / std_s in fp32, with mean_s = fp32(mean) * fp32(1 / rescale_factor) and std_s
+    likewise (fp32 products, rescale_factor = 1/255).  Verified bit-exact against the processor in tests/test_preprocess.py."""
+    inv = np.float32(1.0 / (1.0 / 255))
+    mean = np.array([np.float32(m) * inv for m in IMAGE_MEAN], dtype=np.float32)
+    std = np.array([np.float32(v) * inv for v in IMAGE_STD], dtype=np.float32)
+    return mean, std
+
+
+class GpuPreprocessor:
+    """uint8 tiles -> ``pixel_values`` / ``image_grid_thw`` on the device (``sr_preprocess_tile``), bit-exact with PIL resize +
+    HF processor.  Coefficient tables are built once per (in, out) size pair and kept on the device."""
+
+    def __init__(self, device="cuda", min_pixels: int = 56 * 56, max_pixels: int = REFERENCE_MAX_PIXELS, patch_size: int = 14,
+                 merge_size: int = 2):
+        self.device = torch.device(device)
+        self.min_pixels, self.max_pixels, self.patch, self.merge = min_pixels, max_pixels, patch_size, merge_size
+        self.mean, self.std = normalize_constants()
+        self._tabs = {}
+        self._scratch = None
+
+    def _tab(self, n_in: int, n_out: int):
+        if n_in == n_out:
+            return None
+        key = (n_in, n_out)
+        if key not in self._tabs:
+            b, k = pil_bicubic_coeffs(n_in, n_out)
+            self._tabs[key] = (torch.from_numpy(b).to(self.device), torch.from_numpy(np.ascontiguousarray(k)).to(self.device))
+        return self._tabs[key]
+
+    def target_size(self, h: int, w: int) -> Tuple[int, int]:
+        return smart_resize(h, w, factor=self.patch * self.merge, min_pixels=self.min_pixels, max_pixels=self.max_pixels)
+
+    def __call__(self, tiles, out_dtype=torch.float32, out: torch.Tensor = None, row_maps=None):
+        """tiles: sequence of uint8 [H, W, 3] tensors / arrays (host or device; host tensors are copied, pinned ones asynchronously).
+        Returns (pixel_values [sum N, 1176], image_grid_thw int64 [n, 3] (host))."""
+        from . import lib
+
+        sizes, grids = [], []
+        for t in tiles:
+            h, w = int(t.shape[0]), int(t.shape[1])
+            oh, ow = self.target_size(h, w)
+            sizes.append((h, w, oh, ow))
+            grids.append([1, oh // self.patch, ow // self.patch])
+        n_rows = [g[1] * g[2] for g in grids]
+        cols = 3 * 2 * self.patch * self.patch
+        if out is None:
+            out = torch.empty((sum(n_rows), cols), dtype=out_dtype, device=self.device)
+        r0 = 0
+        for i, (t, (h, w, oh, ow)) in enumerate(zip(tiles, sizes)):
+            timg = t if torch.is_tensor(t) else torch.from_numpy(np.ascontiguousarray(t))
+            timg = timg.to(self.device, non_blocking=True).contiguous()
+            scratch = None
+            if ow != w:
+                need = h * ow * 3
+                if self._scratch is None or self._scratch.numel() < need:
+                    self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+                scratch = self._scratch
+            lib.preprocess_tile(timg, oh, ow, self._tab(w, ow), self._tab(h, oh), scratch, self.mean, self.std, out[r0:r0 + n_rows[i]],
+                                row_map=None if row_maps is None else row_maps[i], patch_size=self.patch)
+            r0 += n_rows[i]
+        return out, torch.tensor(grids, dtype=torch.int64)

@@ -154,11 +154,17 @@ class B200InferStrategy(InferenceStrategy):
     fuse_log_probs = True  # forward_step(forward_func_log_probs) -> fused LM head + log-prob / entropy kernel
 
     def initialize(self, model_provider):
-        """Sets ``self.model`` / ``self.tokenizer`` and the worker's rank_info (dispatch depends on it,
-        decorator.py:113-121).  One process per GPU; torch.distributed (NCCL) is initialised by the launcher."""
+        """hf_strategy.py:34-47: sets ``self.tokenizer`` (``default_tokenizer_provider``, read back by the workers:
+        base_worker.py:49,129-131), ``self.model`` and the worker's rank_info (dispatch depends on it, decorator.py:113-121).
+        The processor (image min / max pixels) is loaded too: the vLLM-form rollout input carries PIL images, not pixel rows.
+        One process per GPU; torch.distributed (NCCL) is initialised by the launcher."""
         import torch.distributed as dist
+        from .model_providers import default_processor_provider, default_tokenizer_provider
         wc = self.worker_config
         model_args = getattr(wc, "model_args", None)
+        if model_args is not None:
+            self.tokenizer = default_tokenizer_provider(model_args=model_args)
+            self.processor = default_processor_provider(model_args=model_args)
         self.model = model_provider(tokenizer=self.tokenizer, model_args=model_args, is_trainable=False)
         ri = getattr(self.worker, "rank_info", None)
         if ri is not None:
@@ -196,9 +202,76 @@ class B200InferStrategy(InferenceStrategy):
             losses_reduced.append(loss_reduced)
         return collate_fn_to_dict_list(losses_reduced)
 
-    def generate(self, batch: DataProto, generation_config: dict) -> torch.Tensor:
-        """hf_strategy.py:96-129: micro-batched ``model.generate`` then pad_sequence with pad_token_id."""
+    processor = None
+    _preprocessor = None
+
+    def _image_preprocessor(self):
+        """Device image path (``sr_preprocess_tile``) with the pixel budget of the checkpoint's processor, the one the
+        collator's token expansion was made with (collator.py:456-462); the reference-effective default otherwise."""
+        if self._preprocessor is None:
+            from ..preprocess import GpuPreprocessor, REFERENCE_MAX_PIXELS
+            ip = getattr(self.processor, "image_processor", None)
+            mn, mx = getattr(ip, "min_pixels", None), getattr(ip, "max_pixels", None)
+            if mn is None or mx is None:  # transformers 5.x keeps them in `size`
+                size = getattr(ip, "size", None) or {}
+                mn, mx = size.get("shortest_edge", 56 * 56), size.get("longest_edge", REFERENCE_MAX_PIXELS)
+            self._preprocessor = GpuPreprocessor(self._sync_device(), min_pixels=int(mn), max_pixels=int(mx))
+        return self._preprocessor
+
+    def _generate_engine_form(self, batch: DataProto, generation_config: dict) -> torch.Tensor:
+        """The input form the pipeline actually sends (rlvr_socioseg_vlm_pipeline_infer.py:645-657, consumed by
+        vllm_strategy.py:114-141): ``non_tensor_batch["multi_modal_data"][i] = {"prompt_token_ids": [...], "multi_modal_data":
+        {"image": [PIL, ...]}}`` next to the left-padded ``input_ids`` / ``attention_mask`` / ``position_ids`` (already expanded
+        to one placeholder per merged patch by the collator's processor call).  vLLM re-runs the image processor on the PIL
+        images; here they go through the device preprocessing kernel.  Returns what ``VllmStrategy.generate`` returns:
+        ``[b * n, S_in + max response length]``, responses right-padded with ``pad_token_id`` (stop token included)."""
         from torch.nn.utils.rnn import pad_sequence
+        gc = generation_config
+        if gc.get("num_beams", 1) > 1:
+            raise NotImplementedError("beam search is not on the SocioSeg path")
+        n = int(gc.get("num_return_sequences", 1))
+        temperature = float(gc.get("temperature", 1.0))
+        top_k = gc.get("top_k", 0)
+        pad = gc["pad_token_id"]
+        batch_size = batch.batch.batch_size[0]
+        micro = batch.meta_info.get("micro_batch_size", batch_size)
+        outs: List[torch.Tensor] = []
+        dev = self._sync_device()
+        for data in batch.chunk(chunks=max(batch_size // micro, 1)):
+            images = []
+            for item in data.non_tensor_batch["multi_modal_data"]:
+                mm = item.get("multi_modal_data") if isinstance(item, dict) else None
+                for img in (mm or {}).get("image", []):
+                    images.append(np.asarray(img.convert("RGB") if hasattr(img, "convert") else img, dtype=np.uint8))
+            pv, thw = (None, None)
+            if images:
+                pv, thw = self._image_preprocessor()(images, out_dtype=torch.bfloat16)
+            pos = data.batch["position_ids"] if "position_ids" in data.batch else None
+            if pos is not None and pos.dim() == 3 and pos.shape[0] != 3:
+                pos = pos.transpose(0, 1)
+            seq = self.model.generate(input_ids=data.batch["input_ids"].to(dev), attention_mask=data.batch["attention_mask"].to(dev),
+                                      position_ids=pos, use_cache=True, pixel_values=pv, image_grid_thw=thw,
+                                      max_new_tokens=int(gc["max_new_tokens"]), do_sample=temperature > 0 and top_k != 1,
+                                      temperature=temperature if temperature > 0 else 1.0, top_p=float(gc.get("top_p", 1.0)),
+                                      top_k=0 if top_k in (None, -1) else int(top_k), num_return_sequences=n,
+                                      repetition_penalty=float(gc.get("repetition_penalty", 1.0)),
+                                      eos_token_id=gc.get("eos_token_id"), pad_token_id=pad)
+            s_in = data.batch["input_ids"].shape[1]
+            for row in seq[:, s_in:]:
+                keep = int((row != pad).nonzero().max().item()) + 1 if bool((row != pad).any()) else 0
+                outs.append(row[:keep])
+        output_ids = pad_sequence(outs, batch_first=True, padding_value=pad)           # gather_outputs_to_pad_tensor
+        input_ids = batch.batch["input_ids"].to(output_ids.device)
+        b, s_in = input_ids.shape
+        repeated = input_ids.unsqueeze(1).repeat(1, n, 1).view(b * n, s_in)           # concatenate_input_and_output
+        return torch.cat((repeated, output_ids), dim=1)
+
+    def generate(self, batch: DataProto, generation_config: dict) -> torch.Tensor:
+        """hf_strategy.py:96-129: micro-batched ``model.generate`` then pad_sequence with pad_token_id; the vLLM input form
+        (``multi_modal_data`` in the non-tensor batch) goes through ``_generate_engine_form``."""
+        from torch.nn.utils.rnn import pad_sequence
+        if "multi_modal_data" in batch.non_tensor_batch:
+            return self._generate_engine_form(batch, generation_config)
         batch_size = batch.batch.batch_size[0]
         micro_batch_size = batch.meta_info["micro_batch_size"]
         num_microbatches = max(batch_size // micro_batch_size, 1)

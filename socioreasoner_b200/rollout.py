@@ -33,20 +33,23 @@ class TileBatch:
     input_ids: torch.Tensor          # [b,S] int64 (left padded)
     attention_mask: torch.Tensor     # [b,S]
     position_ids: Optional[torch.Tensor]  # [3,b,S] or None (-> reference get_rope_index semantics)
-    pixel_values: torch.Tensor       # [sum N, 1176] fp32
+    pixel_values: Optional[torch.Tensor]  # [sum N, 1176] fp32 (HF processor rows), or None when raw tiles are given
     image_grid_thw: torch.Tensor     # [b,3] (cpu)
     mask_logits: torch.Tensor        # [b, n_obj, 3, h, w] fp32  (SAM-style low-res logits)
     mask_scores: torch.Tensor        # [b, n_obj, 3] fp32
     gt_masks: torch.Tensor           # [b, out, out] uint8
+    tiles_u8: Optional[torch.Tensor] = None  # [b, H, W, 3] uint8 raw tiles: preprocessed ON THE DEVICE (sr_preprocess_tile) when
+                                             # pixel_values is None -- 3 MB instead of 13.7 MB of fp32 pixel rows per 1024^2 tile
 
     def pin(self) -> "TileBatch":
         f = lambda t: t.pin_memory() if (t is not None and not t.is_cuda and torch.cuda.is_available()) else t
         return TileBatch(f(self.input_ids), f(self.attention_mask), f(self.position_ids), f(self.pixel_values),
-                         self.image_grid_thw, f(self.mask_logits), f(self.mask_scores), f(self.gt_masks))
+                         self.image_grid_thw, f(self.mask_logits), f(self.mask_scores), f(self.gt_masks), f(self.tiles_u8))
 
     def h2d_bytes(self) -> int:
-        ts = [self.input_ids, self.attention_mask, self.position_ids, self.pixel_values, self.mask_logits, self.mask_scores, self.gt_masks]
-        return int(sum(t.numel() * t.element_size() for t in ts if t is not None))
+        ts = [self.input_ids, self.attention_mask, self.position_ids, self.pixel_values, self.mask_logits, self.mask_scores, self.gt_masks,
+              self.tiles_u8]
+        return int(sum(t.numel() * t.element_size() for t in ts if t is not None and not t.is_cuda))
 
 
 @dataclass
@@ -65,6 +68,7 @@ class DataParallelRollout:
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self._gbuf = None
         self._slot_bytes = 0
+        self._pre = None
 
     # layout of one rank's slot in the gather buffer: [b_max masks][b_max iou f32][b_max*T tokens i64][count i64]
     def _slot_layout(self, b_max: int):
@@ -82,19 +86,45 @@ class DataParallelRollout:
             self._slot_bytes = total
         return self._gbuf
 
+    def resolve_b_max(self, b: int, b_max: Optional[int]) -> int:
+        """The gather slots of all ranks must have ONE size: with ``np.array_split`` shards the ranks hold different b, so an
+        unspecified ``b_max`` is agreed on with an all-reduce(MAX) instead of defaulting to the local shard size."""
+        if b_max is not None:
+            return int(b_max)
+        if self.world == 1:
+            return max(b, 1)
+        dev = self.engine.device if self.engine is not None else "cpu"
+        t = torch.tensor([b], dtype=torch.int64, device=dev if (dist.get_backend(self.group) == "nccl") else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return max(int(t.item()), 1)
+
     def step(self, batch: TileBatch, b_max: Optional[int] = None) -> RolloutResult:
-        """Runs this rank's shard.  Host tensors are copied to the device here (pinned -> async H2D)."""
+        """Runs this rank's shard.  Host tensors are copied to the device here (pinned -> async H2D); raw uint8 tiles are
+        resized / normalised / patchified on the device.  An empty shard (b == 0) only publishes count 0."""
         dev = self.engine.device
         b = batch.input_ids.shape[0]
-        b_max = b_max or b
+        b_max = self.resolve_b_max(b, b_max)
+        assert b <= b_max
         gbuf = self._ensure_gbuf(b_max, dev)
+        if b == 0:
+            self.pack_slot(b_max, torch.zeros((0, self.T), dtype=torch.int64, device=dev), torch.zeros((0,), dtype=torch.float32, device=dev))
+            return RolloutResult(torch.zeros((0, self.T), dtype=torch.int64, device=dev), self.slot_masks(b_max)[:0],
+                                 torch.zeros((0,), dtype=torch.float32, device=dev))
         mask_b, iou_off, tok_off, cnt_off, _ = self._slot_layout(b_max)
         slot = gbuf[self.rank]
         masks = slot[:mask_b].view(b_max, self.out_size, self.out_size)
         to = lambda t: t if (t is None or t.is_cuda) else t.to(dev, non_blocking=True)
         pv, ml, ms, gt = to(batch.pixel_values), to(batch.mask_logits), to(batch.mask_scores), to(batch.gt_masks)
-        tokens = self.engine.generate_greedy(batch.input_ids, batch.attention_mask, batch.position_ids, pv,
-                                             batch.image_grid_thw, self.T)
+        grid = batch.image_grid_thw
+        if pv is None:
+            if self._pre is None:
+                from .preprocess import GpuPreprocessor
+                self._pre = GpuPreprocessor(dev)
+            tiles = to(batch.tiles_u8)
+            pv, grid2 = self._pre([tiles[i] for i in range(tiles.shape[0])], out_dtype=torch.bfloat16)
+            assert grid is None or grid2.tolist() == [list(map(int, g)) for g in grid.tolist()], "tile sizes do not match image_grid_thw"
+            grid = grid2
+        tokens = self.engine.generate_greedy(batch.input_ids, batch.attention_mask, batch.position_ids, pv, grid, self.T)
         for i in range(b):
             lib.mask_epilogue(ml[i], ms[i], self.image_size, self.out_size, out=masks[i])
         iou = lib.mask_iou(masks[:b], gt, 1.0)
@@ -115,6 +145,14 @@ class DataParallelRollout:
         slot[iou_off:iou_off + b * 4].view(torch.float32).copy_(iou)
         slot[tok_off:tok_off + b * self.T * 8].view(torch.int64).copy_(tokens.reshape(-1))
         slot[cnt_off:cnt_off + 8].view(torch.int64).fill_(b)
+
+    def gather_to_host(self, b_max: int, dst_rank: int = 0):
+        """``gather`` + ONE device -> host copy of the whole gather buffer on ``dst_rank`` only (the reference collects on the
+        driver only, decorator.py:151-180); the other ranks return None.  Returns host (tokens, masks, iou)."""
+        res = self.gather(b_max)
+        if self.rank != dst_rank:
+            return None
+        return res.tokens.cpu(), res.masks.cpu(), res.iou.cpu()
 
     def gather(self, b_max: int) -> RolloutResult:
         """ONE all-gather of every rank's slot; returns the concatenation in rank order (= reference concat order)."""

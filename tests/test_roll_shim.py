@@ -228,3 +228,67 @@ def test_dp_shard_and_gather_world2_gloo(total):
         assert toks[:, 0].tolist() == [100 * i for i in range(total)]
         assert masks[:, 0, 0].tolist() == [i + 1 for i in range(total)]
         assert torch.allclose(iou, torch.arange(total).float() / 10)
+
+
+# ---- initialize + the vLLM input form (what the unchanged entry script sends) ----------------------------------------------
+def test_initialize_sets_tokenizer_processor_model_and_rank_info(tmp_path, oracle_tiny):
+    """hf_strategy.py:34-47 / base_worker.py:46-49,129-131: after initialize the worker reads strategy.tokenizer (eos / pad ids)."""
+    import ckpt_util
+    path = ckpt_util.write_checkpoint(str(tmp_path / "ckpt"), oracle_tiny)
+    w = worker("vllm")
+    w.worker_config.model_args = SimpleNamespace(model_name_or_path=path)
+    st = create_strategy(w)
+    seen = {}
+
+    def provider(tokenizer, model_args, is_trainable=False):
+        seen.update(tokenizer=tokenizer, path=model_args.model_name_or_path, trainable=is_trainable)
+        return FakeModel()
+
+    st.initialize(provider)
+    assert st.tokenizer is seen["tokenizer"] and st.tokenizer is not None and seen["path"] == path and seen["trainable"] is False
+    assert st.tokenizer.eos_token_id == 7002 and st.tokenizer.pad_token_id == 7000 and st.tokenizer.padding_side == "left"
+    assert st.processor is not None and isinstance(st.model, FakeModel)
+    assert w.rank_info.dp_rank == 0 and w.rank_info.dp_size == 1
+
+
+def test_generate_accepts_the_vllm_input_form(monkeypatch):
+    """vllm_strategy.py:114-141: prompts = {prompt_token_ids, multi_modal_data: {image: [PIL, ...]}}; output = prompt + responses
+    right-padded to the longest response of the WHOLE batch (gather_outputs_to_pad_tensor + concatenate_input_and_output)."""
+    from PIL import Image
+    st = create_strategy(worker("vllm"))
+    calls = []
+
+    class GenModel:
+        device = "cpu"
+
+        def generate(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens, eos_token_id,
+                     pad_token_id, do_sample, temperature, top_p, top_k, num_return_sequences, **kw):
+            calls.append(dict(b=input_ids.shape[0], rows=pixel_values.shape[0], grid=image_grid_thw.tolist(), pos=tuple(position_ids.shape),
+                              sample=(do_sample, temperature, top_p, top_k, num_return_sequences)))
+            new = torch.full((input_ids.shape[0], max_new_tokens), pad_token_id)
+            for i in range(input_ids.shape[0]):
+                k = 2 + int(input_ids[i, -1]) % 3                      # ragged response lengths, stop token included
+                new[i, :k] = 11
+                new[i, k - 1] = eos_token_id[0]
+            return torch.cat([input_ids, new], 1)
+
+    st.model = GenModel()
+    monkeypatch.setattr(type(st), "_image_preprocessor", lambda self: (lambda images, out_dtype=None: (
+        torch.zeros(sum((im.shape[0] // 14) * (im.shape[1] // 14) for im in images), 1176),
+        torch.tensor([[1, im.shape[0] // 14, im.shape[1] // 14] for im in images]))))
+    n = 5
+    ids = torch.arange(n * 6).view(n, 6)
+    mm = [{"prompt_token_ids": [1, 2, 3], "multi_modal_data": {"image": [Image.new("RGB", (56, 28 * (1 + i % 2))), Image.new("RGB", (28, 28))]}}
+          for i in range(n)]
+    d = DataProto.from_dict(tensors=dict(input_ids=ids, attention_mask=torch.ones_like(ids), position_ids=torch.zeros(n, 3, 6, dtype=torch.long)),
+                            non_tensors=dict(multi_modal_data=mm), meta_info=dict(micro_batch_size=2))
+    gc = dict(max_new_tokens=8, temperature=1.0, top_p=0.8, top_k=100, num_beams=1, repetition_penalty=1.0, num_return_sequences=1,
+              eos_token_id=[99, 98], pad_token_id=0)
+    out = st.generate(d, gc)
+    assert [c["b"] for c in calls] == [3, 2] and calls[0]["pos"] == (3, 3, 6)               # micro-batches; (b,3,S) -> (3,b,S)
+    assert calls[0]["grid"] == [[1, 2, 4], [1, 2, 2], [1, 4, 4], [1, 2, 2], [1, 2, 4], [1, 2, 2]]   # two images per prompt, in order
+    assert calls[0]["sample"] == (True, 1.0, 0.8, 100, 1)
+    assert out.shape == (n, 6 + 4) and torch.equal(out[:, :6], ids)                        # longest response: 2 + 2 tokens
+    lens = [2 + int(ids[i, -1]) % 3 for i in range(n)]
+    for i, k in enumerate(lens):
+        assert out[i, 6 + k - 1] == 99 and (out[i, 6 + k:] == 0).all() and (out[i, 6:6 + k - 1] == 11).all()

@@ -173,6 +173,9 @@ def _ref_pair_worker(rank, port, q, done):
         spec = importlib.util.spec_from_file_location("ref_pg_utils", REF_PG_UTILS)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
+        # the reference picks the option keyword by a STRING compare (`str(torch.__version__) >= "2.6"`, pg_utils.py:59), which
+        # misfires on torch 2.11 ("2.11" < "2.6"); it was written for torch 2.6 -- present that version string to it
+        torch.__version__ = "2.6.0"
         pg = mod.init_custom_process_group(backend="gloo", init_method=f"tcp://127.0.0.1:{port}", world_size=2, rank=0,
                                            group_name="model_update_ref_pair")      # collective.py:24-32 of the reference
         dist.all_reduce(torch.zeros(1), group=pg)                                  # megatron_strategy.py warm-up

@@ -97,25 +97,77 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------
-def build_batch(rank: int, cfg):
+def build_batch(rank: int, cfg, sides=None, max_pixels=None, images_per_prompt: int = 1, n_prompts: int = TILES_PER_GPU):
+    """One rank's step: ``n_prompts`` prompts with ``images_per_prompt`` raw uint8 tiles each (sides cycle through ``sides``)."""
     from socioreasoner_b200 import preprocess as pp
     from socioreasoner_b200.rollout import TileBatch
 
-    ids = [rank * TILES_PER_GPU + i for i in range(TILES_PER_GPU)]
-    tiles = torch.stack([torch.from_numpy(np.ascontiguousarray(pp.synth_tile(i, TILE_SIDE).transpose(1, 2, 0))) for i in ids])  # [b,H,W,3]
-    oh, ow = pp.smart_resize(TILE_SIDE, TILE_SIDE, max_pixels=pp.REFERENCE_MAX_PIXELS)
-    grid = torch.tensor([[1, oh // 14, ow // 14]] * len(ids), dtype=torch.int64)
-    prompts = [pp.synth_prompt(i, int(g[0] * g[1] * g[2]) // 4, cfg.image_token_id, cfg.vision_start_token_id,
-                               cfg.vision_end_token_id, n_text=N_TEXT) for i, g in zip(ids, grid)]
+    sides = sides or [TILE_SIDE]
+    max_pixels = max_pixels or pp.REFERENCE_MAX_PIXELS
+    n_tiles = n_prompts * images_per_prompt
+    ids = [rank * n_tiles + i for i in range(n_tiles)]
+    tl = [torch.from_numpy(np.ascontiguousarray(pp.synth_tile(i, sides[j % len(sides)]).transpose(1, 2, 0))) for j, i in enumerate(ids)]
+    tiles = torch.stack(tl) if len(set(t.shape for t in tl)) == 1 else tl                      # [n,H,W,3], or a list for mixed sizes
+    grid = torch.tensor([[1, oh // 14, ow // 14] for oh, ow in (pp.smart_resize(t.shape[0], t.shape[1], max_pixels=max_pixels) for t in tl)],
+                        dtype=torch.int64)
+    prompts = []
+    for j in range(n_prompts):
+        g = grid[j * images_per_prompt:(j + 1) * images_per_prompt]
+        p = pp.synth_prompt(ids[j * images_per_prompt], int(g[0].prod()) // 4, cfg.image_token_id, cfg.vision_start_token_id,
+                            cfg.vision_end_token_id, n_text=N_TEXT)
+        for extra in g[1:]:   # further images of the prompt (the reference sends map + sat): one more vision span after the first
+            span = torch.tensor([cfg.vision_start_token_id] + [cfg.image_token_id] * (int(extra.prod()) // 4) + [cfg.vision_end_token_id])
+            cut = 3 + 2 + int(g[0].prod()) // 4
+            p = torch.cat([p[:cut], span, p[cut:]])
+        prompts.append(p)
     input_ids, mask = pp.left_pad(prompts)
-    ml, ms, gt = zip(*[pp.synth_mask_inputs(i, N_OBJ) for i in ids])
+    ml, ms, gt = zip(*[pp.synth_mask_inputs(rank * n_prompts + j, N_OBJ) for j in range(n_prompts)])
     return TileBatch(input_ids, mask, None, None, grid, torch.stack(ml), torch.stack(ms), torch.stack(gt), tiles_u8=tiles)
 
 
 def to_device(b, dev):
     from socioreasoner_b200.rollout import TileBatch
+    tiles = [t.to(dev) for t in b.tiles_u8] if isinstance(b.tiles_u8, (list, tuple)) else b.tiles_u8.to(dev)
     return TileBatch(b.input_ids, b.attention_mask, b.position_ids, None, b.image_grid_thw,
-                     b.mask_logits.to(dev), b.mask_scores.to(dev), b.gt_masks.to(dev), tiles_u8=b.tiles_u8.to(dev))
+                     b.mask_logits.to(dev), b.mask_scores.to(dev), b.gt_masks.to(dev), tiles_u8=tiles)
+
+
+def extra_lines(model, cfg, dev, rank):
+    """The other stated inputs of SURVEY.md 8(d), device-timed on this GPU (3 steps each after 1 warm-up; parity of these shapes is
+    covered by the -m gpu tests): the yaml-intended 1344^2 pixel cap (1024^2 -> 1036^2, N = 5476), cfg-1 (one 448^2 tile), the
+    reference's two-image prompt (map + sat, S ~ 1.6 k: the decode kernel's multi-pass attention), cfg-4 mixed {448, 896, 1344}^2."""
+    from socioreasoner_b200 import preprocess as pp
+    from socioreasoner_b200.rollout import DataParallelRollout
+    out = {}
+    cases = {
+        "max_pixels_1344sq_1036": dict(max_pixels=pp.YAML_MAX_PIXELS),
+        "cfg1_single_448": dict(sides=[448], n_prompts=1),
+        "two_image_prompt_756": dict(images_per_prompt=2),
+        "cfg4_mixed_448_896_1344": dict(sides=[448, 896, 1344], max_pixels=pp.YAML_MAX_PIXELS, n_prompts=6),
+    }
+    for name, kw in cases.items():
+        try:
+            ro = DataParallelRollout(model, max_new_tokens=NEW_TOKENS, group=None, max_pixels=kw.get("max_pixels"))
+            ro.world, ro.rank = 1, 0
+            hb = build_batch(rank, cfg, **kw)
+            db = to_device(hb, dev)
+            n = hb.input_ids.shape[0]
+            ro.step(db, n)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                ro.step(db, n)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            out[name] = {"prompts_per_step": n, "images_per_step": int(hb.image_grid_thw.shape[0]), "patches": hb.image_grid_thw.prod(-1).tolist()[:3],
+                         "prompt_tokens": int(hb.attention_mask.sum(1).max()), "ms_per_step": round(ms, 2),
+                         "prompts_per_s": round(n / (ms * 1e-3), 2)}
+            model.engine.free_buffers()
+        except Exception as e:  # noqa: BLE001  -- an extra line must never cost the headline
+            out[name] = {"error": repr(e)[:200]}
+    return out
 
 
 def run_ours(args):
@@ -266,6 +318,8 @@ def run_ours(args):
         "gpu_launches": int(launches) * args.steps,
         "clocks": clk, "roofline": roofline, "roofline_gemm": roofline_gemm,
     }
+    if world == 1 and os.environ.get("SR_BENCH_EXTRAS", "1") != "0":
+        line["extra"] = extra_lines(model, cfg, dev, rank)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_subprocess(float(os.environ.get("SR_CPU_BASELINE_TIMEOUT", "420")))

@@ -247,8 +247,8 @@ class B200InferStrategy(InferenceStrategy):
             if images:
                 pv, thw = self._image_preprocessor()(images, out_dtype=torch.bfloat16)
             pos = data.batch["position_ids"] if "position_ids" in data.batch else None
-            if pos is not None and pos.dim() == 3 and pos.shape[0] != 3:
-                pos = pos.transpose(0, 1)
+            if pos is not None and pos.dim() == 3:
+                pos = pos.transpose(0, 1)  # DataProto keeps (bsz, 3, seqlen); the model takes (3, bsz, seqlen) (hf_strategy.py:65-67)
             seq = self.model.generate(input_ids=data.batch["input_ids"].to(dev), attention_mask=data.batch["attention_mask"].to(dev),
                                       position_ids=pos, use_cache=True, pixel_values=pv, image_grid_thw=thw,
                                       max_new_tokens=int(gc["max_new_tokens"]), do_sample=temperature > 0 and top_k != 1,
@@ -286,10 +286,15 @@ class B200InferStrategy(InferenceStrategy):
 
 
 class B200SegStrategy(InferenceStrategy):
-    """Mask side (seg_strategy.py:26-72).  The SAM2 network itself is the ranked next component; this
-    strategy owns the epilogue the reference runs on the CPU: argmax-score candidate pick, OR over objects, nearest resize
-    to 768, uint8.  ``predictor(image, prompt) -> (low_res_logits [3,h,w], scores [3])`` is injected (a SAM2 wrapper in
-    production, synthetic logits in tests / bench)."""
+    """Mask side (seg_strategy.py:12-79).  ``initialize(model_provider)`` receives what the reference's provider returns
+    (``sam2_seg_model_provider``, model_providers.py:515-562): an object with the ``SAM2ImagePredictor`` API --
+    ``set_image(PIL 756x756)`` once per sample, ``predict(box=, point_coords=, point_labels=) -> (masks [3,H,W], scores [3],
+    low_res_logits [3,256,256])`` per object.  This strategy owns everything the reference then does on the CPU: best-score
+    candidate pick, the predictor's own post-processing of the picked candidate (bilinear up-sample of the low-res logits to the
+    image size, > 0), OR over objects, cv2 nearest resize to 768, uint8 -- one fused kernel per sample (``sr_mask_epilogue``).
+    Predictors are used in this order: the B200-native SAM2 (``socioreasoner_b200.sam2``: logits stay on the device), any object
+    with the reference API (its third return value feeds the kernel; if it is None the thresholded masks do), or a plain callable
+    ``predictor(image, prompt) -> (low_res_logits [3,h,w], scores [3])`` (synthetic logits in tests / bench)."""
     strategy_name = "seg_infer"
 
     def __init__(self, worker, image_size: int = 756, out_size: int = 768):
@@ -299,7 +304,30 @@ class B200SegStrategy(InferenceStrategy):
 
     def initialize(self, model_provider):
         self.predictor = model_provider(model_args=getattr(self.worker_config, "model_args", None), is_trainable=False)
+        self.model = self.predictor
         return self
+
+    def _has_predictor_api(self) -> bool:
+        return hasattr(self.predictor, "set_image") and hasattr(self.predictor, "predict")
+
+    def _predict_one(self, image, single_vp):
+        """-> (candidate logits [3, h, w] fp32, scores [3] fp32) for one object prompt."""
+        if not self._has_predictor_api():
+            l, s = self.predictor(image, single_vp)
+            return torch.as_tensor(l, dtype=torch.float32), torch.as_tensor(s, dtype=torch.float32)
+        prompt = {}
+        if "point_coords" in single_vp and "point_labels" in single_vp:  # seg_strategy.py:51-56
+            prompt["point_coords"] = single_vp["point_coords"]
+            prompt["point_labels"] = single_vp["point_labels"]
+        if "box" in single_vp:
+            prompt["box"] = single_vp["box"]
+        pred_masks, scores, low_res = self.predictor.predict(**prompt)
+        scores = torch.as_tensor(np.asarray(scores) if not torch.is_tensor(scores) else scores, dtype=torch.float32)
+        if low_res is not None:
+            low = low_res if torch.is_tensor(low_res) else torch.from_numpy(np.asarray(low_res))
+            return low.to(torch.float32), scores
+        m = pred_masks if torch.is_tensor(pred_masks) else torch.from_numpy(np.asarray(pred_masks))
+        return (m > 0).to(torch.float32) * 2.0 - 1.0, scores  # already thresholded at image size: +-1 "logits", identity up-sample
 
     def segment(self, batch: DataProto) -> dict:
         from .. import lib
@@ -310,19 +338,24 @@ class B200SegStrategy(InferenceStrategy):
             if len(visual_prompt) == 0:  # seg_strategy.py:40-45: zero mask, model untouched
                 masks.append({"mask": np.zeros((self.out_size, self.out_size), dtype=np.uint8)})
                 continue
+            if self._has_predictor_api():
+                if hasattr(image, "resize"):
+                    image = image.resize((self.image_size, self.image_size))     # seg_strategy.py:37
+                self.predictor.set_image(image)                                   # seg_strategy.py:47
             logits, scores = [], []
             for single_vp in visual_prompt:
                 try:
-                    l, s = self.predictor(image, single_vp)
-                    logits.append(torch.as_tensor(l, dtype=torch.float32))
-                    scores.append(torch.as_tensor(s, dtype=torch.float32))
+                    l, s = self._predict_one(image, single_vp)
+                    logits.append(l)
+                    scores.append(s)
                 except Exception:  # seg_strategy.py:62-63: a failing object is skipped
                     continue
             if not logits:
                 # every object failed: the reference still resizes its zero 756 mask -> zero 768 mask
                 masks.append({"mask": np.zeros((self.out_size, self.out_size), dtype=np.uint8)})
                 continue
-            m = lib.mask_epilogue(torch.stack(logits).cuda(), torch.stack(scores).cuda(), self.image_size, self.out_size)
+            m = lib.mask_epilogue(torch.stack(logits).cuda().contiguous(), torch.stack(scores).cuda().contiguous(), self.image_size,
+                                  self.out_size)
             masks.append({"mask": m.cpu().numpy()})
         return collate_fn_to_dict_list(masks)
 

@@ -38,18 +38,24 @@ class TileBatch:
     mask_logits: torch.Tensor        # [b, n_obj, 3, h, w] fp32  (SAM-style low-res logits)
     mask_scores: torch.Tensor        # [b, n_obj, 3] fp32
     gt_masks: torch.Tensor           # [b, out, out] uint8
-    tiles_u8: Optional[torch.Tensor] = None  # [b, H, W, 3] uint8 raw tiles: preprocessed ON THE DEVICE (sr_preprocess_tile) when
+    tiles_u8: Optional[torch.Tensor] = None  # [n, H, W, 3] uint8 raw tiles (or a list for mixed sizes): preprocessed ON THE DEVICE when
                                              # pixel_values is None -- 3 MB instead of 13.7 MB of fp32 pixel rows per 1024^2 tile
 
     def pin(self) -> "TileBatch":
-        f = lambda t: t.pin_memory() if (t is not None and not t.is_cuda and torch.cuda.is_available()) else t
+        def f(t):
+            if isinstance(t, (list, tuple)):
+                return [f(x) for x in t]
+            return t.pin_memory() if (t is not None and not t.is_cuda and torch.cuda.is_available()) else t
         return TileBatch(f(self.input_ids), f(self.attention_mask), f(self.position_ids), f(self.pixel_values),
                          self.image_grid_thw, f(self.mask_logits), f(self.mask_scores), f(self.gt_masks), f(self.tiles_u8))
 
     def h2d_bytes(self) -> int:
         ts = [self.input_ids, self.attention_mask, self.position_ids, self.pixel_values, self.mask_logits, self.mask_scores, self.gt_masks,
               self.tiles_u8]
-        return int(sum(t.numel() * t.element_size() for t in ts if t is not None and not t.is_cuda))
+        flat = []
+        for t in ts:
+            flat.extend(t if isinstance(t, (list, tuple)) else [t])
+        return int(sum(t.numel() * t.element_size() for t in flat if t is not None and not t.is_cuda))
 
 
 @dataclass
@@ -60,7 +66,8 @@ class RolloutResult:
 
 
 class DataParallelRollout:
-    def __init__(self, model, max_new_tokens: int = 32, image_size: int = 756, out_size: int = 768, group=None):
+    def __init__(self, model, max_new_tokens: int = 32, image_size: int = 756, out_size: int = 768, group=None,
+                 max_pixels: Optional[int] = None):
         self.model, self.engine = model, (model.engine if model is not None else None)
         self.T, self.image_size, self.out_size = max_new_tokens, image_size, out_size
         self.group = group
@@ -69,6 +76,7 @@ class DataParallelRollout:
         self._gbuf = None
         self._slot_bytes = 0
         self._pre = None
+        self.max_pixels = max_pixels
 
     # layout of one rank's slot in the gather buffer: [b_max masks][b_max iou f32][b_max*T tokens i64][count i64]
     def _slot_layout(self, b_max: int):
@@ -118,10 +126,10 @@ class DataParallelRollout:
         grid = batch.image_grid_thw
         if pv is None:
             if self._pre is None:
-                from .preprocess import GpuPreprocessor
-                self._pre = GpuPreprocessor(dev)
-            tiles = to(batch.tiles_u8)
-            pv, grid2 = self._pre([tiles[i] for i in range(tiles.shape[0])], out_dtype=torch.bfloat16)
+                from .preprocess import GpuPreprocessor, REFERENCE_MAX_PIXELS
+                self._pre = GpuPreprocessor(dev, max_pixels=self.max_pixels or REFERENCE_MAX_PIXELS)
+            tiles = [to(t) for t in batch.tiles_u8] if isinstance(batch.tiles_u8, (list, tuple)) else to(batch.tiles_u8)
+            pv, grid2 = self._pre([tiles[i] for i in range(len(tiles))], out_dtype=torch.bfloat16)
             assert grid is None or grid2.tolist() == [list(map(int, g)) for g in grid.tolist()], "tile sizes do not match image_grid_thw"
             grid = grid2
         tokens = self.engine.generate_greedy(batch.input_ids, batch.attention_mask, batch.position_ids, pv, grid, self.T)

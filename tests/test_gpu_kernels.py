@@ -403,3 +403,47 @@ def test_mask_epilogue_edge_cases():
     assert torch.equal(a, both)                                              # OR is idempotent
     ones = torch.ones(1, 768, 768, dtype=torch.uint8, device=DEV) * 255
     assert lib.mask_iou(ones, ones, 1.0).item() == 1.0
+
+
+def test_seg_strategy_with_the_reference_predictor_api():
+    """seg_strategy.py:26-72 through ``create_strategy('seg_infer')`` with a predictor exposing the SAM2ImagePredictor API
+    (``set_image`` / ``predict`` -> (masks, scores, low_res_logits)), as ``sam2_seg_model_provider`` returns
+    (model_providers.py:515-562): byte-exact with the reference semantics (oracle pinned on the reference's own segment())."""
+    from types import SimpleNamespace
+    from PIL import Image
+    import torch.nn.functional as F
+    from socioreasoner_b200.roll_shim import DataProto, create_strategy
+
+    class FakeSam2Predictor:
+        def __init__(self, with_low_res=True):
+            self.images, self.calls, self.with_low_res = [], [], with_low_res
+
+        def set_image(self, image):
+            assert image.size == (756, 756)
+            self.images.append(image)
+
+        def predict(self, point_coords=None, point_labels=None, box=None):
+            self.calls.append((point_coords, point_labels, box))
+            if box is not None and box[0] < 0:
+                raise ValueError("bad box")                           # the reference skips objects whose predict() raises
+            i = len(self.calls) - 1
+            low = ML[i % ML.shape[0]]
+            up = F.interpolate(low[None], size=(756, 756), mode="bilinear", align_corners=False)[0]
+            return (up > 0).numpy(), MS[i % ML.shape[0]].numpy(), (low.numpy() if self.with_low_res else None)
+
+    ML, MS, _ = O.synth_mask_inputs(5, 4)
+    vps = [dict(box=[10, 20, 300, 400]), dict(point_coords=[[50, 60]], point_labels=[1]), dict(box=[-1, 0, 5, 5]),
+           dict(box=[1, 2, 3, 4], point_coords=[[5, 6]], point_labels=[1])]
+    img = Image.new("RGB", (1024, 1024))
+    for with_low in (True, False):
+        pred = FakeSam2Predictor(with_low)
+        w = SimpleNamespace(worker_config=SimpleNamespace(strategy_args=SimpleNamespace(strategy_name="seg_infer"), model_args=None))
+        st = create_strategy(w).initialize(lambda model_args, is_trainable=False: pred)
+        d = DataProto.from_dict(tensors=dict(x=torch.zeros(2, 1)), non_tensors=dict(seg_image=[img, img], visual_prompt=[vps, []]))
+        out = st.segment(d)["mask"]
+        assert len(pred.images) == 1 and len(pred.calls) == 4                 # empty prompt list: the model is not touched
+        assert pred.calls[3] == ([[5, 6]], [1], [1, 2, 3, 4])
+        keep = [0, 1, 3]                                                      # the failing object is skipped
+        ref = host_ref.mask_epilogue(ML[keep], MS[keep])
+        assert out[0].dtype == np.uint8 and np.array_equal(out[0], ref)
+        assert out[1].shape == (768, 768) and out[1].max() == 0

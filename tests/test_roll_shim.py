@@ -264,6 +264,7 @@ def test_generate_accepts_the_vllm_input_form(monkeypatch):
         def generate(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens, eos_token_id,
                      pad_token_id, do_sample, temperature, top_p, top_k, num_return_sequences, **kw):
             calls.append(dict(b=input_ids.shape[0], rows=pixel_values.shape[0], grid=image_grid_thw.tolist(), pos=tuple(position_ids.shape),
+                              pos_t=position_ids.clone(),
                               sample=(do_sample, temperature, top_p, top_k, num_return_sequences)))
             new = torch.full((input_ids.shape[0], max_new_tokens), pad_token_id)
             for i in range(input_ids.shape[0]):
@@ -280,12 +281,14 @@ def test_generate_accepts_the_vllm_input_form(monkeypatch):
     ids = torch.arange(n * 6).view(n, 6)
     mm = [{"prompt_token_ids": [1, 2, 3], "multi_modal_data": {"image": [Image.new("RGB", (56, 28 * (1 + i % 2))), Image.new("RGB", (28, 28))]}}
           for i in range(n)]
-    d = DataProto.from_dict(tensors=dict(input_ids=ids, attention_mask=torch.ones_like(ids), position_ids=torch.zeros(n, 3, 6, dtype=torch.long)),
+    pos_b3s = torch.arange(n * 3 * 6).view(n, 3, 6)
+    d = DataProto.from_dict(tensors=dict(input_ids=ids, attention_mask=torch.ones_like(ids), position_ids=pos_b3s),
                             non_tensors=dict(multi_modal_data=mm), meta_info=dict(micro_batch_size=2))
     gc = dict(max_new_tokens=8, temperature=1.0, top_p=0.8, top_k=100, num_beams=1, repetition_penalty=1.0, num_return_sequences=1,
               eos_token_id=[99, 98], pad_token_id=0)
     out = st.generate(d, gc)
     assert [c["b"] for c in calls] == [3, 2] and calls[0]["pos"] == (3, 3, 6)               # micro-batches; (b,3,S) -> (3,b,S)
+    assert torch.equal(calls[0]["pos_t"], pos_b3s[:3].transpose(0, 1)) and torch.equal(calls[1]["pos_t"], pos_b3s[3:].transpose(0, 1))
     assert calls[0]["grid"] == [[1, 2, 4], [1, 2, 2], [1, 4, 4], [1, 2, 2], [1, 2, 4], [1, 2, 2]]   # two images per prompt, in order
     assert calls[0]["sample"] == (True, 1.0, 0.8, 100, 1)
     assert out.shape == (n, 6 + 4) and torch.equal(out[:, :6], ids)                        # longest response: 2 + 2 tokens

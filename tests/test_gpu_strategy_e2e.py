@@ -60,7 +60,7 @@ def test_generate_vllm_form_matches_oracle_greedy(setup):
     assert out.shape[0] == 3 and torch.equal(out[:, :S].cpu(), b.input_ids)
     new = out[:, S:].cpu()
     top2 = lg_ref.topk(2, -1).values
-    decisive = (top2[..., 0] - top2[..., 1]) > 0.1
+    decisive = (top2[..., 0] - top2[..., 1]) > 0.05   # as tests/test_gpu_e2e.py: below that bf16 cannot decide
     checked = 0
     for i in range(3):
         for t in range(min(T, new.shape[1])):
@@ -68,7 +68,7 @@ def test_generate_vllm_form_matches_oracle_greedy(setup):
                 break
             assert int(new[i, t]) == int(toks_ref[i, t]), (i, t)
             checked += 1
-    assert checked >= 6
+    assert checked >= 8
     # stop ids: make the oracle's second token of sample 0 a stop id -> its response ends there, padded afterwards
     stop = int(toks_ref[0, 1])
     if decisive[0, 0] and decisive[0, 1]:

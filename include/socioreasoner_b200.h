@@ -251,6 +251,41 @@ int sr_preprocess_tile(const uint8_t* image, int height, int width, int out_heig
                        uint8_t* scratch, const float* mean3, const float* std3, void* pixel_values, int out_dtype, int64_t ld_out,
                        const int32_t* row_map, int patch_size, void* stream);
 
+/* ---- SAM2 image path -------------------------------------------------------
+ * What SAM2ImagePredictor.set_image / predict compute behind roll/distributed/strategy/seg_strategy.py:47-58 (the external ``sam2``
+ * package loaded by roll/models/model_providers.py:540-545; arithmetic pinned on transformers/models/sam2/modeling_sam2.py).  The
+ * linear layers and the Hiera window / global attention run on sr_gemm_bf16 / sr_attention_fwd; these are the remaining pieces. */
+/* uint8 HWC image -> fp32 [3, size, size]: /255, bilinear resize (align_corners = false), (v - mean) / std; mean3 / std3 HOST float[3]. */
+int sr_sam2_preprocess(const uint8_t* image, int height, int width, int size, const float* mean3, const float* std3, float* out,
+                       void* stream);
+/* Sam2PatchEmbeddings + windowed positional embedding: Conv2d(3 -> channels, kernel, stride, padding) of fp32 [3,size,size] + bias +
+ * pos_table[row], written as bf16 rows at dst_rows[y * R + x] (window-major token order).  weight fp32 [channels, 3*kernel^2]. */
+int sr_sam2_patch_embed(const float* pixels, int size, int channels, int kernel, int stride, int padding, const float* weight,
+                        const float* bias, const float* pos_table, const int32_t* dst_rows, void* out, void* stream);
+/* nn.LayerNorm over the last dimension (Sam2MultiScaleBlock.layer_norm1/2, the two-way transformer's norms): bf16 rows, fp32 params. */
+int sr_layernorm_bf16(const void* x, int64_t ldx, int rows, int cols, const float* weight, const float* bias, float eps, void* out,
+                      int64_t ldo, void* stream);
+/* do_pool (2x2 max-pool of queries / residual at Hiera stage changes): out[j] = max over rows idx4[j][0..3] of x. */
+int sr_pool4_rows(const void* x, int64_t ldx, const int32_t* idx4, int n_out, int cols, void* out, void* stream);
+/* Sam2VisionNeck top-down path: out[(y,x)] = fine[(y,x)] + coarse[(y/2, x/2)] (nearest 2x), rows in (y, x) order. */
+int sr_upsample2x_add(const void* fine, const void* coarse, int coarse_res, int cols, void* out, void* stream);
+/* op 0: out = a + b (bf16); 1: relu in place on a (bf16); 2: sigmoid in place on a (fp32).  n elements. */
+int sr_elementwise(int op, void* a, const void* b, void* out, int64_t n, void* stream);
+/* Sam2PromptEncoder point / box-corner embedding: coords fp32 [n,2] (model-input pixels), labels int32 [n] (1/0 point, 2/3 box corner,
+ * -1 "not a point"); gauss fp32 [2, hidden/2], point_embed fp32 [4, hidden], not_a_point fp32 [hidden] -> bf16 [n, hidden]. */
+int sr_sam2_prompt_embed(const float* coords, const int32_t* labels, int n_points, const float* gauss, const float* point_embed,
+                         const float* not_a_point, int hidden, float image_size, void* out, void* stream);
+/* Sam2Attention core for the mask decoder (token <-> image, head_dim 16 or 32): softmax(q k^T / sqrt(d)) v, rows [*, heads*head_dim]. */
+int sr_small_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int n_q, int n_k, int heads,
+                       int head_dim, void* out, int64_t ldo, void* stream);
+/* Mask-decoder upscaling step: y [in_res^2, 4*channels] = GEMM form of ConvTranspose2d(k=2,s=2) (columns dy,dx,c) -> pixel shuffle,
+ * + bias + feat [(2 in_res)^2, channels], optional channel LayerNorm (ln_weight != NULL), exact GELU -> bf16 [(2 in_res)^2, channels]. */
+int sr_sam2_upscale(const void* y, const void* feat, const float* bias, const float* ln_weight, const float* ln_bias, float eps, int in_res,
+                    int channels, void* out, void* stream);
+/* masks = hyper_in @ upscaled^T: out fp32 [count, n_pixels] from hyper bf16 [*, channels] rows first..first+count, upscaled bf16 [n_pixels, channels]. */
+int sr_sam2_mask_logits(const void* hyper, const void* upscaled, int first, int count, int channels, int64_t n_pixels, float* out,
+                        void* stream);
+
 /* ---- mask epilogue + IoU -------------------------------------------------------------------- */
 /* seg_strategy.py:47-65: per object pick argmax(scores) of 3 candidates, bilinear up-sample h x w -> image_size^2
  * (align_corners=False), > 0, OR over objects, cv2.INTER_NEAREST resize to out_size^2, uint8 {0,1}. */

@@ -61,6 +61,16 @@ SYMBOLS = {
     "sr_decode_step_persistent": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P,
                                           c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "sr_sam2_preprocess": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "sr_sam2_patch_embed": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
+    "sr_layernorm_bf16": (c_int, [_P, c_int64, c_int, c_int, _P, _P, c_float, _P, c_int64, _P]),
+    "sr_pool4_rows": (c_int, [_P, c_int64, _P, c_int, c_int, _P, _P]),
+    "sr_upsample2x_add": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "sr_elementwise": (c_int, [c_int, _P, _P, _P, c_int64, _P]),
+    "sr_sam2_prompt_embed": (c_int, [_P, _P, c_int, _P, _P, _P, c_int, c_float, _P, _P]),
+    "sr_small_attention": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int64, _P]),
+    "sr_sam2_upscale": (c_int, [_P, _P, _P, _P, _P, c_float, c_int, c_int, _P, _P]),
+    "sr_sam2_mask_logits": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P, _P]),
     "sr_preprocess_tile": (c_int, [_P, c_int, c_int, c_int, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P, _P, c_int, c_int64, _P,
                                    c_int, _P]),
     "sr_mask_iou": (c_int, [_P, _P, c_int, c_int64, c_float, _P, _P, _P]),

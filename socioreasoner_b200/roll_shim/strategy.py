@@ -321,6 +321,8 @@ class B200SegStrategy(InferenceStrategy):
             prompt["point_labels"] = single_vp["point_labels"]
         if "box" in single_vp:
             prompt["box"] = single_vp["box"]
+        if hasattr(self.predictor, "predict_logits"):   # B200-native SAM2: candidate logits and scores stay on the device
+            return self.predictor.predict_logits(**prompt)
         pred_masks, scores, low_res = self.predictor.predict(**prompt)
         scores = torch.as_tensor(np.asarray(scores) if not torch.is_tensor(scores) else scores, dtype=torch.float32)
         if low_res is not None:

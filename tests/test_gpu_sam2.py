@@ -1,0 +1,139 @@
+"""GPU (-m gpu): the B200 SAM2 image path against the HF port of SAM2 (transformers.models.sam2, fp32 CPU,
+random-init with randomised embeddings / biases): every SAM2-specific kernel against a plain-torch statement of the same op, the
+Hiera trunk + neck features, the mask decoder's low-res logits and IoU predictions per prompt type, and the predictor behind
+``create_strategy('seg_infer')`` (seg_strategy.py:26-72) down to the uint8 768 x 768 mask."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from sam2_torch_ops import TorchOps
+from test_sam2_host import small_hf_model
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_rms(got, ref):
+    got, ref = torch.as_tensor(got).float().cpu(), torch.as_tensor(ref).float().cpu()
+    assert torch.isfinite(got).all()
+    return ((got - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from socioreasoner_b200.sam2.ops_cuda import CudaOps
+    return CudaOps("cuda"), TorchOps()
+
+
+def test_small_kernels_match_torch(ops):
+    C, T = ops
+    g = torch.Generator().manual_seed(0)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    bf = lambda t: t.to(torch.bfloat16)
+    x = bf(rn(777, 144) * 2 + 0.5)
+    w, b = rn(144) * 0.2 + 1, rn(144) * 0.1
+    assert rel_rms(C.layernorm(x.cuda(), w.cuda(), b.cuda(), 1e-6), T.layernorm(x.float(), w, b, 1e-6)) < 6e-3
+    idx = torch.randint(0, 777, (300, 4), generator=g, dtype=torch.int32)
+    assert torch.equal(C.pool4(x.cuda()[:, 16:80], idx.cuda()).cpu(), x[:, 16:80][idx.long()].amax(1))           # strided source rows
+    a, c = bf(rn(64 * 64, 32)), bf(rn(32 * 32, 32))
+    assert rel_rms(C.upsample2x_add(a.cuda(), c.cuda(), 32), T.upsample2x_add(a.float(), c.float(), 32)) < 4e-3
+    assert rel_rms(C.add(a.cuda(), a.cuda()), 2 * a.float()) < 4e-3
+    r = C.relu(a.cuda().clone())
+    assert torch.equal(r.cpu(), a.clamp_min(0))
+    for d, H in ((16, 8), (32, 8)):
+        for mq, mk in ((9, 4096), (4096, 9), (7, 7)):
+            q, k, v = bf(rn(mq, H * d)), bf(rn(mk, H * d)), bf(rn(mk, H * d))
+            got = C.small_attention(q.cuda(), k.cuda(), v.cuda(), H)
+            assert rel_rms(got, T.small_attention(q.float(), k.float(), v.float(), H)) < 8e-3, (d, mq, mk)
+    Wp = SimpleNamespace(pe_gauss=rn(2, 128), point_embed=rn(4, 256), not_a_point=rn(256))
+    Wc = SimpleNamespace(**{k2: v2.cuda() for k2, v2 in vars(Wp).items()})
+    coords, labels = np.array([[30, 40], [200.5, 180], [100, 120], [0, 0]], np.float32), np.array([2, 3, 1, -1])
+    assert rel_rms(C.prompt_embed(coords, labels, Wc, 1024), T.prompt_embed(coords, labels, Wp, 1024)) < 5e-3
+    y, feat, bias = bf(rn(16 * 16, 4 * 64)), bf(rn(32 * 32, 64)), rn(64) * 0.1
+    lw, lb = rn(64) * 0.2 + 1, rn(64) * 0.1
+    assert rel_rms(C.upscale1(y.cuda(), feat.cuda(), bias.cuda(), lw.cuda(), lb.cuda(), 16),
+                   T.upscale1(y.float(), feat.float(), bias, lw, lb, 16)) < 6e-3
+    y2, f2, b2 = bf(rn(32 * 32, 4 * 32)), bf(rn(64 * 64, 32)), rn(32) * 0.1
+    assert rel_rms(C.upscale2(y2.cuda(), f2.cuda(), b2.cuda(), 32), T.upscale2(y2.float(), f2.float(), b2, 32)) < 6e-3
+    hy, up = bf(rn(4, 32)), bf(rn(4096, 32))
+    assert rel_rms(C.mask_logits(hy.cuda(), up.cuda(), 1, 3), T.mask_logits(hy.float(), up.float(), 1, 3)) < 1e-5
+    img = torch.randint(0, 256, (189, 252, 3), generator=g, dtype=torch.uint8).numpy()
+    from socioreasoner_b200.sam2.predictor import IMAGENET_MEAN, IMAGENET_STD
+    want = torch.nn.functional.interpolate(torch.from_numpy(img).permute(2, 0, 1)[None].float() / 255, size=(256, 256), mode="bilinear",
+                                           align_corners=False)[0]
+    want = (want - torch.tensor(IMAGENET_MEAN)[:, None, None]) / torch.tensor(IMAGENET_STD)[:, None, None]
+    got = C.preprocess_image(img, 256, IMAGENET_MEAN, IMAGENET_STD)
+    assert (got.cpu() - want).abs().max().item() < 2e-5
+
+
+@pytest.fixture(scope="module")
+def pair():
+    from socioreasoner_b200.sam2 import B200Sam2ImagePredictor
+    hf = small_hf_model()
+    return hf, B200Sam2ImagePredictor.from_hf_model(hf, "cuda")
+
+
+def test_trunk_and_neck_match_hf(pair):
+    hf, pred = pair
+    eng = pred.engine
+    px = torch.randn(3, 256, 256, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        out = hf.get_image_features(px[None], return_dict=True)
+        emb = hf(pixel_values=px[None], input_points=torch.tensor([[[[10.0, 20.0]]]]), input_labels=torch.tensor([[[1]]])).image_embeddings
+        hs = hf.vision_encoder.backbone(px[None], output_hidden_states=True).hidden_states
+    caps = []
+    eng.set_image(px.cuda(), capture=caps)
+    assert rel_rms(eng.feat_s0, out.fpn_hidden_states[0][:, 0]) < 2e-2
+    assert rel_rms(eng.feat_s1, out.fpn_hidden_states[1][:, 0]) < 2e-2
+    want = emb[-1][0].flatten(1).t() + hf.prompt_encoder.no_mask_embed.weight
+    assert rel_rms(eng.image_embed, want.detach()) < 2e-2
+
+
+@pytest.mark.parametrize("prompt", ["point", "box", "box+points"])
+def test_mask_logits_and_iou_match_hf(pair, prompt):
+    hf, pred = pair
+    px = torch.randn(3, 256, 256, generator=torch.Generator().manual_seed(4))
+    pred.engine.set_image(px.cuda())
+    kw, coords, labels = {}, [], []
+    if "box" in prompt:
+        kw["input_boxes"] = torch.tensor([[[30.0, 40.0, 200.0, 180.0]]])
+        coords += [[30.0, 40.0], [200.0, 180.0]]; labels += [2, 3]
+    if "point" in prompt:
+        pts = [[100.0, 120.0], [50.0, 60.0]] if prompt != "point" else [[100.0, 120.0]]
+        kw["input_points"], kw["input_labels"] = torch.tensor([[pts]]), torch.tensor([[[1, 0][:len(pts)]]])
+        coords += pts; labels += [1, 0][:len(pts)]
+    coords.append([0.0, 0.0]); labels.append(-1)
+    with torch.no_grad():
+        out = hf(pixel_values=px[None], multimask_output=True, **kw)
+    logits, iou = pred.engine.predict_logits(np.asarray(coords, np.float32), np.asarray(labels, np.int64))
+    ref = out.pred_masks[0, 0]
+    assert rel_rms(logits, ref) < 3e-2
+    np.testing.assert_allclose(iou.cpu().numpy(), out.iou_scores[0, 0].numpy(), atol=2e-2)
+    agree = ((logits.cpu() > 0) == (ref > 0)).float().mean().item()
+    assert agree > 0.99, agree
+
+
+def test_predictor_behind_seg_strategy(pair):
+    """create_strategy('seg_infer') + the B200 predictor: set_image / predict per object, best-score pick, OR, 768 nearest resize."""
+    from PIL import Image
+    from oracle import host_ref
+    from socioreasoner_b200.roll_shim import DataProto, create_strategy
+    hf, pred = pair
+    g = torch.Generator().manual_seed(9)
+    img = Image.fromarray(torch.randint(0, 256, (640, 480, 3), generator=g, dtype=torch.uint8).numpy())
+    vps = [dict(box=[100, 150, 500, 600]), dict(point_coords=[[300, 300]], point_labels=[1])]
+    w = SimpleNamespace(worker_config=SimpleNamespace(strategy_args=SimpleNamespace(strategy_name="seg_infer"), model_args=None))
+    st = create_strategy(w).initialize(lambda model_args, is_trainable=False: pred)
+    d = DataProto.from_dict(tensors=dict(x=torch.zeros(1, 1)), non_tensors=dict(seg_image=[img], visual_prompt=[vps]))
+    mask = st.segment(d)["mask"][0]
+    assert mask.shape == (768, 768) and mask.dtype == np.uint8
+    # the same through the predictor's numpy API + the reference's CPU epilogue semantics
+    pred.set_image(img.resize((756, 756)))
+    lows, scs = [], []
+    for vp in vps:
+        m, s, low = pred.predict(**vp)
+        assert m.shape == (3, 756, 756) and m.dtype == np.bool_ and low.shape == (3, 64, 64)
+        lows.append(torch.from_numpy(low)); scs.append(torch.from_numpy(s))
+    ref = host_ref.mask_epilogue(torch.stack(lows), torch.stack(scs))
+    assert np.array_equal(mask, ref)

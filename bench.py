@@ -145,6 +145,37 @@ def extra_lines(model, cfg, dev, rank):
         "two_image_prompt_756": dict(images_per_prompt=2),
         "cfg4_mixed_448_896_1344": dict(sides=[448, 896, 1344], max_pixels=pp.YAML_MAX_PIXELS, n_prompts=6),
     }
+    try:   # the SAM2 image path at the production geometry: hiera-large, 756^2 seg image -> 1024^2, 3 object prompts
+        from PIL import Image
+        from socioreasoner_b200.sam2 import B200Sam2ImagePredictor, Sam2Cfg
+        from socioreasoner_b200.sam2.weights import random_state_dict
+        from socioreasoner_b200 import lib as _lib
+        pred = B200Sam2ImagePredictor.from_state_dict(random_state_dict(Sam2Cfg(), seed=7), Sam2Cfg(), dev)
+        img = np.ascontiguousarray(pp.synth_tile(0, 756).transpose(1, 2, 0))
+        prompts = [dict(box=[100, 150, 500, 600]), dict(point_coords=[[300, 300]], point_labels=[1]), dict(box=[50, 60, 700, 650])]
+
+        def one_tile():
+            pred.set_image(img)
+            ls, ss = zip(*[pred.predict_logits(**p) for p in prompts])
+            return _lib.mask_epilogue(torch.stack(ls), torch.stack(ss))
+        one_tile(); torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record(); pred.set_image(img); ev[1].record()
+        for p in prompts:
+            pred.predict_logits(**p)
+        ev[2].record(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            m = one_tile()
+        e1.record(); torch.cuda.synchronize()
+        out["sam2_hiera_large"] = {"ms_per_tile": round(e0.elapsed_time(e1) / 4, 2), "set_image_ms": round(ev[0].elapsed_time(ev[1]), 2),
+                                   "predict_3_objects_ms": round(ev[1].elapsed_time(ev[2]), 2), "mask_pixels_set": int(m.sum().item()),
+                                   "note": "random-init weights; parity vs the HF port: tests/test_gpu_sam2.py"}
+        del pred
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["sam2_hiera_large"] = {"error": repr(e)[:200]}
     for name, kw in cases.items():
         try:
             ro = DataParallelRollout(model, max_new_tokens=NEW_TOKENS, group=None, max_pixels=kw.get("max_pixels"))

@@ -249,3 +249,86 @@ def pack(sd: Dict[str, torch.Tensor], cfg: Sam2Cfg, device, act_dtype=torch.bflo
     for s in range(4):   # stage outputs back to row-major (for the neck)
         T[f"to_rm{s}"] = torch.from_numpy(layout.inverse(layout.wm_perm(R[s], ws[s]))).to(dev)
     return out
+
+
+def random_state_dict(cfg: Sam2Cfg, seed: int = 0, std: float = 0.02) -> Dict[str, torch.Tensor]:
+    """HF-named random weights of the right shapes (bench / smoke without a checkpoint: there is no network on the box)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def lin(name, n, k, bias=True):
+        sd[name + ".weight"] = torch.randn(n, k, generator=g) * std
+        if bias:
+            sd[name + ".bias"] = torch.randn(n, generator=g) * std
+
+    def norm(name, n):
+        sd[name + ".weight"] = 1 + torch.randn(n, generator=g) * 0.1
+        sd[name + ".bias"] = torch.randn(n, generator=g) * 0.05
+
+    p = "vision_encoder.backbone."
+    C0, k = cfg.embed_dims[0], cfg.patch_kernel
+    sd[p + "patch_embed.projection.weight"] = torch.randn(C0, 3, k, k, generator=g) * std
+    sd[p + "patch_embed.projection.bias"] = torch.randn(C0, generator=g) * std
+    sd[p + "pos_embed"] = torch.randn(1, C0, *cfg.pos_embed_bkg, generator=g) * std
+    sd[p + "pos_embed_window"] = torch.randn(1, C0, cfg.window_sizes[0], cfg.window_sizes[0], generator=g) * std
+    for i, b in enumerate(block_specs(cfg)):
+        q = f"{p}blocks.{i}."
+        norm(q + "layer_norm1", b.dim_in)
+        lin(q + "attn.qkv", 3 * b.dim, b.dim_in)
+        lin(q + "attn.proj", b.dim, b.dim)
+        norm(q + "layer_norm2", b.dim)
+        lin(q + "mlp.proj_in", int(b.dim * cfg.mlp_ratio), b.dim)
+        lin(q + "mlp.proj_out", b.dim, int(b.dim * cfg.mlp_ratio))
+        if b.pool:
+            lin(q + "proj", b.dim, b.dim_in)
+    for j, c in enumerate(reversed(cfg.embed_dims)):
+        sd[f"vision_encoder.neck.convs.{j}.weight"] = torch.randn(cfg.fpn_hidden, c, 1, 1, generator=g) * std
+        sd[f"vision_encoder.neck.convs.{j}.bias"] = torch.randn(cfg.fpn_hidden, generator=g) * std
+    Hd = cfg.dec_hidden
+    sd["no_memory_embedding"] = torch.randn(1, 1, Hd, generator=g) * std
+    sd["shared_image_embedding.positional_embedding"] = torch.randn(2, Hd // 2, generator=g)
+    sd["prompt_encoder.shared_embedding.positional_embedding"] = torch.randn(2, Hd // 2, generator=g)
+    sd["prompt_encoder.no_mask_embed.weight"] = torch.randn(1, Hd, generator=g) * std
+    sd["prompt_encoder.point_embed.weight"] = torch.randn(4, Hd, generator=g) * std
+    sd["prompt_encoder.not_a_point_embed.weight"] = torch.randn(1, Hd, generator=g) * std
+    d = "mask_decoder."
+    sd[d + "iou_token.weight"] = torch.randn(1, Hd, generator=g) * std
+    sd[d + "obj_score_token.weight"] = torch.randn(1, Hd, generator=g) * std
+    sd[d + "mask_tokens.weight"] = torch.randn(cfg.num_multimask + 1, Hd, generator=g) * std
+
+    def attn(name, internal):
+        for nm in ("q", "k", "v"):
+            lin(f"{name}.{nm}_proj", internal, Hd)
+        lin(f"{name}.o_proj", Hd, internal)
+
+    for l in range(cfg.dec_layers):
+        kk = f"{d}transformer.layers.{l}."
+        attn(kk + "self_attn", Hd)
+        attn(kk + "cross_attn_token_to_image", Hd // cfg.dec_downsample)
+        attn(kk + "cross_attn_image_to_token", Hd // cfg.dec_downsample)
+        for j in (1, 2, 3, 4):
+            norm(f"{kk}layer_norm{j}", Hd)
+        lin(kk + "mlp.proj_in", cfg.dec_mlp, Hd)
+        lin(kk + "mlp.proj_out", Hd, cfg.dec_mlp)
+    attn(d + "transformer.final_attn_token_to_image", Hd // cfg.dec_downsample)
+    norm(d + "transformer.layer_norm_final_attn", Hd)
+    sd[d + "upscale_conv1.weight"] = torch.randn(Hd, Hd // 4, 2, 2, generator=g) * std
+    sd[d + "upscale_conv1.bias"] = torch.randn(Hd // 4, generator=g) * std
+    sd[d + "upscale_conv2.weight"] = torch.randn(Hd // 4, Hd // 8, 2, 2, generator=g) * std
+    sd[d + "upscale_conv2.bias"] = torch.randn(Hd // 8, generator=g) * std
+    norm(d + "upscale_layer_norm", Hd // 4)
+
+    def mlp(name, hidden, n_out, depth):
+        lin(name + ".proj_in", hidden, Hd)
+        for j in range(depth - 2):
+            lin(f"{name}.layers.{j}", hidden, hidden)
+        lin(name + ".proj_out", n_out, hidden)
+
+    for t in range(cfg.num_multimask + 1):
+        mlp(f"{d}output_hypernetworks_mlps.{t}", Hd, Hd // 8, cfg.iou_depth)
+    mlp(d + "iou_prediction_head", cfg.iou_hidden, cfg.num_multimask + 1, cfg.iou_depth)
+    lin(d + "conv_s0", Hd // 8, Hd)
+    lin(d + "conv_s1", Hd // 4, Hd)
+    sd[d + "conv_s0.weight"] = sd[d + "conv_s0.weight"].reshape(Hd // 8, Hd, 1, 1)
+    sd[d + "conv_s1.weight"] = sd[d + "conv_s1.weight"].reshape(Hd // 4, Hd, 1, 1)
+    return sd

@@ -137,3 +137,49 @@ def test_predictor_behind_seg_strategy(pair):
         lows.append(torch.from_numpy(low)); scs.append(torch.from_numpy(s))
     ref = host_ref.mask_epilogue(torch.stack(lows), torch.stack(scs))
     assert np.array_equal(mask, ref)
+
+
+def large_hf_model(seed=0):
+    """sam2-hiera-large geometry (sam2_hiera_l.yaml: the checkpoint the reference loads), random init."""
+    from transformers.models.sam2 import configuration_sam2 as c, modeling_sam2 as m
+    bc = dict(hidden_size=144, embed_dim_per_stage=[144, 288, 576, 1152], num_attention_heads_per_stage=[2, 4, 8, 16],
+              blocks_per_stage=[2, 6, 36, 4], global_attention_blocks=[23, 33, 43], window_size_per_stage=[8, 4, 16, 8],
+              image_size=[1024, 1024], num_attention_heads=2)
+    vc = dict(backbone_config=bc, backbone_channel_list=[1152, 576, 288, 144])
+    cfg = c.Sam2Config(vision_config=vc)
+    torch.manual_seed(seed)
+    model = m.Sam2Model(cfg).eval()
+    with torch.no_grad():
+        gen = torch.Generator().manual_seed(seed + 1)
+        for n, p in model.named_parameters():
+            if p.dim() == 1 or "embed" in n or "token" in n:
+                p.copy_(torch.randn(p.shape, generator=gen) * (0.5 if "embed" in n or "token" in n else 0.1) + (1.0 if "norm" in n and n.endswith("weight") else 0.0))
+    return model
+
+
+def test_hiera_large_full_size_against_hf():
+    """The production geometry end to end: 1024^2 input, 48 Hiera blocks (65536 -> 1024 tokens), box + point prompt: low-res logits,
+    IoU predictions, and the IoU between the thresholded masks of the two implementations (the number SURVEY.md 8d asks for)."""
+    import os
+    from socioreasoner_b200.sam2 import B200Sam2ImagePredictor, Sam2Cfg
+    torch.set_num_threads(os.cpu_count())
+    hf = large_hf_model()
+    cfg = Sam2Cfg.from_hf(hf.config)
+    assert cfg == Sam2Cfg()                                                   # the defaults ARE hiera-large
+    pred = B200Sam2ImagePredictor.from_hf_model(hf, "cuda")
+    px = torch.randn(3, 1024, 1024, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        out = hf(pixel_values=px[None], input_boxes=torch.tensor([[[200.0, 300.0, 800.0, 900.0]]]),
+                 input_points=torch.tensor([[[[500.0, 600.0]]]]), input_labels=torch.tensor([[[1]]]), multimask_output=True)
+    pred.engine.set_image(px.cuda())
+    coords = np.array([[200, 300], [800, 900], [500, 600], [0, 0]], np.float32)
+    logits, iou = pred.engine.predict_logits(coords, np.array([2, 3, 1, -1]))
+    ref = out.pred_masks[0, 0]
+    err = rel_rms(logits, ref)
+    a, b = (logits.cpu() > 0), (ref > 0)
+    miou = ((a & b).flatten(1).sum(1).float() / (a | b).flatten(1).sum(1).clamp_min(1).float())
+    print(f"\nSAM2 hiera-large @1024^2: logits rel-rms {err:.4f}, mask IoU vs HF fp32 {miou.tolist()}, iou-pred diff "
+          f"{(iou.cpu() - out.iou_scores[0, 0]).abs().max().item():.4f}")
+    assert err < 8e-2
+    assert (a == b).float().mean().item() > 0.98
+    np.testing.assert_allclose(iou.cpu().numpy(), out.iou_scores[0, 0].numpy(), atol=3e-2)

@@ -38,7 +38,7 @@ namespace sr {
 
 constexpr int DP_CONSUMERS = 8;
 constexpr int DP_CTHREADS = DP_CONSUMERS * 32;
-constexpr int DP_THREADS = DP_CTHREADS + 64;          // warp 0 = producer, warps 1-8 = consumers, warp 9 = L2 prefetcher
+constexpr int DP_THREADS = DP_CTHREADS + 32;          // warp 0 = producer, warps 1-8 = consumers
 constexpr int DP_STAGE_BLOCKS = 16;                   // 1 KB weight blocks per ring stage
 constexpr int DP_STAGE_BYTES = DP_STAGE_BLOCKS * 1024;
 constexpr int DP_STAGES = 10;
@@ -62,9 +62,11 @@ constexpr int DP_RED_WQ = 8 * 20;                                     // floats 
 constexpr int DP_RED_BYTES = 2 * DP_CONSUMERS * 2 * DP_RED_WQ * 4;    // 20480
 constexpr int DP_OFF_BAR = DP_OFF_RED + DP_RED_BYTES;
 constexpr int DP_OFF_LAYERS = DP_OFF_BAR + 2 * DP_STAGES * 8 + 32;    // DpLayer[DP_MAX_LAYERS]
-constexpr int DP_OFF_ROPE = DP_OFF_LAYERS + DP_MAX_LAYERS * 56;       // cos[8][64], sin[8][64] fp32 of this step
+constexpr int DP_OFF_ROPE = DP_OFF_LAYERS + DP_MAX_LAYERS * 64;       // cos[8][64], sin[8][64] fp32 of this step
 constexpr int DP_OFF_SCAL = DP_OFF_ROPE + 2 * 8 * 64 * 4;             // kv_start[8], kv_len[8], cache_row[8], epoch, gate, pcnt
-constexpr int DP_SMEM_BYTES = DP_OFF_SCAL + 4 * 8 * 4 + 1024;         // + alignment slack
+constexpr int DP_OFF_ACT = DP_OFF_SCAL + 4 * 8 * 4;                   // bf16 [8 batch][16 k]: SwiGLU output of the current unit
+constexpr int DP_OFF_RED4 = DP_OFF_ACT + 256;                         // float [4][64][2] (partial-sum reduction) + float [8][16]
+constexpr int DP_SMEM_BYTES = DP_OFF_RED4 + 4 * 64 * 2 * 4 + 8 * 16 * 4 + 1024;  // + alignment slack
 static_assert(DP_SMEM_BYTES <= 232448, "shared-memory budget of one sm_100 CTA");
 
 struct DpLayer {  // == sr_decode_layer (include/socioreasoner_b200.h)
@@ -74,7 +76,8 @@ struct DpLayer {  // == sr_decode_layer (include/socioreasoner_b200.h)
   const __nv_bfloat16* o_wp;
   const float* ln2;
   const __nv_bfloat16* gu_wp;
-  const __nv_bfloat16* down_wp;
+  const __nv_bfloat16* down_wk;  // K-sliced: [I/16 units][4 stages][8 warps][4][16 rows][16 k (quad order)] (weights.py::_kslice_pack)
+  const void* reserved;
 };
 
 struct DpParams {
@@ -109,6 +112,7 @@ struct DpParams {
   uint4* ao_ll;
   unsigned int* act_flags; // [gridDim.x] generation of each CTA's last complete SwiGLU output (plain bf16 in `act`)
   uint4* part_ll;          // [B*nkv][ns][DP_PART_LINES]
+  uint4* xpart_ll;         // [gridDim.x][2048 rows * 4]: every CTA's fp32 partial of the down projection, line (row, batch pair)
   int ns;
   int stop_after;          // debug: run only the first `stop_after` phases (<= 0: all)
   int ring_stages;         // shared-memory ring stages in use (2 .. DP_STAGES)
@@ -217,8 +221,7 @@ struct DpRing {
 // from L2 by every CTA: without the rotation all CTAs request the same lines at the same time (hot L2 slices).
 SR_DEVINL int dp_rot(int u, int nst) { return (u * 7) % nst; }
 template <int RG, bool ROT>
-SR_DEVINL void dp_produce(DpRing& r, int v0, const __nv_bfloat16* Wp, int n_units, int nchunks, uint64_t policy, bool hint,
-                          volatile int* pcnt, int& issued, int stride) {
+SR_DEVINL void dp_produce(DpRing& r, int v0, const __nv_bfloat16* Wp, int n_units, int nchunks, uint64_t policy, bool hint, int stride) {
   constexpr int CPS = DP_STAGE_BLOCKS / RG;
   const int nst = (nchunks + CPS - 1) / CPS;
   for (int u = v0; u < n_units; u += stride) {
@@ -242,44 +245,44 @@ SR_DEVINL void dp_produce(DpRing& r, int v0, const __nv_bfloat16* Wp, int n_unit
         }
       }
       r.advance();
-      *pcnt = ++issued;
       if (ROT && ++st == nst) st = 0;
       if (!ROT) ++st;
     }
   }
 }
 
-// L2 prefetcher (warp 9, one thread): walks the SAME stage sequence as the producer, at most `lead` stages ahead of it, and asks
-// the memory system to bring each stage into L2 (cp.async.bulk.prefetch.L2).  The shared-memory ring holds 128-160 KB per CTA
-// (3 us of HBM time chip-wide), but a layer spends ~18 us in the qkv -> attention -> o-proj chain of cross-CTA exchanges during
-// which the ring is full and HBM would idle; with the prefetcher the HBM stream continues into L2 (`lead` x 16 KB x 148 CTAs),
-// and the ring later refills at L2 speed.  (Round 1 measured no gain from this -- its chain was made of grid barriers whose
-// many round trips slowed down under the extra traffic; the flag-carrying exchanges are insensitive to it: gating the weight
-// stream off during the chain does not shorten it.)
-template <int RG, bool ROT>
-SR_DEVINL void dp_prefetch_l2(int& sidx, const volatile int* pcnt, int lead, int v0, const __nv_bfloat16* Wp, int n_units, int nchunks,
-                               int stride) {
-  constexpr int CPS = DP_STAGE_BLOCKS / RG;
+// Fused gate/up + down schedule: for every gate/up unit of this CTA (32 packed rows = 16 SwiGLU columns, 8 ring stages of two
+// 8 KB halves) directly followed by the K-slice of the down projection that consumes exactly those 16 columns (2048 x 16 =
+// 64 KB contiguous = 4 ring stages).
+SR_DEVINL void dp_produce_de(DpRing& r, int v0, const __nv_bfloat16* Wgu, const __nv_bfloat16* Wdk, int n_units, int nchunks, uint64_t policy,
+                             bool hint, int stride) {
+  constexpr int CPS = DP_STAGE_BLOCKS / 2;
   const int nst = (nchunks + CPS - 1) / CPS;
+  auto issue = [&](uint8_t* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    if (hint)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                       smem_u32(dst)),
+                   "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                   : "memory");
+    else
+      dp_bulk_g2s(dst, src, bytes, bar);
+  };
   for (int u = v0; u < n_units; u += stride) {
-    int st = ROT ? dp_rot(u, nst) : 0;
-    for (int i = 0; i < nst; ++i) {
-      int pc = *pcnt;
-      while (sidx >= pc + lead) {
-        __nanosleep(100);
-        pc = *pcnt;
-      }
-      if (sidx > pc) {  // (the producer is about to request stage `pc` itself)
-        const int nch = min(CPS, nchunks - st * CPS);
+    for (int st = 0; st < nst; ++st) {
+      mbar_wait(&r.empty[r.slot], r.phase ^ 1);
+      const int nch = min(CPS, nchunks - st * CPS);
+      mbar_arrive_expect_tx(&r.full[r.slot], static_cast<uint32_t>(2 * nch * 1024));
 #pragma unroll
-        for (int g = 0; g < RG; ++g) {
-          const __nv_bfloat16* src = Wp + (static_cast<int64_t>(u * RG + g) * nchunks + st * CPS) * 512;
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(static_cast<uint32_t>(nch * 1024)) : "memory");
-        }
-      }
-      ++sidx;
-      if (ROT && ++st == nst) st = 0;
-      if (!ROT) ++st;
+      for (int g = 0; g < 2; ++g)
+        issue(r.data + r.slot * DP_STAGE_BYTES + g * (CPS * 1024), Wgu + (static_cast<int64_t>(u * 2 + g) * nchunks + st * CPS) * 512,
+              static_cast<uint32_t>(nch * 1024), &r.full[r.slot]);
+      r.advance();
+    }
+    for (int st = 0; st < 4; ++st) {
+      mbar_wait(&r.empty[r.slot], r.phase ^ 1);
+      mbar_arrive_expect_tx(&r.full[r.slot], static_cast<uint32_t>(DP_STAGE_BYTES));
+      issue(r.data + r.slot * DP_STAGE_BYTES, Wdk + (static_cast<int64_t>(u) * 4 + st) * (DP_STAGE_BYTES / 2), DP_STAGE_BYTES, &r.full[r.slot]);
+      r.advance();
     }
   }
 }
@@ -535,6 +538,143 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int v0, int n_units, int nchunks, const 
       }
     }
     red_par ^= 1;  // the next unit writes the other buffer; its barrier orders this unit's reads before the reuse after it
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fused gate/up + down phase
+// For every gate/up unit of this CTA: [gate|up] = xs . Wgu^T (as dp_gemv_phase<2, SWIGLU>), act = silu(gate) * up for the unit's 16
+// columns lands in shared memory (never in global memory), and the down projection's K-slice for exactly these columns is applied
+// right away: acc_e[row group][..] += Wd[:, 16u .. 16u+15] . act^T, one mma.m16n8k16 per 16-row group, 16 row groups per warp.  The
+// SwiGLU output therefore never crosses CTAs; what crosses is every CTA's fp32 partial of x (2048 x 8), published as LL lines and
+// summed in a fixed order by the CTA that owns the 16 output rows (dp_reduce_x).  Compared with "all CTAs read all of act" this
+// removes 176 KB of activation reads per CTA and one exchange from the middle of the weight stream.
+SR_DEVINL int dp_kpos(int k) { return ((k & 7) >> 1) * 4 + (k >> 3) * 2 + (k & 1); }  // position of k inside a 16-wide k group
+SR_DEVINL void dp_de_phase(DpRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, uint8_t* s_act, int M, float* red, int& red_par,
+                           __nv_bfloat16* dbg_act, int I, float (&acc_e)[16][4], int cw, int lane, int stride) {
+  constexpr int CPS = DP_STAGE_BLOCKS / 2;
+  const int g = lane >> 2, t = lane & 3;
+  const int ct = threadIdx.x - 32;
+  const int eb = ct & 7, efg = (ct >> 3) & 3;
+  const bool epi_thread = ct < 32 && eb < M;
+  const int nst = (nchunks + CPS - 1) / CPS;
+  const uint8_t* xrow = xs + g * DP_XS_STRIDE + t * 16;
+  for (int u = v0; u < n_units; u += stride) {
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int st = 0; st < nst; ++st) {
+      mbar_wait(&r.full[r.slot], r.phase);
+      const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
+      const int c = st * CPS + cw;
+      if (c < nchunks) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint8_t* blk = stage + q * (CPS * 1024) + cw * 1024;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
+          dp_mma(acc[q], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
+          dp_mma(acc[q], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&r.empty[r.slot]);
+      r.advance();
+    }
+    float* rp = red + red_par * (DP_CONSUMERS * 2 * DP_RED_WQ);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float* d = rp + (cw * 2 + q) * DP_RED_WQ;
+      d[(2 * t) * 20 + g] = acc[q][0];
+      d[(2 * t + 1) * 20 + g] = acc[q][1];
+      d[(2 * t) * 20 + g + 8] = acc[q][2];
+      d[(2 * t + 1) * 20 + g + 8] = acc[q][3];
+    }
+    dp_cbar();
+    if (epi_thread) {
+      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+#pragma unroll
+      for (int w8 = 0; w8 < DP_CONSUMERS; ++w8) {
+        const float4 a = *reinterpret_cast<const float4*>(rp + (w8 * 2) * DP_RED_WQ + eb * 20 + efg * 4);
+        const float4 b = *reinterpret_cast<const float4*>(rp + (w8 * 2 + 1) * DP_RED_WQ + eb * 20 + efg * 4);
+        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+      }
+      const float gt[4] = {s0.x, s0.y, s0.z, s0.w}, up[4] = {s1.x, s1.y, s1.z, s1.w};
+      __nv_bfloat16 a4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a4[j] = __float2bfloat16((gt[j] / (1.0f + __expf(-gt[j]))) * up[j]);
+        reinterpret_cast<__nv_bfloat16*>(s_act)[eb * 16 + dp_kpos(efg * 4 + j)] = a4[j];
+      }
+      if (dbg_act != nullptr) *reinterpret_cast<uint2*>(dbg_act + static_cast<int64_t>(eb) * I + u * 16 + efg * 4) = *reinterpret_cast<const uint2*>(a4);
+    }
+    red_par ^= 1;
+    dp_cbar();
+    // down-projection slice of this unit: B fragment = act (batch g; k quad t), A fragments straight from the ring
+    const uint2 bv = *reinterpret_cast<const uint2*>(s_act + g * 32 + t * 8);
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      mbar_wait(&r.full[r.slot], r.phase);
+      const uint8_t* wb = r.data + r.slot * DP_STAGE_BYTES + cw * 2048;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint2 a_lo = *reinterpret_cast<const uint2*>(wb + j * 512 + g * 32 + t * 8);
+        const uint2 a_hi = *reinterpret_cast<const uint2*>(wb + j * 512 + (g + 8) * 32 + t * 8);
+        dp_mma(acc_e[st * 4 + j], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bv.x, bv.y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&r.empty[r.slot]);
+      r.advance();
+    }
+  }
+}
+
+// Sum of the 148 partials for this CTA's 16 output rows (fixed order: deterministic), + residual, -> next x as LL lines.
+SR_DEVINL void dp_reduce_x(const DpParams& p, int ud, uint32_t gen, const uint4* res_ll, uint4* out_ll, float* red4, int ct,
+                           __nv_bfloat16* dbg, int64_t ld_dbg) {
+  const int G = static_cast<int>(gridDim.x);
+  const int item = ct & 63, grp = ct >> 6;            // item = line inside the unit: row = item / 4, batch pair = item % 4
+  const int eb = ct & 7, efg = (ct >> 3) & 3;
+  uint4 resl = make_uint4(0, 0, 0, 0);
+  const uint4* res_ptr = res_ll + eb * DP_HL + ud * 4 + efg;
+  if (ct < 32 && eb < p.B) resl = ll_load(res_ptr);
+  float s0 = 0.f, s1 = 0.f;
+  const uint4* base = p.xpart_ll + static_cast<int64_t>(ud) * 64 + item;
+  for (int p0 = grp; p0 < G; p0 += 32) {
+    uint4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int pi = p0 + 4 * j;
+      v[j] = pi < G ? ll_load(base + static_cast<int64_t>(pi) * (DP_H * 4)) : make_uint4(0, gen, 0, gen);
+    }
+    ll_wait(v, [&](int j) { return base + static_cast<int64_t>(p0 + 4 * j) * (DP_H * 4); }, gen);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s0 += __uint_as_float(v[j].x);
+      s1 += __uint_as_float(v[j].z);
+    }
+  }
+  red4[(grp * 64 + item) * 2] = s0;
+  red4[(grp * 64 + item) * 2 + 1] = s1;
+  dp_cbar();
+  float* sx = red4 + 4 * 64 * 2;  // [8 batch][16 rows]
+  if (ct < 64) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      a += red4[(q * 64 + ct) * 2];
+      b += red4[(q * 64 + ct) * 2 + 1];
+    }
+    const int row = ct >> 2, t = ct & 3;
+    sx[(2 * t) * 16 + row] = a;
+    sx[(2 * t + 1) * 16 + row] = b;
+  }
+  dp_cbar();
+  if (ct < 32 && eb < p.B) {
+    ll_spin(resl, res_ptr, gen);
+    const float4 v = *reinterpret_cast<const float4*>(sx + eb * 16 + efg * 4);
+    const uint32_t d0 = pack_bf16x2(v.x + bf16_lo(resl.x), v.y + bf16_hi(resl.x)), d1 = pack_bf16x2(v.z + bf16_lo(resl.z), v.w + bf16_hi(resl.z));
+    ll_store(out_ll + eb * DP_HL + ud * 4 + efg, d0, d1, gen);
+    if (dbg != nullptr) *reinterpret_cast<uint2*>(dbg + static_cast<int64_t>(eb) * ld_dbg + ud * 16 + efg * 4) = make_uint2(d0, d1);
   }
 }
 
@@ -926,12 +1066,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   float* s_cos = reinterpret_cast<float*>(smem + DP_OFF_ROPE);
   float* s_sin = s_cos + 8 * 64;
   int* s_scal = reinterpret_cast<int*>(smem + DP_OFF_SCAL);
-  volatile int* s_pcnt = reinterpret_cast<volatile int*>(s_scal + 26);  // stages issued by the producer (read by the prefetcher)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {  // per-launch constants -> shared memory (pointer / scalar loads off the critical paths)
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.layers);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_layers);
-    for (int i = threadIdx.x; i < p.n_layers * 7; i += DP_THREADS) dst[i] = src[i];
+    for (int i = threadIdx.x; i < p.n_layers * 8; i += DP_THREADS) dst[i] = src[i];
     for (int i = threadIdx.x; i < 8 * 64; i += DP_THREADS) {
       const bool ok = i < p.B * 64;
       s_cos[i] = ok ? p.cosb[i] : 0.f;
@@ -945,7 +1084,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     }
     if (threadIdx.x == 8) s_scal[24] = static_cast<int>(*reinterpret_cast<volatile unsigned int*>(p.epoch));
     if (threadIdx.x == 9) s_scal[25] = 0;
-    if (threadIdx.x == 10) s_scal[26] = 0;
+    if (threadIdx.x >= 32 && threadIdx.x < 96) reinterpret_cast<uint32_t*>(smem + DP_OFF_ACT)[threadIdx.x - 32] = 0u;
   }
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -981,57 +1120,47 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       uint64_t policy = 0;
       const bool hint = (p.flags & 1) != 0;
       if (hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      int ph = 0, issued = 0;
+      int ph = 0;
       dp_trace_at(p, 0, 0);
       for (int l = 0; l < p.n_layers; ++l) {
         const DpLayer L = s_layers[l];
         if (ph++ >= limit) return;
-        dp_produce<2, false>(ring, vq, L.qkv_wp, n_qkv / 2, kq, policy, hint, s_pcnt, issued, G);
+        dp_produce<2, false>(ring, vq, L.qkv_wp, n_qkv / 2, kq, policy, hint, G);
         dp_trace_at(p, 0, 1 + 4 * l);
         if (ph++ >= limit) return;  // attention phase: no weights
         if (ph++ >= limit) return;
-        dp_produce<1, false>(ring, vo, L.o_wp, n_o, kq, policy, hint, s_pcnt, issued, G);
+        dp_produce<1, false>(ring, vo, L.o_wp, n_o, kq, policy, hint, G);
         dp_trace_at(p, 0, 2 + 4 * l);
         if (ph++ >= limit) return;
         if (p.flags & 4) {  // diagnostic: no gate/up streaming before this CTA's consumers reach phase D (idle HBM during the chain)
           volatile int* gate = s_scal + 25;
           while (*gate < l + 1) __nanosleep(20);
         }
-        dp_produce<2, false>(ring, vg, L.gu_wp, n_gu, kq, policy, hint, s_pcnt, issued, G);
+        if (p.pf_stages > 0) {
+          // L2 prefetch BURST of the head of this CTA's gate/up + down stream: issued once per layer at the moment the ring is about
+          // to fill up (the consumers are in the qkv -> attention -> o-proj exchange chain for the next ~20 us and HBM would idle);
+          // pf_stages x 16 KB per CTA.  No prefetching while the stream itself runs (that only doubles the L2 traffic).
+          int left = p.pf_stages * DP_STAGE_BYTES;
+          for (int u = vg; u < n_gu && left > 0; u += G) {
+            const char* a = reinterpret_cast<const char*>(L.gu_wp) + static_cast<int64_t>(u) * (2 * kq * 1024);
+            const char* b = reinterpret_cast<const char*>(L.down_wk) + static_cast<int64_t>(u) * (4 * DP_STAGE_BYTES);
+            for (int o2 = 0; o2 < 2 * kq * 1024 && left > 0; o2 += 32768, left -= 32768)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a + o2), "r"(32768u) : "memory");
+            for (int o2 = 0; o2 < 4 * DP_STAGE_BYTES && left > 0; o2 += 32768, left -= 32768)
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b + o2), "r"(32768u) : "memory");
+          }
+        }
+        dp_produce_de(ring, vg, L.gu_wp, L.down_wk, n_gu, kq, policy, hint, G);
         dp_trace_at(p, 0, 3 + 4 * l);
         if (ph++ >= limit) return;
-        dp_produce<1, true>(ring, vd, L.down_wp, n_o, kd, policy, hint, s_pcnt, issued, G);
         dp_trace_at(p, 0, 4 + 4 * l);
       }
       if (ph++ >= limit) return;
-      if (hv < n_head) dp_produce<1, false>(ring, hv, p.lm_head_p, n_head, kq, policy, hint, s_pcnt, issued, hs);
+      if (hv < n_head) dp_produce<1, false>(ring, hv, p.lm_head_p, n_head, kq, policy, hint, hs);
       dp_trace_at(p, 0, 1 + 4 * p.n_layers);
     }
     return;
   }
-  if (warp == DP_CONSUMERS + 1) {
-    // ---------------- L2 prefetcher: same walk as the producer, `pf_stages` ahead of it ----------------
-    if (lane == 0 && p.pf_stages > 0) {
-      int ph = 0, sidx = 0;
-      const int lead = p.pf_stages;
-      for (int l = 0; l < p.n_layers; ++l) {
-        const DpLayer L = s_layers[l];
-        if (ph++ >= limit) return;
-        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, vq, L.qkv_wp, n_qkv / 2, kq, G);
-        if (ph++ >= limit) return;
-        if (ph++ >= limit) return;
-        dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, vo, L.o_wp, n_o, kq, G);
-        if (ph++ >= limit) return;
-        dp_prefetch_l2<2, false>(sidx, s_pcnt, lead, vg, L.gu_wp, n_gu, kq, G);
-        if (ph++ >= limit) return;
-        dp_prefetch_l2<1, true>(sidx, s_pcnt, lead, vd, L.down_wp, n_o, kd, G);
-      }
-      if (ph++ >= limit) return;
-      if (hv < n_head) dp_prefetch_l2<1, false>(sidx, s_pcnt, lead, hv, p.lm_head_p, n_head, kq, hs);
-    }
-    return;
-  }
-
   // ---------------- consumers ----------------
   const int cw = warp - 1;
   const int ct = threadIdx.x - 32;
@@ -1095,24 +1224,34 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       DP_TRACE(4);
     }
     DP_TRACE(5);
-    // D: act = silu(gate) * up, [gate|up] = rmsnorm(x; ln2) . Wgu^T
+    // D+E: act = silu(gate) * up of this CTA's gate/up units, immediately multiplied by the matching K-slices of Wdown
     if (ph++ >= limit) break;
     dp_cbar();
     dp_stage_rows<true>(xs, p.xa_ll, gen, p.B, L.ln2, p.eps, cw, lane);
     dp_cbar();
     DP_TRACE(6);
     if (tracer) *reinterpret_cast<volatile int*>(s_scal + 25) = l + 1;
-    o = DpOut{nullptr, 0, gen, nullptr, 0, nullptr, nullptr, 0, p.act, p.I};  // plain bf16 + one release flag per CTA
-    dp_gemv_phase<2, DP_EPI_SWIGLU, true>(ring, vg, n_gu, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
-    dp_publish_act(p.act_flags, gen, ct);
-    DP_TRACE(7);
-    // E: x += act . Wdown^T
-    if (ph++ >= limit) break;
-    o = DpOut{p.xb_ll, DP_HL, gen, p.xa_ll, gen, nullptr, nullptr, 0, dump ? p.x : nullptr, p.ldx};
-    if (vd < n_o) {
-      dp_wait_act(p.act_flags, gen, ct);
-      dp_gemv_phase<1, DP_EPI_RESIDUAL, false>(ring, vd, n_o, kd, nullptr, p.act, p.I, p.B, red, red_par, o, cw, lane, G);
+    {
+      float acc_e[16][4];
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc_e[i][j] = 0.f;
+      dp_de_phase(ring, vg, n_gu, kq, xs, smem + DP_OFF_ACT, p.B, red, red_par, dump ? p.act : nullptr, p.I, acc_e, cw, lane, G);
+      // publish this CTA's partial of Wdown . act^T: line (row, batch pair t) = (x[2t][row], x[2t+1][row])
+      uint4* part = p.xpart_ll + static_cast<int64_t>(blockIdx.x) * (DP_H * 4);
+      const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int row = (16 * cw + i) * 16 + g;
+        ll_store(part + row * 4 + t, __float_as_uint(acc_e[i][0]), __float_as_uint(acc_e[i][1]), gen);
+        ll_store(part + (row + 8) * 4 + t, __float_as_uint(acc_e[i][2]), __float_as_uint(acc_e[i][3]), gen);
+      }
     }
+    DP_TRACE(7);
+    // E': x += sum over CTAs of the partials (rows of this CTA's unit), fixed order
+    if (ph++ >= limit) break;
+    if (vd < n_o) dp_reduce_x(p, vd, gen, p.xa_ll, p.xb_ll, reinterpret_cast<float*>(smem + DP_OFF_RED4), ct, dump ? p.x : nullptr, p.ldx);
     DP_TRACE(8);
     dp_cbar();  // phase E's epilogue reads of `red` / phase D's of xs are done before the next layer restages
   }
@@ -1141,7 +1280,7 @@ using namespace sr;
 
 static inline int64_t dp_align(int64_t v) { return (v + 255) / 256 * 256; }
 struct DpWsLayout {
-  int64_t xa, xb, qkv, ao, act, flags, part, total;
+  int64_t xa, xb, qkv, ao, act, flags, part, xpart, total;
 };
 static DpWsLayout dp_ws_layout(int n_q_heads, int n_kv_heads, int intermediate) {
   DpWsLayout w;
@@ -1153,6 +1292,7 @@ static DpWsLayout dp_ws_layout(int n_q_heads, int n_kv_heads, int intermediate) 
   w.act = off; off += dp_align(8LL * intermediate * 2);
   w.flags = off; off += dp_align(4096);
   w.part = off; off += dp_align(8LL * n_kv_heads * DP_NS_MAX * DP_PART_LINES * 16);
+  w.xpart = off; off += dp_align(256LL * DP_H * 4 * 16);   // up to 256 CTAs x (2048 rows x 4 lines)
   w.total = off;
   return w;
 }
@@ -1253,6 +1393,7 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
   p.ao_ll = reinterpret_cast<uint4*>(ws + w.ao);
   p.act_flags = reinterpret_cast<unsigned int*>(ws + w.flags);
   p.part_ll = reinterpret_cast<uint4*>(ws + w.part);
+  p.xpart_ll = reinterpret_cast<uint4*>(ws + w.xpart);
   SR_REQUIRE(bk <= grid_cached, "sr_decode_step_persistent: batch * n_kv_heads must not exceed the SM count");
   int ns = grid_cached / static_cast<int>(bk);
   p.ns = ns < 1 ? 1 : (ns > DP_NS_MAX ? DP_NS_MAX : ns);

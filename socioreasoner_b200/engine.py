@@ -401,7 +401,8 @@ class Engine:
     def _persistent_ok(self, B: int) -> bool:
         t = self.cfg.text
         return (self.use_persistent_decode and B <= 8 and self.w.lm_head_p is not None and len(self.w.layers) > 0
-                and self.w.layers[0].qkv_wp is not None and t.intermediate_size % 32 == 0 and t.vocab_size % 16 == 0)
+                and self.w.layers[0].qkv_wp is not None and self.w.layers[0].down_wk is not None and t.intermediate_size % 32 == 0
+                and t.vocab_size % 16 == 0)
 
     def _pick_token(self, st, sampling) -> None:
         if st.get("use_forced"):  # teacher forcing (parity tests): token of this step from a given [B, T] table

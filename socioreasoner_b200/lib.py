@@ -396,12 +396,12 @@ def decode_advance(nxt, tokens, step, row0, len0, pos0, cache_row, kv_len, pos3)
 
 
 def decode_layer_table(layers, device) -> torch.Tensor:
-    """Device array of ``sr_decode_layer`` structs (7 pointers per layer) for ``decode_step_persistent``."""
+    """Device array of ``sr_decode_layer`` structs (8 pointers per layer) for ``decode_step_persistent``."""
     rows = []
     for L in layers:
-        assert L.qkv_wp is not None and L.o_wp is not None and L.gu_wp is not None and L.down_wp is not None
+        assert L.qkv_wp is not None and L.o_wp is not None and L.gu_wp is not None and L.down_wk is not None
         rows.append([L.qkv_wp.data_ptr(), L.qkv_b.data_ptr() if L.qkv_b is not None else 0, L.ln1.data_ptr(), L.o_wp.data_ptr(),
-                     L.ln2.data_ptr(), L.gu_wp.data_ptr(), L.down_wp.data_ptr()])
+                     L.ln2.data_ptr(), L.gu_wp.data_ptr(), L.down_wk.data_ptr(), 0])
     return torch.tensor(rows, dtype=torch.int64).to(device)
 
 
@@ -436,7 +436,7 @@ def decode_step_persistent(layer_table: torch.Tensor, lm_head_p: torch.Tensor, f
     _req(cache_row, torch.int32, "decode_persistent.cache_row"); _req(kv_start, torch.int32, "decode_persistent.kv_start")
     _req(kv_len, torch.int32, "decode_persistent.kv_len"); _req(cos, torch.float32, "decode_persistent.cos")
     B = x.shape[0]
-    assert kc.dim() == 4 and vt.dim() == 3 and kc.is_contiguous() and vt.is_contiguous() and layer_table.shape[1] == 7
+    assert kc.dim() == 4 and vt.dim() == 3 and kc.is_contiguous() and vt.is_contiguous() and layer_table.shape[1] == 8
     assert cos.is_contiguous() and sin.is_contiguous()
     if qkv is not None:
         assert qkv.is_contiguous() and ao.is_contiguous() and act.is_contiguous()

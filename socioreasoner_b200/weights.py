@@ -76,6 +76,9 @@ class DecLayerW:
     o_wp: Optional[torch.Tensor] = None
     gu_wp: Optional[torch.Tensor] = None
     down_wp: Optional[torch.Tensor] = None
+    # third copy of the down projection for the persistent decode kernel, sliced along K to match the gate/up units (see
+    # ``_kslice_pack``): the CTA that produced 16 SwiGLU columns multiplies them by "its" 2048 x 16 slice right away
+    down_wk: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -116,11 +119,27 @@ def _stream_pack(w: torch.Tensor) -> torch.Tensor:
     return w.view(N // 16, 16, K // 32, 32).permute(0, 2, 1, 3).contiguous()
 
 
+_KPERM = [2 * (p >> 2) + 8 * ((p >> 1) & 1) + (p & 1) for p in range(16)]   # position -> k inside a 16-wide k group
+
+
+def _kslice_pack(w: torch.Tensor) -> torch.Tensor:
+    """down_proj [2048, K] -> [K/16 units][4 stages][8 warps][4][16 rows][16 k]: unit u = the 16 input columns 16u.. (one gate/up
+    unit of the persistent decode kernel), 64 KB contiguous, cut into 4 ring stages in which warp w finds the 16 x 16 blocks of its
+    row groups 16w + 4s + j; inside a block every row's k values are stored in the order thread t of an mma.m16n8k16 quad reads
+    them ({2t, 2t+1, 2t+8, 2t+9} contiguous), so that one 8-byte shared-memory load is half an A fragment."""
+    N, K = w.shape
+    assert N == 2048 and K % 16 == 0, "the persistent decode kernel fixes hidden = 2048"
+    x = w.view(8, 4, 4, 16, K // 16, 16)[..., _KPERM]        # [w, s, j, r, u, pos]
+    return x.permute(4, 1, 0, 2, 3, 5).contiguous()
+
+
 def add_decode_streaming_copies(W: "PackedWeights") -> "PackedWeights":
     """Second copy of the decoder linears in the layout the weight-streaming decode kernel reads fastest (1 KB blocks of
     16 rows x 32 k: +6.2 GB for the 3B model, measured +12..20% HBM throughput at M = 8; 180 GB of HBM make this cheap)."""
     for L in W.layers:
         L.qkv_wp, L.o_wp, L.gu_wp, L.down_wp = _stream_pack(L.qkv_w), _stream_pack(L.o_w), _stream_pack(L.gu_w), _stream_pack(L.down_w)
+        if L.down_w.shape[0] == 2048:
+            L.down_wk = _kslice_pack(L.down_w)
     W.lm_head_p = _stream_pack(W.lm_head)
     return W
 
@@ -307,4 +326,6 @@ def update_weights(W: PackedWeights, named_tensors, cfg: SocioReasonerConfig) ->
             src, dst = {"qkv": (L.qkv_w, L.qkv_wp), "o": (L.o_w, L.o_wp), "gu": (L.gu_w, L.gu_wp), "down": (L.down_w, L.down_wp)}[which]
             if dst is not None:
                 dst.copy_(_stream_pack(src))
+            if which == "down" and L.down_wk is not None:
+                L.down_wk.copy_(_kslice_pack(L.down_w))
     return done

@@ -23,11 +23,14 @@ def rnd_packed(n, k, std=0.02):
 
 
 def make_layers(n_layers):
+    from socioreasoner_b200.weights import _kslice_pack
     out = []
     for _ in range(n_layers):
         out.append(SimpleNamespace(
             qkv_wp=rnd_packed(QKV, H), qkv_b=(torch.randn(QKV, device=dev) * 0.02), ln1=1 + 0.1 * torch.randn(H, device=dev),
             o_wp=rnd_packed(H, H), ln2=1 + 0.1 * torch.randn(H, device=dev), gu_wp=rnd_packed(2 * I, H), down_wp=rnd_packed(H, I)))
+        L = out[-1]   # the persistent kernel reads the down projection K-sliced (same matrix, third layout)
+        L.down_wk = _kslice_pack(L.down_wp.permute(0, 2, 1, 3).reshape(H, I).contiguous())
     return out
 
 

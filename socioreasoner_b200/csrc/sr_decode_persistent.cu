@@ -38,14 +38,16 @@ namespace sr {
 
 constexpr int DP_CONSUMERS = 8;
 constexpr int DP_CTHREADS = DP_CONSUMERS * 32;
-constexpr int DP_THREADS = DP_CTHREADS + 32;          // warp 0 = producer, warps 1-8 = consumers
+constexpr int DP_THREADS = 512;                       // 4 warpgroups: warp 0 = producer, warps 1-3 and 12 = bankers (shared memory ->
+                                                      // TMEM), warps 4-11 = consumers; registers re-balanced with setmaxnreg
+constexpr int DP_CT0 = 128;                           // first consumer thread
+constexpr int DP_TSLOTS = 16;                         // TMEM weight slots: 32 columns x 128 lanes x 4 B = one 16 KB stage each
 constexpr int DP_STAGE_BLOCKS = 16;                   // 1 KB weight blocks per ring stage
 constexpr int DP_STAGE_BYTES = DP_STAGE_BLOCKS * 1024;
 constexpr int DP_STAGES = 10;
 constexpr int DP_H = 2048;                            // staged activation width (hidden size = n_q_heads * 128)
 constexpr int DP_HL = DP_H / 4;                       // LL lines per hidden row (4 bf16 per line)
 constexpr int DP_XS_STRIDE = DP_H * 2 + 64;           // bytes per staged row (+64 B: conflict-free 16 B fragment reads)
-constexpr int DP_XPF = 4;                             // activation prefetch distance (stages) of the down projection
 constexpr int DP_MAX_LAYERS = 64;                     // layer table staged in shared memory
 constexpr int DP_GMAX = 8;                            // query heads per kv head (max)
 constexpr int DP_KEYS = 128;                          // keys per attention pass
@@ -61,7 +63,7 @@ constexpr int DP_OFF_RED = DP_OFF_XS + DP_XS_BYTES;                   // [2][8 w
 constexpr int DP_RED_WQ = 8 * 20;                                     // floats per (warp, row group): [batch][16 features + 4 pad]
 constexpr int DP_RED_BYTES = 2 * DP_CONSUMERS * 2 * DP_RED_WQ * 4;    // 20480
 constexpr int DP_OFF_BAR = DP_OFF_RED + DP_RED_BYTES;
-constexpr int DP_OFF_LAYERS = DP_OFF_BAR + 2 * DP_STAGES * 8 + 32;    // DpLayer[DP_MAX_LAYERS]
+constexpr int DP_OFF_LAYERS = DP_OFF_BAR + 2 * DP_STAGES * 8 + 2 * DP_TSLOTS * 8 + 32;  // DpLayer[DP_MAX_LAYERS]
 constexpr int DP_OFF_ROPE = DP_OFF_LAYERS + DP_MAX_LAYERS * 64;       // cos[8][64], sin[8][64] fp32 of this step
 constexpr int DP_OFF_SCAL = DP_OFF_ROPE + 2 * 8 * 64 * 4;             // kv_start[8], kv_len[8], cache_row[8], epoch, gate, pcnt
 constexpr int DP_OFF_ACT = DP_OFF_SCAL + 4 * 8 * 4;                   // bf16 [8 batch][16 k]: SwiGLU output of the current unit
@@ -201,7 +203,7 @@ SR_DEVINL void ll_wait(uint4 (&v)[N], F addr, uint32_t gen) {
   }
 }
 
-struct DpRing {
+struct DpRing {   // shared-memory landing ring (producer -> bankers)
   uint8_t* data;
   uint64_t* full;
   uint64_t* empty;
@@ -212,6 +214,91 @@ struct DpRing {
     if (++slot == n) { slot = 0; phase ^= 1; }
   }
 };
+// TMEM weight ring (bankers -> consumers).  The shared-memory ring alone holds 128 KB per SM = 3 us of the HBM stream chip-wide,
+// but a layer spends ~20 us in the qkv -> attention -> o-proj exchange chain during which no weights are consumed; L2 is no
+// buffer for this (measured: prefetching into L2 does not shorten the streaming phases -- an L2 hit costs the same L2 throughput
+// as a miss's fill + read, and the stream already runs at that limit).  The 256 KB of tensor memory next to every SM are: banker
+// warps move every landed stage smem -> registers -> TMEM (tcgen05.st), laid out so that the consumer thread that needs a
+// fragment finds it in ITS lane (tcgen05.ld, 16 registers = its 64 bytes of the stage); 16 more stages of look-ahead per SM.
+struct DpTRing {
+  uint64_t* full;
+  uint64_t* empty;
+  uint32_t tbase;
+  int slot;
+  uint32_t phase;
+  SR_DEVINL void advance() {
+    if (++slot == DP_TSLOTS) { slot = 0; phase ^= 1; }
+  }
+};
+SR_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+SR_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// consumer side: this thread's 64 bytes of the next stage (warp cw: lanes of quarter cw % 4, columns 16 * (cw / 4) .. + 15 of the slot)
+SR_DEVINL void dp_fetch(DpTRing& tr, int cw, uint32_t (&wr)[16]) {
+  mbar_wait(&tr.full[tr.slot], tr.phase);
+  tc_fence_after();
+  tmem_ld_32x32b_x16(tr.tbase + (static_cast<uint32_t>(32 * (cw & 3)) << 16) + tr.slot * 32 + (cw >> 2) * 16, wr);
+  tmem_ld_wait();
+}
+SR_DEVINL void dp_release(DpTRing& tr, int lane) {
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&tr.empty[tr.slot]);
+  tr.advance();
+}
+enum { DP_FMT_RG1 = 0, DP_FMT_RG2 = 1, DP_FMT_SLICE = 2 };
+// banker: stage `n` landed stages of one format from the shared-memory ring into TMEM slots.  Lane i of the banker of quarter qd
+// collects the fragments consumer threads (warp qd, lane i) and (warp qd + 4, lane i) will ask for.
+template <int FMT>
+SR_DEVINL void dp_bank(DpRing& r, DpTRing& tr, int n, int qd, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  for (int i = 0; i < n; ++i) {
+    mbar_wait(&r.full[r.slot], r.phase);
+    mbar_wait(&tr.empty[tr.slot], tr.phase ^ 1);
+    const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
+    uint32_t v[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int cwv = qd + 4 * h;
+      if (FMT == DP_FMT_SLICE) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint2 lo = *reinterpret_cast<const uint2*>(stage + cwv * 2048 + j * 512 + g * 32 + t * 8);
+          const uint2 hi = *reinterpret_cast<const uint2*>(stage + cwv * 2048 + j * 512 + (g + 8) * 32 + t * 8);
+          v[16 * h + 4 * j] = lo.x; v[16 * h + 4 * j + 1] = lo.y; v[16 * h + 4 * j + 2] = hi.x; v[16 * h + 4 * j + 3] = hi.y;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint8_t* blk = (FMT == DP_FMT_RG2) ? stage + j * (DP_STAGE_BYTES / 2) + cwv * 1024 : stage + (cwv + 8 * j) * 1024;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
+          const int o = 16 * h + 8 * j;
+          v[o] = w0.x; v[o + 1] = w0.y; v[o + 2] = w0.z; v[o + 3] = w0.w;
+          v[o + 4] = w1.x; v[o + 5] = w1.y; v[o + 6] = w1.z; v[o + 7] = w1.w;
+        }
+      }
+    }
+    tmem_st_32x32b_x32(tr.tbase + (static_cast<uint32_t>(32 * qd) << 16) + tr.slot * 32, v);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&tr.full[tr.slot]);
+      mbar_arrive(&r.empty[r.slot]);
+    }
+    r.advance();
+    tr.advance();
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ producer
 // Streams this CTA's units of one packed matrix: unit u = RG consecutive 16-row groups; stage = 16 blocks of 1 KB
@@ -333,121 +420,24 @@ SR_DEVINL void dp_stage_rows(uint8_t* xs, const uint4* src, uint32_t gen, int M,
 
 // K loop of one unit with the activations staged in shared memory (K = DP_H).
 template <int RG>
-SR_DEVINL void dp_consume_staged(DpRing& r, int nchunks, const uint8_t* xs, float (&acc)[RG][4], int cw, int lane) {
+SR_DEVINL void dp_consume_staged(DpTRing& r, int nchunks, const uint8_t* xs, float (&acc)[RG][4], int cw, int lane) {
   constexpr int CPS = DP_STAGE_BLOCKS / RG;
   const int g = lane >> 2, t = lane & 3;
-  const int nst = (nchunks + CPS - 1) / CPS;
+  const int nst = nchunks / CPS;  // (K = DP_H: whole stages)
   const uint8_t* xrow = xs + g * DP_XS_STRIDE + t * 16;
   for (int st = 0; st < nst; ++st) {
-    mbar_wait(&r.full[r.slot], r.phase);
-    const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
-    if (RG == 2) {
-      const int c = st * CPS + cw;
-      if (c < nchunks) {
-        const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
-#pragma unroll
-        for (int q = 0; q < RG; ++q) {
-          const uint8_t* blk = stage + q * (CPS * 1024) + cw * 1024;
-          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
-          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
-          dp_mma(acc[q], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
-          dp_mma(acc[q], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int c = st * CPS + cw + 8 * j;
-        if (c < nchunks) {
-          const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
-          const uint8_t* blk = stage + (cw + 8 * j) * 1024;
-          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
-          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
-          dp_mma(acc[0], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
-          dp_mma(acc[0], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
-        }
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&r.empty[r.slot]);
-    r.advance();
-  }
-}
-
-// K loop of one unit (RG = 1) with the activations read as plain bf16 from L2 (long K: the down projection reads the SwiGLU
-// output of ALL CTAs, 176 KB per CTA -- as flag-carrying lines that would be 352 KB per CTA, as much as the weights, and the
-// phase becomes L2-throughput bound; the caller has already waited for every producer's release flag, see dp_wait_act).
-// Stage order rotated per unit (see dp_produce<.., ROT>); activation fragments are requested DP_XPF stages ahead.
-SR_DEVINL void dp_consume_l2(DpRing& r, int u, int nchunks, const __nv_bfloat16* xg, int64_t ldx, int M, float (&acc)[1][4], int cw,
-                             int lane) {
-  constexpr int CPS = DP_STAGE_BLOCKS;
-  const int g = lane >> 2, t = lane & 3;
-  const int nst = (nchunks + CPS - 1) / CPS;
-  const int rot = dp_rot(u, nst);
-  const bool xok = g < M;
-  const __nv_bfloat16* xrow = xg + static_cast<int64_t>(xok ? g : 0) * ldx + t * 8;
-  uint4 xq[DP_XPF][2];
-  auto stage_of = [&](int i) { const int s2 = i + rot; return s2 >= nst ? s2 - nst : s2; };
-  auto load_x = [&](int slot_i, int i) {
-    const int st = stage_of(i);
+    uint32_t w[16];  // RG = 2: row group q: w0 = w[8q .. 8q+3], w1 = w[8q+4 .. 8q+7];  RG = 1: the same for chunk cw + 8j
+    dp_fetch(r, cw, w);
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const int c = st * CPS + cw + 8 * j;
-      xq[slot_i][j] = (xok && i < nst && c < nchunks) ? dp_ldcg(xrow + c * 32) : make_uint4(0, 0, 0, 0);
+      const int c = (RG == 2) ? st * CPS + cw : st * CPS + cw + 8 * j;
+      const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
+      float (&a)[4] = acc[RG == 2 ? j : 0];
+      dp_mma(a, w[8 * j], w[8 * j + 4], w[8 * j + 1], w[8 * j + 5], xv.x, xv.y);
+      dp_mma(a, w[8 * j + 2], w[8 * j + 6], w[8 * j + 3], w[8 * j + 7], xv.z, xv.w);
     }
-  };
-#pragma unroll
-  for (int i = 0; i < DP_XPF; ++i) load_x(i, i);
-  for (int i0 = 0; i0 < nst; i0 += DP_XPF) {
-#pragma unroll
-    for (int q = 0; q < DP_XPF; ++q) {
-      const int i = i0 + q;
-      if (i < nst) {
-        const int st = stage_of(i);
-        mbar_wait(&r.full[r.slot], r.phase);
-        const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int c = st * CPS + cw + 8 * j;
-          if (c < nchunks) {
-            const uint4 xv = xq[q][j];
-            const uint8_t* blk = stage + (cw + 8 * j) * 1024;
-            const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
-            const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
-            dp_mma(acc[0], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
-            dp_mma(acc[0], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&r.empty[r.slot]);
-        load_x(q, i + DP_XPF);
-        r.advance();
-      }
-    }
+    dp_release(r, lane);
   }
-}
-
-// The SwiGLU output is the one exchange that does NOT use flag-carrying lines (see dp_consume_l2): every CTA writes its columns
-// as plain bf16 and, after its last gate/up unit, publishes ONE release flag (its writer threads fence, then one of them stores
-// the generation); a down-projection CTA polls the flags of all CTAs, fences, and then reads the activations with plain loads.
-SR_DEVINL void dp_publish_act(unsigned int* flags, uint32_t gen, int ct) {
-  if (ct < 32) {  // the epilogue threads of the gate/up phase are the first consumer warp
-    __threadfence();
-    __syncwarp();
-    if (ct == 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flags + blockIdx.x), "r"(gen) : "memory");
-  }
-}
-SR_DEVINL void dp_wait_act(const unsigned int* flags, uint32_t gen, int ct) {
-  if (ct < static_cast<int>(gridDim.x)) {
-    unsigned int v, spins = 0;
-    while (true) {
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + ct) : "memory");
-      if (v == gen) break;
-      if (++spins > SR_LL_SPIN_LIMIT) ll_timeout(gen);
-    }
-    __threadfence();
-  }
-  dp_cbar();
 }
 
 enum { DP_EPI_BIAS = 0, DP_EPI_RESIDUAL = 1, DP_EPI_SWIGLU = 2, DP_EPI_F32 = 3 };
@@ -469,10 +459,10 @@ struct DpOut {
 // Epilogue: thread (row group q, batch b, feature quad fg) sums the 8 warps' partials of 4 consecutive output columns and writes
 // one LL line (4 bf16) -- or 4 fp32 logits.
 template <int RG, int EPI, bool STAGED>
-SR_DEVINL void dp_gemv_phase(DpRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, const __nv_bfloat16* xg, int64_t ldxg,
+SR_DEVINL void dp_gemv_phase(DpTRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, const __nv_bfloat16* xg, int64_t ldxg,
                              int M, float* red, int& red_par, const DpOut& o, int cw, int lane, int stride) {
   const int g = lane >> 2, t = lane & 3;
-  const int ct = threadIdx.x - 32;
+  const int ct = threadIdx.x - DP_CT0;
   constexpr int NG = (EPI == DP_EPI_SWIGLU) ? 1 : RG;   // independent 16-column groups per unit
   const int eq = ct >> 5, eb = ct & 7, efg = (ct >> 3) & 3;
   const bool epi_thread = ct < 32 * NG && eb < M;
@@ -490,12 +480,8 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int v0, int n_units, int nchunks, const 
       if (EPI == DP_EPI_BIAS && o.bias != nullptr) bias4 = __ldg(reinterpret_cast<const float4*>(o.bias + col));
       if (EPI == DP_EPI_RESIDUAL) resl = ll_load(o.res_ll + eb * DP_HL + (col >> 2));
     }
-    if constexpr (STAGED) {
-      dp_consume_staged<RG>(r, nchunks, xs, acc, cw, lane);
-    } else {
-      static_assert(STAGED || RG == 1, "the L2 activation path handles single row groups");
-      dp_consume_l2(r, u, nchunks, xg, ldxg, M, acc, cw, lane);
-    }
+    static_assert(STAGED, "activations are always staged in shared memory");
+    dp_consume_staged<RG>(r, nchunks, xs, acc, cw, lane);
     // cross-warp reduction: C fragment (feature g | g+8, batch 2t | 2t+1) -> red[par][warp][q][batch * 20 + feature]
     float* rp = red + red_par * (DP_CONSUMERS * 2 * DP_RED_WQ);
 #pragma unroll
@@ -549,36 +535,15 @@ SR_DEVINL void dp_gemv_phase(DpRing& r, int v0, int n_units, int nchunks, const 
 // summed in a fixed order by the CTA that owns the 16 output rows (dp_reduce_x).  Compared with "all CTAs read all of act" this
 // removes 176 KB of activation reads per CTA and one exchange from the middle of the weight stream.
 SR_DEVINL int dp_kpos(int k) { return ((k & 7) >> 1) * 4 + (k >> 3) * 2 + (k & 1); }  // position of k inside a 16-wide k group
-SR_DEVINL void dp_de_phase(DpRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, uint8_t* s_act, int M, float* red, int& red_par,
+SR_DEVINL void dp_de_phase(DpTRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, uint8_t* s_act, int M, float* red, int& red_par,
                            __nv_bfloat16* dbg_act, int I, float (&acc_e)[16][4], int cw, int lane, int stride) {
-  constexpr int CPS = DP_STAGE_BLOCKS / 2;
   const int g = lane >> 2, t = lane & 3;
-  const int ct = threadIdx.x - 32;
+  const int ct = threadIdx.x - DP_CT0;
   const int eb = ct & 7, efg = (ct >> 3) & 3;
   const bool epi_thread = ct < 32 && eb < M;
-  const int nst = (nchunks + CPS - 1) / CPS;
-  const uint8_t* xrow = xs + g * DP_XS_STRIDE + t * 16;
   for (int u = v0; u < n_units; u += stride) {
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int st = 0; st < nst; ++st) {
-      mbar_wait(&r.full[r.slot], r.phase);
-      const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
-      const int c = st * CPS + cw;
-      if (c < nchunks) {
-        const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const uint8_t* blk = stage + q * (CPS * 1024) + cw * 1024;
-          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
-          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
-          dp_mma(acc[q], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
-          dp_mma(acc[q], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&r.empty[r.slot]);
-      r.advance();
-    }
+    dp_consume_staged<2>(r, nchunks, xs, acc, cw, lane);
     float* rp = red + red_par * (DP_CONSUMERS * 2 * DP_RED_WQ);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -613,17 +578,11 @@ SR_DEVINL void dp_de_phase(DpRing& r, int v0, int n_units, int nchunks, const ui
     const uint2 bv = *reinterpret_cast<const uint2*>(s_act + g * 32 + t * 8);
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
-      mbar_wait(&r.full[r.slot], r.phase);
-      const uint8_t* wb = r.data + r.slot * DP_STAGE_BYTES + cw * 2048;
+      uint32_t w[16];  // block j of this warp: a_lo = w[4j], w[4j+1] (row g), a_hi = w[4j+2], w[4j+3] (row g + 8)
+      dp_fetch(r, cw, w);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint2 a_lo = *reinterpret_cast<const uint2*>(wb + j * 512 + g * 32 + t * 8);
-        const uint2 a_hi = *reinterpret_cast<const uint2*>(wb + j * 512 + (g + 8) * 32 + t * 8);
-        dp_mma(acc_e[st * 4 + j], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bv.x, bv.y);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&r.empty[r.slot]);
-      r.advance();
+      for (int j = 0; j < 4; ++j) dp_mma(acc_e[st * 4 + j], w[4 * j], w[4 * j + 2], w[4 * j + 1], w[4 * j + 3], bv.x, bv.y);
+      dp_release(r, lane);
     }
   }
 }
@@ -739,7 +698,7 @@ struct DpAttnFrag {
 // keys [p0, p0 + nk) of the split, all of them OLD keys (the caller clips the range at the newest key)
 SR_DEVINL void dp_attn_load(const DpParams& p, const DpAttnUnit& U, const __nv_bfloat16* Kc, const __nv_bfloat16* Vt, int p0, int nk,
                              DpAttnFrag& f) {
-  const int ct = threadIdx.x - 32, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
+  const int ct = threadIdx.x - DP_CT0, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
   const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -776,7 +735,7 @@ SR_DEVINL void dp_attn_prefetch_l2(const DpParams& p, int layer, const DpAttnUni
   const int ke = dp_attn_old_end(U);
   const int n = ke - U.k_begin;
   if (n <= 0) return;
-  const int ct = threadIdx.x - 32;
+  const int ct = threadIdx.x - DP_CT0;
   const __nv_bfloat16* Kc = p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride;
   const __nv_bfloat16* Vt = p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride;
   for (int k = ct; k < n; k += DP_CTHREADS) {
@@ -792,7 +751,7 @@ SR_DEVINL void dp_attn_prefetch_l2(const DpParams& p, int layer, const DpAttnUni
 
 SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, uint32_t gen, uint8_t* sm, const float* s_cos, const float* s_sin,
                                    const DpAttnUnit& U, DpAttnFrag& f, int tr_base) {
-  const int ct = threadIdx.x - 32, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
+  const int ct = threadIdx.x - DP_CT0, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
   const int G = p.nq / p.nkv, ns = p.ns;
   float* s_red = reinterpret_cast<float*>(sm + DPB_RED);
   float* s_knew = reinterpret_cast<float*>(sm + DPB_KNEW);
@@ -1059,6 +1018,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   ring.slot = 0;
   ring.phase = 0;
   ring.n = p.ring_stages;
+  DpTRing tring;
+  tring.full = ring.empty + DP_STAGES;
+  tring.empty = tring.full + DP_TSLOTS;
+  tring.slot = 0;
+  tring.phase = 0;
   uint8_t* xs = smem + DP_OFF_XS;
   float* red = reinterpret_cast<float*>(smem + DP_OFF_RED);
 
@@ -1084,23 +1048,33 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     }
     if (threadIdx.x == 8) s_scal[24] = static_cast<int>(*reinterpret_cast<volatile unsigned int*>(p.epoch));
     if (threadIdx.x == 9) s_scal[25] = 0;
-    if (threadIdx.x >= 32 && threadIdx.x < 96) reinterpret_cast<uint32_t*>(smem + DP_OFF_ACT)[threadIdx.x - 32] = 0u;
+    if (threadIdx.x >= 32 && threadIdx.x < 96) reinterpret_cast<uint32_t*>(smem + DP_OFF_ACT)[threadIdx.x - DP_CT0] = 0u;
   }
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < DP_STAGES; ++i) {
       mbar_init(&ring.full[i], 1);
-      mbar_init(&ring.empty[i], DP_CONSUMERS);
+      mbar_init(&ring.empty[i], 4);            // the four banker warps
+    }
+#pragma unroll
+    for (int i = 0; i < DP_TSLOTS; ++i) {
+      mbar_init(&tring.full[i], 4);
+      mbar_init(&tring.empty[i], DP_CONSUMERS);
     }
     fence_mbar_init();
   }
+  if (warp == 12) tmem_alloc<512>(reinterpret_cast<uint32_t*>(s_scal + 27));   // all of tensor memory: 16 slots of 32 columns
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  tring.tbase = *reinterpret_cast<volatile uint32_t*>(s_scal + 27);
+  // register budget: the two consumer warpgroups (warps 4-11) take 192 registers per thread, the producer / banker warpgroups 64
+  const bool is_consumer = warp >= 4 && warp < 12;
 
   const int kq = DP_H >> 5;                       // k-chunks of the hidden-size matrices
   const int n_qkv = (p.nq + 2 * p.nkv) * 128 / 16;  // 16-row units
   const int n_o = DP_H / 16;
   const int n_gu = p.I / 16;                      // units of 32 packed rows (gate|up pairs) = I/16
-  const int kd = p.I >> 5;
   const int n_head = p.vocab / 16;
   const int limit = p.stop_after > 0 ? p.stop_after : 0x7fffffff;
   // Unit -> CTA mapping, rotated per matrix: unit u of a matrix goes to CTA (u + offset) mod gridDim.  The unit counts (80 / 128
@@ -1114,9 +1088,9 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   const int hs = half_head ? (G + 1) / 2 : G;
   const int hv = half_head ? ((blockIdx.x & 1) ? 0x7fffffff : static_cast<int>(blockIdx.x >> 1)) : static_cast<int>(blockIdx.x);
 
-  if (warp == 0) {
+  auto producer_role = [&]() {
     // ---------------- producer: weights only; runs ahead of the consumers across phases ----------------
-    if (lane == 0) {
+    {
       uint64_t policy = 0;
       const bool hint = (p.flags & 1) != 0;
       if (hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
@@ -1159,11 +1133,31 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       if (hv < n_head) dp_produce<1, false>(ring, hv, p.lm_head_p, n_head, kq, policy, hint, hs);
       dp_trace_at(p, 0, 1 + 4 * p.n_layers);
     }
-    return;
-  }
+  };
+  auto banker_role = [&](int qd) {
+    // ---------------- bankers: the producer's schedule again, stage by stage: shared memory -> TMEM ----------------
+    auto units = [&](int v0, int n, int stride) { return v0 < n ? (n - v0 + stride - 1) / stride : 0; };
+    int ph = 0;
+    for (int l = 0; l < p.n_layers; ++l) {
+      if (ph++ >= limit) return;
+      dp_bank<DP_FMT_RG2>(ring, tring, units(vq, n_qkv / 2, G) * 8, qd, lane);
+      if (ph++ >= limit) return;
+      if (ph++ >= limit) return;
+      dp_bank<DP_FMT_RG1>(ring, tring, units(vo, n_o, G) * 4, qd, lane);
+      if (ph++ >= limit) return;
+      for (int u = vg; u < n_gu; u += G) {
+        dp_bank<DP_FMT_RG2>(ring, tring, 8, qd, lane);
+        dp_bank<DP_FMT_SLICE>(ring, tring, 4, qd, lane);
+      }
+      if (ph++ >= limit) return;
+    }
+    if (ph++ >= limit) return;
+    dp_bank<DP_FMT_RG1>(ring, tring, units(hv, n_head, hs) * 4, qd, lane);
+  };
+  auto consumer_role = [&]() {
   // ---------------- consumers ----------------
-  const int cw = warp - 1;
-  const int ct = threadIdx.x - 32;
+  const int cw = warp - 4;
+  const int ct = threadIdx.x - DP_CT0;
   const uint32_t epoch_raw = static_cast<uint32_t>(s_scal[24]);
   const uint32_t epoch = epoch_raw + 1u;  // generations epoch .. epoch + n_layers: never 0 on a zero-initialised workspace
   const bool dump = (p.flags & 2) != 0;
@@ -1197,7 +1191,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       dp_cbar();
       DP_TRACE(0);
       o = DpOut{p.qkv_ll, n_qkv * 4, gen, nullptr, 0, L.qkv_b, nullptr, 0, p.qkv, static_cast<int64_t>(n_qkv) * 16};
-      dp_gemv_phase<2, DP_EPI_BIAS, true>(ring, vq, n_qkv / 2, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
+      dp_gemv_phase<2, DP_EPI_BIAS, true>(tring, vq, n_qkv / 2, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
     } else {
       DP_TRACE(0);
     }
@@ -1219,7 +1213,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       dp_cbar();
       DP_TRACE(4);
       o = DpOut{p.xa_ll, DP_HL, gen, p.xb_ll, gin, nullptr, nullptr, 0, dump ? p.x : nullptr, p.ldx};
-      dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, vo, n_o, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
+      dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(tring, vo, n_o, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
     } else {
       DP_TRACE(4);
     }
@@ -1237,7 +1231,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       for (int i = 0; i < 16; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc_e[i][j] = 0.f;
-      dp_de_phase(ring, vg, n_gu, kq, xs, smem + DP_OFF_ACT, p.B, red, red_par, dump ? p.act : nullptr, p.I, acc_e, cw, lane, G);
+      dp_de_phase(tring, vg, n_gu, kq, xs, smem + DP_OFF_ACT, p.B, red, red_par, dump ? p.act : nullptr, p.I, acc_e, cw, lane, G);
       // publish this CTA's partial of Wdown . act^T: line (row, batch pair t) = (x[2t][row], x[2t+1][row])
       uint4* part = p.xpart_ll + static_cast<int64_t>(blockIdx.x) * (DP_H * 4);
       const int g = lane >> 2, t = lane & 3;
@@ -1260,7 +1254,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     dp_stage_rows<true>(xs, p.xb_ll, epoch + static_cast<uint32_t>(p.n_layers), p.B, p.final_norm, p.eps, cw, lane);
     dp_cbar();
     DpOut o = DpOut{nullptr, 0, 0, nullptr, 0, nullptr, p.logits, p.ld_logits, nullptr, 0};
-    if (hv < n_head) dp_gemv_phase<1, DP_EPI_F32, true>(ring, hv, n_head, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, hs);
+    if (hv < n_head) dp_gemv_phase<1, DP_EPI_F32, true>(tring, hv, n_head, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, hs);
     DP_TRACE(0);
   }
 #undef DP_TRACE
@@ -1272,6 +1266,23 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       p.epoch[0] = epoch_raw + static_cast<uint32_t>(p.n_layers) + 2u;
     }
   }
+  };  // consumer_role
+
+  if (is_consumer) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+    consumer_role();
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 0) {
+      if (lane == 0) producer_role();
+    } else if (warp <= 3 || warp == 12) {
+      banker_role(warp & 3);               // a warp reaches the TMEM lanes 32 * (warp % 4) .. + 31 only
+    }
+  }
+  // common exit: nobody touches tensor memory any more -> release it
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc<512>(tring.tbase);
 }
 
 }  // namespace sr

@@ -217,16 +217,17 @@ typedef struct sr_decode_layer {
   const void* o_wp;     /* packed [2048, 2048] */
   const float* ln2;     /* post_attention_layernorm weight [2048] */
   const void* gu_wp;    /* packed [2*intermediate, 2048], rows interleaved 16 gate | 16 up */
-  const void* down_wp;  /* packed [2048, intermediate] */
+  const void* down_wk;  /* K-sliced [intermediate/16][4][8][4][16 rows][16 k]: socioreasoner_b200.weights._kslice_pack */
+  const void* reserved; /* NULL */
 } sr_decode_layer;
 int64_t sr_decode_persistent_workspace_bytes(int n_q_heads, int n_kv_heads, int intermediate);
-/* Tuning knobs (none changes results; negative = keep).  flags (env SR_DECODE_FLAGS, default 1): bit 0 = L2 evict_first hint on
+/* Tuning knobs (none changes results; negative = keep).  flags (env SR_DECODE_FLAGS, default 17): bit 0 = L2 evict_first hint on
  * the weight copies, bit 1 = dump plain intermediates into x / the scratch buffers, bit 4 = L2 prefetch of each layer's K/V slice at
- * the start of the layer; bits 2, 3 are measurement aids (weight stream gated off during the exchange chain; K/V requested only
- * after q arrived).  ring_stages: 16 KB shared-memory ring stages in use, 2..10 (0 = default 8; env SR_DECODE_RING).  pf_stages:
- * look-ahead of the L2 prefetcher warp beyond the ring, 16 KB stages per CTA (env SR_DECODE_PF_STAGES).  off_*: unit -> CTA rotation
- * per matrix (unit u runs on CTA (u + offset) mod #SMs; default 96, 40, 0, 20; env SR_DECODE_UNIT_OFFSETS="q,o,g,d"). */
-int sr_set_decode_persistent_tuning(int flags, int ring_stages, int pf_stages, int off_qkv, int off_o, int off_gate_up, int off_down);
+ * the start of the layer; bits 2, 3, 5 are measurement aids (weight stream gated off during the exchange chain; K/V requested only
+ * after q arrived; LM head on every second CTA).  ring_stages: 16 KB shared-memory ring stages in use, 2..10 (0 = default 8; env
+ * SR_DECODE_RING).  off_*: unit -> CTA rotation per matrix (unit u runs on CTA (u + offset) mod #SMs; default 96, 40, 0, 20; env
+ * SR_DECODE_UNIT_OFFSETS="q,o,g,d"). */
+int sr_set_decode_persistent_tuning(int flags, int ring_stages, int off_qkv, int off_o, int off_gate_up, int off_down);
 /* Tuning aid: when buffer != NULL every later sr_decode_step_persistent launch records (globaltimer ns, clock64) pairs at its
  * phase boundaries into buffer[n_SMs][2 roles: producer, consumer][events_per_role][2] (uint64); NULL switches it off. */
 int sr_set_decode_persistent_trace(void* buffer, int events_per_role);

@@ -21,13 +21,19 @@
 // Round 2: NO grid barriers.  Round 1 separated the phases by 5 grid barriers per layer (release-add + acquire-poll + the
 // dependent activation load after it = 3-4 serialized L2 round trips each, 21 us of the 58 us a layer took, against 24 us of
 // weight streaming).  Now every activation that crosses CTAs (x after o-proj / after down, qkv, attention partials, attention
-// output, SwiGLU output) travels in FLAG-CARRYING lines, the "LL" protocol NCCL uses for latency-bound collectives: a 16-byte
-// line = {data0, gen, data1, gen}; the writer's store is fire-and-forget, the reader polls THE DATA ITSELF until both
-// generation words match (each 8-byte half is written atomically and carries its own flag, so no fence, no counter, no acquire
-// is needed) -- one L2 round trip per exchange instead of three or four, and a CTA only ever waits for the lines it actually
-// reads.  gen = epoch + 1 + layer; the epoch lives in the workspace and is advanced by the last CTA to leave the kernel, so
-// stale lines (previous layer / launch / CUDA-graph replay) never match.  Buffers are rewritten once per layer; a writer of
+// output, the down projection's partial sums) travels in FLAG-CARRYING lines, the "LL" protocol NCCL uses for latency-bound
+// collectives: a 16-byte line = {data0, gen, data1, gen}; the writer's store is fire-and-forget, the reader polls THE DATA ITSELF
+// until both generation words match (each 8-byte half is written atomically and carries its own flag, so no fence, no counter, no
+// acquire is needed) -- one L2 round trip per exchange instead of three or four, and a CTA only ever waits for the lines it
+// actually reads.  gen = epoch + 1 + layer; the epoch lives in the workspace and is advanced by the last CTA to leave the kernel,
+// so stale lines (previous layer / launch / CUDA-graph replay) never match.  Buffers are rewritten once per layer; a writer of
 // layer l+1 has (transitively, through the data it polled) observed results of every reader of the layer-l version.
+// The SwiGLU output does not cross CTAs at all: the CTA that computes 16 gate/up columns multiplies them by the matching
+// 2048 x 16 K-slice of the down projection right away (dp_de_phase) and only the fp32 partial of x is exchanged and reduced in a
+// fixed order (dp_reduce_x).
+// Measured and NOT adopted: L2 prefetching of the weight stream during the exchange chain (an L2 hit costs
+// the same L2 throughput as a miss's fill + read and the stream already runs at that limit); a TMEM-backed weight ring with banker
+// warps (16 more stages of look-ahead per SM: 2 % faster stand-alone, 4 % slower inside the power-capped bench step).
 // HBM-bound: algorithmic bytes per launch = all decoder weights + LM head (N*K*2 each) + KV cache of the live sequences.
 #include <stdio.h>
 #include <stdlib.h>
@@ -38,10 +44,7 @@ namespace sr {
 
 constexpr int DP_CONSUMERS = 8;
 constexpr int DP_CTHREADS = DP_CONSUMERS * 32;
-constexpr int DP_THREADS = 512;                       // 4 warpgroups: warp 0 = producer, warps 1-3 and 12 = bankers (shared memory ->
-                                                      // TMEM), warps 4-11 = consumers; registers re-balanced with setmaxnreg
-constexpr int DP_CT0 = 128;                           // first consumer thread
-constexpr int DP_TSLOTS = 16;                         // TMEM weight slots: 32 columns x 128 lanes x 4 B = one 16 KB stage each
+constexpr int DP_THREADS = DP_CTHREADS + 32;          // warp 0 = producer, warps 1-8 = consumers
 constexpr int DP_STAGE_BLOCKS = 16;                   // 1 KB weight blocks per ring stage
 constexpr int DP_STAGE_BYTES = DP_STAGE_BLOCKS * 1024;
 constexpr int DP_STAGES = 10;
@@ -63,7 +66,7 @@ constexpr int DP_OFF_RED = DP_OFF_XS + DP_XS_BYTES;                   // [2][8 w
 constexpr int DP_RED_WQ = 8 * 20;                                     // floats per (warp, row group): [batch][16 features + 4 pad]
 constexpr int DP_RED_BYTES = 2 * DP_CONSUMERS * 2 * DP_RED_WQ * 4;    // 20480
 constexpr int DP_OFF_BAR = DP_OFF_RED + DP_RED_BYTES;
-constexpr int DP_OFF_LAYERS = DP_OFF_BAR + 2 * DP_STAGES * 8 + 2 * DP_TSLOTS * 8 + 32;  // DpLayer[DP_MAX_LAYERS]
+constexpr int DP_OFF_LAYERS = DP_OFF_BAR + 2 * DP_STAGES * 8 + 32;    // DpLayer[DP_MAX_LAYERS]
 constexpr int DP_OFF_ROPE = DP_OFF_LAYERS + DP_MAX_LAYERS * 64;       // cos[8][64], sin[8][64] fp32 of this step
 constexpr int DP_OFF_SCAL = DP_OFF_ROPE + 2 * 8 * 64 * 4;             // kv_start[8], kv_len[8], cache_row[8], epoch, gate, pcnt
 constexpr int DP_OFF_ACT = DP_OFF_SCAL + 4 * 8 * 4;                   // bf16 [8 batch][16 k]: SwiGLU output of the current unit
@@ -92,7 +95,7 @@ struct DpParams {
   int64_t ldx;
   __nv_bfloat16* qkv;      // debug dumps (flags bit 1): [B, (nq + 2 nkv) * 128], [B, nq * 128]
   __nv_bfloat16* ao;
-  __nv_bfloat16* act;      // [B, I] SwiGLU output, plain bf16 (workspace; the caller's act_scratch when dumping)
+  __nv_bfloat16* act;      // debug dump of the SwiGLU output [B, I] (it never leaves the SMs otherwise)
   float* logits;
   int64_t ld_logits;
   const float* cosb;       // [B, 64]
@@ -112,13 +115,11 @@ struct DpParams {
   uint4* xb_ll;
   uint4* qkv_ll;
   uint4* ao_ll;
-  unsigned int* act_flags; // [gridDim.x] generation of each CTA's last complete SwiGLU output (plain bf16 in `act`)
   uint4* part_ll;          // [B*nkv][ns][DP_PART_LINES]
   uint4* xpart_ll;         // [gridDim.x][2048 rows * 4]: every CTA's fp32 partial of the down projection, line (row, batch pair)
   int ns;
   int stop_after;          // debug: run only the first `stop_after` phases (<= 0: all)
   int ring_stages;         // shared-memory ring stages in use (2 .. DP_STAGES)
-  int pf_stages;           // L2 prefetch look-ahead beyond the ring, in 16 KB stages per CTA (0 = off)
   int unit_off[4];         // unit -> CTA rotation of the qkv / o / gate-up / down matrices
   int flags;               // bit 0: L2 evict_first hint on the ring copies; bit 1: dump plain intermediates (bring-up)
   unsigned long long* trace;  // optional [gridDim.x][2 roles][trace_events][2] (globaltimer ns, clock64)
@@ -203,7 +204,7 @@ SR_DEVINL void ll_wait(uint4 (&v)[N], F addr, uint32_t gen) {
   }
 }
 
-struct DpRing {   // shared-memory landing ring (producer -> bankers)
+struct DpRing {
   uint8_t* data;
   uint64_t* full;
   uint64_t* empty;
@@ -214,91 +215,6 @@ struct DpRing {   // shared-memory landing ring (producer -> bankers)
     if (++slot == n) { slot = 0; phase ^= 1; }
   }
 };
-// TMEM weight ring (bankers -> consumers).  The shared-memory ring alone holds 128 KB per SM = 3 us of the HBM stream chip-wide,
-// but a layer spends ~20 us in the qkv -> attention -> o-proj exchange chain during which no weights are consumed; L2 is no
-// buffer for this (measured: prefetching into L2 does not shorten the streaming phases -- an L2 hit costs the same L2 throughput
-// as a miss's fill + read, and the stream already runs at that limit).  The 256 KB of tensor memory next to every SM are: banker
-// warps move every landed stage smem -> registers -> TMEM (tcgen05.st), laid out so that the consumer thread that needs a
-// fragment finds it in ITS lane (tcgen05.ld, 16 registers = its 64 bytes of the stage); 16 more stages of look-ahead per SM.
-struct DpTRing {
-  uint64_t* full;
-  uint64_t* empty;
-  uint32_t tbase;
-  int slot;
-  uint32_t phase;
-  SR_DEVINL void advance() {
-    if (++slot == DP_TSLOTS) { slot = 0; phase ^= 1; }
-  }
-};
-SR_DEVINL void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
-      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
-      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-SR_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// consumer side: this thread's 64 bytes of the next stage (warp cw: lanes of quarter cw % 4, columns 16 * (cw / 4) .. + 15 of the slot)
-SR_DEVINL void dp_fetch(DpTRing& tr, int cw, uint32_t (&wr)[16]) {
-  mbar_wait(&tr.full[tr.slot], tr.phase);
-  tc_fence_after();
-  tmem_ld_32x32b_x16(tr.tbase + (static_cast<uint32_t>(32 * (cw & 3)) << 16) + tr.slot * 32 + (cw >> 2) * 16, wr);
-  tmem_ld_wait();
-}
-SR_DEVINL void dp_release(DpTRing& tr, int lane) {
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&tr.empty[tr.slot]);
-  tr.advance();
-}
-enum { DP_FMT_RG1 = 0, DP_FMT_RG2 = 1, DP_FMT_SLICE = 2 };
-// banker: stage `n` landed stages of one format from the shared-memory ring into TMEM slots.  Lane i of the banker of quarter qd
-// collects the fragments consumer threads (warp qd, lane i) and (warp qd + 4, lane i) will ask for.
-template <int FMT>
-SR_DEVINL void dp_bank(DpRing& r, DpTRing& tr, int n, int qd, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  for (int i = 0; i < n; ++i) {
-    mbar_wait(&r.full[r.slot], r.phase);
-    mbar_wait(&tr.empty[tr.slot], tr.phase ^ 1);
-    const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
-    uint32_t v[32];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int cwv = qd + 4 * h;
-      if (FMT == DP_FMT_SLICE) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint2 lo = *reinterpret_cast<const uint2*>(stage + cwv * 2048 + j * 512 + g * 32 + t * 8);
-          const uint2 hi = *reinterpret_cast<const uint2*>(stage + cwv * 2048 + j * 512 + (g + 8) * 32 + t * 8);
-          v[16 * h + 4 * j] = lo.x; v[16 * h + 4 * j + 1] = lo.y; v[16 * h + 4 * j + 2] = hi.x; v[16 * h + 4 * j + 3] = hi.y;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint8_t* blk = (FMT == DP_FMT_RG2) ? stage + j * (DP_STAGE_BYTES / 2) + cwv * 1024 : stage + (cwv + 8 * j) * 1024;
-          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
-          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
-          const int o = 16 * h + 8 * j;
-          v[o] = w0.x; v[o + 1] = w0.y; v[o + 2] = w0.z; v[o + 3] = w0.w;
-          v[o + 4] = w1.x; v[o + 5] = w1.y; v[o + 6] = w1.z; v[o + 7] = w1.w;
-        }
-      }
-    }
-    tmem_st_32x32b_x32(tr.tbase + (static_cast<uint32_t>(32 * qd) << 16) + tr.slot * 32, v);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-      mbar_arrive(&tr.full[tr.slot]);
-      mbar_arrive(&r.empty[r.slot]);
-    }
-    r.advance();
-    tr.advance();
-  }
-}
 
 // ------------------------------------------------------------------------------------------------ producer
 // Streams this CTA's units of one packed matrix: unit u = RG consecutive 16-row groups; stage = 16 blocks of 1 KB
@@ -420,23 +336,44 @@ SR_DEVINL void dp_stage_rows(uint8_t* xs, const uint4* src, uint32_t gen, int M,
 
 // K loop of one unit with the activations staged in shared memory (K = DP_H).
 template <int RG>
-SR_DEVINL void dp_consume_staged(DpTRing& r, int nchunks, const uint8_t* xs, float (&acc)[RG][4], int cw, int lane) {
+SR_DEVINL void dp_consume_staged(DpRing& r, int nchunks, const uint8_t* xs, float (&acc)[RG][4], int cw, int lane) {
   constexpr int CPS = DP_STAGE_BLOCKS / RG;
   const int g = lane >> 2, t = lane & 3;
-  const int nst = nchunks / CPS;  // (K = DP_H: whole stages)
+  const int nst = (nchunks + CPS - 1) / CPS;
   const uint8_t* xrow = xs + g * DP_XS_STRIDE + t * 16;
   for (int st = 0; st < nst; ++st) {
-    uint32_t w[16];  // RG = 2: row group q: w0 = w[8q .. 8q+3], w1 = w[8q+4 .. 8q+7];  RG = 1: the same for chunk cw + 8j
-    dp_fetch(r, cw, w);
+    mbar_wait(&r.full[r.slot], r.phase);
+    const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
+    if (RG == 2) {
+      const int c = st * CPS + cw;
+      if (c < nchunks) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int c = (RG == 2) ? st * CPS + cw : st * CPS + cw + 8 * j;
-      const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
-      float (&a)[4] = acc[RG == 2 ? j : 0];
-      dp_mma(a, w[8 * j], w[8 * j + 4], w[8 * j + 1], w[8 * j + 5], xv.x, xv.y);
-      dp_mma(a, w[8 * j + 2], w[8 * j + 6], w[8 * j + 3], w[8 * j + 7], xv.z, xv.w);
+        for (int q = 0; q < RG; ++q) {
+          const uint8_t* blk = stage + q * (CPS * 1024) + cw * 1024;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
+          dp_mma(acc[q], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
+          dp_mma(acc[q], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = st * CPS + cw + 8 * j;
+        if (c < nchunks) {
+          const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
+          const uint8_t* blk = stage + (cw + 8 * j) * 1024;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
+          dp_mma(acc[0], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
+          dp_mma(acc[0], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
+        }
+      }
     }
-    dp_release(r, lane);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&r.empty[r.slot]);
+    r.advance();
   }
 }
 
@@ -459,10 +396,10 @@ struct DpOut {
 // Epilogue: thread (row group q, batch b, feature quad fg) sums the 8 warps' partials of 4 consecutive output columns and writes
 // one LL line (4 bf16) -- or 4 fp32 logits.
 template <int RG, int EPI, bool STAGED>
-SR_DEVINL void dp_gemv_phase(DpTRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, const __nv_bfloat16* xg, int64_t ldxg,
+SR_DEVINL void dp_gemv_phase(DpRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, const __nv_bfloat16* xg, int64_t ldxg,
                              int M, float* red, int& red_par, const DpOut& o, int cw, int lane, int stride) {
   const int g = lane >> 2, t = lane & 3;
-  const int ct = threadIdx.x - DP_CT0;
+  const int ct = threadIdx.x - 32;
   constexpr int NG = (EPI == DP_EPI_SWIGLU) ? 1 : RG;   // independent 16-column groups per unit
   const int eq = ct >> 5, eb = ct & 7, efg = (ct >> 3) & 3;
   const bool epi_thread = ct < 32 * NG && eb < M;
@@ -535,15 +472,36 @@ SR_DEVINL void dp_gemv_phase(DpTRing& r, int v0, int n_units, int nchunks, const
 // summed in a fixed order by the CTA that owns the 16 output rows (dp_reduce_x).  Compared with "all CTAs read all of act" this
 // removes 176 KB of activation reads per CTA and one exchange from the middle of the weight stream.
 SR_DEVINL int dp_kpos(int k) { return ((k & 7) >> 1) * 4 + (k >> 3) * 2 + (k & 1); }  // position of k inside a 16-wide k group
-SR_DEVINL void dp_de_phase(DpTRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, uint8_t* s_act, int M, float* red, int& red_par,
+SR_DEVINL void dp_de_phase(DpRing& r, int v0, int n_units, int nchunks, const uint8_t* xs, uint8_t* s_act, int M, float* red, int& red_par,
                            __nv_bfloat16* dbg_act, int I, float (&acc_e)[16][4], int cw, int lane, int stride) {
+  constexpr int CPS = DP_STAGE_BLOCKS / 2;
   const int g = lane >> 2, t = lane & 3;
-  const int ct = threadIdx.x - DP_CT0;
+  const int ct = threadIdx.x - 32;
   const int eb = ct & 7, efg = (ct >> 3) & 3;
   const bool epi_thread = ct < 32 && eb < M;
+  const int nst = (nchunks + CPS - 1) / CPS;
+  const uint8_t* xrow = xs + g * DP_XS_STRIDE + t * 16;
   for (int u = v0; u < n_units; u += stride) {
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    dp_consume_staged<2>(r, nchunks, xs, acc, cw, lane);
+    for (int st = 0; st < nst; ++st) {
+      mbar_wait(&r.full[r.slot], r.phase);
+      const uint8_t* stage = r.data + r.slot * DP_STAGE_BYTES;
+      const int c = st * CPS + cw;
+      if (c < nchunks) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xrow + c * 64);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const uint8_t* blk = stage + q * (CPS * 1024) + cw * 1024;
+          const uint4 w0 = *reinterpret_cast<const uint4*>(blk + g * 64 + t * 16);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(blk + (g + 8) * 64 + t * 16);
+          dp_mma(acc[q], w0.x, w1.x, w0.y, w1.y, xv.x, xv.y);
+          dp_mma(acc[q], w0.z, w1.z, w0.w, w1.w, xv.z, xv.w);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&r.empty[r.slot]);
+      r.advance();
+    }
     float* rp = red + red_par * (DP_CONSUMERS * 2 * DP_RED_WQ);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -578,11 +536,17 @@ SR_DEVINL void dp_de_phase(DpTRing& r, int v0, int n_units, int nchunks, const u
     const uint2 bv = *reinterpret_cast<const uint2*>(s_act + g * 32 + t * 8);
 #pragma unroll
     for (int st = 0; st < 4; ++st) {
-      uint32_t w[16];  // block j of this warp: a_lo = w[4j], w[4j+1] (row g), a_hi = w[4j+2], w[4j+3] (row g + 8)
-      dp_fetch(r, cw, w);
+      mbar_wait(&r.full[r.slot], r.phase);
+      const uint8_t* wb = r.data + r.slot * DP_STAGE_BYTES + cw * 2048;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dp_mma(acc_e[st * 4 + j], w[4 * j], w[4 * j + 2], w[4 * j + 1], w[4 * j + 3], bv.x, bv.y);
-      dp_release(r, lane);
+      for (int j = 0; j < 4; ++j) {
+        const uint2 a_lo = *reinterpret_cast<const uint2*>(wb + j * 512 + g * 32 + t * 8);
+        const uint2 a_hi = *reinterpret_cast<const uint2*>(wb + j * 512 + (g + 8) * 32 + t * 8);
+        dp_mma(acc_e[st * 4 + j], a_lo.x, a_hi.x, a_lo.y, a_hi.y, bv.x, bv.y);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&r.empty[r.slot]);
+      r.advance();
     }
   }
 }
@@ -698,7 +662,7 @@ struct DpAttnFrag {
 // keys [p0, p0 + nk) of the split, all of them OLD keys (the caller clips the range at the newest key)
 SR_DEVINL void dp_attn_load(const DpParams& p, const DpAttnUnit& U, const __nv_bfloat16* Kc, const __nv_bfloat16* Vt, int p0, int nk,
                              DpAttnFrag& f) {
-  const int ct = threadIdx.x - DP_CT0, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
+  const int ct = threadIdx.x - 32, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
   const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -735,7 +699,7 @@ SR_DEVINL void dp_attn_prefetch_l2(const DpParams& p, int layer, const DpAttnUni
   const int ke = dp_attn_old_end(U);
   const int n = ke - U.k_begin;
   if (n <= 0) return;
-  const int ct = threadIdx.x - DP_CT0;
+  const int ct = threadIdx.x - 32;
   const __nv_bfloat16* Kc = p.Kc + static_cast<int64_t>(layer) * p.k_layer_stride;
   const __nv_bfloat16* Vt = p.Vt + static_cast<int64_t>(layer) * p.vt_layer_stride;
   for (int k = ct; k < n; k += DP_CTHREADS) {
@@ -751,7 +715,7 @@ SR_DEVINL void dp_attn_prefetch_l2(const DpParams& p, int layer, const DpAttnUni
 
 SR_DEVINL void dp_attention_phase(const DpParams& p, int layer, uint32_t gen, uint8_t* sm, const float* s_cos, const float* s_sin,
                                    const DpAttnUnit& U, DpAttnFrag& f, int tr_base) {
-  const int ct = threadIdx.x - DP_CT0, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
+  const int ct = threadIdx.x - 32, lane = ct & 31, w = ct >> 5, g = lane >> 2, t = lane & 3;
   const int G = p.nq / p.nkv, ns = p.ns;
   float* s_red = reinterpret_cast<float*>(sm + DPB_RED);
   float* s_knew = reinterpret_cast<float*>(sm + DPB_KNEW);
@@ -1018,11 +982,6 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   ring.slot = 0;
   ring.phase = 0;
   ring.n = p.ring_stages;
-  DpTRing tring;
-  tring.full = ring.empty + DP_STAGES;
-  tring.empty = tring.full + DP_TSLOTS;
-  tring.slot = 0;
-  tring.phase = 0;
   uint8_t* xs = smem + DP_OFF_XS;
   float* red = reinterpret_cast<float*>(smem + DP_OFF_RED);
 
@@ -1048,28 +1007,17 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     }
     if (threadIdx.x == 8) s_scal[24] = static_cast<int>(*reinterpret_cast<volatile unsigned int*>(p.epoch));
     if (threadIdx.x == 9) s_scal[25] = 0;
-    if (threadIdx.x >= 32 && threadIdx.x < 96) reinterpret_cast<uint32_t*>(smem + DP_OFF_ACT)[threadIdx.x - DP_CT0] = 0u;
+    if (threadIdx.x >= 32 && threadIdx.x < 96) reinterpret_cast<uint32_t*>(smem + DP_OFF_ACT)[threadIdx.x - 32] = 0u;
   }
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < DP_STAGES; ++i) {
       mbar_init(&ring.full[i], 1);
-      mbar_init(&ring.empty[i], 4);            // the four banker warps
-    }
-#pragma unroll
-    for (int i = 0; i < DP_TSLOTS; ++i) {
-      mbar_init(&tring.full[i], 4);
-      mbar_init(&tring.empty[i], DP_CONSUMERS);
+      mbar_init(&ring.empty[i], DP_CONSUMERS);
     }
     fence_mbar_init();
   }
-  if (warp == 12) tmem_alloc<512>(reinterpret_cast<uint32_t*>(s_scal + 27));   // all of tensor memory: 16 slots of 32 columns
-  tc_fence_before();
   __syncthreads();
-  tc_fence_after();
-  tring.tbase = *reinterpret_cast<volatile uint32_t*>(s_scal + 27);
-  // register budget: the two consumer warpgroups (warps 4-11) take 192 registers per thread, the producer / banker warpgroups 64
-  const bool is_consumer = warp >= 4 && warp < 12;
 
   const int kq = DP_H >> 5;                       // k-chunks of the hidden-size matrices
   const int n_qkv = (p.nq + 2 * p.nkv) * 128 / 16;  // 16-row units
@@ -1088,9 +1036,9 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
   const int hs = half_head ? (G + 1) / 2 : G;
   const int hv = half_head ? ((blockIdx.x & 1) ? 0x7fffffff : static_cast<int>(blockIdx.x >> 1)) : static_cast<int>(blockIdx.x);
 
-  auto producer_role = [&]() {
+  if (warp == 0) {
     // ---------------- producer: weights only; runs ahead of the consumers across phases ----------------
-    {
+    if (lane == 0) {
       uint64_t policy = 0;
       const bool hint = (p.flags & 1) != 0;
       if (hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
@@ -1110,20 +1058,6 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
           volatile int* gate = s_scal + 25;
           while (*gate < l + 1) __nanosleep(20);
         }
-        if (p.pf_stages > 0) {
-          // L2 prefetch BURST of the head of this CTA's gate/up + down stream: issued once per layer at the moment the ring is about
-          // to fill up (the consumers are in the qkv -> attention -> o-proj exchange chain for the next ~20 us and HBM would idle);
-          // pf_stages x 16 KB per CTA.  No prefetching while the stream itself runs (that only doubles the L2 traffic).
-          int left = p.pf_stages * DP_STAGE_BYTES;
-          for (int u = vg; u < n_gu && left > 0; u += G) {
-            const char* a = reinterpret_cast<const char*>(L.gu_wp) + static_cast<int64_t>(u) * (2 * kq * 1024);
-            const char* b = reinterpret_cast<const char*>(L.down_wk) + static_cast<int64_t>(u) * (4 * DP_STAGE_BYTES);
-            for (int o2 = 0; o2 < 2 * kq * 1024 && left > 0; o2 += 32768, left -= 32768)
-              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a + o2), "r"(32768u) : "memory");
-            for (int o2 = 0; o2 < 4 * DP_STAGE_BYTES && left > 0; o2 += 32768, left -= 32768)
-              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b + o2), "r"(32768u) : "memory");
-          }
-        }
         dp_produce_de(ring, vg, L.gu_wp, L.down_wk, n_gu, kq, policy, hint, G);
         dp_trace_at(p, 0, 3 + 4 * l);
         if (ph++ >= limit) return;
@@ -1133,31 +1067,11 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       if (hv < n_head) dp_produce<1, false>(ring, hv, p.lm_head_p, n_head, kq, policy, hint, hs);
       dp_trace_at(p, 0, 1 + 4 * p.n_layers);
     }
-  };
-  auto banker_role = [&](int qd) {
-    // ---------------- bankers: the producer's schedule again, stage by stage: shared memory -> TMEM ----------------
-    auto units = [&](int v0, int n, int stride) { return v0 < n ? (n - v0 + stride - 1) / stride : 0; };
-    int ph = 0;
-    for (int l = 0; l < p.n_layers; ++l) {
-      if (ph++ >= limit) return;
-      dp_bank<DP_FMT_RG2>(ring, tring, units(vq, n_qkv / 2, G) * 8, qd, lane);
-      if (ph++ >= limit) return;
-      if (ph++ >= limit) return;
-      dp_bank<DP_FMT_RG1>(ring, tring, units(vo, n_o, G) * 4, qd, lane);
-      if (ph++ >= limit) return;
-      for (int u = vg; u < n_gu; u += G) {
-        dp_bank<DP_FMT_RG2>(ring, tring, 8, qd, lane);
-        dp_bank<DP_FMT_SLICE>(ring, tring, 4, qd, lane);
-      }
-      if (ph++ >= limit) return;
-    }
-    if (ph++ >= limit) return;
-    dp_bank<DP_FMT_RG1>(ring, tring, units(hv, n_head, hs) * 4, qd, lane);
-  };
-  auto consumer_role = [&]() {
+    return;
+  }
   // ---------------- consumers ----------------
-  const int cw = warp - 4;
-  const int ct = threadIdx.x - DP_CT0;
+  const int cw = warp - 1;
+  const int ct = threadIdx.x - 32;
   const uint32_t epoch_raw = static_cast<uint32_t>(s_scal[24]);
   const uint32_t epoch = epoch_raw + 1u;  // generations epoch .. epoch + n_layers: never 0 on a zero-initialised workspace
   const bool dump = (p.flags & 2) != 0;
@@ -1191,7 +1105,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       dp_cbar();
       DP_TRACE(0);
       o = DpOut{p.qkv_ll, n_qkv * 4, gen, nullptr, 0, L.qkv_b, nullptr, 0, p.qkv, static_cast<int64_t>(n_qkv) * 16};
-      dp_gemv_phase<2, DP_EPI_BIAS, true>(tring, vq, n_qkv / 2, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
+      dp_gemv_phase<2, DP_EPI_BIAS, true>(ring, vq, n_qkv / 2, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
     } else {
       DP_TRACE(0);
     }
@@ -1213,7 +1127,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       dp_cbar();
       DP_TRACE(4);
       o = DpOut{p.xa_ll, DP_HL, gen, p.xb_ll, gin, nullptr, nullptr, 0, dump ? p.x : nullptr, p.ldx};
-      dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(tring, vo, n_o, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
+      dp_gemv_phase<1, DP_EPI_RESIDUAL, true>(ring, vo, n_o, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, G);
     } else {
       DP_TRACE(4);
     }
@@ -1231,7 +1145,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       for (int i = 0; i < 16; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc_e[i][j] = 0.f;
-      dp_de_phase(tring, vg, n_gu, kq, xs, smem + DP_OFF_ACT, p.B, red, red_par, dump ? p.act : nullptr, p.I, acc_e, cw, lane, G);
+      dp_de_phase(ring, vg, n_gu, kq, xs, smem + DP_OFF_ACT, p.B, red, red_par, dump ? p.act : nullptr, p.I, acc_e, cw, lane, G);
       // publish this CTA's partial of Wdown . act^T: line (row, batch pair t) = (x[2t][row], x[2t+1][row])
       uint4* part = p.xpart_ll + static_cast<int64_t>(blockIdx.x) * (DP_H * 4);
       const int g = lane >> 2, t = lane & 3;
@@ -1254,7 +1168,7 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
     dp_stage_rows<true>(xs, p.xb_ll, epoch + static_cast<uint32_t>(p.n_layers), p.B, p.final_norm, p.eps, cw, lane);
     dp_cbar();
     DpOut o = DpOut{nullptr, 0, 0, nullptr, 0, nullptr, p.logits, p.ld_logits, nullptr, 0};
-    if (hv < n_head) dp_gemv_phase<1, DP_EPI_F32, true>(tring, hv, n_head, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, hs);
+    if (hv < n_head) dp_gemv_phase<1, DP_EPI_F32, true>(ring, hv, n_head, kq, xs, nullptr, 0, p.B, red, red_par, o, cw, lane, hs);
     DP_TRACE(0);
   }
 #undef DP_TRACE
@@ -1266,23 +1180,6 @@ __global__ void __launch_bounds__(DP_THREADS, 1) decode_persistent_kernel(const 
       p.epoch[0] = epoch_raw + static_cast<uint32_t>(p.n_layers) + 2u;
     }
   }
-  };  // consumer_role
-
-  if (is_consumer) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
-    consumer_role();
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp == 0) {
-      if (lane == 0) producer_role();
-    } else if (warp <= 3 || warp == 12) {
-      banker_role(warp & 3);               // a warp reaches the TMEM lanes 32 * (warp % 4) .. + 31 only
-    }
-  }
-  // common exit: nobody touches tensor memory any more -> release it
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 12) tmem_dealloc<512>(tring.tbase);
 }
 
 }  // namespace sr
@@ -1291,7 +1188,7 @@ using namespace sr;
 
 static inline int64_t dp_align(int64_t v) { return (v + 255) / 256 * 256; }
 struct DpWsLayout {
-  int64_t xa, xb, qkv, ao, act, flags, part, xpart, total;
+  int64_t xa, xb, qkv, ao, part, xpart, total;
 };
 static DpWsLayout dp_ws_layout(int n_q_heads, int n_kv_heads, int intermediate) {
   DpWsLayout w;
@@ -1300,8 +1197,7 @@ static DpWsLayout dp_ws_layout(int n_q_heads, int n_kv_heads, int intermediate) 
   w.xb = off; off += dp_align(8LL * DP_HL * 16);
   w.qkv = off; off += dp_align(8LL * (n_q_heads + 2 * n_kv_heads) * 32 * 16);
   w.ao = off; off += dp_align(8LL * DP_HL * 16);
-  w.act = off; off += dp_align(8LL * intermediate * 2);
-  w.flags = off; off += dp_align(4096);
+  (void)intermediate;
   w.part = off; off += dp_align(8LL * n_kv_heads * DP_NS_MAX * DP_PART_LINES * 16);
   w.xpart = off; off += dp_align(256LL * DP_H * 4 * 16);   // up to 256 CTAs x (2048 rows x 4 lines)
   w.total = off;
@@ -1322,14 +1218,11 @@ extern "C" int sr_set_decode_persistent_trace(void* buffer, int events_per_role)
 
 static int g_dp_flags = -1;      // -1: env SR_DECODE_FLAGS
 static int g_dp_ring = 0;        // 0: env SR_DECODE_RING (default below)
-static int g_dp_pf = -1;         // -1: env SR_DECODE_PF_STAGES (default below)
 static int g_dp_unit_off[4] = {-1, 0, 0, 0};  // -1: env SR_DECODE_UNIT_OFFSETS="q,o,g,d" (default below)
-extern "C" int sr_set_decode_persistent_tuning(int flags, int ring_stages, int pf_stages, int off_qkv, int off_o, int off_gate_up,
-                                               int off_down) {
-  if (ring_stages == 1 || ring_stages > DP_STAGES || ring_stages < 0 || pf_stages > 4096) return SR_ERR_INVALID;
+extern "C" int sr_set_decode_persistent_tuning(int flags, int ring_stages, int off_qkv, int off_o, int off_gate_up, int off_down) {
+  if (ring_stages == 1 || ring_stages > DP_STAGES || ring_stages < 0) return SR_ERR_INVALID;
   if (flags >= 0) g_dp_flags = flags & 0xff;
   g_dp_ring = ring_stages;
-  if (pf_stages >= 0) g_dp_pf = pf_stages;
   if (off_qkv >= 0 && off_o >= 0 && off_gate_up >= 0 && off_down >= 0) {
     g_dp_unit_off[0] = off_qkv;
     g_dp_unit_off[1] = off_o;
@@ -1402,7 +1295,6 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
   p.xb_ll = reinterpret_cast<uint4*>(ws + w.xb);
   p.qkv_ll = reinterpret_cast<uint4*>(ws + w.qkv);
   p.ao_ll = reinterpret_cast<uint4*>(ws + w.ao);
-  p.act_flags = reinterpret_cast<unsigned int*>(ws + w.flags);
   p.part_ll = reinterpret_cast<uint4*>(ws + w.part);
   p.xpart_ll = reinterpret_cast<uint4*>(ws + w.xpart);
   SR_REQUIRE(bk <= grid_cached, "sr_decode_step_persistent: batch * n_kv_heads must not exceed the SM count");
@@ -1420,11 +1312,6 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
     if (ring_stages < 2 || ring_stages > DP_STAGES) ring_stages = DP_STAGES;
   }
   p.ring_stages = g_dp_ring > 0 ? g_dp_ring : ring_stages;
-  if (g_dp_pf < 0) {
-    const char* e = getenv("SR_DECODE_PF_STAGES");
-    g_dp_pf = e ? atoi(e) : 0;
-  }
-  p.pf_stages = g_dp_pf;
   if (g_dp_unit_off[0] < 0) {
     const int dflt[4] = {96, 40, 0, 20};
     for (int i = 0; i < 4; ++i) g_dp_unit_off[i] = dflt[i];
@@ -1437,7 +1324,7 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
   SR_REQUIRE(!dump || (qkv_scratch && ao_scratch && act_scratch), "sr_decode_step_persistent: dump flag needs the three scratch buffers");
   p.qkv = dump ? reinterpret_cast<__nv_bfloat16*>(qkv_scratch) : nullptr;
   p.ao = dump ? reinterpret_cast<__nv_bfloat16*>(ao_scratch) : nullptr;
-  p.act = dump ? reinterpret_cast<__nv_bfloat16*>(act_scratch) : reinterpret_cast<__nv_bfloat16*>(ws + w.act);
+  p.act = dump ? reinterpret_cast<__nv_bfloat16*>(act_scratch) : nullptr;
   p.trace = g_dp_trace;
   p.trace_events = g_dp_trace_events;
   cudaLaunchConfig_t cfg = {};

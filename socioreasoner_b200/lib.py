@@ -57,7 +57,7 @@ SYMBOLS = {
     "sr_decode_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "sr_decode_persistent_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "sr_set_decode_persistent_trace": (c_int, [_P, c_int]),
-    "sr_set_decode_persistent_tuning": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "sr_set_decode_persistent_tuning": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "sr_decode_step_persistent": (c_int, [_P, c_int, _P, _P, c_int, _P, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, _P,
                                           c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float, c_float, _P, c_int, _P]),
     "sr_mask_epilogue": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
@@ -411,12 +411,11 @@ def decode_persistent_workspace(n_q_heads: int, n_kv_heads: int, intermediate: i
                        device=device)
 
 
-def decode_persistent_tuning(flags: int = -1, ring_stages: int = 0, pf_stages: int = -1, offsets=None) -> None:
+def decode_persistent_tuning(flags: int = -1, ring_stages: int = 0, offsets=None) -> None:
     """flags bit 0 = evict_first hint on the weight stream, bit 1 = dump plain intermediates (x / qkv / ao / act) for tests,
-    bit 4 = K/V L2 prefetch; pf_stages = look-ahead of the L2 prefetcher warp (16 KB stages per CTA)."""
+    bit 4 = K/V L2 prefetch (default 17); ring_stages = shared-memory ring depth; offsets = unit -> CTA rotation per matrix."""
     o = offsets if offsets is not None else (-1, -1, -1, -1)
-    _check(load().sr_set_decode_persistent_tuning(int(flags), int(ring_stages), int(pf_stages), *[int(v) for v in o]),
-           "sr_set_decode_persistent_tuning")
+    _check(load().sr_set_decode_persistent_tuning(int(flags), int(ring_stages), *[int(v) for v in o]), "sr_set_decode_persistent_tuning")
 
 
 def decode_step_persistent(layer_table: torch.Tensor, lm_head_p: torch.Tensor, final_norm: torch.Tensor, vocab: int,

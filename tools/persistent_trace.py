@@ -1,11 +1,11 @@
 """In-kernel timeline of the persistent decode step (sr_set_decode_persistent_trace): where does a layer's time go?
 The kernel has no grid barrier; its consumers record 9 events per layer (CTA-local thread 32):
   0 A-staged (x polled + normed)   1 A-done (qkv written)       2 B-q-ready (q/k/v polled)   3 B-partial-published
-  4 C-staged (attention out polled) 5 C-done (x after o-proj)    6 D-staged (x polled + normed) 7 D-done (SwiGLU written)
-  8 E-done (x after down written)
+  4 C-staged (attention out polled) 5 C-done (x after o-proj)    6 D-staged (x polled + normed) 7 DE-done (gate/up + down slices
+  streamed, fp32 partial of x published)   8 E-done (partials of all CTAs reduced, x written)
 Reported per segment: mean / max over CTAs of the segment's duration (us) in the steady-state layers, i.e. the wait for the
 other CTAs' data (the "staged" / "ready" segments) versus the streaming compute (the "done" segments), plus the producer's lead.
-Usage: python tools/persistent_trace.py [layers] [vocab] [flags] [ring] [pf_stages]"""
+Usage: python tools/persistent_trace.py [layers] [vocab] [flags] [ring]"""
 import os, sys
 import numpy as np
 import torch
@@ -17,9 +17,8 @@ n_layers = int(sys.argv[1]) if len(sys.argv) > 1 else 36
 vocab = int(sys.argv[2]) if len(sys.argv) > 2 else 151936
 flags = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 ring = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-pf = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-lib.decode_persistent_tuning(flags=flags, ring_stages=ring, pf_stages=pf)
-print(f"flags={flags} ring={ring or 'default'} pf_stages={pf}")
+lib.decode_persistent_tuning(flags=flags, ring_stages=ring)
+print(f"flags={flags} ring={ring or 'default'}")
 torch.manual_seed(0)
 layers = PB.make_layers(n_layers)
 S = PB.State(8, n_layers, 1024, [900 - 7 * i for i in range(8)], vocab)
@@ -46,7 +45,7 @@ total_ns = gt[:, cons, last].max() - t0
 cyc = (ck[:, cons, last] - ck[:, cons, 0]).mean()
 ghz = cyc / max(gt[:, cons, last].mean() - gt[:, cons, 0].mean(), 1)
 print(f"kernel span {total_ns / 1e3:.1f} us, SM clock ~{ghz:.3f} GHz")
-names = ["A wait x", "A qkv gemv", "B wait q", "B attention", "C wait ao(+merge)", "C o-proj", "D wait x", "D gate/up", "E down"]
+names = ["A wait x", "A qkv gemv", "B wait q", "B attention", "C wait ao(+merge)", "C o-proj", "D wait x", "DE gate/up+down", "E reduce partials"]
 lo = 2 if n_layers > 4 else 0
 print(f"steady-state layers {lo}..{n_layers - 1}; per segment: duration in us (clock64 / {ghz:.3f} GHz within a CTA)")
 print(f"{'segment':20s} {'mean':>8s} {'p50':>8s} {'max':>8s}")

@@ -6,8 +6,7 @@ import persistent_bringup as PB
 from socioreasoner_b200 import lib
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 ring = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-pf = int(sys.argv[3]) if len(sys.argv) > 3 else -1
-lib.decode_persistent_tuning(flags=flags, ring_stages=ring, pf_stages=pf)
+lib.decode_persistent_tuning(flags=flags, ring_stages=ring)
 torch.manual_seed(0)
 layers = PB.make_layers(36)
 S = PB.State(8, 36, 1024, [900 - 7 * i for i in range(8)], 151936)

@@ -562,16 +562,17 @@ SR_DEVINL void dp_reduce_x(const DpParams& p, int ud, uint32_t gen, const uint4*
   if (ct < 32 && eb < p.B) resl = ll_load(res_ptr);
   float s0 = 0.f, s1 = 0.f;
   const uint4* base = p.xpart_ll + static_cast<int64_t>(ud) * 64 + item;
-  for (int p0 = grp; p0 < G; p0 += 32) {
-    uint4 v[8];
+  constexpr int RB = 13;  // partials per thread and round trip (148 CTAs / 4 thread groups = 37 = 3 x 13 - 2)
+  for (int p0 = grp; p0 < G; p0 += 4 * RB) {
+    uint4 v[RB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < RB; ++j) {
       const int pi = p0 + 4 * j;
       v[j] = pi < G ? ll_load(base + static_cast<int64_t>(pi) * (DP_H * 4)) : make_uint4(0, gen, 0, gen);
     }
     ll_wait(v, [&](int j) { return base + static_cast<int64_t>(p0 + 4 * j) * (DP_H * 4); }, gen);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < RB; ++j) {
       s0 += __uint_as_float(v[j].x);
       s1 += __uint_as_float(v[j].z);
     }

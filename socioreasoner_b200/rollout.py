@@ -77,6 +77,11 @@ class DataParallelRollout:
         self._slot_bytes = 0
         self._pre = None
         self.max_pixels = max_pixels
+        # double-buffered upload of the NEXT step's host inputs on a copy stream while the current step computes
+        self._copy_stream = None
+        self._sets = [None, None]          # device copies (TileBatch) of two host batches
+        self._set_done = [None, None]      # event: last device use of that set
+        self._pref = None                  # (host batch, set index, copy-finished event)
 
     # layout of one rank's slot in the gather buffer: [b_max masks][b_max iou f32][b_max*T tokens i64][count i64]
     def _slot_layout(self, b_max: int):
@@ -106,10 +111,35 @@ class DataParallelRollout:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return max(int(t.item()), 1)
 
+    def prefetch(self, batch: TileBatch) -> None:
+        """Start copying a HOST batch (pinned) to the device on the copy stream; the next ``step(batch)`` with the same object
+        uses the device copy.  Call it right after ``step`` of the current batch: the upload then overlaps the current step's
+        compute instead of preceding the next step's first kernel."""
+        dev = self.engine.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        i = 0 if (self._pref is None or self._pref[1] == 1) else 1
+        cs = self._copy_stream
+        if self._set_done[i] is not None:
+            cs.wait_event(self._set_done[i])          # the set's previous contents are no longer being read
+        with torch.cuda.stream(cs):
+            up = lambda t: None if t is None else ([x.to(dev, non_blocking=True) for x in t] if isinstance(t, (list, tuple))
+                                                   else (t if t.is_cuda else t.to(dev, non_blocking=True)))
+            self._sets[i] = TileBatch(batch.input_ids, batch.attention_mask, batch.position_ids, up(batch.pixel_values), batch.image_grid_thw,
+                                      up(batch.mask_logits), up(batch.mask_scores), up(batch.gt_masks), tiles_u8=up(batch.tiles_u8))
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._pref = (batch, i, ev)
+
     def step(self, batch: TileBatch, b_max: Optional[int] = None) -> RolloutResult:
         """Runs this rank's shard.  Host tensors are copied to the device here (pinned -> async H2D); raw uint8 tiles are
         resized / normalised / patchified on the device.  An empty shard (b == 0) only publishes count 0."""
         dev = self.engine.device
+        used_set = None
+        if self._pref is not None and self._pref[0] is batch:       # inputs were uploaded ahead of time
+            _, used_set, ev = self._pref
+            torch.cuda.current_stream(dev).wait_event(ev)
+            batch = self._sets[used_set]
         b = batch.input_ids.shape[0]
         b_max = self.resolve_b_max(b, b_max)
         assert b <= b_max
@@ -137,6 +167,9 @@ class DataParallelRollout:
             lib.mask_epilogue(ml[i], ms[i], self.image_size, self.out_size, out=masks[i])
         iou = lib.mask_iou(masks[:b], gt, 1.0)
         self.pack_slot(b_max, tokens, iou)
+        if used_set is not None:
+            self._set_done[used_set] = torch.cuda.Event()
+            self._set_done[used_set].record(torch.cuda.current_stream(dev))
         return RolloutResult(tokens, masks[:b], iou)
 
     def slot_masks(self, b_max: int, device=None) -> torch.Tensor:
@@ -155,15 +188,27 @@ class DataParallelRollout:
         slot[cnt_off:cnt_off + 8].view(torch.int64).fill_(b)
 
     def gather_to_host(self, b_max: int, dst_rank: int = 0):
-        """``gather`` + ONE device -> host copy of the whole gather buffer on ``dst_rank`` only (the reference collects on the
-        driver only, decorator.py:151-180); the other ranks return None.  Returns host (tokens, masks, iou)."""
-        res = self.gather(b_max)
+        """``gather`` + ONE device -> host copy of the whole gather buffer into a PINNED host buffer on ``dst_rank`` only (the
+        reference collects on the driver only, decorator.py:151-180); the other ranks return None.  Returns host
+        (tokens, masks, iou) views of that buffer (valid until the next call)."""
+        self._all_gather()
         if self.rank != dst_rank:
             return None
-        return res.tokens.cpu(), res.masks.cpu(), res.iou.cpu()
+        gbuf = self._gbuf
+        if getattr(self, "_hbuf", None) is None or self._hbuf.shape != gbuf.shape:
+            self._hbuf = torch.empty(gbuf.shape, dtype=torch.uint8, pin_memory=gbuf.is_cuda)
+        self._hbuf.copy_(gbuf, non_blocking=True)
+        if gbuf.is_cuda:
+            torch.cuda.current_stream(gbuf.device).synchronize()
+        res = self._unpack(self._hbuf, b_max)
+        return res.tokens, res.masks, res.iou
 
     def gather(self, b_max: int) -> RolloutResult:
         """ONE all-gather of every rank's slot; returns the concatenation in rank order (= reference concat order)."""
+        self._all_gather()
+        return self._unpack(self._gbuf, b_max)
+
+    def _all_gather(self) -> None:
         gbuf = self._gbuf
         if self.world > 1:
             if gbuf.is_cuda:  # NCCL in-place all-gather (send buffer = this rank's slot of the receive buffer)
@@ -172,6 +217,8 @@ class DataParallelRollout:
                 parts = [torch.empty_like(gbuf[0]) for _ in range(self.world)]
                 dist.all_gather(parts, gbuf[self.rank].clone(), group=self.group)
                 gbuf.copy_(torch.stack(parts))
+
+    def _unpack(self, gbuf: torch.Tensor, b_max: int) -> RolloutResult:
         mask_b, iou_off, tok_off, cnt_off, _ = self._slot_layout(b_max)
         counts = gbuf[:, cnt_off:cnt_off + 8].contiguous().view(torch.int64).view(-1).tolist()
         toks, masks, ious = [], [], []

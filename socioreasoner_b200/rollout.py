@@ -65,6 +65,20 @@ class RolloutResult:
     iou: torch.Tensor     # [B] fp32
 
 
+class PendingResult:
+    """A result read-back in flight (``DataParallelRollout.gather_to_host_async``).  ``wait()`` blocks until the pinned host
+    buffer is complete and returns host (tokens, masks, iou): lists of per-rank views in rank order (no host-side copy;
+    ``torch.cat`` them if one tensor is needed), valid until the buffer is reused two read-backs later."""
+
+    def __init__(self, rollout, hbuf, done, b_max):
+        self._ro, self._hbuf, self._done, self._b_max = rollout, hbuf, done, b_max
+
+    def wait(self):
+        if self._done is not None:
+            self._done.synchronize()
+        return self._ro._unpack(self._hbuf, self._b_max, cat=False)
+
+
 class DataParallelRollout:
     def __init__(self, model, max_new_tokens: int = 32, image_size: int = 756, out_size: int = 768, group=None,
                  max_pixels: Optional[int] = None):
@@ -82,6 +96,11 @@ class DataParallelRollout:
         self._sets = [None, None]          # device copies (TileBatch) of two host batches
         self._set_done = [None, None]      # event: last device use of that set
         self._pref = None                  # (host batch, set index, copy-finished event)
+        # pipelined result read-back (rank 0): gather buffer -> one of two pinned host buffers on a copy stream
+        self._d2h_stream = None
+        self._d2h_done = None              # event: the last read-back of the gather buffer has finished
+        self._hbufs = [None, None]
+        self._h_i = 0
 
     # layout of one rank's slot in the gather buffer: [b_max masks][b_max iou f32][b_max*T tokens i64][count i64]
     def _slot_layout(self, b_max: int):
@@ -163,6 +182,9 @@ class DataParallelRollout:
             assert grid is None or grid2.tolist() == [list(map(int, g)) for g in grid.tolist()], "tile sizes do not match image_grid_thw"
             grid = grid2
         tokens = self.engine.generate_greedy(batch.input_ids, batch.attention_mask, batch.position_ids, pv, grid, self.T)
+        if self._d2h_done is not None:     # the previous step's read-back of the gather buffer must finish before it is rewritten
+            torch.cuda.current_stream(dev).wait_event(self._d2h_done)
+            self._d2h_done = None
         for i in range(b):
             lib.mask_epilogue(ml[i], ms[i], self.image_size, self.out_size, out=masks[i])
         iou = lib.mask_iou(masks[:b], gt, 1.0)
@@ -190,18 +212,38 @@ class DataParallelRollout:
     def gather_to_host(self, b_max: int, dst_rank: int = 0):
         """``gather`` + ONE device -> host copy of the whole gather buffer into a PINNED host buffer on ``dst_rank`` only (the
         reference collects on the driver only, decorator.py:151-180); the other ranks return None.  Returns host
-        (tokens, masks, iou) views of that buffer (valid until the next call)."""
+        (tokens, masks, iou): per-rank VIEWS of that buffer concatenated lazily -- lists of tensors in rank order, no host-side copy
+        (``torch.cat`` them if one tensor is needed); valid until the next call."""
+        pend = self.gather_to_host_async(b_max, dst_rank)
+        return None if pend is None else pend.wait()
+
+    def gather_to_host_async(self, b_max: int, dst_rank: int = 0) -> Optional["PendingResult"]:
+        """``gather_to_host`` without blocking the host: the copy into one of two pinned host buffers runs on a copy stream behind
+        the all-gather, so the driver-side consumer reads step k's result (``PendingResult.wait()``) while step k + 1 is already
+        running; the next step's epilogue waits for the copy before it rewrites the gather buffer.  None on the other ranks."""
         self._all_gather()
         if self.rank != dst_rank:
             return None
         gbuf = self._gbuf
-        if getattr(self, "_hbuf", None) is None or self._hbuf.shape != gbuf.shape:
-            self._hbuf = torch.empty(gbuf.shape, dtype=torch.uint8, pin_memory=gbuf.is_cuda)
-        self._hbuf.copy_(gbuf, non_blocking=True)
-        if gbuf.is_cuda:
-            torch.cuda.current_stream(gbuf.device).synchronize()
-        res = self._unpack(self._hbuf, b_max)
-        return res.tokens, res.masks, res.iou
+        self._h_i ^= 1
+        hb = self._hbufs[self._h_i]
+        if hb is None or hb.shape != gbuf.shape:
+            hb = self._hbufs[self._h_i] = torch.empty(gbuf.shape, dtype=torch.uint8, pin_memory=gbuf.is_cuda)
+        if not gbuf.is_cuda:
+            hb.copy_(gbuf)
+            return PendingResult(self, hb, None, b_max)
+        dev = gbuf.device
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream(device=dev)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        self._d2h_stream.wait_event(ready)
+        with torch.cuda.stream(self._d2h_stream):
+            hb.copy_(gbuf, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self._d2h_stream)
+        self._d2h_done = done
+        return PendingResult(self, hb, done, b_max)
 
     def gather(self, b_max: int) -> RolloutResult:
         """ONE all-gather of every rank's slot; returns the concatenation in rank order (= reference concat order)."""
@@ -218,7 +260,7 @@ class DataParallelRollout:
                 dist.all_gather(parts, gbuf[self.rank].clone(), group=self.group)
                 gbuf.copy_(torch.stack(parts))
 
-    def _unpack(self, gbuf: torch.Tensor, b_max: int) -> RolloutResult:
+    def _unpack(self, gbuf: torch.Tensor, b_max: int, cat: bool = True):
         mask_b, iou_off, tok_off, cnt_off, _ = self._slot_layout(b_max)
         counts = gbuf[:, cnt_off:cnt_off + 8].contiguous().view(torch.int64).view(-1).tolist()
         toks, masks, ious = [], [], []
@@ -227,4 +269,6 @@ class DataParallelRollout:
             masks.append(gbuf[r, :mask_b].view(b_max, self.out_size, self.out_size)[:c])
             ious.append(gbuf[r, iou_off:iou_off + b_max * 4].view(torch.float32)[:c])
             toks.append(gbuf[r, tok_off:tok_off + b_max * self.T * 8].view(torch.int64).view(b_max, self.T)[:c])
+        if not cat:
+            return toks, masks, ious
         return RolloutResult(torch.cat(toks), torch.cat(masks), torch.cat(ious))

@@ -276,6 +276,23 @@ def test_rollout_step_matches_oracle_epilogue(model, tiny_batch):
         assert int((res.masks[i].cpu().numpy() != ref).sum()) == 0
         assert abs(res.iou[i].item() - host_ref.compute_giou(ref, gt[i])) < 1e-6
     assert res.tokens.shape == (n, 4)
+    # pipelined host loop (what bench.py's e2e leg does): prefetched upload, read-back of step k while step k + 1 is queued;
+    # GT masks differ per step so a stale or torn read-back would be seen
+    host = [tb.pin(), TileBatch(b.input_ids, b.attention_mask, b.position_ids, b.pixel_values, b.image_grid_thw, torch.stack(ml),
+                                torch.stack(ms), torch.from_numpy(np.stack(gt[::-1]).copy())).pin()]
+    want = [[host_ref.compute_giou(host_ref.mask_epilogue(ml[i], ms[i]), g[i]) for i in range(n)] for g in (gt, gt[::-1])]
+    ro.prefetch(host[0])
+    pend, got = None, []
+    for k in range(4):
+        ro.step(host[k % 2], n)
+        ro.prefetch(host[(k + 1) % 2])
+        prev, pend = pend, ro.gather_to_host_async(n)
+        if prev is not None:
+            got.append(prev.wait())
+    got.append(pend.wait())
+    for k, (toks, masks, iou) in enumerate(got):
+        assert not masks[0].is_cuda and torch.equal(toks[0], res.tokens.cpu()) and torch.equal(masks[0], res.masks.cpu())
+        assert np.allclose(iou[0].numpy(), want[k % 2], atol=1e-6)
 
 
 def test_load_weights_in_place_equals_a_fresh_model_and_keeps_decode_graphs(oracle_tiny, tiny_batch):

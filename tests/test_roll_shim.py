@@ -202,6 +202,13 @@ def _dp_worker(rank, world, port, total, T, out_q):
         toks = torch.stack([torch.arange(T) + 100 * int(i) for i in mine]) if len(mine) else torch.zeros(0, T, dtype=torch.int64)
         ro.pack_slot(b_max, toks, torch.tensor([float(i) / 10 for i in mine]))
         res = ro.gather(b_max)
+        # driver-side collect: destination rank gets per-rank host views (no concatenation), the others None
+        pend = ro.gather_to_host_async(b_max, dst_rank=1)
+        assert (pend is None) == (rank != 1)
+        if pend is not None:
+            ht, hm, hi = pend.wait()
+            assert [len(t) for t in ht] == [len(s) for s in shards]
+            assert torch.equal(torch.cat(ht), res.tokens) and torch.equal(torch.cat(hm), res.masks) and torch.equal(torch.cat(hi), res.iou)
         # plain numpy through the queue: torch tensors travel as shared-memory handles that die with the producer process
         out_q.put((rank, res.tokens.numpy().copy(), res.masks.numpy().copy(), res.iou.numpy().copy()))
     finally:

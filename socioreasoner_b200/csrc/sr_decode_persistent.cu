@@ -158,6 +158,12 @@ SR_DEVINL uint4 dp_ldcg(const void* p) { return __ldcg(reinterpret_cast<const ui
 SR_DEVINL void ll_store(uint4* p, uint32_t d0, uint32_t d1, uint32_t gen) {
   asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(d0), "r"(gen), "r"(d1), "r"(gen) : "memory");
 }
+// Optional back-off between polling rounds (compile-time experiment: -DSR_LL_BACKOFF=<ns>); off by default.
+#ifdef SR_LL_BACKOFF
+#define SR_LL_BACKOFF_SLEEP() __nanosleep(SR_LL_BACKOFF)
+#else
+#define SR_LL_BACKOFF_SLEEP() ((void)0)
+#endif
 SR_DEVINL uint4 ll_load(const uint4* p) {
   uint4 v;
   asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -171,6 +177,7 @@ __device__ __noinline__ uint4 ll_spin_slow(const uint4* p, uint32_t gen) {
   unsigned int spins = 0;
   uint4 v = ll_load(p);
   while (!ll_ok(v, gen)) {
+    SR_LL_BACKOFF_SLEEP();
     v = ll_load(p);
     if (++spins > SR_LL_SPIN_LIMIT) {
       printf("sr: LL wait timeout block=%d thread=%d want=%u have=%u/%u\n", blockIdx.x, threadIdx.x, gen, v.y, v.w);
@@ -197,6 +204,7 @@ SR_DEVINL void ll_wait(uint4 (&v)[N], F addr, uint32_t gen) {
 #pragma unroll
     for (int i = 0; i < N; ++i) ok = ok && ll_ok(v[i], gen);
     if (ok) break;
+    SR_LL_BACKOFF_SLEEP();
 #pragma unroll
     for (int i = 0; i < N; ++i)
       if (!ll_ok(v[i], gen)) v[i] = ll_load(addr(i));

@@ -11,8 +11,13 @@
 //   warp 1   : MMA issuer    -- one thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) x4 per k-block into a
 //              double-buffered TMEM accumulator (2 x BLOCK_N fp32 columns); tcgen05.commit frees smem stages
 //              and publishes finished accumulators.
-//   warps 2-5: epilogue      -- tcgen05.ld 32 lanes x 32 columns, fused bias / residual / SwiGLU / GELU,
+//   warps 2-9: epilogue      -- tcgen05.ld 32 lanes x 32 columns, fused bias / residual / SwiGLU / GELU,
 //              bf16 (or fp32) vector stores.  Overlaps with the next tile's MMAs through the 2nd TMEM buffer.
+//              EIGHT warps (two per TMEM lane quarter, each taking half of the tile's columns): with four, one
+//              latency-exposed warp per scheduler needed ~2100 cycles per 32-column chunk = 16 900 cycles per
+//              128 x 256 tile, more than the 10 240 MMA cycles of a K = 1280 tile -- the short-K shapes were
+//              epilogue-paced (profiles/r01_gemm_vit_qkv.json: 320 865 cycles for 19 tile waves).  The residual rows of
+//              a warp's whole column half are requested before it waits for the accumulator.
 // Both operands are K-major (activations [M,K] row-major; weights in nn.Linear layout [N,K]).
 #include "sr_host.h"
 #include "../../include/socioreasoner_b200.h"
@@ -22,7 +27,16 @@ namespace sr {
 constexpr int SR_EPI_LSE = 4;  // internal: no C; per (row, N tile) softmax statistics for sr_lmhead_logprob_entropy
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;
+#ifndef SR_GEMM_EPI_WARPS
+#define SR_GEMM_EPI_WARPS 8  // 4 or 8 (compile-time A/B switch; 8 is the product configuration)
+#endif
+// epilogue warps per instantiation: the LSE epilogue keeps one warp per row quarter (its per-row statistics run over all
+// columns of the tile), as do the 32-column tiles (a single chunk)
+template <int BLOCK_N, int EPI>
+struct GemmEpi {
+  static constexpr int kWarps = (EPI == SR_EPI_LSE || BLOCK_N < 64) ? 4 : SR_GEMM_EPI_WARPS;
+};
+constexpr int GEMM_MAX_THREADS = 64 + 32 * SR_GEMM_EPI_WARPS;
 
 struct GemmParams {
   void* C;
@@ -31,9 +45,29 @@ struct GemmParams {
   int64_t ldc, ldr;
   int M, N, K;
   int num_m_blocks, num_n_blocks;
+  int band_rows;          // tile order: row blocks per band (gemm_tile_coords)
+  int wide;               // 1: C (and the residual) rows allow 32-byte accesses -> 256-bit LDG / STG (one full sector per thread)
   const int64_t* labels;  // SR_EPI_LSE: [M] target column per row (out of range: no target)
   float4* partial;        // SR_EPI_LSE: [num_n_blocks][M] (max, sum exp(x - max), sum exp(x - max) * x, x[label] or 0)
 };
+
+// Tile order: bands of GEMM_BAND row blocks, inside a band the row block runs fastest and the column block slowest.  The ~148
+// tiles in flight then cover (a few column blocks) x (one band): the band's A rows (GEMM_BAND x 128 x K) are fetched from HBM
+// once and re-used from L2 by every column block, and neighbouring CTAs share B tiles.  Row-major-over-M order (round 1) swept
+// all of A once per column block: 1.46 x the algorithmic DRAM bytes on the ViT qkv shape and 5 x A for the N = 1280 shapes
+// whose A (161 MB at K = 3456) does not fit in L2.
+// Band height (chosen on the host, measured with tools/gemm_bench.py): 37 row blocks (a wave = 4 column blocks x 37 row blocks:
+// weights larger than L2, e.g. the decoder gate/up at 90 MB, are then swept only once per 37 row blocks), 8 for long-K shapes
+// with small weights (ViT fc2, decoder down: A is the large operand).
+SR_DEVINL void gemm_tile_coords(int tile, int num_m_blocks, int num_n_blocks, int band_rows, int& m_blk, int& n_blk) {
+  const int per_band = band_rows * num_n_blocks;
+  const int band = tile / per_band;
+  const int r = tile - band * per_band;
+  const int m0 = band * band_rows;
+  const int rows = min(band_rows, num_m_blocks - m0);
+  n_blk = r / rows;
+  m_blk = m0 + (r - n_blk * rows);
+}
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -46,14 +80,39 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
 };
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256).  A thread of the epilogue owns one output ROW, so its stores can never
+// coalesce with its neighbours'; 32-byte stores at least write whole sectors (16-byte ones leave L2 with two partial-sector
+// writes per sector, twice the requests).
+SR_DEVINL void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y),
+               "r"(b.z), "r"(b.w)
+               : "memory");
+}
+SR_DEVINL void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+SR_DEVINL void store_row16(void* dst, const uint4& a, const uint4& b, bool wide) {
+  if (wide) {
+    stg256(dst, a, b);
+  } else {
+    *reinterpret_cast<uint4*>(dst) = a;
+    *(reinterpret_cast<uint4*>(dst) + 1) = b;
+  }
+}
+
 SR_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 SR_DEVINL float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 template <int BLOCK_N, int EPI, bool OUT_F32>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_MAX_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kEpiWarps = GemmEpi<BLOCK_N, EPI>::kWarps;
+  constexpr int kEpiThreads = 32 * kEpiWarps;
+  constexpr int kChunks = BLOCK_N / 32 / (kEpiWarps / 4);  // 32-column chunks per epilogue warp
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -78,8 +137,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     mbar_init(&tmem_full_bar[0], 1);
     mbar_init(&tmem_full_bar[1], 1);
-    mbar_init(&tmem_empty_bar[0], 4);
-    mbar_init(&tmem_empty_bar[1], 4);
+    mbar_init(&tmem_empty_bar[0], kEpiWarps);
+    mbar_init(&tmem_empty_bar[1], kEpiWarps);
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
@@ -97,8 +156,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.num_m_blocks;
-        const int n_blk = tile / p.num_m_blocks;
+        int m_blk, n_blk;
+        gemm_tile_coords(tile, p.num_m_blocks, p.num_n_blocks, p.band_rows, m_blk, n_blk);
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -142,38 +201,51 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ---------------- epilogue warps (2..5) ----------------
+    // ---------------- epilogue warps (2 .. 2 + kEpiWarps) ----------------
     // Global-memory operands of the epilogue are kept off the critical path: the tile's bias slice is staged once in
     // shared memory (a per-use __ldg costs one L2 round trip per 8 columns -- ncu showed 60% of all stall samples
-    // there), and the residual rows of chunk c+1 are prefetched while chunk c is converted and stored.
-    const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;   // 0..127 within the epilogue group
+    // there), and the residual rows of the warp's column half are requested before the accumulator is waited for.
+    const int quarter = warp_idx & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp_idx - 2) >> 2;       // which kChunks-chunk column range of the tile
+    const int et = threadIdx.x - 64;            // 0 .. kEpiThreads-1 within the epilogue group
+    constexpr int kResChunks = (EPI == SR_EPI_RESIDUAL) ? kChunks : 1;
     int acc = 0;
     uint32_t acc_phase = 0;
     int tile_par = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.num_m_blocks;
-      const int n_blk = tile / p.num_m_blocks;
+      int m_blk, n_blk;
+      gemm_tile_coords(tile, p.num_m_blocks, p.num_n_blocks, p.band_rows, m_blk, n_blk);
       float* sb = s_bias + tile_par * BLOCK_N;
       if (p.bias != nullptr) {
-        for (int j = et; j < BLOCK_N; j += 128) {
+        for (int j = et; j < BLOCK_N; j += kEpiThreads) {
           const int col = n_blk * BLOCK_N + j;
           sb[j] = col < p.N ? __ldg(p.bias + col) : 0.f;
         }
       }
       const int row = m_blk * GEMM_BLOCK_M + quarter * 32 + lane;
       const bool row_ok = row < p.M;
-      uint4 rnext[4];
-      const __nv_bfloat16* rrow = nullptr;
+      const int chunk0 = half * kChunks;
+      uint4 rres[kResChunks][4];
       if (EPI == SR_EPI_RESIDUAL) {
-        rrow = reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<int64_t>(row_ok ? row : 0) * p.ldr;
+        const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.residual) + static_cast<int64_t>(row_ok ? row : 0) * p.ldr;
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int col = n_blk * BLOCK_N + g8 * 8;
-          rnext[g8] = (row_ok && col < p.N) ? *reinterpret_cast<const uint4*>(rrow + col) : make_uint4(0, 0, 0, 0);
+        for (int c = 0; c < kResChunks; ++c) {
+#pragma unroll
+          for (int g16 = 0; g16 < 2; ++g16) {
+            const int col = n_blk * BLOCK_N + (chunk0 + c) * 32 + g16 * 16;
+            rres[c][2 * g16] = rres[c][2 * g16 + 1] = make_uint4(0, 0, 0, 0);
+            if (row_ok && col < p.N) {
+              if (p.wide) {
+                ldg256(rrow + col, rres[c][2 * g16], rres[c][2 * g16 + 1]);
+              } else {
+                rres[c][2 * g16] = *reinterpret_cast<const uint4*>(rrow + col);
+                if (col + 8 < p.N) rres[c][2 * g16 + 1] = *reinterpret_cast<const uint4*>(rrow + col + 8);
+              }
+            }
+          }
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // bias slice visible to the 4 epilogue warps
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // bias slice visible to the epilogue warps
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
@@ -183,8 +255,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int64_t lb = p.labels[row];
         lse_label = (lb >= 0 && lb < p.N) ? static_cast<int>(lb) : -1;
       }
-#pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+#pragma unroll
+      for (int ci = 0; ci < kChunks; ++ci) {
+        const int chunk = chunk0 + ci;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + static_cast<uint32_t>(chunk * 32), v);
         const int col0 = n_blk * BLOCK_N + chunk * 32;
@@ -212,18 +285,6 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           continue;
         }
-        uint4 rcur[4];
-        if (EPI == SR_EPI_RESIDUAL) {
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) rcur[g8] = rnext[g8];
-          if (chunk + 1 < BLOCK_N / 32) {
-#pragma unroll
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const int col = col0 + 32 + g8 * 8;
-              rnext[g8] = (row_ok && col < p.N) ? *reinterpret_cast<const uint4*>(rrow + col) : make_uint4(0, 0, 0, 0);
-            }
-          }
-        }
         tmem_ld_wait();
         const float* sbc = sb + chunk * 32;
         if (EPI == SR_EPI_SWIGLU) {
@@ -242,50 +303,69 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (row_ok && oc0 < (p.N >> 1)) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + oc0;
+            uint4 pk[2];
 #pragma unroll
             for (int g8 = 0; g8 < 2; ++g8) {
-              uint4 pk;
-              pk.x = pack_bf16x2(o[g8 * 8 + 0], o[g8 * 8 + 1]);
-              pk.y = pack_bf16x2(o[g8 * 8 + 2], o[g8 * 8 + 3]);
-              pk.z = pack_bf16x2(o[g8 * 8 + 4], o[g8 * 8 + 5]);
-              pk.w = pack_bf16x2(o[g8 * 8 + 6], o[g8 * 8 + 7]);
-              *reinterpret_cast<uint4*>(dst + g8 * 8) = pk;
+              pk[g8].x = pack_bf16x2(o[g8 * 8 + 0], o[g8 * 8 + 1]);
+              pk[g8].y = pack_bf16x2(o[g8 * 8 + 2], o[g8 * 8 + 3]);
+              pk[g8].z = pack_bf16x2(o[g8 * 8 + 4], o[g8 * 8 + 5]);
+              pk[g8].w = pack_bf16x2(o[g8 * 8 + 6], o[g8 * 8 + 7]);
             }
+            store_row16(dst, pk[0], pk[1], p.wide != 0);
           }
         } else {
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const int col = col0 + g8 * 8;
-            if (col >= p.N) break;  // N % 8 == 0 (checked on the host)
-            float x[8];
+          for (int g16 = 0; g16 < 2; ++g16) {
+            const int col = col0 + g16 * 16;
+            if (col >= p.N) break;
+            const bool second = col + 8 < p.N;  // N % 8 == 0 (checked on the host); N % 16 == 0 whenever p.wide
+            float x[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g8 * 8 + j]);
+            for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[g16 * 16 + j]);
             if (p.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) x[j] += sbc[g8 * 8 + j];
+              for (int j = 0; j < 16; ++j) x[j] += sbc[g16 * 16 + j];
             }
             if (EPI == SR_EPI_GELU) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) x[j] = gelu_erf(x[j]);
+              for (int j = 0; j < 16; ++j) x[j] = gelu_erf(x[j]);
             }
             if (row_ok) {
               if (EPI == SR_EPI_RESIDUAL) {
-                const uint4 r = rcur[g8];
-                x[0] += bf16_lo(r.x); x[1] += bf16_hi(r.x); x[2] += bf16_lo(r.y); x[3] += bf16_hi(r.y);
-                x[4] += bf16_lo(r.z); x[5] += bf16_hi(r.z); x[6] += bf16_lo(r.w); x[7] += bf16_hi(r.w);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint4 r = rres[EPI == SR_EPI_RESIDUAL ? ci : 0][2 * g16 + h];
+                  float* xx = x + 8 * h;
+                  xx[0] += bf16_lo(r.x); xx[1] += bf16_hi(r.x); xx[2] += bf16_lo(r.y); xx[3] += bf16_hi(r.y);
+                  xx[4] += bf16_lo(r.z); xx[5] += bf16_hi(r.z); xx[6] += bf16_lo(r.w); xx[7] += bf16_hi(r.w);
+                }
               }
               if (OUT_F32) {
                 float* dst = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
-                *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  if (h == 1 && !second) break;
+                  const float* xx = x + 8 * h;
+                  const uint4 a = make_uint4(__float_as_uint(xx[0]), __float_as_uint(xx[1]), __float_as_uint(xx[2]), __float_as_uint(xx[3]));
+                  const uint4 b = make_uint4(__float_as_uint(xx[4]), __float_as_uint(xx[5]), __float_as_uint(xx[6]), __float_as_uint(xx[7]));
+                  store_row16(dst + 8 * h, a, b, p.wide != 0);
+                }
               } else {
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
-                uint4 pk;
-                pk.x = pack_bf16x2(x[0], x[1]);
-                pk.y = pack_bf16x2(x[2], x[3]);
-                pk.z = pack_bf16x2(x[4], x[5]);
-                pk.w = pack_bf16x2(x[6], x[7]);
-                *reinterpret_cast<uint4*>(dst) = pk;
+                uint4 pk[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  pk[h].x = pack_bf16x2(x[8 * h + 0], x[8 * h + 1]);
+                  pk[h].y = pack_bf16x2(x[8 * h + 2], x[8 * h + 3]);
+                  pk[h].z = pack_bf16x2(x[8 * h + 4], x[8 * h + 5]);
+                  pk[h].w = pack_bf16x2(x[8 * h + 6], x[8 * h + 7]);
+                }
+                if (p.wide) {
+                  stg256(dst, pk[0], pk[1]);
+                } else {
+                  *reinterpret_cast<uint4*>(dst) = pk[0];
+                  if (second) *reinterpret_cast<uint4*>(dst + 8) = pk[1];
+                }
               }
             }
           }
@@ -322,7 +402,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  kern<<<grid, 64 + 32 * GemmEpi<BLOCK_N, EPI>::kWarps, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
   SR_CHECK_CUDA(cudaGetLastError());
   return SR_OK;
 }
@@ -433,8 +513,16 @@ extern "C" int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t l
   p.K = K;
   p.num_m_blocks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   p.num_n_blocks = (N + bn - 1) / bn;
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int f32 = out_dtype == SR_DTYPE_F32;
+  p.band_rows = (K >= 3072 && static_cast<int64_t>(N) * K * 2 <= (64ll << 20)) ? 8 : 37;
+  {  // 32-byte accesses: every row start and every 16-column group (8 for fp32 / SwiGLU halves) must be 32-byte aligned
+    const int64_t c_el = f32 ? 4 : 2;
+    bool ok = (reinterpret_cast<uintptr_t>(C) & 31) == 0 && (ldc * c_el) % 32 == 0 && N % 16 == 0;
+    if (epilogue == SR_EPI_SWIGLU) ok = ok && N % 32 == 0;
+    if (epilogue == SR_EPI_RESIDUAL) ok = ok && (reinterpret_cast<uintptr_t>(residual) & 31) == 0 && (ldr * 2) % 32 == 0;
+    p.wide = ok ? 1 : 0;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (bn == 256) return dispatch_epi<256>(epilogue, f32, tmA, tmB, p, s);
   if (bn == 128) return dispatch_epi<128>(epilogue, f32, tmA, tmB, p, s);
   return dispatch_epi<32>(epilogue, f32, tmA, tmB, p, s);
@@ -480,6 +568,7 @@ extern "C" int sr_lmhead_logprob_entropy(const void* A, int64_t lda, const void*
   p.num_m_blocks = (M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   p.num_n_blocks = (N + bn - 1) / bn;
   p.labels = labels;
+  p.band_rows = 37;
   p.partial = reinterpret_cast<float4*>(workspace);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int rc = launch_gemm<bn, SR_EPI_LSE, false>(tmA, tmB, p, s);

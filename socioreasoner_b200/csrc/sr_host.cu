@@ -1,4 +1,7 @@
 // sr_host.cu -- host helpers (see sr_host.h) + library-level C-ABI entry points.
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include "sr_host.h"
 
 #include <stdarg.h>
@@ -68,10 +71,46 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// A tensor map is a pure function of (address, shape, strides, box, swizzle): the ~300 GEMM / attention launches of a step use
+// the same few dozen operands step after step, so encoded maps are kept in a small per-process cache instead of calling the
+// driver's encoder twice or three times per launch.
+namespace {
+struct TmapKey {
+  uint64_t w[16];
+  bool operator==(const TmapKey& o) const { return std::memcmp(w, o.w, sizeof(w)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint64_t x : k.w) h = (h ^ x) * 0x100000001b3ull;
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+constexpr size_t kTmapCacheMax = 8192;
+}  // namespace
+
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return SR_ERR_DRIVER;
+  TmapKey key = {};
+  key.w[0] = reinterpret_cast<uint64_t>(base);
+  key.w[1] = (static_cast<uint64_t>(rank) << 32) | static_cast<uint32_t>(swizzle_bytes);
+  for (int i = 0; i < rank && i < 5; ++i) {
+    key.w[2 + i] = dims[i];
+    key.w[7 + i] = (i > 0) ? strides_bytes[i - 1] : 0;
+    key.w[12 + (i >> 1)] |= static_cast<uint64_t>(box[i]) << (32 * (i & 1));
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return SR_OK;
+    }
+  }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
     set_last_error("tensor map base %p not 16-byte aligned", base);
     return SR_ERR_INVALID;
@@ -103,6 +142,11 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
     set_last_error("cuTensorMapEncodeTiled failed: CUresult=%d (rank=%d dims=%llu,%llu box=%u,%u)", (int)r, rank,
                    (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0), bx[0], rank > 1 ? bx[1] : 0);
     return SR_ERR_DRIVER;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
   }
   return SR_OK;
 }

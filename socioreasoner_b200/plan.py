@@ -28,18 +28,38 @@ class AttnPlan:
     row_hi: np.ndarray   # int32 [n_rows]
 
 
-def plan_from_segments(seg_bounds: np.ndarray, n_rows: int, break_at: Optional[np.ndarray] = None) -> AttnPlan:
+def plan_from_segments(seg_bounds: np.ndarray, n_rows: int, break_at: Optional[np.ndarray] = None,
+                       pack_whole: bool = False) -> AttnPlan:
     """Bidirectional attention inside each segment.  ``seg_bounds`` = sorted boundaries [0, ..., n_rows] (q rows and
     key rows share one index space).  Tiles are 128-row chunks of each span between consecutive ``break_at`` boundaries
-    (default: one span = everything)."""
+    (default: one span = everything).  ``pack_whole``: a tile is a maximal run of WHOLE segments with at most 128 rows
+    (short segments: the ViT windows of 36-64 tokens), so that its key range is its own rows -- one 128-key block per tile,
+    where blind 128-row chunks straddle three windows and need two."""
     seg_bounds = np.asarray(seg_bounds, dtype=np.int64)
     assert seg_bounds[0] == 0 and seg_bounds[-1] == n_rows and np.all(np.diff(seg_bounds) > 0)
     seg_id = np.searchsorted(seg_bounds, np.arange(n_rows), side="right") - 1
     row_lo = seg_bounds[seg_id].astype(np.int32)
     row_hi = seg_bounds[seg_id + 1].astype(np.int32)
+    tiles = []
+    if pack_whole:
+        i, n_seg = 0, len(seg_bounds) - 1
+        while i < n_seg:
+            r0 = int(seg_bounds[i])
+            if seg_bounds[i + 1] - r0 > TILE_ROWS:          # a long segment: 128-row chunks, all keys of the segment
+                for c0 in range(r0, int(seg_bounds[i + 1]), TILE_ROWS):
+                    c1 = min(c0 + TILE_ROWS, int(seg_bounds[i + 1]))
+                    tiles.append((c0, c1 - c0, r0, int(seg_bounds[i + 1])))
+                i += 1
+                continue
+            j = i + 1
+            while j < n_seg and seg_bounds[j + 1] - r0 <= TILE_ROWS:
+                j += 1
+            r1 = int(seg_bounds[j])
+            tiles.append((r0, r1 - r0, r0, r1))
+            i = j
+        return AttnPlan(np.asarray(tiles, dtype=np.int32).reshape(-1, 4), row_lo, row_hi)
     if break_at is None:
         break_at = np.array([0, n_rows], dtype=np.int64)
-    tiles = []
     for a, b in zip(break_at[:-1], break_at[1:]):
         for r0 in range(int(a), int(b), TILE_ROWS):
             r1 = min(r0 + TILE_ROWS, int(b))
@@ -61,6 +81,9 @@ def plan_causal(lengths: Sequence[int], q_starts: Sequence[int], kv_starts: Sequ
         for r0 in range(0, L, TILE_ROWS):
             r1 = min(r0 + TILE_ROWS, L)
             tiles.append((q0 + r0, r1 - r0, k0, k0 + r1))
+    # longest key range first: CTAs are scheduled in tile order, so the 7-block tiles of a long prompt start in the first
+    # wave instead of forming the tail of the launch
+    tiles.sort(key=lambda t: t[2] - t[3])
     return AttnPlan(np.asarray(tiles, dtype=np.int32).reshape(-1, 4), row_lo, row_hi)
 
 
@@ -124,7 +147,7 @@ def vit_plan(grid_thw: np.ndarray, spatial_merge_size: int = 2, window_size: int
     return VitPlan(
         n=n, m=m, row_perm=row_perm.astype(np.int32), merged_reverse=np.argsort(window_index).astype(np.int32),
         hpos=hpos.astype(np.int32), wpos=wpos.astype(np.int32), cu_window_seqlens=cu_win, cu_seqlens=cu,
-        window_plan=plan_from_segments(cu_win, n), full_plan=plan_from_segments(cu, n, break_at=cu),
+        window_plan=plan_from_segments(cu_win, n, pack_whole=True), full_plan=plan_from_segments(cu, n, break_at=cu),
     )
 
 

@@ -315,6 +315,294 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// "P in tensor memory" variant (the product configuration, SR_ATTN_LEAN = 2).  Same tiles, same arithmetic and the same bits as
+// the kernels above, different plumbing of one K/V block:
+//   * the probabilities go back into TENSOR MEMORY, over the S columns they were computed from (tcgen05.st, 2 bf16 per 32-bit
+//     column), and P V is issued with the A operand in TMEM (tcgen05.mma [d], [a], b-desc).  No P tile in shared memory, no
+//     generic -> async proxy fence, and -- the point -- the K tile is dead as soon as S = Q K^T has completed;
+//   * K and V have their own barriers: K_{j+1} is loaded while block j is in its softmax, V is double-buffered (head_dim_v 80:
+//     2 x 20 KB) and lands long before its P V.  In the lean kernel above the next block's loads started only after P V, so
+//     every block paid a full L2 round trip (3.9 us per block against ~1.3 us of softmax);
+//   * 104 KB (head_dim_v 80) / 96 KB (128, single V stage) of shared memory and 256 TMEM columns: still two CTAs per SM.
+template <int HDV>
+struct AttnTpCfg {
+  static constexpr int kVStages = (HDV <= 80) ? 2 : 1;
+  static constexpr int kQBytes = ATT_BM * ATT_D * 2;
+  static constexpr int kKBytes = ATT_BN * ATT_D * 2;
+  static constexpr int kVBoxBytes = HDV * 128;
+  static constexpr int kVBytes = 2 * kVBoxBytes;
+  static constexpr int kVStage = ((kVBytes + 1023) / 1024) * 1024;
+  static constexpr int kSmemBytes = kQBytes + kKBytes + kVStages * kVStage + 1024 + 256;
+  static constexpr int kTmemCols = 256;
+  static constexpr uint32_t kTmemPV = 128;
+};
+
+SR_DEVINL void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+SR_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: A is [128 lanes = rows] x [K = 16 bf16 = 8 columns], K-major
+SR_DEVINL void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int HDV>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using Cfg = AttnTpCfg<HDV>;
+  constexpr int VS = Cfg::kVStages;
+  static_assert(HDV % 16 == 0 && HDV <= 128, "HDV");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + Cfg::kQBytes;
+  uint8_t* sV = sK + Cfg::kKBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + VS * Cfg::kVStage);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 2;
+  uint64_t* v_full = bars + 3;   // [2]
+  uint64_t* v_empty = bars + 5;  // [2]
+  uint64_t* s_full = bars + 7;
+  uint64_t* p_ready = bars + 8;
+  uint64_t* pv_full = bars + 9;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int4 tile = p.tiles[blockIdx.x];
+  const int q_row0 = tile.x, q_nrows = tile.y, kv_lo = tile.z & ~7, kv_hi = tile.w;  // see attn_fwd_kernel
+  const int head = blockIdx.y;
+  const int kv_head = head / p.group;
+  const int nblk = (kv_hi - kv_lo + ATT_BN - 1) / ATT_BN;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(&v_full[0], 1);
+    mbar_init(&v_full[1], 1);
+    mbar_init(&v_empty[0], 1);
+    mbar_init(&v_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(pv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  constexpr uint32_t kTmemPV = Cfg::kTmemPV;
+
+  if (nblk > 0) {
+    if (warp_idx == 0) {
+      // ---------------- TMA producer ----------------
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+        tma_load_3d(sQ, &tmQ, q_full, 0, head, q_row0);
+        tma_load_3d(sQ + 16384, &tmQ, q_full, 64, head, q_row0);
+        for (int j = 0; j < nblk; ++j) {
+          const int kbase = kv_lo + j * ATT_BN;
+          mbar_wait(k_empty, (j & 1) ^ 1);            // S_{j-1} = Q K_{j-1}^T has completed
+          mbar_arrive_expect_tx(k_full, Cfg::kKBytes);
+          tma_load_3d(sK, &tmK, k_full, 0, kv_head, kbase);
+          tma_load_3d(sK + 16384, &tmK, k_full, 64, kv_head, kbase);
+          const int vs = j % VS;
+          mbar_wait(&v_empty[vs], ((j / VS) & 1) ^ 1);  // P V of the block that used this V stage has completed
+          mbar_arrive_expect_tx(&v_full[vs], Cfg::kVBytes);
+          uint8_t* dv = sV + vs * Cfg::kVStage;
+          tma_load_2d(dv, &tmV, &v_full[vs], kbase, kv_head * HDV);
+          tma_load_2d(dv + Cfg::kVBoxBytes, &tmV, &v_full[vs], kbase + 64, kv_head * HDV);
+        }
+      }
+    } else if (warp_idx == 1) {
+      // ---------------- MMA issuer ----------------
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, ATT_BN);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, HDV);
+        const uint32_t aQ = smem_u32(sQ);
+        const uint32_t aK = smem_u32(sK);
+        mbar_wait(q_full, 0);
+        for (int j = 0; j < nblk; ++j) {
+          // S_j overwrites the columns P_{j-1} lives in: it is issued after P V_{j-1} (the tensor pipe runs one thread's MMAs in
+          // issue order), and the softmax warps were done with S_{j-1} before they signalled p_ready for block j-1
+          mbar_wait(k_full, j & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(aQ + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
+            const uint64_t db = umma_desc_k_sw128(aK + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
+            umma_bf16_ss(tmem_base, da, db, idesc_s, k != 0 ? 1u : 0u);
+          }
+          umma_commit(s_full);
+          umma_commit(k_empty);
+          const int vs = j % VS;
+          mbar_wait(&v_full[vs], (j / VS) & 1);
+          mbar_wait(p_ready, j & 1);
+          tc_fence_after();
+          const uint32_t aV = smem_u32(sV + vs * Cfg::kVStage);
+#pragma unroll
+          for (int k = 0; k < ATT_BN / 16; ++k) {
+            const uint64_t db = umma_desc_k_sw128(aV + (k >> 2) * Cfg::kVBoxBytes) + static_cast<uint64_t>((k & 3) * 2);
+            umma_bf16_ts(tmem_base + kTmemPV, tmem_base + static_cast<uint32_t>(k * 8), db, idesc_pv, k != 0 ? 1u : 0u);
+          }
+          umma_commit(pv_full);
+          umma_commit(&v_empty[vs]);
+        }
+      }
+    } else {
+      // ---------------- softmax / output warps: one query row per thread ----------------
+      const int quarter = warp_idx & 3;
+      const int r = quarter * 32 + lane;
+      const bool row_ok = r < q_nrows;
+      int lo = 0, hi = 0;
+      if (row_ok) {
+        lo = __ldg(p.row_lo + q_row0 + r);
+        hi = __ldg(p.row_hi + q_row0 + r);
+      }
+      const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+      const uint32_t tS = tmem_base + lane_off;
+      float m = -INFINITY, l = 0.f;
+      float o[HDV];
+#pragma unroll
+      for (int i = 0; i < HDV; ++i) o[i] = 0.f;
+
+      for (int j = 0; j < nblk; ++j) {
+        const int kbase = kv_lo + j * ATT_BN;
+        mbar_wait(s_full, j & 1);
+        tc_fence_after();
+        const bool all_visible = kbase >= lo && kbase + ATT_BN <= hi;
+        // pass 1: row max (of the raw scores: scale_log2 > 0, so max commutes with the scaling)
+        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + c * 32, v);
+          tmem_ld_wait();
+          if (all_visible) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int key = kbase + c * 32 + i;
+              mxa[i & 3] = fmaxf(mxa[i & 3], (key >= lo && key < hi) ? __uint_as_float(v[i]) : -INFINITY);
+            }
+          }
+        }
+        const float mx = fmaxf(m, fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * p.scale_log2);
+        const float m_use = (mx == -INFINITY) ? 0.f : mx;
+        const float alpha = exp2f(m - m_use);
+        const float neg_m = -m_use;
+        float rsa[4] = {0.f, 0.f, 0.f, 0.f};
+        // pass 2: probabilities -> bf16 pairs over the S columns already consumed: chunk c (S columns 32c .. 32c+31) becomes
+        // P columns 16c .. 16c+15, which lie in S chunks <= c / 2 of this thread's own lane
+#pragma unroll 1
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + c * 32, v);
+          tmem_ld_wait();
+          float pr[32];
+          if (all_visible) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+              rsa[i & 3] += pr[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int key = kbase + c * 32 + i;
+              const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
+              pr[i] = (key >= lo && key < hi) ? e : 0.f;
+              rsa[i & 3] += pr[i];
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+          tmem_st_32x32b_x16(tS + c * 16, pk);
+        }
+        const float rowsum = (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
+        l = l * alpha + rowsum;
+        m = mx;
+        tmem_st_wait();
+        tc_fence_before();  // our TMEM accesses (S / PV reads, P stores) are ordered before the MMAs released below
+        mbar_arrive(p_ready);
+        // O = O * alpha + P V
+        mbar_wait(pv_full, j & 1);
+        tc_fence_after();
+        const uint32_t tPV = tmem_base + lane_off + kTmemPV;
+#pragma unroll
+        for (int c = 0; c < HDV / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(tPV + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[c * 16 + i] = o[c * 16 + i] * alpha + __uint_as_float(v[i]);
+        }
+      }
+      if (row_ok) {
+        const float inv = (l > 0.f) ? 1.0f / l : 0.f;
+        __nv_bfloat16* dst = p.O + static_cast<int64_t>(q_row0 + r) * p.o_row_stride + static_cast<int64_t>(head) * p.o_head_stride;
+#pragma unroll
+        for (int g = 0; g < HDV / 8; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv);
+          pk.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
+          pk.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
+          pk.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int HDV>
+static int launch_attn_tp(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p, int n_tiles,
+                          int n_heads, cudaStream_t stream) {
+  using Cfg = AttnTpCfg<HDV>;
+  auto kern = attn_fwd_tp_kernel<HDV>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  dim3 grid(n_tiles, n_heads);
+  kern<<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(q, k, v, p);
+  SR_CHECK_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
 template <int HDV, int STAGES>
 static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnParams& p, int n_tiles,
                        int n_heads, cudaStream_t stream) {
@@ -331,12 +619,12 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
   return SR_OK;
 }
 
-static int g_attn_lean = -1;  // -1: env SR_ATTN_LEAN (default 1)
+static int g_attn_lean = -1;  // -1: env SR_ATTN_LEAN (default 2); 0 = one CTA / SM, 1 = lean, 2 = lean with P in tensor memory
 
 }  // namespace sr
 
 extern "C" int sr_set_attention_lean(int enabled) {
-  sr::g_attn_lean = enabled ? 1 : 0;
+  sr::g_attn_lean = enabled < 0 ? -1 : (enabled > 2 ? 2 : enabled);
   return SR_OK;
 }
 
@@ -388,7 +676,11 @@ extern "C" int sr_attention_fwd(const void* Q, int64_t q_row_stride, int64_t q_h
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (g_attn_lean < 0) {
     const char* e = getenv("SR_ATTN_LEAN");
-    g_attn_lean = (e != nullptr && e[0] == '0') ? 0 : 1;
+    g_attn_lean = (e != nullptr && e[0] >= '0' && e[0] <= '2') ? (e[0] - '0') : 2;
+  }
+  if (g_attn_lean == 2) {
+    if (head_dim_v == 80) return launch_attn_tp<80>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
+    return launch_attn_tp<128>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);
   }
   if (g_attn_lean) {
     if (head_dim_v == 80) return launch_attn<80, 1>(tmQ, tmK, tmV, p, n_tiles, n_q_heads, s);

@@ -1,5 +1,5 @@
 """tcgen05 attention kernel at the bench geometry (8 tiles of 54x54 patches; 8 prompts of 867 tokens): the one-CTA-per-SM
-variant against the lean two-CTAs-per-SM variant -- bit-identical outputs, CUDA-event timings per attention shape.
+variant against the lean two-CTAs-per-SM variants (P in shared memory / P in tensor memory) -- bit-identical outputs, CUDA-event timings per attention shape.
 Usage: python tools/attn_bench.py"""
 import os, sys
 import numpy as np
@@ -20,7 +20,7 @@ def case(name, pl, n_rows, n_keys, H, Hkv, hdv, d_real, flops):
     tiles, lo, hi = torch.from_numpy(pl.tiles).to(dev), torch.from_numpy(pl.row_lo).to(dev), torch.from_numpy(pl.row_hi).to(dev)
     outs, times = [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for lean in (0, 1):
+    for lean in (0, 1, 2):
         lib.load().sr_set_attention_lean(lean)
         out = torch.zeros(n_rows, H, hdv, dtype=torch.bfloat16, device=dev)
         run = lambda: lib.attention(q, k, vt, out, tiles, lo, hi, d_real ** -0.5, hdv)
@@ -32,10 +32,12 @@ def case(name, pl, n_rows, n_keys, H, Hkv, hdv, d_real, flops):
             run()
         e1.record(); torch.cuda.synchronize()
         outs.append(out.clone()); times.append(e0.elapsed_time(e1) / 10 * 1e3)
-    same = torch.equal(outs[0], outs[1])
-    finite = torch.isfinite(outs[1].float()).all().item()
+    same = torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    finite = torch.isfinite(outs[2].float()).all().item()
+    maxdiff = (outs[0].float() - outs[2].float()).abs().max().item()
     print(f"{name:28s} tiles={tiles.shape[0]:5d} x {H:2d} heads  1 CTA/SM {times[0]:8.1f} us ({flops / times[0] / 1e6:6.1f} TF/s)   "
-          f"lean 2 CTA/SM {times[1]:8.1f} us ({flops / times[1] / 1e6:6.1f} TF/s)   bit-identical: {same}  finite: {finite}", flush=True)
+          f"lean {times[1]:8.1f} us ({flops / times[1] / 1e6:6.1f} TF/s)   lean + P in TMEM {times[2]:8.1f} us ({flops / times[2] / 1e6:6.1f} TF/s)   "
+          f"bit-identical: {same} (max diff {maxdiff:.3g})  finite: {finite}", flush=True)
     return same and finite
 
 

@@ -317,8 +317,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// "P in tensor memory" variant (the product configuration, SR_ATTN_LEAN = 2).  Same tiles, same arithmetic and the same bits as
-// the kernels above, different plumbing of one K/V block:
+// "P and O in tensor memory" variant (the product configuration, SR_ATTN_LEAN = 2).  Same tiles and the same mathematics as the
+// kernels above (not the same bits: the softmax reference point is lazy, see the softmax warps), different plumbing of a block:
 //   * the probabilities go back into TENSOR MEMORY, over the S columns they were computed from (tcgen05.st, 2 bf16 per 32-bit
 //     column), and P V is issued with the A operand in TMEM (tcgen05.mma [d], [a], b-desc).  No P tile in shared memory, no
 //     generic -> async proxy fence, and -- the point -- the K tile is dead as soon as S = Q K^T has completed;
@@ -465,14 +465,21 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int k = 0; k < ATT_BN / 16; ++k) {
             const uint64_t db = umma_desc_k_sw128(aV + (k >> 2) * Cfg::kVBoxBytes) + static_cast<uint64_t>((k & 3) * 2);
-            umma_bf16_ts(tmem_base + kTmemPV, tmem_base + static_cast<uint32_t>(k * 8), db, idesc_pv, k != 0 ? 1u : 0u);
+            umma_bf16_ts(tmem_base + kTmemPV, tmem_base + static_cast<uint32_t>(k * 8), db, idesc_pv, (j | k) != 0 ? 1u : 0u);
           }
-          umma_commit(pv_full);
           umma_commit(&v_empty[vs]);
+          if (j + 1 == nblk) umma_commit(pv_full);
         }
       }
     } else {
       // ---------------- softmax / output warps: one query row per thread ----------------
+      // O is accumulated by the tensor core IN tensor memory (P V with accumulate); this thread keeps only (m, l) of its row
+      // and the whole 128-key score row in registers: one TMEM round trip per block instead of 13 (two passes of four chunk
+      // loads + five O chunk loads in the kernels above).  The running maximum is LAZY: the reference point m moves only when
+      // the block maximum exceeds it by more than 2^8 (probabilities then stay <= 256, harmless in fp32 / bf16), in which case
+      // the warp rescales its O rows in TMEM -- rare after the first block, so O normally never leaves tensor memory until
+      // the epilogue.  S_j complete implies P V_{j-1} complete (one thread's MMAs finish in issue order), so O may be touched
+      // as soon as s_full fires.
       const int quarter = warp_idx & 3;
       const int r = quarter * 32 + lane;
       const bool row_ok = r < q_nrows;
@@ -483,97 +490,100 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t tS = tmem_base + lane_off;
+      const uint32_t tPV = tmem_base + lane_off + kTmemPV;
       float m = -INFINITY, l = 0.f;
-      float o[HDV];
-#pragma unroll
-      for (int i = 0; i < HDV; ++i) o[i] = 0.f;
 
       for (int j = 0; j < nblk; ++j) {
         const int kbase = kv_lo + j * ATT_BN;
         mbar_wait(s_full, j & 1);
         tc_fence_after();
+        uint32_t v0[32], v1[32], v2[32], v3[32];  // the row's 128 scores (separate arrays: they must stay in registers)
+        tmem_ld_32x32b_x32(tS, v0);
+        tmem_ld_32x32b_x32(tS + 32, v1);
+        tmem_ld_32x32b_x32(tS + 64, v2);
+        tmem_ld_32x32b_x32(tS + 96, v3);
+        tmem_ld_wait();
         const bool all_visible = kbase >= lo && kbase + ATT_BN <= hi;
-        // pass 1: row max (of the raw scores: scale_log2 > 0, so max commutes with the scaling)
         float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll 1
-        for (int c = 0; c < ATT_BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + c * 32, v);
-          tmem_ld_wait();
-          if (all_visible) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(v[i]));
-          } else {
+        auto max_chunk = [&](uint32_t(&vv)[32], int c) {
+          if (!all_visible) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               const int key = kbase + c * 32 + i;
-              mxa[i & 3] = fmaxf(mxa[i & 3], (key >= lo && key < hi) ? __uint_as_float(v[i]) : -INFINITY);
+              if (!(key >= lo && key < hi)) vv[i] = 0xff800000u;  // -inf: exp2 -> 0, never the maximum
             }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mxa[i & 3] = fmaxf(mxa[i & 3], __uint_as_float(vv[i]));
+        };
+        max_chunk(v0, 0);
+        max_chunk(v1, 1);
+        max_chunk(v2, 2);
+        max_chunk(v3, 3);
+        const float mblk = fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * p.scale_log2;
+        float alpha = 1.f;
+        bool moved = false;
+        if (m == -INFINITY) {
+          m = mblk;                       // nothing accumulated for this row yet (O row and l are 0)
+        } else if (mblk > m + 8.f) {
+          alpha = exp2f(m - mblk);
+          m = mblk;
+          moved = true;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, moved)) {
+#pragma unroll
+          for (int c = 0; c < HDV / 16; ++c) {
+            uint32_t ov[16];
+            tmem_ld_32x32b_x16(tPV + c * 16, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st_32x32b_x16(tPV + c * 16, ov);
           }
         }
-        const float mx = fmaxf(m, fmaxf(fmaxf(mxa[0], mxa[1]), fmaxf(mxa[2], mxa[3])) * p.scale_log2);
-        const float m_use = (mx == -INFINITY) ? 0.f : mx;
-        const float alpha = exp2f(m - m_use);
-        const float neg_m = -m_use;
+        const float neg_m = (m == -INFINITY) ? 0.f : -m;
         float rsa[4] = {0.f, 0.f, 0.f, 0.f};
-        // pass 2: probabilities -> bf16 pairs over the S columns already consumed: chunk c (S columns 32c .. 32c+31) becomes
-        // P columns 16c .. 16c+15, which lie in S chunks <= c / 2 of this thread's own lane
-#pragma unroll 1
-        for (int c = 0; c < ATT_BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + c * 32, v);
-          tmem_ld_wait();
-          float pr[32];
-          if (all_visible) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              pr[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-              rsa[i & 3] += pr[i];
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int key = kbase + c * 32 + i;
-              const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, neg_m));
-              pr[i] = (key >= lo && key < hi) ? e : 0.f;
-              rsa[i & 3] += pr[i];
-            }
-          }
+        auto exp_chunk = [&](const uint32_t(&vv)[32], int c) {
           uint32_t pk[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(pr[2 * i], pr[2 * i + 1]);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(vv[2 * i]), p.scale_log2, neg_m));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(vv[2 * i + 1]), p.scale_log2, neg_m));
+            rsa[i & 3] += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
           tmem_st_32x32b_x16(tS + c * 16, pk);
-        }
-        const float rowsum = (rsa[0] + rsa[1]) + (rsa[2] + rsa[3]);
-        l = l * alpha + rowsum;
-        m = mx;
+        };
+        exp_chunk(v0, 0);
+        exp_chunk(v1, 1);
+        exp_chunk(v2, 2);
+        exp_chunk(v3, 3);
+        l = l * alpha + ((rsa[0] + rsa[1]) + (rsa[2] + rsa[3]));
         tmem_st_wait();
-        tc_fence_before();  // our TMEM accesses (S / PV reads, P stores) are ordered before the MMAs released below
+        tc_fence_before();  // our TMEM accesses (S reads, P / O stores) are ordered before the MMAs released below
         mbar_arrive(p_ready);
-        // O = O * alpha + P V
-        mbar_wait(pv_full, j & 1);
-        tc_fence_after();
-        const uint32_t tPV = tmem_base + lane_off + kTmemPV;
-#pragma unroll
-        for (int c = 0; c < HDV / 16; ++c) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(tPV + c * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[c * 16 + i] = o[c * 16 + i] * alpha + __uint_as_float(v[i]);
-        }
       }
-      if (row_ok) {
+      mbar_wait(pv_full, 0);  // committed once, after the last P V
+      tc_fence_after();
+      {
         const float inv = (l > 0.f) ? 1.0f / l : 0.f;
         __nv_bfloat16* dst = p.O + static_cast<int64_t>(q_row0 + r) * p.o_row_stride + static_cast<int64_t>(head) * p.o_head_stride;
 #pragma unroll
-        for (int g = 0; g < HDV / 8; ++g) {
-          uint4 pk;
-          pk.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv);
-          pk.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
-          pk.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
-          pk.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
-          *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+        for (int c = 0; c < HDV / 16; ++c) {
+          uint32_t ov[16];
+          tmem_ld_32x32b_x16(tPV + c * 16, ov);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint4 pk;
+              pk.x = pack_bf16x2(__uint_as_float(ov[g * 8 + 0]) * inv, __uint_as_float(ov[g * 8 + 1]) * inv);
+              pk.y = pack_bf16x2(__uint_as_float(ov[g * 8 + 2]) * inv, __uint_as_float(ov[g * 8 + 3]) * inv);
+              pk.z = pack_bf16x2(__uint_as_float(ov[g * 8 + 4]) * inv, __uint_as_float(ov[g * 8 + 5]) * inv);
+              pk.w = pack_bf16x2(__uint_as_float(ov[g * 8 + 6]) * inv, __uint_as_float(ov[g * 8 + 7]) * inv);
+              *reinterpret_cast<uint4*>(dst + c * 16 + g * 8) = pk;
+            }
+          }
         }
       }
     }

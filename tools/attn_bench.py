@@ -32,12 +32,14 @@ def case(name, pl, n_rows, n_keys, H, Hkv, hdv, d_real, flops):
             run()
         e1.record(); torch.cuda.synchronize()
         outs.append(out.clone()); times.append(e0.elapsed_time(e1) / 10 * 1e3)
-    same = torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    # variants 0 and 1 are bit-identical; variant 2 keeps a lazy softmax reference point (same mathematics, other rounding)
+    rel = ((outs[0].float() - outs[2].float()).norm() / outs[0].float().norm()).item()
+    same = torch.equal(outs[0], outs[1]) and rel < 4e-3
     finite = torch.isfinite(outs[2].float()).all().item()
     maxdiff = (outs[0].float() - outs[2].float()).abs().max().item()
     print(f"{name:28s} tiles={tiles.shape[0]:5d} x {H:2d} heads  1 CTA/SM {times[0]:8.1f} us ({flops / times[0] / 1e6:6.1f} TF/s)   "
-          f"lean {times[1]:8.1f} us ({flops / times[1] / 1e6:6.1f} TF/s)   lean + P in TMEM {times[2]:8.1f} us ({flops / times[2] / 1e6:6.1f} TF/s)   "
-          f"bit-identical: {same} (max diff {maxdiff:.3g})  finite: {finite}", flush=True)
+          f"lean {times[1]:8.1f} us ({flops / times[1] / 1e6:6.1f} TF/s)   lean + P,O in TMEM {times[2]:8.1f} us ({flops / times[2] / 1e6:6.1f} TF/s)   "
+          f"0 == 1 bitwise, 2 within 4e-3: {same} (rel {rel:.2e}, max diff {maxdiff:.3g})  finite: {finite}", flush=True)
     return same and finite
 
 

@@ -50,6 +50,7 @@ struct AttnParams {
   const int* row_hi;
   float scale_log2;
   int group;  // q heads per kv head
+  int n_tiles, n_heads;  // work items of the tensor-memory variant: (tile, head), head fastest
 };
 
 template <int HDV, int STAGES>
@@ -316,6 +317,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 
+static int g_attn_persistent = 1;  // SR_ATTN_PERSISTENT=0 / sr_set_attention_lean(3): one CTA per item in the variant below
+
 // ---------------------------------------------------------------------------------------------------------------------
 // "P and O in tensor memory" variant (the product configuration, SR_ATTN_LEAN = 2).  Same tiles and the same mathematics as the
 // kernels above (not the same bits: the softmax reference point is lazy, see the softmax warps), different plumbing of a block:
@@ -382,15 +385,17 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* s_full = bars + 7;
   uint64_t* p_ready = bars + 8;
   uint64_t* pv_full = bars + 9;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* q_empty = bars + 10;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int4 tile = p.tiles[blockIdx.x];
-  const int q_row0 = tile.x, q_nrows = tile.y, kv_lo = tile.z & ~7, kv_hi = tile.w;  // see attn_fwd_kernel
-  const int head = blockIdx.y;
-  const int kv_head = head / p.group;
-  const int nblk = (kv_hi - kv_lo + ATT_BN - 1) / ATT_BN;
+  // Work items = (tile, head), HEAD fastest: the CTAs resident at any moment work on all heads of a few tiles, so that their Q / K
+  // row reads (256 B per head out of a 4 KB token row) add up to whole rows and q heads of one kv head share its K / V tiles
+  // in L2.  CTA c takes items c, c + gridDim.x, ...  The host launches either one CTA per
+  // item or a PERSISTENT grid of two CTAs per SM (many short items: the single-block ViT window tiles spent most of their
+  // 9 us CTA lifetime in set-up, first loads and tear-down).  All barrier phases run on counters that continue across items.
+  const int n_items = p.n_tiles * p.n_heads;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -406,6 +411,7 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_init(s_full, 1);
     mbar_init(p_ready, 128);
     mbar_init(pv_full, 1);
+    mbar_init(q_empty, 1);
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr_smem);
@@ -415,25 +421,38 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr_smem;
   constexpr uint32_t kTmemPV = Cfg::kTmemPV;
 
-  if (nblk > 0) {
+  {
     if (warp_idx == 0) {
       // ---------------- TMA producer ----------------
       if (lane == 0) {
-        mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
-        tma_load_3d(sQ, &tmQ, q_full, 0, head, q_row0);
-        tma_load_3d(sQ + 16384, &tmQ, q_full, 64, head, q_row0);
-        for (int j = 0; j < nblk; ++j) {
-          const int kbase = kv_lo + j * ATT_BN;
-          mbar_wait(k_empty, (j & 1) ^ 1);            // S_{j-1} = Q K_{j-1}^T has completed
-          mbar_arrive_expect_tx(k_full, Cfg::kKBytes);
-          tma_load_3d(sK, &tmK, k_full, 0, kv_head, kbase);
-          tma_load_3d(sK + 16384, &tmK, k_full, 64, kv_head, kbase);
-          const int vs = j % VS;
-          mbar_wait(&v_empty[vs], ((j / VS) & 1) ^ 1);  // P V of the block that used this V stage has completed
-          mbar_arrive_expect_tx(&v_full[vs], Cfg::kVBytes);
-          uint8_t* dv = sV + vs * Cfg::kVStage;
-          tma_load_2d(dv, &tmV, &v_full[vs], kbase, kv_head * HDV);
-          tma_load_2d(dv + Cfg::kVBoxBytes, &tmV, &v_full[vs], kbase + 64, kv_head * HDV);
+        uint32_t nq = 0, nk = 0, nv = 0;  // Q tiles / K blocks / V blocks loaded so far
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+          const int4 tile = p.tiles[item / p.n_heads];
+          const int head = item % p.n_heads;
+          const int kv_head = head / p.group;
+          const int q_row0 = tile.x, kv_lo = tile.z & ~7, kv_hi = tile.w;  // see attn_fwd_kernel
+          const int nblk = (kv_hi - kv_lo + ATT_BN - 1) / ATT_BN;
+          if (nblk <= 0) continue;
+          mbar_wait(q_empty, (nq & 1) ^ 1);             // the previous item's last S = Q K^T has completed
+          mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+          tma_load_3d(sQ, &tmQ, q_full, 0, head, q_row0);
+          tma_load_3d(sQ + 16384, &tmQ, q_full, 64, head, q_row0);
+          ++nq;
+          for (int j = 0; j < nblk; ++j) {
+            const int kbase = kv_lo + j * ATT_BN;
+            mbar_wait(k_empty, (nk & 1) ^ 1);           // the previous S = Q K^T has completed
+            mbar_arrive_expect_tx(k_full, Cfg::kKBytes);
+            tma_load_3d(sK, &tmK, k_full, 0, kv_head, kbase);
+            tma_load_3d(sK + 16384, &tmK, k_full, 64, kv_head, kbase);
+            ++nk;
+            const int vs = nv % VS;
+            mbar_wait(&v_empty[vs], ((nv / VS) & 1) ^ 1);  // P V of the block that used this V stage has completed
+            mbar_arrive_expect_tx(&v_full[vs], Cfg::kVBytes);
+            uint8_t* dv = sV + vs * Cfg::kVStage;
+            tma_load_2d(dv, &tmV, &v_full[vs], kbase, kv_head * HDV);
+            tma_load_2d(dv + Cfg::kVBoxBytes, &tmV, &v_full[vs], kbase + 64, kv_head * HDV);
+            ++nv;
+          }
         }
       }
     } else if (warp_idx == 1) {
@@ -443,32 +462,42 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, HDV);
         const uint32_t aQ = smem_u32(sQ);
         const uint32_t aK = smem_u32(sK);
-        mbar_wait(q_full, 0);
-        for (int j = 0; j < nblk; ++j) {
-          // S_j overwrites the columns P_{j-1} lives in: it is issued after P V_{j-1} (the tensor pipe runs one thread's MMAs in
-          // issue order), and the softmax warps were done with S_{j-1} before they signalled p_ready for block j-1
-          mbar_wait(k_full, j & 1);
-          tc_fence_after();
+        uint32_t nq = 0, nb = 0;  // items / blocks issued so far
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+          const int4 tile = p.tiles[item / p.n_heads];
+          const int nblk = (tile.w - (tile.z & ~7) + ATT_BN - 1) / ATT_BN;
+          if (nblk <= 0) continue;
+          mbar_wait(q_full, nq & 1);
+          ++nq;
+          for (int j = 0; j < nblk; ++j, ++nb) {
+            // S_j overwrites the columns the previous P lives in: it is issued after the previous P V (the tensor pipe runs one
+            // thread's MMAs in issue order), and the softmax warps were done with the previous S before they signalled p_ready
+            mbar_wait(k_full, nb & 1);
+            tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < ATT_D / 16; ++k) {
-            const uint64_t da = umma_desc_k_sw128(aQ + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
-            const uint64_t db = umma_desc_k_sw128(aK + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
-            umma_bf16_ss(tmem_base, da, db, idesc_s, k != 0 ? 1u : 0u);
-          }
-          umma_commit(s_full);
-          umma_commit(k_empty);
-          const int vs = j % VS;
-          mbar_wait(&v_full[vs], (j / VS) & 1);
-          mbar_wait(p_ready, j & 1);
-          tc_fence_after();
-          const uint32_t aV = smem_u32(sV + vs * Cfg::kVStage);
+            for (int k = 0; k < ATT_D / 16; ++k) {
+              const uint64_t da = umma_desc_k_sw128(aQ + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
+              const uint64_t db = umma_desc_k_sw128(aK + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
+              umma_bf16_ss(tmem_base, da, db, idesc_s, k != 0 ? 1u : 0u);
+            }
+            umma_commit(s_full);
+            umma_commit(k_empty);
+            if (j + 1 == nblk) umma_commit(q_empty);
+            const int vs = nb % VS;
+            mbar_wait(&v_full[vs], (nb / VS) & 1);
+            // the first P V of an item overwrites O: the softmax warps signal p_ready for it only after they have read the
+            // previous item's O (program order in each of the 128 threads)
+            mbar_wait(p_ready, nb & 1);
+            tc_fence_after();
+            const uint32_t aV = smem_u32(sV + vs * Cfg::kVStage);
 #pragma unroll
-          for (int k = 0; k < ATT_BN / 16; ++k) {
-            const uint64_t db = umma_desc_k_sw128(aV + (k >> 2) * Cfg::kVBoxBytes) + static_cast<uint64_t>((k & 3) * 2);
-            umma_bf16_ts(tmem_base + kTmemPV, tmem_base + static_cast<uint32_t>(k * 8), db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < ATT_BN / 16; ++k) {
+              const uint64_t db = umma_desc_k_sw128(aV + (k >> 2) * Cfg::kVBoxBytes) + static_cast<uint64_t>((k & 3) * 2);
+              umma_bf16_ts(tmem_base + kTmemPV, tmem_base + static_cast<uint32_t>(k * 8), db, idesc_pv, (j | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&v_empty[vs]);
+            if (j + 1 == nblk) umma_commit(pv_full);
           }
-          umma_commit(&v_empty[vs]);
-          if (j + 1 == nblk) umma_commit(pv_full);
         }
       }
     } else {
@@ -482,20 +511,37 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // as soon as s_full fires.
       const int quarter = warp_idx & 3;
       const int r = quarter * 32 + lane;
-      const bool row_ok = r < q_nrows;
-      int lo = 0, hi = 0;
-      if (row_ok) {
-        lo = __ldg(p.row_lo + q_row0 + r);
-        hi = __ldg(p.row_hi + q_row0 + r);
-      }
       const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
       const uint32_t tS = tmem_base + lane_off;
       const uint32_t tPV = tmem_base + lane_off + kTmemPV;
+      uint32_t nb = 0, ni = 0;  // blocks / items processed so far
+      // this row's key range of the NEXT item is fetched one item ahead (an L2 round trip at the head of every item otherwise)
+      auto row_range = [&](int item, int& lo_, int& hi_) {
+        lo_ = hi_ = 0;
+        if (item < n_items) {
+          const int4 t = p.tiles[item / p.n_heads];
+          if (r < t.y) {
+            lo_ = __ldg(p.row_lo + t.x + r);
+            hi_ = __ldg(p.row_hi + t.x + r);
+          }
+        }
+      };
+      int lo_next, hi_next;
+      row_range(blockIdx.x, lo_next, hi_next);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int4 tile = p.tiles[item / p.n_heads];
+      const int head = item % p.n_heads;
+      const int q_row0 = tile.x, q_nrows = tile.y, kv_lo = tile.z & ~7, kv_hi = tile.w;
+      const int nblk = (kv_hi - kv_lo + ATT_BN - 1) / ATT_BN;
+      const bool row_ok = r < q_nrows;
+      const int lo = lo_next, hi = hi_next;
+      row_range(item + gridDim.x, lo_next, hi_next);
+      if (nblk <= 0) continue;
       float m = -INFINITY, l = 0.f;
 
-      for (int j = 0; j < nblk; ++j) {
+      for (int j = 0; j < nblk; ++j, ++nb) {
         const int kbase = kv_lo + j * ATT_BN;
-        mbar_wait(s_full, j & 1);
+        mbar_wait(s_full, nb & 1);
         tc_fence_after();
         uint32_t v0[32], v1[32], v2[32], v3[32];  // the row's 128 scores (separate arrays: they must stay in registers)
         tmem_ld_32x32b_x32(tS, v0);
@@ -563,7 +609,8 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_before();  // our TMEM accesses (S reads, P / O stores) are ordered before the MMAs released below
         mbar_arrive(p_ready);
       }
-      mbar_wait(pv_full, 0);  // committed once, after the last P V
+      mbar_wait(pv_full, ni & 1);  // committed once per item, after its last P V
+      ++ni;
       tc_fence_after();
       {
         const float inv = (l > 0.f) ? 1.0f / l : 0.f;
@@ -586,6 +633,8 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
+      tc_fence_before();  // the O reads above are ordered before the next item's first P V (released through p_ready)
+      }  // items
     }
   }
 
@@ -607,7 +656,12 @@ static int launch_attn_tp(const CUtensorMap& q, const CUtensorMap& k, const CUte
     SR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  dim3 grid(n_tiles, n_heads);
+  // Persistent grid (two CTAs per SM, static round-robin over the items) when every CTA gets many items -- the ViT plans, whose
+  // items are equally long; the causal prefill plan (a few items of 1 .. 7 blocks per CTA) keeps one CTA per item and leaves
+  // the balancing to the hardware scheduler (tiles are sorted longest-first).
+  const int n_items = n_tiles * n_heads;
+  const int resident = 2 * sm_count();
+  const int grid = (g_attn_persistent && n_items >= 6 * resident) ? resident : n_items;
   kern<<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(q, k, v, p);
   SR_CHECK_CUDA(cudaGetLastError());
   return SR_OK;
@@ -634,6 +688,8 @@ static int g_attn_lean = -1;  // -1: env SR_ATTN_LEAN (default 2); 0 = one CTA /
 }  // namespace sr
 
 extern "C" int sr_set_attention_lean(int enabled) {
+  // 0 / 1 / 2: kernel variant (see g_attn_lean); 3: variant 2 with one CTA per work item instead of the persistent grid
+  sr::g_attn_persistent = enabled == 3 ? 0 : 1;
   sr::g_attn_lean = enabled < 0 ? -1 : (enabled > 2 ? 2 : enabled);
   return SR_OK;
 }
@@ -683,6 +739,8 @@ extern "C" int sr_attention_fwd(const void* Q, int64_t q_row_stride, int64_t q_h
   p.row_hi = row_hi;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.group = n_q_heads / n_kv_heads;
+  p.n_tiles = n_tiles;
+  p.n_heads = n_q_heads;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (g_attn_lean < 0) {
     const char* e = getenv("SR_ATTN_LEAN");

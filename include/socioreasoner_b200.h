@@ -55,7 +55,9 @@ int sr_set_pdl(int enabled);
  * proj), HF:77-88 (ViT MLP), HF:133-146 (merger), HF:704-707 (decoder q/k/v/o), HF:611-624 (decoder MLP),
  * HF:1385 (lm_head).  lda/ldw/ldc/ldr are row strides in ELEMENTS (multiples of 8).  bias: fp32[N] or NULL.
  * SR_EPI_SWIGLU: W/bias rows are packed in groups of 32 = [16 gate rows | 16 up rows]; n_out = N/2.
- * block_n: 0 = auto (M <= 32 -> sr_gemm_skinny_bf16; 256 for M > 64, else 32), or 32 / 128 / 256 to force a tcgen05 tile. */
+ * block_n: 0 = auto (M <= 32 -> sr_gemm_skinny_bf16; 256 for M > 64, else 32), or 32 / 128 / 256 to force a tcgen05 tile.
+ * Output / residual rows whose start and row stride are 32-byte aligned (ldc % 16 == 0 for bf16, N % 16 == 0) are written /
+ * read with 256-bit accesses; anything else takes 16-byte accesses (same results). */
 int sr_gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, void* C, int64_t ldc, const float* bias,
                  const void* residual, int64_t ldr, int M, int N, int K, int epilogue, int out_dtype, int block_n,
                  void* stream);
@@ -101,9 +103,14 @@ int sr_set_gemv_warps(int warps);
 /* Tuning knob: weight-load instruction flavour of the skinny GEMM at M <= 8 (0 nc/no-allocate, 1 + L2::256B, 2 plain). */
 int sr_set_gemv_load(int flavour);
 
-/* Attention kernel variant: 1 (default; env SR_ATTN_LEAN) = two CTAs per SM, single K/V stage, P aliases K, 256 TMEM columns;
- * 0 = one CTA per SM with a 2-stage K/V ring and double-buffered S.  Results are bit-identical. */
-int sr_set_attention_lean(int enabled);
+/* Attention kernel variant (env SR_ATTN_LEAN; default 2):
+ *   2 = two CTAs per SM, P and O in tensor memory (TS-form P.V MMA, lazy softmax reference point), K reloaded during the
+ *       softmax, double-buffered V, persistent grid for plans with many equally long work items;
+ *   3 = variant 2 with one CTA per work item (A/B measurements; same bits as 2);
+ *   1 = round-1 lean kernel: two CTAs per SM, single K/V stage, P in shared memory aliasing K;
+ *   0 = round-1 kernel with one CTA per SM, 2-stage K/V ring and double-buffered S (same bits as 1).
+ * Variants 2 / 3 agree with 0 / 1 to bf16 rounding (relative RMS <= 3e-3 at 2916 keys), not bit for bit. */
+int sr_set_attention_lean(int variant);
 
 /* ---- attention (tcgen05 + TMA) --------------------------------------------------------------
  * Variable-length softmax(Q K^T * scale) V; query row r attends key rows k with row_lo[r] <= k < row_hi[r].

@@ -45,6 +45,25 @@ def test_vit_plan_matches_hf(oracle_tiny, grid):
         assert np.all(cover == 1)
 
 
+def test_window_plan_packs_whole_windows():
+    """ViT window tiles are runs of whole windows: every tile's key range is exactly its own rows (one key block), rows are covered
+    once, and a segment longer than a tile is chunked with the whole segment as key range."""
+    vp = plan.vit_plan(np.array([[1, 54, 54]] * 2 + [[1, 32, 32]]))
+    wp = vp.window_plan
+    cov = np.zeros(vp.n, dtype=int)
+    bounds = set(vp.cu_window_seqlens.tolist())
+    for r0, nr, lo, hi in wp.tiles.tolist():
+        cov[r0:r0 + nr] += 1
+        assert nr <= 128 and (lo, hi) == (r0, r0 + nr) and r0 in bounds and r0 + nr in bounds
+    assert (cov == 1).all()
+    blind = plan.plan_from_segments(vp.cu_window_seqlens, vp.n)          # round-1 tiling: 128-row chunks regardless of windows
+    blocks = lambda t: int(((t[:, 3] - t[:, 2] + 127) // 128).sum())
+    assert blocks(wp.tiles) < 0.7 * blocks(blind.tiles)
+    assert np.array_equal(wp.row_lo, blind.row_lo) and np.array_equal(wp.row_hi, blind.row_hi)
+    long = plan.plan_from_segments(np.array([0, 40, 340, 400]), 400, pack_whole=True)
+    assert long.tiles.tolist() == [[0, 40, 0, 40], [40, 128, 40, 340], [168, 128, 40, 340], [296, 44, 40, 340], [340, 60, 340, 400]]
+
+
 def test_causal_plan():
     lens, L = [5, 300, 128], 384
     qs = np.concatenate([[0], np.cumsum(lens)[:-1]])

@@ -651,11 +651,8 @@ static int launch_attn_tp(const CUtensorMap& q, const CUtensorMap& k, const CUte
                           int n_heads, cudaStream_t stream) {
   using Cfg = AttnTpCfg<HDV>;
   auto kern = attn_fwd_tp_kernel<HDV>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;  // per device
+  SR_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
   // Persistent grid (two CTAs per SM, static round-robin over the items) when every CTA gets many items -- the ViT plans, whose
   // items are equally long; the causal prefill plan (a few items of 1 .. 7 blocks per CTA) keeps one CTA per item and leaves
   // the balancing to the hardware scheduler (tiles are sorted longest-first).
@@ -672,11 +669,8 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
                        int n_heads, cudaStream_t stream) {
   using Cfg = AttnCfg<HDV, STAGES>;
   auto kern = attn_fwd_kernel<HDV, STAGES>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;  // per device
+  SR_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
   dim3 grid(n_tiles, n_heads);
   kern<<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(q, k, v, p);
   SR_CHECK_CUDA(cudaGetLastError());

@@ -1261,15 +1261,20 @@ extern "C" int sr_decode_step_persistent(const void* layer_table, int n_layers, 
                  (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && ld_logits % 4 == 0,
              "sr_decode_step_persistent: alignment");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  static int grid_cached = 0;
-  if (grid_cached == 0) {
+  static int grid_by_dev[64] = {0};  // per device: the function attribute and the SM count belong to the current device
+  int dev = 0;
+  SR_CHECK_CUDA(cudaGetDevice(&dev));
+  SR_REQUIRE(dev >= 0 && dev < 64, "sr_decode_step_persistent: device ordinal %d", dev);
+  if (grid_by_dev[dev] == 0) {
     SR_CHECK_CUDA(cudaFuncSetAttribute(decode_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DP_SMEM_BYTES));
     int per_sm = 0;
     SR_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_persistent_kernel, DP_THREADS, DP_SMEM_BYTES));
     SR_REQUIRE(per_sm >= 1, "sr_decode_step_persistent: kernel does not fit on an SM (smem %d B)", DP_SMEM_BYTES);
-    grid_cached = sm_count();  // one CTA per SM: all co-resident (the CTAs wait for each other's data)
-    SR_REQUIRE(grid_cached <= 1024 && grid_cached <= DP_CTHREADS, "sr_decode_step_persistent: at most %d SMs", DP_CTHREADS);
+    const int n_sm = sm_count();  // one CTA per SM: all co-resident (the CTAs wait for each other's data)
+    SR_REQUIRE(n_sm <= 1024 && n_sm <= DP_CTHREADS, "sr_decode_step_persistent: at most %d SMs", DP_CTHREADS);
+    grid_by_dev[dev] = n_sm;
   }
+  const int grid_cached = grid_by_dev[dev];
   DpParams p;
   p.layers = reinterpret_cast<const DpLayer*>(layer_table);
   p.n_layers = n_layers;

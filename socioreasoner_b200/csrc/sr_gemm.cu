@@ -395,11 +395,8 @@ template <int BLOCK_N, int EPI, bool OUT_F32>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   auto kern = gemm_bf16_tn_kernel<BLOCK_N, EPI, OUT_F32>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;  // per device
+  SR_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
   const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
   kern<<<grid, 64 + 32 * GemmEpi<BLOCK_N, EPI>::kWarps, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);

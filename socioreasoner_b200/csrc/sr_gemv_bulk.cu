@@ -219,11 +219,8 @@ template <int RG, int EPI, bool OUT_F32, bool NORM>
 static int launch_bulk(const GemvBulkParams& p, int grid, cudaStream_t s) {
   using Cfg = GbCfg<RG>;
   auto kern = gemv_bulk_kernel<RG, EPI, OUT_F32, NORM>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SR_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;  // per device
+  SR_CHECK_CUDA(ensure_dynamic_smem(kern, Cfg::kSmemBytes, &attr_done));
   SR_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GB_THREADS), static_cast<size_t>(Cfg::kSmemBytes), s, p));
   return SR_OK;
 }

@@ -24,6 +24,20 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 bool pdl_enabled();  // SR_PDL env (default 1) / sr_set_pdl()
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE function attribute: set it once per (kernel instantiation, device).
+// `done` is the caller's function-local static bitmask (one bit per device ordinal < 64).
+template <typename K>
+static inline cudaError_t ensure_dynamic_smem(K kern, int bytes, unsigned long long* done) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+  if (bit != 0 && (*done & bit) != 0) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) *done |= bit;
+  return e;
+}
+
 // Launch with the programmatic-dependent-launch attribute (kernels must call pdl_wait() before touching global memory).
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {

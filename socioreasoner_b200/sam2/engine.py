@@ -4,7 +4,12 @@
 ``Sam2MaskDecoder.forward`` with ``multimask_output=True`` -- the HF port of the ``sam2`` package the reference's
 ``SAM2ImagePredictor`` runs (roll/models/model_providers.py:540-545; roll/distributed/strategy/seg_strategy.py:47,58).
 
-All device work goes through an ``ops`` object (``ops_cuda.CudaOps``: the C ABI kernels; there is no other product backend)."""
+All device work goes through an ``ops`` object (``ops_cuda.CudaOps``: the C ABI kernels; there is no other product backend).
+
+Both halves are launch-bound when issued from Python (hiera-large: ~430 launches per image, ~100 per object prompt, 15-20 us of host
+time each), so with a backend that says ``supports_graph`` they are captured ONCE as CUDA graphs -- one per image geometry, one
+per prompt length -- and replayed: the image lands in a static input buffer, the prompt in static device buffers fed from a
+pinned host pair, the outputs of a prompt replay are cloned (the next replay overwrites them)."""
 from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -23,6 +28,9 @@ class Sam2Engine:
         self.cfg, self.w, self.ops = cfg, weights, ops
         self._plans: Dict[Tuple, object] = {}
         self.feat_s0 = self.feat_s1 = self.image_embed = None
+        self.use_graph = bool(getattr(ops, "supports_graph", False))
+        self._img_graph = None       # (graph, static input, (feat_s0, feat_s1, image_embed))
+        self._pred_graphs: Dict[int, tuple] = {}
 
     # ------------------------------------------------------------------ planning
     def _plan(self, kind: str, *a):
@@ -36,6 +44,37 @@ class Sam2Engine:
     def set_image(self, pixel_values: torch.Tensor, capture: Optional[list] = None) -> None:
         """pixel_values fp32 [3, S, S] (normalised; S = cfg.image_size).  Leaves feat_s0 [N0, 32], feat_s1 [N1, 64] and
         image_embed [N2, 256] (+ no-memory and no-mask embeddings) on the device, all in row-major (y, x) token order."""
+        if not (self.use_graph and capture is None and pixel_values.is_cuda):
+            self._set_image(pixel_values, capture)
+            self._pred_graphs.clear()       # prompt graphs read the features at their captured addresses
+            self._img_graph = None
+            return
+        if self._img_graph is None or self._img_graph[1].shape != pixel_values.shape:
+            static_in = pixel_values.detach().to(torch.float32).clone()
+            self._set_image(static_in)      # warm-up outside capture: attention plans, function attributes, tensor maps
+            self._pred_graphs.clear()
+            g = self._capture(lambda: self._set_image(static_in))
+            self._img_graph = (g, static_in, (self.feat_s0, self.feat_s1, self.image_embed))
+        g, static_in, feats = self._img_graph
+        static_in.copy_(pixel_values, non_blocking=True)
+        g.replay()
+        self.feat_s0, self.feat_s1, self.image_embed = feats
+
+    @staticmethod
+    def _capture(fn):
+        """Capture ``fn`` (already warmed up) into a CUDA graph; kernel launches recorded by the capture are not counted."""
+        from .. import lib
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        l0 = lib.launch_count
+        with torch.cuda.graph(g):
+            fn()
+        lib.launch_count = l0
+        return g
+
+    def _set_image(self, pixel_values: torch.Tensor, capture: Optional[list] = None) -> None:
         cfg, W, ops = self.cfg, self.w, self.ops
         res = [cfg.grid >> s for s in range(4)]
         x = ops.patch_embed(pixel_values, W)                                   # [N0, C0], window-major(ws_0), + pos embed
@@ -93,8 +132,35 @@ class Sam2Engine:
         """One object prompt.  coords fp32 [n, 2] in MODEL input pixels (x, y; already scaled to cfg.image_size), labels int [n]:
         1 / 0 foreground / background point, 2 / 3 box corners, -1 padding ("not a point").  Returns (low-res mask logits fp32
         [num_multimask, 4E, 4E], predicted IoU fp32 [num_multimask]) of the multi-mask outputs (tokens 1..3)."""
-        cfg, W, ops = self.cfg, self.w, self.ops
         assert self.image_embed is not None, "set_image first"
+        if not (self.use_graph and self._img_graph is not None):
+            return self._predict(coords, labels)
+        coords = np.asarray(coords, np.float32).reshape(-1, 2)
+        labels = np.asarray(labels, np.int32).reshape(-1)
+        n = int(labels.shape[0])
+        st = self._pred_graphs.get(n)
+        dev = self.image_embed.device
+        if st is None:
+            c_host = torch.empty((n, 2), dtype=torch.float32, pin_memory=True)
+            l_host = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+            c_host.copy_(torch.from_numpy(coords)); l_host.copy_(torch.from_numpy(labels))
+            c_dev, l_dev = c_host.to(dev), l_host.to(dev)
+            self._predict(c_dev, l_dev)       # warm-up outside capture
+            out = []
+            g = self._capture(lambda: out.extend(self._predict(c_dev, l_dev)))
+            st = self._pred_graphs[n] = [g, c_host, l_host, c_dev, l_dev, out[0], out[1], None]
+        g, c_host, l_host, c_dev, l_dev, logits, iou, uploaded = st
+        if uploaded is not None:
+            uploaded.synchronize()            # the previous prompt's upload has left the pinned pair
+        c_host.copy_(torch.from_numpy(coords)); l_host.copy_(torch.from_numpy(labels))
+        c_dev.copy_(c_host, non_blocking=True); l_dev.copy_(l_host, non_blocking=True)
+        st[7] = torch.cuda.Event()
+        st[7].record(torch.cuda.current_stream(dev))
+        g.replay()
+        return logits.clone(), iou.clone()
+
+    def _predict(self, coords, labels) -> Tuple[torch.Tensor, torch.Tensor]:
+        cfg, W, ops = self.cfg, self.w, self.ops
         Hh = cfg.dec_heads
         sparse = ops.prompt_embed(coords, labels, W, cfg.image_size)           # [n, 256]
         pe = ops.cat_rows(W.out_tokens, sparse)                                # query positional embedding = the initial tokens

@@ -19,6 +19,7 @@ class DevPlan:
 
 class CudaOps:
     act_dtype = torch.bfloat16
+    supports_graph = True   # every op is a stream-ordered launch on torch's current stream: the engine may capture CUDA graphs
 
     def __init__(self, device="cuda"):
         self.device = torch.device(device)
@@ -125,8 +126,12 @@ class CudaOps:
         return out
 
     def prompt_embed(self, coords, labels, W, image_size):
-        c = torch.as_tensor(np.asarray(coords, np.float32)).to(self.device)
-        l = torch.as_tensor(np.asarray(labels, np.int32)).to(self.device)
+        if torch.is_tensor(coords):   # static device buffers of a captured prompt graph
+            c, l = coords, labels
+            assert c.is_cuda and c.dtype == torch.float32 and l.dtype == torch.int32 and c.is_contiguous()
+        else:
+            c = torch.as_tensor(np.asarray(coords, np.float32)).to(self.device)
+            l = torch.as_tensor(np.asarray(labels, np.int32)).to(self.device)
         hidden = W.point_embed.shape[1]
         out = torch.empty((c.shape[0], hidden), dtype=torch.bfloat16, device=self.device)
         lib._check(self.L.sr_sam2_prompt_embed(c.data_ptr(), l.data_ptr(), c.shape[0], W.pe_gauss.data_ptr(), W.point_embed.data_ptr(),

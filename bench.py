@@ -229,9 +229,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
+    def step_seq():
         ro.step(devb, TILES_PER_GPU)
         return ro.gather(TILES_PER_GPU)
+
+    # The timed loops use the software-pipelined form of the step (DataParallelRollout.submit / flush): ViT + prefill of batch
+    # k + 1 are submitted with the decode steps of batch k in between (two engines over one set of weights).  Every batch still
+    # runs the whole path; the timed region starts with an empty pipeline and ends after flush(), so the un-overlapped first
+    # prefill and last decode are inside it.  SR_BENCH_PIPELINE=0 times the sequential step instead.
+    PIPELINE = os.environ.get("SR_BENCH_PIPELINE", "1") != "0"
+
+    def step_device():
+        if not PIPELINE:
+            return step_seq()
+        return ro.gather(TILES_PER_GPU) if ro.submit(devb, TILES_PER_GPU) is not None else None
+
+    def drain_device():
+        return ro.gather(TILES_PER_GPU) if (PIPELINE and ro.flush() is not None) else None
 
     pending = [None]
 
@@ -239,21 +253,33 @@ def run_ours(args):
         # software pipeline around the device step: inputs of step k + 1 are uploaded, and the result of step k - 1 is read
         # by the host, while step k computes.  Every step's inputs are uploaded once and every step's result is read once,
         # all inside the timed region (the last result is drained before the closing event).
-        ro.step(host, TILES_PER_GPU)      # uses the upload started during the previous step
+        if PIPELINE:
+            done = ro.submit(host, TILES_PER_GPU) is not None   # uses the upload started during the previous step
+        else:
+            ro.step(host, TILES_PER_GPU)
+            done = True
         ro.prefetch(host)                 # the NEXT step's inputs: H2D on the copy stream
+        if not done:
+            return None
         prev, pending[0] = pending[0], ro.gather_to_host_async(TILES_PER_GPU)   # rank 0: read-back on a copy stream; None elsewhere
-        return prev.wait() if prev is not None else None   # (tokens, masks, iou) of the PREVIOUS step, on the host
+        return prev.wait() if prev is not None else None   # (tokens, masks, iou) of an earlier step, on the host
 
     def drain_host():
+        out = None
+        if PIPELINE and ro.flush() is not None:
+            prev, pending[0] = pending[0], ro.gather_to_host_async(TILES_PER_GPU)
+            out = prev.wait() if prev is not None else None
         p, pending[0] = pending[0], None
-        return p.wait() if p is not None else None
+        return p.wait() if p is not None else out
 
     def timed(fn, steps, drain=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        out = None
         for _ in range(steps):
-            out = fn()
+            r = fn()
+            out = r if r is not None else out
         if drain is not None:
             last = drain()
             out = last if last is not None else out
@@ -266,17 +292,18 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step_device()
+    drain_device()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     l0 = lib.launch_count
-    ms_dev, res = timed(step_device, args.steps)
+    ms_dev, res = timed(step_device, args.steps, drain=drain_device)
     launches = (lib.launch_count - l0) // max(args.steps, 1)
     clk = clocks.stop() if rank == 0 else None
-    # stage split of one more (un-instrumented, graph-replaying) step: CUDA events at the stage boundaries
+    # stage split of one more (un-instrumented, graph-replaying) SEQUENTIAL step: CUDA events at the stage boundaries
     model.engine.stage_events = []
     torch.cuda.synchronize()
-    step_device()
+    step_seq()
     torch.cuda.synchronize()
     evs, model.engine.stage_events = model.engine.stage_events, None
     stages = {evs[i + 1][0] + "_ms": round(evs[i][1].elapsed_time(evs[i + 1][1]), 2) for i in range(len(evs) - 1)}
@@ -290,7 +317,7 @@ def run_ours(args):
     # template that carries > 85 % of the step's FLOPs (tensor-bound).
     lib.timeline = []
     torch.cuda.synchronize()
-    step_device()
+    step_seq()
     torch.cuda.synchronize()
     tl, lib.timeline = lib.timeline, None
     big_f = big_ms = small_ms = att_ms = dec_b = dec_ms = 0.0
@@ -361,10 +388,13 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "tiles_per_gpu": TILES_PER_GPU, "global_batch": TILES_PER_GPU * world,
                    "patches_per_tile": n_patches, "prompt_tokens": S, "new_tokens": NEW_TOKENS, "objects_per_tile": N_OBJ,
                    "parallelism": f"dp{world}", "l2": "7.5 GB of weights are streamed every step (>> 126 MB L2); no explicit flush",
-                   "mean_iou": round(float(res.iou.float().mean().item()), 6), "stage_split": stages},
+                   "mean_iou": round(float(res.iou.float().mean().item()), 6), "stage_split": stages,
+                   "schedule": ("pipelined over consecutive batches: decode steps of batch k submitted between the ViT / prefill layers of "
+                                "batch k+1 (two engines, one set of weights); timed region = empty pipeline -> K submits -> flush; "
+                                "stage_split and the rooflines come from one sequential step") if PIPELINE else "sequential steps"},
         "e2e": {"value": round(total_imgs / (ms_e2e * 1e-3), 3), "unit": "images/s", "h2d_bytes_per_step": host.h2d_bytes() * world,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 3),
-                "pipeline": "inputs of step k+1 uploaded and result of step k-1 read on copy streams while step k computes",
+                "pipeline": "inputs of step k+1 uploaded and results of finished steps read on copy streams while the device computes; same batch pipelining as `value` (config.schedule)",
                 "note": "h2d = all ranks' inputs (uint8 tiles, ids, mask logits, GT masks), every step's inputs uploaded once, double-buffered on a copy stream during the previous step; d2h = the gathered result on rank 0 only"},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clk, "roofline": roofline, "roofline_gemm": roofline_gemm,

@@ -75,6 +75,61 @@ class KVCache:
         return np.arange(self.batch, dtype=np.int64) * self.l_max
 
 
+class PendingDecode:
+    """The decode half of ``Engine.generate_greedy`` on the CUDA-graph path: ViT + prefill have been submitted, the first token's
+    logits are in ``st['logits']`` and the captured decode step can be replayed ``T - 1`` times.  ``advance(n)`` submits up to n
+    replays (a pipelined caller interleaves them with the next batch's prefill, which must run on ANOTHER ``Engine`` over the same
+    weights: buffers, KV cache and decode state belong to the engine); ``finish()`` submits the rest and returns the tokens."""
+
+    def __init__(self, engine, st, cache, sp, graph, T, sampling, pad_id, check_every, ev):
+        self.engine, self.st, self.cache, self.sp, self.graph, self.T = engine, st, cache, sp, graph, T
+        self.sampling, self.pad_id, self.check_every, self.ev = sampling, pad_id, check_every, ev
+        self.done_steps, self.stopped = 0, False
+
+    @property
+    def remaining(self) -> int:
+        return 0 if self.stopped else self.T - 1 - self.done_steps
+
+    def advance(self, n: int) -> int:
+        st, run = self.st, 0
+        while run < n and self.remaining > 0:
+            self.graph.replay()
+            run += 1
+            self.done_steps += 1
+            if st["track_eos"] and self.done_steps % self.check_every == 0 and bool(st["done"].all().item()):
+                self.stopped = True
+        lib.launch_count += run * self.engine._decode_launches
+        return run
+
+    def ticker(self, n_ticks: int):
+        """A ``tick`` callback that spreads the remaining decode steps evenly over ``n_ticks`` calls."""
+        total, state = self.remaining, {"i": 0, "done": 0}
+
+        def tick():
+            state["i"] += 1
+            want = (total * state["i"] + n_ticks - 1) // n_ticks
+            if want > state["done"]:
+                state["done"] += self.advance(want - state["done"])
+        return tick
+
+    def finish(self) -> torch.Tensor:
+        eng, st = self.engine, self.st
+        self.advance(self.remaining)
+        if not self.stopped:  # the last token: pick + append (no further forward needed)
+            eng._pick_token(st, self.sampling)
+            lib.decode_advance(st["nxt"], st["tokens"], st["step"], st["row0"], st["len0"], st["pos0"], st["cache_row"],
+                               st["kv_len"], st["pos3"])
+        self.cache.lengths = self.sp.lengths + self.T - 1
+        if self.ev is not None:
+            self.ev.append(("decode", eng._event()))
+        tokens = st["tokens"].clone()
+        if st["track_eos"]:  # everything after a sequence's first stop id is padding
+            is_eos = (tokens.unsqueeze(-1) == st["eos"].view(1, 1, -1)).any(-1)
+            after = (is_eos.cumsum(1) - is_eos.long()) > 0
+            tokens = torch.where(after, torch.full_like(tokens, self.pad_id), tokens)
+        return tokens
+
+
 class Engine:
     def __init__(self, cfg: SocioReasonerConfig, weights: PackedWeights, device="cuda"):
         cfg.validate()
@@ -138,7 +193,7 @@ class Engine:
             self._vit_plans[key] = p
         return p
 
-    def vit(self, pixel_values: torch.Tensor, grid_thw, capture: Optional[List[torch.Tensor]] = None
+    def vit(self, pixel_values: torch.Tensor, grid_thw, capture: Optional[List[torch.Tensor]] = None, tick=None
             ) -> Tuple[torch.Tensor, DevVitPlan]:
         """pixel_values [N,1176] (fp32 or bf16, processor row order) -> merged embeddings [M, 2048] in WINDOW order
         (``vp.host.merged_reverse`` maps original order -> window order) and the plan."""
@@ -171,6 +226,8 @@ class Engine:
             lib.gemm(act, b.down_w, out=h, bias=b.down_b, residual=h, block_n=bn_narrow)
             if capture is not None:
                 capture.append(h.clone())
+            if tick is not None:
+                tick()
         lib.rmsnorm(h, W.merger_ln, v.rms_norm_eps, out=y)
         m = vp.host.m
         hm = D * v.spatial_merge_size ** 2
@@ -197,7 +254,7 @@ class Engine:
     # ------------------------------------------------------------------ decoder
     def _decoder_layers(self, x: torch.Tensor, cos, sin, cache: KVCache, cache_row: torch.Tensor,
                         attn_plan: Optional[DevAttnPlan], decode: Optional[Tuple[torch.Tensor, torch.Tensor, int]],
-                        capture: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+                        capture: Optional[List[torch.Tensor]] = None, tick=None) -> torch.Tensor:
         t, W = self.cfg.text, self.w
         S = x.shape[0]
         Hq, Hkv, hd = t.num_attention_heads, t.num_key_value_heads, t.head_dim
@@ -243,11 +300,17 @@ class Engine:
             lib.gemm(act, L.down_w, out=x, residual=x)
             if capture is not None:
                 capture.append(x.clone())
+            if tick is not None:
+                tick()
         return x
+
+    def prefill_ticks(self, with_images: bool = True) -> int:
+        """How often ``prefill(..., tick=f)`` calls ``f``: once per ViT block and once per decoder layer."""
+        return (len(self.w.vit_blocks) if with_images else 0) + len(self.w.layers)
 
     def prefill(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, position_ids: Optional[torch.Tensor],
                 pixel_values: Optional[torch.Tensor], image_grid_thw, cache: Optional[KVCache] = None,
-                reserve_new_tokens: int = 0, capture: Optional[List[torch.Tensor]] = None):
+                reserve_new_tokens: int = 0, capture: Optional[List[torch.Tensor]] = None, tick=None):
         """Runs ViT + embed/scatter + all decoder layers over the packed tokens.
         Returns (hidden [T, 2048] packed (pre final-norm), SeqPlan, KVCache, position_ids [3,B,S] numpy)."""
         cfg, t = self.cfg, self.cfg.text
@@ -272,7 +335,7 @@ class Engine:
         merged, vis_idx = None, None
         if pixel_values is not None:
             pv = pixel_values if pixel_values.is_cuda else pixel_values.to(self.device, non_blocking=True)
-            merged, vp = self.vit(pv, grid_cpu)
+            merged, vp = self.vit(pv, grid_cpu, tick=tick)
             is_img = ids_packed == cfg.image_token_id
             n_img_tok = int(is_img.sum())
             if n_img_tok != vp.host.m:  # same check as HF get_placeholder_mask (HF:1179-1218)
@@ -294,7 +357,7 @@ class Engine:
         cache_row = _dev(cache_row_np, self.device)
         x = lib.embed_scatter(self.w.embed, ids_d, merged, vis_idx, out=self._buf("p_x", (sp.total, t.hidden_size)))
         cos, sin = lib.mrope_table(pos_d, self.txt_inv_freq, t.mrope_section)
-        x = self._decoder_layers(x, cos, sin, cache, cache_row, ap, None, capture)
+        x = self._decoder_layers(x, cos, sin, cache, cache_row, ap, None, capture, tick=tick)
         return x, sp, cache, pos3
 
     def final_logits(self, hidden_rows: torch.Tensor, out_dtype=torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -438,7 +501,7 @@ class Engine:
     def generate_greedy(self, input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, max_new_tokens: int,
                         return_logits: bool = False, use_graph: Optional[bool] = None, sampling=None, uniforms=None,
                         forced_tokens: Optional[torch.Tensor] = None, eos_ids: Optional[Sequence[int]] = None, pad_id: int = 0,
-                        check_every: int = 16):
+                        check_every: int = 16, tick=None, defer_decode: bool = False):
         """Greedy decode, EOS ignored, fixed ``max_new_tokens``.  Response positions continue from the
         last prompt position + 1 on all three axes (roll/utils/functionals.py:838-852).  The decode step is captured
         once per (batch, cache) into a CUDA graph and replayed (launch-bound loop, ~300 kernels per token).
@@ -450,6 +513,10 @@ class Engine:
         device-side flag is read back every ``check_every`` steps and the loop ends as soon as every sequence has finished (at the
         reference's 2048-token cap a fixed-length loop would decode for seconds after the last stop).  Positions after a sequence's
         stop token, and steps that never ran, hold ``pad_id``.
+        ``tick``: called ``prefill_ticks()`` times during ViT + prefill (after every ViT block / decoder layer) -- the hook a pipelined
+        caller uses to submit another batch's decode steps in between.  ``defer_decode``: run ViT + prefill, set the decode up and
+        return a ``PendingDecode`` instead of tokens; its ``advance(n)`` / ``finish()`` replay the captured decode step (graph path
+        only).  ``generate_greedy(...)`` == ``generate_greedy(..., defer_decode=True).finish()``.
         Returns new tokens [B, T] (int64, device) and optionally fp32 logits [B, T, V]."""
         t = self.cfg.text
         T = max_new_tokens
@@ -462,7 +529,7 @@ class Engine:
         if ev is not None:
             ev.append(("start", self._event()))
         x, sp, cache, pos3 = self.prefill(input_ids, attention_mask, position_ids, pixel_values, image_grid_thw, cache=cache,
-                                          reserve_new_tokens=T)
+                                          reserve_new_tokens=T, tick=tick)
         if ev is not None:
             ev.append(("vit+prefill", self._event()))
         V = t.vocab_size
@@ -513,15 +580,12 @@ class Engine:
                 lib.launch_count = l0  # capture launches nothing
                 st["logits"].copy_(keep["logits"]); st["step"].copy_(keep["step"])
                 self._graphs[gkey] = g
-            n_run = 0
-            for i in range(T - 1):
-                g.replay()
-                n_run += 1
-                if st["track_eos"] and (i + 1) % check_every == 0 and bool(st["done"].all().item()):
-                    stopped = True
-                    break
-            lib.launch_count += n_run * self._decode_launches
+            pend = PendingDecode(self, st, cache, sp, g, T, sampling, int(pad_id), check_every, ev)
+            if defer_decode:
+                return pend
+            return pend.finish()
         else:
+            assert not defer_decode, "defer_decode needs the CUDA-graph decode path"
             for step in range(T - 1):
                 if return_logits:
                     all_logits[:, step] = st["logits"]

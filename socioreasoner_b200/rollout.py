@@ -101,6 +101,10 @@ class DataParallelRollout:
         self._d2h_done = None              # event: the last read-back of the gather buffer has finished
         self._hbufs = [None, None]
         self._h_i = 0
+        # software pipeline over consecutive batches (submit / flush)
+        self._engines = None               # [engine, a second Engine over the same weights]
+        self._n_submitted = 0
+        self._inflight = None
 
     # layout of one rank's slot in the gather buffer: [b_max masks][b_max iou f32][b_max*T tokens i64][count i64]
     def _slot_layout(self, b_max: int):
@@ -153,6 +157,43 @@ class DataParallelRollout:
     def step(self, batch: TileBatch, b_max: Optional[int] = None) -> RolloutResult:
         """Runs this rank's shard.  Host tensors are copied to the device here (pinned -> async H2D); raw uint8 tiles are
         resized / normalised / patchified on the device.  An empty shard (b == 0) only publishes count 0."""
+        return self._back(self._front(batch, b_max, self.engine, None, defer=False))
+
+    # ---- software-pipelined form: the decode of batch k is interleaved with ViT + prefill of batch k + 1
+    def submit(self, batch: TileBatch, b_max: Optional[int] = None) -> Optional[RolloutResult]:
+        """Pipelined ``step``: submits ViT + prefill of ``batch`` with the decode steps of the PREVIOUSLY submitted batch spread
+        between its layers, then finishes that previous batch (last decode steps, mask epilogue, IoU, gather slot) and returns its
+        result -- None on the first call; ``flush()`` finishes the last batch.  Same results as ``step`` batch for batch.
+
+        Why: ViT + prefill run at the board's power cap and leave the SM clock low; a decode stage that follows as one block pays
+        for it for tens of milliseconds ("clock after the prefill").  Alternating the two kinds of work keeps
+        the load -- and the clock -- even: 160 GEMM launches + 31 decode steps take 138 ms back to back and 131 ms interleaved
+        (tools/decode_after_gemm_probe.py).  Consecutive batches live on two ``Engine`` objects over the SAME weights (buffers,
+        KV cache, decode state and captured graphs belong to an engine).  Do not call ``step`` while a batch is in flight."""
+        if self._engines is None:
+            from .engine import Engine
+            e0 = self.engine
+            e1 = Engine(e0.cfg, e0.w, e0.device)
+            e1.use_persistent_decode, e1.use_cuda_graph, e1.vit_narrow_block_n = e0.use_persistent_decode, e0.use_cuda_graph, e0.vit_narrow_block_n
+            self._engines = [e0, e1]
+        eng = self._engines[self._n_submitted % 2]
+        self._n_submitted += 1
+        prev, self._inflight = self._inflight, None
+        tick = None
+        if prev is not None and prev.get("pending") is not None:
+            with_images = batch.pixel_values is not None or batch.tiles_u8 is not None
+            tick = prev["pending"].ticker(eng.prefill_ticks(with_images))
+        self._inflight = self._front(batch, b_max, eng, tick, defer=True)
+        return self._back(prev) if prev is not None else None
+
+    def flush(self) -> Optional[RolloutResult]:
+        """Finishes the batch still in flight after the last ``submit`` (None if there is none)."""
+        prev, self._inflight = self._inflight, None
+        return self._back(prev) if prev is not None else None
+
+    def _front(self, batch: TileBatch, b_max: Optional[int], eng, tick, defer: bool) -> dict:
+        """Upload (or take the prefetched copy), device preprocessing, ViT + prefill; the decode is deferred when ``tick`` / a
+        pipelined engine asks for it."""
         dev = self.engine.device
         used_set = None
         if self._pref is not None and self._pref[0] is batch:       # inputs were uploaded ahead of time
@@ -162,14 +203,10 @@ class DataParallelRollout:
         b = batch.input_ids.shape[0]
         b_max = self.resolve_b_max(b, b_max)
         assert b <= b_max
-        gbuf = self._ensure_gbuf(b_max, dev)
+        self._ensure_gbuf(b_max, dev)
+        fl = dict(b=b, b_max=b_max, used_set=used_set, pending=None, tokens=None)
         if b == 0:
-            self.pack_slot(b_max, torch.zeros((0, self.T), dtype=torch.int64, device=dev), torch.zeros((0,), dtype=torch.float32, device=dev))
-            return RolloutResult(torch.zeros((0, self.T), dtype=torch.int64, device=dev), self.slot_masks(b_max)[:0],
-                                 torch.zeros((0,), dtype=torch.float32, device=dev))
-        mask_b, iou_off, tok_off, cnt_off, _ = self._slot_layout(b_max)
-        slot = gbuf[self.rank]
-        masks = slot[:mask_b].view(b_max, self.out_size, self.out_size)
+            return fl
         to = lambda t: t if (t is None or t.is_cuda) else t.to(dev, non_blocking=True)
         pv, ml, ms, gt = to(batch.pixel_values), to(batch.mask_logits), to(batch.mask_scores), to(batch.gt_masks)
         grid = batch.image_grid_thw
@@ -181,17 +218,37 @@ class DataParallelRollout:
             pv, grid2 = self._pre([tiles[i] for i in range(len(tiles))], out_dtype=torch.bfloat16)
             assert grid is None or grid2.tolist() == [list(map(int, g)) for g in grid.tolist()], "tile sizes do not match image_grid_thw"
             grid = grid2
-        tokens = self.engine.generate_greedy(batch.input_ids, batch.attention_mask, batch.position_ids, pv, grid, self.T)
+        pipelined = defer and self.T > 1 and eng.use_cuda_graph and lib.timeline is None
+        out = eng.generate_greedy(batch.input_ids, batch.attention_mask, batch.position_ids, pv, grid, self.T, tick=tick,
+                                  defer_decode=pipelined)
+        fl.update(ml=ml, ms=ms, gt=gt)
+        if pipelined:
+            fl["pending"] = out
+        else:
+            fl["tokens"] = out
+        return fl
+
+    def _back(self, fl: dict) -> RolloutResult:
+        """Remaining decode steps, mask epilogue straight into this rank's gather slot, IoU, slot packing."""
+        dev = self.engine.device
+        b, b_max = fl["b"], fl["b_max"]
+        if b == 0:
+            self.pack_slot(b_max, torch.zeros((0, self.T), dtype=torch.int64, device=dev), torch.zeros((0,), dtype=torch.float32, device=dev))
+            return RolloutResult(torch.zeros((0, self.T), dtype=torch.int64, device=dev), self.slot_masks(b_max)[:0],
+                                 torch.zeros((0,), dtype=torch.float32, device=dev))
+        tokens = fl["pending"].finish() if fl["pending"] is not None else fl["tokens"]
+        masks = self.slot_masks(b_max)
         if self._d2h_done is not None:     # the previous step's read-back of the gather buffer must finish before it is rewritten
             torch.cuda.current_stream(dev).wait_event(self._d2h_done)
             self._d2h_done = None
+        ml, ms, gt = fl["ml"], fl["ms"], fl["gt"]
         for i in range(b):
             lib.mask_epilogue(ml[i], ms[i], self.image_size, self.out_size, out=masks[i])
         iou = lib.mask_iou(masks[:b], gt, 1.0)
         self.pack_slot(b_max, tokens, iou)
-        if used_set is not None:
-            self._set_done[used_set] = torch.cuda.Event()
-            self._set_done[used_set].record(torch.cuda.current_stream(dev))
+        if fl["used_set"] is not None:
+            self._set_done[fl["used_set"]] = torch.cuda.Event()
+            self._set_done[fl["used_set"]].record(torch.cuda.current_stream(dev))
         return RolloutResult(tokens, masks[:b], iou)
 
     def slot_masks(self, b_max: int, device=None) -> torch.Tensor:

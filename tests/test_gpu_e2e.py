@@ -297,6 +297,39 @@ def test_rollout_step_matches_oracle_epilogue(model, tiny_batch):
         assert np.allclose(iou[0].numpy(), want[k % 2], atol=1e-6)
 
 
+def test_rollout_pipelined_submit_equals_sequential_steps(model, tiny_batch):
+    """``submit`` / ``flush`` (decode of batch k interleaved with ViT + prefill of batch k + 1 on a second engine over the same
+    weights) returns, batch for batch, what ``step`` returns: same tokens, same masks, same IoU."""
+    from socioreasoner_b200.rollout import DataParallelRollout, TileBatch
+    b = tiny_batch
+    n = b.input_ids.shape[0]
+    batches = []
+    for k in range(4):
+        ml, ms, gt = zip(*[O.synth_mask_inputs(10 * k + i, 3) for i in range(n)])
+        ids = b.input_ids.clone()
+        ids[:, -3] = (ids[:, -3] + 17 * k) % 4000 + 10          # a different prompt token per batch: different continuations
+        batches.append(TileBatch(ids, b.attention_mask, b.position_ids, b.pixel_values, b.image_grid_thw, torch.stack(ml),
+                                 torch.stack(ms), torch.from_numpy(np.stack(gt))).pin())
+    T = 6
+    ro = DataParallelRollout(model, max_new_tokens=T)
+    want = []
+    for tb in batches:
+        r = ro.step(tb, n)
+        want.append((r.tokens.cpu().clone(), r.masks.cpu().clone(), r.iou.cpu().clone()))
+    assert not all(torch.equal(want[0][0], w[0]) for w in want[1:])      # the batches really differ
+    got = []
+    for tb in batches:
+        r = ro.submit(tb, n)
+        if r is not None:
+            got.append((r.tokens.cpu().clone(), r.masks.cpu().clone(), r.iou.cpu().clone()))
+    assert len(got) == len(batches) - 1
+    r = ro.flush()
+    got.append((r.tokens.cpu().clone(), r.masks.cpu().clone(), r.iou.cpu().clone()))
+    assert ro.flush() is None
+    for k, (w, g) in enumerate(zip(want, got)):
+        assert torch.equal(w[0], g[0]) and torch.equal(w[1], g[1]) and torch.equal(w[2], g[2]), k
+
+
 def test_load_weights_in_place_equals_a_fresh_model_and_keeps_decode_graphs(oracle_tiny, tiny_batch):
     """Weight sync (worker_helper.py:104-116 -> load_weights): after an in-place update from HF-named tensors the model is
     bit-identical to one built from the new state dict -- logits, and tokens through the decode graph captured BEFORE the

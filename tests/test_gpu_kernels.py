@@ -188,11 +188,14 @@ def attention_ref(q, k, v, lo, hi, scale):
     return out
 
 
-def run_attention(pl, n_rows, n_keys, H, Hkv, hdv, d_real):
+def run_attention(pl, n_rows, n_keys, H, Hkv, hdv, d_real, k_gain=None):
     q = torch.zeros(n_rows, H, 128, dtype=torch.bfloat16)
     k = torch.zeros(n_keys, Hkv, 128, dtype=torch.bfloat16)
     q[:, :, :d_real] = rnd(n_rows, H, d_real).bfloat16()
-    k[:, :, :d_real] = rnd(n_keys, Hkv, d_real, seed=1).bfloat16()
+    kk = rnd(n_keys, Hkv, d_real, seed=1)
+    if k_gain is not None:   # per-key gain on the key vectors: scores whose spread grows along the key axis
+        kk = kk * k_gain.view(n_keys, 1, 1)
+    k[:, :, :d_real] = kk.bfloat16()
     v = rnd(n_keys, Hkv, hdv, seed=2).bfloat16()
     ncol = (n_keys + 7) // 8 * 8
     vt = torch.zeros(Hkv * hdv, ncol, dtype=torch.bfloat16)
@@ -217,6 +220,21 @@ def test_attention_causal_gqa_ragged():
     qs = np.concatenate([[0], np.cumsum(lens)[:-1]])
     ks = np.arange(len(lens)) * L
     assert run_attention(plan.plan_causal(lens, qs, ks), int(sum(lens)), len(lens) * L, 16, 2, 128, 128) < 8e-3
+
+
+@pytest.mark.parametrize("hdv,H,Hkv", [(80, 2, 2), (128, 4, 2)])
+def test_attention_moving_maximum(hdv, H, Hkv):
+    """The product attention kernel keeps a LAZY softmax reference point (it moves only when a block's maximum exceeds it by 2^8)
+    and rescales O in tensor memory when it does.  Random scores never trigger that, so: keys whose magnitude grows 40-fold along
+    the sequence (every later block raises the row maximum by far more than 2^8), bidirectional over 5 blocks and causal."""
+    n = 640
+    gain = torch.linspace(0.25, 10.0, n)
+    full = plan.plan_from_segments(np.array([0, n]), n)
+    assert run_attention(full, n, n, H, Hkv, hdv, hdv, k_gain=gain) < 8e-3
+    cp = plan.plan_causal([n], [0], [0])
+    assert run_attention(cp, n, n, H, Hkv, hdv, hdv, k_gain=gain) < 8e-3
+    # and the other way round (the maximum is set by the first block and never moves again)
+    assert run_attention(full, n, n, H, Hkv, hdv, hdv, k_gain=gain.flip(0)) < 8e-3
 
 
 def test_decode_attention():

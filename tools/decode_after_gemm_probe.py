@@ -56,6 +56,33 @@ for rep in range(REPS):
     for i, d in enumerate(dec):
         per_pos[i].append(d)
     print(f"rep {rep}: GEMM phase {gemm_ms:.1f} ms ({N_GEMM} launches), decode phase {sum(dec):.1f} ms: first {dec[0]:.3f}, 5th {dec[4]:.3f}, 15th {dec[14]:.3f}, last {dec[-1]:.3f} ms", flush=True)
+# Same work, INTERLEAVED: 5 GEMM launches between consecutive decode launches (what a rollout that overlaps the prefill of the
+# next batch with the decode of the current one would submit).  If the clock governor, not the energy, is what slows the
+# sequential arrangement down, this total is lower.
+seq_ms, inter_ms = [], []
+for rep in range(REPS):
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(N_GEMM):
+        gemm()
+    for i in range(N_DEC):
+        P.run(0)
+    a1.record(); torch.cuda.synchronize()
+    seq_ms.append(a0.elapsed_time(a1))
+for rep in range(REPS):
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    done = 0
+    for i in range(N_DEC):
+        n = (N_GEMM * (i + 1)) // N_DEC - done
+        for _ in range(n):
+            gemm()
+        done += n
+        P.run(0)
+    a1.record(); torch.cuda.synchronize()
+    inter_ms.append(a0.elapsed_time(a1))
+print("sequential  (160 GEMMs, then 31 decode steps), ms per rep:", " ".join(f"{v:.1f}" for v in seq_ms))
+print("interleaved (5 GEMMs between decode steps),    ms per rep:", " ".join(f"{v:.1f}" for v in inter_ms))
 stop = True; th.join()
 print("decode launch time by position (mean over reps 1..):", " ".join(f"{sum(v[1:]) / len(v[1:]):.3f}" for v in per_pos))
 for name, sel in (("GEMM phase", lambda t, m: m[0] <= t < m[1]), ("decode phase", lambda t, m: m[1] <= t < m[2])):

@@ -64,9 +64,6 @@ class Sam2Engine:
     def _capture(fn):
         """Capture ``fn`` (already warmed up) into a CUDA graph; kernel launches recorded by the capture are not counted."""
         from .. import lib
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         l0 = lib.launch_count
         with torch.cuda.graph(g):

@@ -215,3 +215,33 @@ def test_ops_fail_loudly_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError):
         lib.rmsnorm(torch.zeros(8, 1280, dtype=torch.bfloat16), torch.ones(1280))
+
+
+def test_pending_decode_ticker_spreads_the_steps_evenly():
+    """``PendingDecode.ticker(n)``: the decode steps still to run are submitted evenly over n calls (the pipelined rollout calls it once
+    per ViT block / decoder layer of the NEXT batch) and are all done after the n-th call, whatever the ratio."""
+    import types
+    from socioreasoner_b200.engine import PendingDecode
+
+    class FakeGraph:
+        def __init__(self):
+            self.replays = 0
+
+        def replay(self):
+            self.replays += 1
+
+    for T, n_ticks in ((32, 68), (32, 36), (5, 68), (40, 7), (2, 1)):
+        g = FakeGraph()
+        eng = types.SimpleNamespace(_decode_launches=3)
+        st = {"track_eos": False}
+        pd = PendingDecode(eng, st, None, None, g, T, None, 0, 16, None)
+        tick = pd.ticker(n_ticks)
+        seen = []
+        for _ in range(n_ticks):
+            tick()
+            seen.append(g.replays)
+        assert seen[-1] == T - 1 and pd.remaining == 0
+        ideal = [(T - 1) * (i + 1) / n_ticks for i in range(n_ticks)]
+        assert all(0 <= s_ - x < 1 + 1e-9 for s_, x in zip(seen, ideal))          # never behind, never more than one step ahead
+        tick()                                                                     # extra calls are harmless
+        assert g.replays == T - 1

@@ -111,6 +111,9 @@ int sr_set_gemv_load(int flavour);
  *   0 = round-1 kernel with one CTA per SM, 2-stage K/V ring and double-buffered S (same bits as 1).
  * Variants 2 / 3 agree with 0 / 1 to bf16 rounding (relative RMS <= 3e-3 at 2916 keys), not bit for bit. */
 int sr_set_attention_lean(int variant);
+/* Diagnostics (tools/attn_trace.py): device buffer of 4 x 16 x 16 int64 that receives clock64 stamps of the first 16 work items of
+ * CTAs 0..3 of the variant-2 kernel (slots 0-7: a softmax thread, 8-11: the MMA thread); NULL (default) switches it off. */
+int sr_set_attention_trace(void* buffer);
 
 /* ---- attention (tcgen05 + TMA) --------------------------------------------------------------
  * Variable-length softmax(Q K^T * scale) V; query row r attends key rows k with row_lo[r] <= k < row_hi[r].

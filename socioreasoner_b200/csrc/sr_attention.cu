@@ -51,7 +51,11 @@ struct AttnParams {
   float scale_log2;
   int group;  // q heads per kv head
   int n_tiles, n_heads;  // work items of the tensor-memory variant: (tile, head), head fastest
+  long long* trace;      // optional (sr_set_attention_trace): clock64 stamps of CTAs 0..3, [cta][item < 16][16 slots]
 };
+SR_DEVINL void att_stamp(const AttnParams& p, int it, int slot) {
+  if (p.trace != nullptr && blockIdx.x < 4 && it < 16) p.trace[(blockIdx.x * 16 + it) * 16 + slot] = clock64();
+}
 
 template <int HDV, int STAGES>
 struct AttnCfg {
@@ -467,6 +471,7 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const int4 tile = p.tiles[item / p.n_heads];
           const int nblk = (tile.w - (tile.z & ~7) + ATT_BN - 1) / ATT_BN;
           if (nblk <= 0) continue;
+          att_stamp(p, static_cast<int>(nq), 8);
           mbar_wait(q_full, nq & 1);
           ++nq;
           for (int j = 0; j < nblk; ++j, ++nb) {
@@ -474,6 +479,7 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             // thread's MMAs in issue order), and the softmax warps were done with the previous S before they signalled p_ready
             mbar_wait(k_full, nb & 1);
             tc_fence_after();
+            if (j == 0) att_stamp(p, static_cast<int>(nq) - 1, 9);
 #pragma unroll
             for (int k = 0; k < ATT_D / 16; ++k) {
               const uint64_t da = umma_desc_k_sw128(aQ + (k >> 2) * 16384) + static_cast<uint64_t>((k & 3) * 2);
@@ -487,8 +493,10 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(&v_full[vs], (nb / VS) & 1);
             // the first P V of an item overwrites O: the softmax warps signal p_ready for it only after they have read the
             // previous item's O (program order in each of the 128 threads)
+            if (j == 0) att_stamp(p, static_cast<int>(nq) - 1, 10);
             mbar_wait(p_ready, nb & 1);
             tc_fence_after();
+            if (j == 0) att_stamp(p, static_cast<int>(nq) - 1, 11);
             const uint32_t aV = smem_u32(sV + vs * Cfg::kVStage);
 #pragma unroll
             for (int k = 0; k < ATT_BN / 16; ++k) {
@@ -538,17 +546,21 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       row_range(item + gridDim.x, lo_next, hi_next);
       if (nblk <= 0) continue;
       float m = -INFINITY, l = 0.f;
+      const bool stamp = r == 0;
+      if (stamp) att_stamp(p, static_cast<int>(ni), 0);
 
       for (int j = 0; j < nblk; ++j, ++nb) {
         const int kbase = kv_lo + j * ATT_BN;
         mbar_wait(s_full, nb & 1);
         tc_fence_after();
+        if (stamp && j == 0) att_stamp(p, static_cast<int>(ni), 1);
         uint32_t v0[32], v1[32], v2[32], v3[32];  // the row's 128 scores (separate arrays: they must stay in registers)
         tmem_ld_32x32b_x32(tS, v0);
         tmem_ld_32x32b_x32(tS + 32, v1);
         tmem_ld_32x32b_x32(tS + 64, v2);
         tmem_ld_32x32b_x32(tS + 96, v3);
         tmem_ld_wait();
+        if (stamp && j == 0) att_stamp(p, static_cast<int>(ni), 2);
         const bool all_visible = kbase >= lo && kbase + ATT_BN <= hi;
         float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         auto max_chunk = [&](uint32_t(&vv)[32], int c) {
@@ -587,6 +599,7 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_st_32x32b_x16(tPV + c * 16, ov);
           }
         }
+        if (stamp && j == 0) att_stamp(p, static_cast<int>(ni), 3);
         const float neg_m = (m == -INFINITY) ? 0.f : -m;
         float rsa[4] = {0.f, 0.f, 0.f, 0.f};
         auto exp_chunk = [&](const uint32_t(&vv)[32], int c) {
@@ -605,11 +618,14 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         exp_chunk(v2, 2);
         exp_chunk(v3, 3);
         l = l * alpha + ((rsa[0] + rsa[1]) + (rsa[2] + rsa[3]));
+        if (stamp && j == 0) att_stamp(p, static_cast<int>(ni), 4);
         tmem_st_wait();
         tc_fence_before();  // our TMEM accesses (S reads, P / O stores) are ordered before the MMAs released below
         mbar_arrive(p_ready);
+        if (stamp && j == 0) att_stamp(p, static_cast<int>(ni), 5);
       }
       mbar_wait(pv_full, ni & 1);  // committed once per item, after its last P V
+      if (stamp) att_stamp(p, static_cast<int>(ni), 6);
       ++ni;
       tc_fence_after();
       {
@@ -633,6 +649,7 @@ attn_fwd_tp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
         }
       }
+      if (stamp) att_stamp(p, static_cast<int>(ni) - 1, 7);
       tc_fence_before();  // the O reads above are ordered before the next item's first P V (released through p_ready)
       }  // items
     }
@@ -677,9 +694,15 @@ static int launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtenso
   return SR_OK;
 }
 
+static long long* g_attn_trace = nullptr;  // sr_set_attention_trace (diagnostics)
 static int g_attn_lean = -1;  // -1: env SR_ATTN_LEAN (default 2); 0 = one CTA / SM, 1 = lean, 2 = lean with P in tensor memory
 
 }  // namespace sr
+
+extern "C" int sr_set_attention_trace(void* buffer) {
+  sr::g_attn_trace = reinterpret_cast<long long*>(buffer);
+  return SR_OK;
+}
 
 extern "C" int sr_set_attention_lean(int enabled) {
   // 0 / 1 / 2: kernel variant (see g_attn_lean); 3: variant 2 with one CTA per work item instead of the persistent grid
@@ -735,6 +758,7 @@ extern "C" int sr_attention_fwd(const void* Q, int64_t q_row_stride, int64_t q_h
   p.group = n_q_heads / n_kv_heads;
   p.n_tiles = n_tiles;
   p.n_heads = n_q_heads;
+  p.trace = g_attn_trace;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (g_attn_lean < 0) {
     const char* e = getenv("SR_ATTN_LEAN");

@@ -52,6 +52,7 @@ SYMBOLS = {
     "sr_sample_topk_topp": (c_int, [_P, c_int64, c_int, c_int, _P, c_int, _P, c_float, c_int, c_float, _P, _P]),
     "sr_logprob_entropy": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sr_set_attention_lean": (c_int, [c_int]),
+    "sr_set_attention_trace": (c_int, [_P]),
     "sr_lmhead_logprob_workspace_bytes": (c_int64, [c_int, c_int]),
     "sr_lmhead_logprob_entropy": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, _P, _P, _P, _P]),
     "sr_decode_advance": (c_int, [_P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),

@@ -101,13 +101,17 @@ class PendingDecode:
         lib.launch_count += run * self.engine._decode_launches
         return run
 
-    def ticker(self, n_ticks: int):
-        """A ``tick`` callback that spreads the remaining decode steps evenly over ``n_ticks`` calls."""
+    def ticker(self, n_ticks: int, first: int = 0, last: Optional[int] = None):
+        """A ``tick`` callback that spreads the remaining decode steps evenly over calls ``first`` .. ``last`` - 1 of ``n_ticks``
+        (default: all of them); calls outside that window submit nothing, the last call of the window completes the count."""
+        last = n_ticks if last is None else last
+        span = max(last - first, 1)
         total, state = self.remaining, {"i": 0, "done": 0}
 
         def tick():
             state["i"] += 1
-            want = (total * state["i"] + n_ticks - 1) // n_ticks
+            k = min(max(state["i"] - first, 0), span)
+            want = (total * k + span - 1) // span
             if want > state["done"]:
                 state["done"] += self.advance(want - state["done"])
         return tick

@@ -12,6 +12,7 @@ moves masks + IoU + generated tokens of all ranks (rank order == chunk order == 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -182,7 +183,11 @@ class DataParallelRollout:
         tick = None
         if prev is not None and prev.get("pending") is not None:
             with_images = batch.pixel_values is not None or batch.tiles_u8 is not None
-            tick = prev["pending"].ticker(eng.prefill_ticks(with_images))
+            n_ticks = eng.prefill_ticks(with_images)
+            n_vit = n_ticks - len(eng.w.layers)
+            where = os.environ.get("SR_PIPELINE_TICKS", "even")   # experiment knob: "vit" / "dec" = only between ViT blocks / decoder layers
+            first, last = (0, n_vit) if (where == "vit" and n_vit > 0) else ((n_vit, n_ticks) if where == "dec" else (0, n_ticks))
+            tick = prev["pending"].ticker(n_ticks, first, last)
         self._inflight = self._front(batch, b_max, eng, tick, defer=True)
         return self._back(prev) if prev is not None else None
 
